@@ -1,0 +1,141 @@
+"""ctypes binding of the C ABI declared in include/auromat_b200.h.
+
+There is deliberately NO fallback: if the shared library is missing or cannot be loaded the
+import of any compute path raises.  The reference's arrays are produced by CUDA kernels or
+not at all.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libauromat_b200.so")
+
+AMT_OK, AMT_ERR_INVALID_ARGUMENT, AMT_ERR_UNSUPPORTED, AMT_ERR_CUDA, AMT_ERR_NO_DEVICE = range(5)
+AMT_SIP_MAX_ORDER = 9
+AMT_SIP_MAX_COEF = 55
+AMT_U8, AMT_U16 = 0, 1
+AMT_PRE_NONE, AMT_PRE_WRAP180, AMT_PRE_POLE = 0, 1, 2
+
+c_double_p = C.POINTER(C.c_double)
+
+
+class AmtFrame(C.Structure):
+    _fields_ = [
+        ("width", C.c_int32), ("height", C.c_int32),
+        ("fast_center", C.c_int32), ("origin_inside", C.c_int32),
+        ("crpix", C.c_double * 2), ("cd", C.c_double * 4), ("rot", C.c_double * 9),
+        ("cam", C.c_double * 3), ("inv_axes", C.c_double * 3),
+        ("m_geo", C.c_double * 9), ("m_sm", C.c_double * 9),
+        ("wgs_a", C.c_double), ("wgs_b", C.c_double),
+        ("sip_order_a", C.c_int32), ("sip_order_b", C.c_int32),
+        ("sip_a", C.c_double * AMT_SIP_MAX_COEF), ("sip_b", C.c_double * AMT_SIP_MAX_COEF),
+    ]
+
+
+class AmtGeorefOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "d_lat_k", "d_lon_k", "d_mlat_k", "d_mlt_k",
+        "d_lat_c", "d_lon_c", "d_mlat_c", "d_mlt_c", "d_elev_c")]
+
+
+class AmtStats(C.Structure):
+    _fields_ = [
+        ("lat_min", C.c_double), ("lat_max", C.c_double),
+        ("lon_min", C.c_double), ("lon_max", C.c_double),
+        ("lon_min_pos", C.c_double), ("lon_max_neg", C.c_double),
+        ("n_valid_corners", C.c_uint64), ("n_boundary_corners", C.c_uint64),
+        ("n_valid_centers", C.c_uint64), ("n_ill_conditioned", C.c_uint64),
+        ("pole_flags", C.c_uint64),
+    ]
+
+
+class AmtGrid(C.Structure):
+    _fields_ = [
+        ("nx", C.c_int32), ("ny", C.c_int32), ("prerotate", C.c_int32), ("reserved", C.c_int32),
+        ("lo_x", C.c_double), ("hi_x", C.c_double), ("step_x", C.c_double),
+        ("lo_y", C.c_double), ("hi_y", C.c_double), ("step_y", C.c_double),
+        ("round_x", C.c_double), ("round_y", C.c_double),
+        ("altitude", C.c_double), ("wgs_a", C.c_double), ("wgs_b", C.c_double),
+        ("rot", C.c_double * 9),
+    ]
+
+
+# name -> (restype, argtypes); every symbol declared in include/auromat_b200.h
+SIGNATURES = {
+    "amt_last_error": (C.c_char_p, []),
+    "amt_abi_version": (C.c_int, []),
+    "amt_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "amt_ctx_destroy": (C.c_int, [C.c_void_p]),
+    "amt_ctx_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "amt_ctx_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "amt_alloc_device": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "amt_free_device": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "amt_alloc_pinned": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "amt_free_pinned": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "amt_copy_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "amt_copy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "amt_memset_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p]),
+    "amt_stream_synchronize": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "amt_georef": (C.c_int, [C.c_void_p, C.POINTER(AmtFrame), C.POINTER(AmtGeorefOut), C.c_void_p, C.c_void_p]),
+    "amt_sanitize": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(AmtGeorefOut), C.c_void_p]),
+    "amt_bbox_stats": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.POINTER(AmtGrid), C.c_void_p, C.c_void_p]),
+    "amt_apply_center_mask": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_double,
+                                        C.POINTER(AmtGeorefOut), C.c_void_p]),
+    "amt_rotate_coords": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(AmtGrid), C.c_void_p]),
+    "amt_plate_carree_coords": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double,
+                                          C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "amt_latlon_to_mlatmlt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_double,
+                                        C.c_double, c_double_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "amt_bin_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                     C.c_int32, C.c_size_t, C.POINTER(AmtGrid), C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]),
+    "amt_cell_indices": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(AmtGrid),
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    "amt_normalise": (C.c_int, [C.c_void_p, C.POINTER(AmtGrid), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "amt_georef_bin_fused": (C.c_int, [C.c_void_p, C.POINTER(AmtFrame), C.c_void_p, C.c_int32, C.c_int32,
+                                       C.POINTER(AmtGrid), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+
+
+class AmtError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libauromat_b200.so (once).  Raises if it has not been built -- run
+    `python -m auromat_b200.csrc.build` (or `__graft_entry__.build()`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "auromat_b200: the CUDA extension %s is missing. Build it with "
+            "`python -m auromat_b200.csrc.build`; there is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the ABI lost a symbol
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.amt_abi_version() != 1:
+        raise ImportError("auromat_b200: ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(status: int):
+    """Map the C status codes onto the exception types the reference raises
+    (error conventions)."""
+    if status == AMT_OK:
+        return
+    msg = load().amt_last_error().decode("utf-8", "replace")
+    if status == AMT_ERR_INVALID_ARGUMENT:
+        raise ValueError(msg)
+    if status == AMT_ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise AmtError(msg)

@@ -1,0 +1,267 @@
+// Device-side FP64 math for the georeference + regrid path (sm_100a).
+//
+// Every function cites the reference lines whose arithmetic it reproduces (paths relative
+// to the reference tree esa/auromat v1.0.8).  This translation unit is compiled with
+// -fmad=false: a*b+c in the source stays a rounded multiply followed by a rounded add, which
+// is what the reference's numpy passes do; fused operations appear only where written
+// explicitly as fma()/__fma_rn().
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/auromat_b200.h"
+
+namespace amt {
+
+constexpr double kRad2Deg = 57.29577951308232;   // numpy rad2deg multiplier: 180/pi
+constexpr double kDeg2Rad = 0.017453292519943295; // numpy deg2rad multiplier: pi/180
+
+__device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
+
+// Device copy of the per-frame constants with everything pre-digested for the kernels.
+struct FrameC {
+    int W, H;
+    int fast_center, origin_inside;
+    double crpix0, crpix1;
+    double cd[4];
+    double rot[9];
+    double cam[3];          // lineOrigin
+    double rad[3];          // (1/a, 1/a, 1/b)          intersection.py:66
+    double otr[3];          // (-cam) * rad             intersection.py:63,68
+    double oDO;             // otr . otr                intersection.py:74
+    double m_geo[9];
+    double m_sm[9];
+    double a, b, e2a, d;    // Bowring constants        transform.py:254-255,290
+    int sip_oa, sip_ob;
+};
+
+// ---------------------------------------------------------------------------------------
+// Stage 1: pixel -> native TAN plane -> unit vector -> celestial (ICRS) direction.
+// coordinates/wcs.py:93-144.  The reference goes (x,y) -> (phi,theta) via atan2/atan and
+// back to Cartesian via sin/cos; the composition is the algebraic identity
+//     (cos t cos p, cos t sin p, sin t) = (-y, x, 180/pi) / sqrt(x^2 + y^2 + (180/pi)^2)
+// with p = atan2(x,-y), t = atan((180/pi)/r), which we evaluate directly: no transcendental
+// call, <= 2 ulp from the reference's value (tested against the oracle to 1e-9 deg after
+// the full chain).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void sip_distort(const double* __restrict__ ca, int oa,
+                                            const double* __restrict__ cb, int ob,
+                                            double& u, double& v) {
+    // f(u,v) = sum_{p+q<=order} C_pq u^p v^q, Horner in v inside Horner in u, highest power
+    // first (same fixed order as oracle/_sip_poly).
+    double fu = 0.0, fv = 0.0;
+    for (int pass = 0; pass < 2; ++pass) {
+        const double* c = pass == 0 ? ca : cb;
+        const int order = pass == 0 ? oa : ob;
+        double acc = 0.0;
+        for (int p = order; p >= 0; --p) {
+            const int base = p * (order + 1) - (p * (p - 1)) / 2;
+            double inner = 0.0;
+            for (int q = order - p; q >= 0; --q) inner = inner * v + c[base + q];
+            acc = acc * u + inner;
+        }
+        if (pass == 0) fu = acc; else fv = acc;
+    }
+    u = u + fu;
+    v = v + fv;
+}
+
+__device__ __forceinline__ void pix2dir(const FrameC& f, const double* __restrict__ sip_a,
+                                        const double* __restrict__ sip_b,
+                                        double px, double py, double dir[3]) {
+    // wcs.py:93-99: (px - CRPIX1) + 1, 0-based pixel coordinates
+    double u = (px - f.crpix0) + 1.0;
+    double v = (py - f.crpix1) + 1.0;
+    if (f.sip_oa | f.sip_ob) sip_distort(sip_a, f.sip_oa, sip_b, f.sip_ob, u, v);
+    // wcs.py:102  xy = CD . pxy
+    const double x = f.cd[0] * u + f.cd[1] * v;
+    const double y = f.cd[2] * u + f.cd[3] * v;
+    // wcs.py:111-144 collapsed (see header comment)
+    const double K = 180.0 / 3.141592653589793;
+    const double n2 = (x * x + y * y) + K * K;
+    const double inv = 1.0 / sqrt(n2);
+    const double l = -y * inv, m = x * inv, n = K * inv;
+    // wcs.py:142  lmnrot = R . lmn
+    dir[0] = (f.rot[0] * l + f.rot[1] * m) + f.rot[2] * n;
+    dir[1] = (f.rot[3] * l + f.rot[4] * m) + f.rot[5] * n;
+    dir[2] = (f.rot[6] * l + f.rot[7] * m) + f.rot[8] * n;
+}
+
+// ---------------------------------------------------------------------------------------
+// Stage 2a: directed ray / inflated-ellipsoid intersection in the J2000 frame.
+// coordinates/intersection.py:58-104, operation for operation (this block is the
+// ill-conditioned one for grazing rays, so no re-association and no FMA).
+// Returns the normalised discriminant rootTerm/dDD for conditioning diagnostics.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double intersect(const FrameC& f, const double dir[3], double P[3]) {
+    const double D0 = dir[0] * f.rad[0], D1 = dir[1] * f.rad[1], D2 = dir[2] * f.rad[2];
+    const double dDO = (D0 * f.otr[0] + D1 * f.otr[1]) + D2 * f.otr[2];
+    const double dDD = (D0 * D0 + D1 * D1) + D2 * D2;
+    double rt = dDO * dDO;
+    rt = rt - f.oDO * dDD;
+    rt = rt + dDD;
+    const double root = sqrt(rt);                    // NaN when the line misses
+    double t = f.origin_inside ? dDO + root : dDO - root;
+    if (t < 0.0) t = qnan();                         // intersection.py:50-56 (behind the camera)
+    t = t / dDD;
+    P[0] = dir[0] * t + f.cam[0];                    // res = direction*dMin - (-lineOrigin)
+    P[1] = dir[1] * t + f.cam[1];
+    P[2] = dir[2] * t + f.cam[2];
+    return rt / dDD;
+}
+
+__device__ __forceinline__ void mat3(const double* __restrict__ M, const double v[3], double o[3]) {
+    o[0] = (M[0] * v[0] + M[1] * v[1]) + M[2] * v[2];
+    o[1] = (M[3] * v[0] + M[4] * v[1]) + M[5] * v[2];
+    o[2] = (M[6] * v[0] + M[7] * v[1]) + M[8] * v[2];
+}
+
+// ---------------------------------------------------------------------------------------
+// Stage 2b: ECEF -> geodetic, single-iteration Bowring 1985.
+// coordinates/transform.py:252-297 (`_ecef2GeodeticOptimized_np`).  Output in radians.
+// `cu3 **= 3` of the reference is libm pow(c,3); we use c*c*c (<= 1 ulp apart; the term it
+// feeds is scaled by e^2 ~ 0.7 %, so the effect on lat is < 1e-18 rad).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void bowring(double a, double b, double e2a, double d,
+                                        double x, double y, double z, double& lat, double& lon) {
+    const double p2 = x * x + y * y;
+    const double p = sqrt(p2);
+    const double r = sqrt(p2 + z * z);
+    double tu = d / r;
+    tu = tu + 1.0;
+    tu = tu * b;
+    tu = tu * z;
+    tu = tu / (a * p);
+    const double tu2 = tu * tu;
+    double c = 1.0 / sqrt(1.0 + tu2);
+    const double cu3 = (c * c) * c;
+    double su3 = tu * cu3;
+    su3 = su3 * tu2;
+    double tp = d * su3 + z;
+    const double pm = p - cu3 * e2a;
+    tp = tp / pm;
+    lat = atan(tp);
+    lon = atan2(y, x);
+}
+
+// geodetic -> ECEF, coordinates/transform.py:156-178 (radians in).
+__device__ __forceinline__ void geodetic2ecef(double a, double e2, double lat, double lon, double h,
+                                              double& x, double& y, double& z) {
+    double sl, cl, so, co;
+    sincos(lat, &sl, &cl);
+    sincos(lon, &so, &co);
+    const double n = a / sqrt(1.0 - e2 * (sl * sl));
+    const double nh = n + h;
+    x = (nh * cl) * co;
+    y = (nh * cl) * so;
+    z = (n * (1.0 - e2) + h) * sl;
+}
+
+// SM Cartesian -> (MLat deg, MLT h): transform.py:104-127 + :419-430 + :373-386.
+__device__ __forceinline__ void sm_to_mlat_mlt(const double S[3], double& mlat, double& mlt) {
+    const double s = sqrt(S[0] * S[0] + S[1] * S[1]);
+    const double smlon = atan2(S[1], S[0]) * kRad2Deg;
+    mlat = atan2(S[2], s) * kRad2Deg;
+    mlt = smlon * (24.0 / 360.0) + 12.0;
+}
+
+// elevation, mapping/astrometry.py:200-212 + utils.py:28-46; `dir` need not be unit
+// (fast centres use the un-normalised mean of four corner directions, astrometry.py:61-62).
+__device__ __forceinline__ double elevation_deg(const double dir[3], const double P[3]) {
+    const double len = sqrt((P[0] * P[0] + P[1] * P[1]) + P[2] * P[2]);
+    const double u0 = P[0] / len, u1 = P[1] / len, u2 = P[2] / len;
+    double dot = ((-dir[0]) * u0 + (-dir[1]) * u1) + (-dir[2]) * u2;
+    // np.clip(dot, -1, 1): NaN propagates
+    if (dot < -1.0) dot = -1.0;
+    if (dot > 1.0) dot = 1.0;
+    return 90.0 - acos(dot) * kRad2Deg;
+}
+
+// One J2000 intersection point -> lat/lon [deg] (+ MLat/MLT).  transform.py:324-343,403-430.
+__device__ __forceinline__ void point_to_geo(const FrameC& f, const double P[3], double& lat, double& lon) {
+    double G[3];
+    mat3(f.m_geo, P, G);
+    double la, lo;
+    bowring(f.a, f.b, f.e2a, f.d, G[0], G[1], G[2], la, lo);
+    lat = la * kRad2Deg;
+    lon = lo * kRad2Deg;
+}
+
+__device__ __forceinline__ void point_to_mag(const FrameC& f, const double P[3], double& mlat, double& mlt) {
+    double S[3];
+    mat3(f.m_sm, P, S);
+    sm_to_mlat_mlt(S, mlat, mlt);
+}
+
+// ---------------------------------------------------------------------------------------
+// Stage 3 helpers: numpy semantics reproduced bit for bit.
+// ---------------------------------------------------------------------------------------
+// numpy.linspace(lo, hi, n+1)[k]  (util/histogram.py:185-186): fl(fl(k*step) + lo), last == hi
+__device__ __forceinline__ double edge_at(double lo, double hi, double step, int n, int k) {
+    return k == n ? hi : __dadd_rn(__dmul_rn((double)k, step), lo);
+}
+
+__device__ __forceinline__ double next_up(double x) {      // toward +inf, finite x
+    if (x == 0.0) return __longlong_as_double(1LL);
+    const long long b = __double_as_longlong(x);
+    return __longlong_as_double(x > 0.0 ? b + 1 : b - 1);
+}
+__device__ __forceinline__ double next_down(double x) { return -next_up(-x); }
+
+// searchsorted(edges, x, 'right') - 1 with the right-edge fix of util/histogram.py:205-224
+// and outliers mapped to -1.  With NEAR, `near` is set when x lies within 1 ulp of one of
+// the bin edges that decided its cell (the samples the parity statement allows to differ
+// when lat/lon themselves differ in the last bit).
+template <bool NEAR>
+__device__ __forceinline__ int bin_index(double x, double lo, double hi, double step, double inv_step,
+                                         int n, double round_scale, bool& near) {
+    near = false;
+    if (!(x == x)) return -1;                        // NaN sorts last -> outlier
+    if (x < lo) {
+        if (NEAR) near = next_up(x) >= lo;
+        return -1;
+    }
+    if (x >= hi) {
+        // util/histogram.py:215-224: np.around(x, decimal) == np.around(hi, decimal)
+        const double rx = rint(__dmul_rn(x, round_scale)) / round_scale;
+        const double rh = rint(__dmul_rn(hi, round_scale)) / round_scale;
+        if (NEAR) near = next_down(x) <= hi;
+        return rx == rh ? n - 1 : -1;
+    }
+    const double g = floor(__dmul_rn(__dsub_rn(x, lo), inv_step));
+    int k = g < 0.0 ? 0 : (g > (double)(n - 1) ? n - 1 : (int)g);
+    // fix up against the true numpy edges: want edges[k] <= x < edges[k+1]
+    while (k > 0 && edge_at(lo, hi, step, n, k) > x) --k;
+    while (k < n - 1 && edge_at(lo, hi, step, n, k + 1) <= x) ++k;
+    if (NEAR) {
+        const double e0 = edge_at(lo, hi, step, n, k), e1 = edge_at(lo, hi, step, n, k + 1);
+        near = (next_down(x) <= e0) || (next_up(x) >= e1);
+    }
+    return k;
+}
+
+// numpy floor_divide / remainder for doubles (npy_divmod), used by the astropy-style wrap
+__device__ __forceinline__ double np_floor_divide(double a, double b) {
+    double mod = fmod(a, b);
+    double div = (a - mod) / b;
+    if (mod != 0.0 && ((b < 0.0) != (mod < 0.0))) div -= 1.0;
+    if (div != 0.0) {
+        double fl = floor(div);
+        if (div - fl > 0.5) fl += 1.0;
+        return fl;
+    }
+    return copysign(0.0, a / b);
+}
+
+// Angle(x deg).wrap_at(180 deg).degree (astropy `_wrap_at`): x - floor((x+180)/360)*360
+// with the two rounding fix-ups.  Oracle: wrap_at_180().
+__device__ __forceinline__ double wrap_at_180(double x) {
+    const double wraps = np_floor_divide(x - (-180.0), 360.0);
+    if (wraps == wraps && wraps != 0.0 && !isinf(wraps)) {
+        x = x - wraps * 360.0;
+        if (x >= 180.0) x -= 360.0;
+        if (x < -180.0) x += 360.0;
+    }
+    return x;
+}
+
+}  // namespace amt

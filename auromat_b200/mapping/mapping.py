@@ -1,0 +1,552 @@
+"""Georeferenced-image objects whose coordinate arrays live in B200 HBM.
+
+API mirror of `auromat/mapping/mapping.py` of the reference (BoundingBox :44-287,
+BaseMapping :293-929, GenericMapping :1233-1310, MappingCollection :1315-1373,
+checkPlateCarree :931-975, convertMappingToSM :1519-1559): same names, same array shapes and
+the same masked-array contract -- `lats, lons` (h+1,w+1), `latsCenter, lonsCenter,
+elevation` (h,w), `img` (h,w,n), `mLatMlt`, `mLatMltCenter`, all `numpy.ma` float64 with
+NaN <=> masked -- but the arrays are *device planes* produced by the CUDA kernels and are
+copied to the host only when a numpy-facing property is read.  `resample()` and the masking
+methods consume the device planes directly.
+"""
+from __future__ import annotations
+
+import copy
+from collections import namedtuple
+
+import numpy as np
+import numpy.ma as ma
+
+from .. import _lib
+from ..coordinates import transform
+from ..coordinates.geodesic import Location, wgs84A, wgs84B
+from ..runtime import get_context
+
+Size = namedtuple('Size', ['width', 'height'])
+MappingProperties = namedtuple('MappingProperties',
+                               'altitude cameraPosGCRS boundingBox photoTime '
+                               'centroid cameraFootpoint identifier')
+
+CORNER_PLANES = ('lat_k', 'lon_k', 'mlat_k', 'mlt_k')
+CENTER_PLANES = ('lat_c', 'lon_c', 'mlat_c', 'mlt_c', 'elev_c')
+
+
+def wrapAt180(x):
+    """`Angle(x deg).wrap_at(180 deg).degree`: values in [-180, 180) are returned unchanged,
+    everything else is shifted by whole turns (astropy's `_wrap_at`)."""
+    a = np.array(x, dtype=np.float64, copy=True, ndmin=1)
+    with np.errstate(invalid='ignore'):
+        wraps = (a + 180.0) // 360.0
+    valid = np.isfinite(wraps) & (wraps != 0)
+    if np.any(valid):
+        a -= wraps * 360.0
+        a[a >= 180.0] -= 360.0
+        a[a < -180.0] += 360.0
+    return a if np.ndim(x) else float(a[0])
+
+
+class BoundingBox(object):
+    """A geographical bounding box that may span the 180-degree discontinuity
+    (reference mapping.py:44-287)."""
+
+    def __init__(self, latSouth, lonWest, latNorth, lonEast):
+        assert -180 <= lonWest <= 180, 'Longitude: ' + str(lonWest)
+        assert -180 <= lonEast <= 180, 'Longitude: ' + str(lonEast)
+        assert -90 <= latSouth <= 90, 'Latitude: ' + str(latSouth)
+        assert -90 <= latNorth <= 90, 'Latitude: ' + str(latNorth)
+        self._box = (latSouth, lonWest, latNorth, lonEast)
+
+    latSouth = property(lambda self: self._box[0])
+    lonWest = property(lambda self: self._box[1])
+    latNorth = property(lambda self: self._box[2])
+    lonEast = property(lambda self: self._box[3])
+    topLeft = property(lambda self: Location(self.latNorth, self.lonWest))
+    bottomLeft = property(lambda self: Location(self.latSouth, self.lonWest))
+    topRight = property(lambda self: Location(self.latNorth, self.lonEast))
+    bottomRight = property(lambda self: Location(self.latSouth, self.lonEast))
+
+    @property
+    def containsDiscontinuity(self):
+        return self.lonWest > self.lonEast or self.containsPole
+
+    @property
+    def containsPole(self):
+        return self.lonWest == -180 and self.lonEast == 180 and (self.latNorth == 90 or self.latSouth == -90)
+
+    @staticmethod
+    def minimumBoundingBox(latLons):
+        return BoundingBox.mergedBoundingBoxes([BoundingBox(lat, lon, lat, lon) for lat, lon in latLons])
+
+    @staticmethod
+    def mergedBoundingBoxes(boundingBoxes):
+        """Smallest box containing all given boxes: latitude by min/max, longitude by
+        removing the largest uncovered gap on the circle (reference mapping.py:236-282)."""
+        boxes = list(boundingBoxes)
+        latSouth = min(bb.latSouth for bb in boxes)
+        latNorth = max(bb.latNorth for bb in boxes)
+        spans = []
+        for bb in boxes:
+            w, e = bb.lonWest, bb.lonEast
+            spans.append((w, e if e >= w else e + 360))
+        xs = np.sort(np.array([[bb.lonWest, bb.lonEast] for bb in boxes]).ravel())
+        xs = np.concatenate((xs, [xs[0] + 360]))
+        best, bestIdx = -1.0, 0
+        for i in range(1, len(xs)):
+            lo, hi = xs[i - 1], xs[i]
+            covered = any((w <= lo and e >= hi) or (w <= lo + 360 and e >= hi + 360) or
+                          (w <= lo - 360 and e >= hi - 360) for w, e in spans)
+            if not covered and hi - lo > best:
+                best, bestIdx = hi - lo, i - 1
+        lonWest = wrapAt180(xs[bestIdx + 1])
+        lonEast = wrapAt180(xs[bestIdx])
+        return BoundingBox(latSouth, lonWest, latNorth, lonEast)
+
+    def __eq__(self, obj):
+        return isinstance(obj, BoundingBox) and self._box == obj._box
+
+    def __ne__(self, obj):
+        return not self == obj
+
+    def __hash__(self):
+        return hash(self._box)
+
+    def __repr__(self):
+        return 'BoundingBox(latSouth={0}, lonWest={1}, latNorth={2}, lonEast={3})'.format(*self._box)
+
+
+class BaseMapping(object):
+    """Base class of all mappings: a georeferenced image at a given altitude.
+
+    Guarantees (reference mapping.py:299-316) hold on the device planes after
+    `_ensurePlanes()`: corner lat/lon are NaN together, centre lat/lon/elevation are NaN
+    together, a centre is defined only if its 4 corners are, a corner only if one of its
+    neighbouring centres is, and `img` is masked exactly where `latsCenter` is.
+
+    Subclasses provide `_computePlanes(ctx, names)` (fill `self._planes` with device
+    tensors) and the image (`img_unmasked`).
+    """
+
+    def __init__(self, altitude, cameraPosGCRS, photoTime, identifier, metadata=None, device=None):
+        assert altitude >= 0
+        cameraPosGCRS = np.asarray(cameraPosGCRS)
+        assert cameraPosGCRS.shape == (3,)
+        self._altitude = altitude
+        self._cameraPosGCRS = cameraPosGCRS
+        self._photoTime = photoTime
+        self._identifier = identifier
+        self._metadata = metadata
+        self._device = device
+        self._planes = {}          # name -> device tensor (float64, NaN == masked)
+        self._host = {}            # name -> numpy masked array cache
+        self._stats = None
+        self._boundingBox = None
+        self._imgDevice = None
+
+    # ------------------------------------------------------------------ device side
+    @property
+    def context(self):
+        return get_context(self._device)
+
+    @property
+    def shape(self):
+        """(h, w) of the image."""
+        raise NotImplementedError
+
+    def _computePlanes(self, ctx, names):
+        raise NotImplementedError
+
+    def _ensurePlanes(self, names):
+        missing = [n for n in names if n not in self._planes]
+        if missing:
+            self._computePlanes(self.context, missing)
+        return self._planes
+
+    def devicePlanes(self, magnetic=False):
+        """Device tensors of the coordinate planes (computing them if necessary)."""
+        names = ['lat_k', 'lon_k', 'lat_c', 'lon_c', 'elev_c']
+        if magnetic:
+            names += ['mlat_k', 'mlt_k', 'mlat_c', 'mlt_c']
+        return self._ensurePlanes(names)
+
+    def prefetch(self, magnetic=True):
+        """Run the georeferencing kernels now (one fused launch) instead of on first access."""
+        self.devicePlanes(magnetic=magnetic)
+        return self
+
+    def deviceImage(self):
+        """The raw (unmasked) image as a device tensor (h, w, n)."""
+        if self._imgDevice is None:
+            img = self.img_unmasked
+            if img.ndim == 2:
+                img = img[..., None]
+            self._imgDevice = self.context.to_device(img)
+        return self._imgDevice
+
+    def _download(self, name):
+        if name not in self._host:
+            h, w = self.shape
+            t = self._ensurePlanes([name])[name]
+            shape = (h + 1, w + 1) if name.endswith('_k') else (h, w)
+            arr = self.context.to_numpy(t).reshape(shape)
+            self._host[name] = ma.masked_invalid(arr, copy=False)
+        return self._host[name]
+
+    def _deviceStats(self):
+        if self._stats is None:
+            ctx = self.context
+            p = self.devicePlanes()
+            h, w = self.shape
+            st = ctx.new_stats()
+            ctx.bbox_stats(w, h, p['lat_k'], p['lon_k'], p['lat_c'], st)
+            s = ctx.read_stats(st)
+            if getattr(self, '_illConditioned', None) is not None:
+                s.n_ill_conditioned = int(ctx.read_stats(self._illConditioned).n_ill_conditioned)
+            self._stats = s
+        return self._stats
+
+    # ------------------------------------------------------------------ plain attributes
+    altitude = property(lambda self: self._altitude)
+    cameraPosGCRS = property(lambda self: self._cameraPosGCRS)
+    photoTime = property(lambda self: self._photoTime)
+    identifier = property(lambda self: self._identifier)
+
+    @property
+    def metadata(self):
+        return {} if self._metadata is None else self._metadata
+
+    @property
+    def properties(self):
+        return MappingProperties(identifier=self.identifier, altitude=self.altitude,
+                                 cameraPosGCRS=self.cameraPosGCRS, boundingBox=self.boundingBox,
+                                 photoTime=self.photoTime, centroid=self.centroid,
+                                 cameraFootpoint=self.cameraFootpoint)
+
+    @property
+    def cameraFootpoint(self):
+        """Camera footpoint in geodetic coordinates (reference mapping.py:443-452)."""
+        et = transform.date2es(self.photoTime)
+        g = transform.mat_j2000_to_geo(et).dot(np.asarray(self.cameraPosGCRS, dtype=np.float64))
+        lat, lon = transform.ecef2GeodeticScalar(g[0], g[1], g[2])
+        return Location(np.rad2deg(lat), np.rad2deg(lon))
+
+    # ------------------------------------------------------------------ numpy-facing arrays
+    lats = property(lambda self: self._download('lat_k'))
+    lons = property(lambda self: self._download('lon_k'))
+    latsCenter = property(lambda self: self._download('lat_c'))
+    lonsCenter = property(lambda self: self._download('lon_c'))
+    elevation = property(lambda self: self._download('elev_c'))
+
+    @property
+    def mLatMlt(self):
+        return self._download('mlat_k'), self._download('mlt_k')
+
+    @property
+    def mLatMltCenter(self):
+        return self._download('mlat_c'), self._download('mlt_c')
+
+    @property
+    def img_unmasked(self):
+        raise NotImplementedError
+
+    @property
+    def img(self):
+        """Masked (h,w,n) image; masked exactly where `latsCenter` is."""
+        if 'img' not in self._host:
+            data = self.img_unmasked
+            mask = ma.getmaskarray(self.latsCenter)
+            if data.ndim == 3:
+                mask = np.repeat(mask[:, :, None], data.shape[2], 2)
+            self._host['img'] = ma.masked_array(data, mask=mask)
+        return self._host['img']
+
+    @property
+    def rgb_unmasked(self):
+        img = self.img_unmasked
+        if img.dtype == np.uint16:
+            img = (img * (255 / 65535)).astype(np.uint8)
+        elif img.dtype != np.uint8:
+            raise NotImplementedError
+        if img.ndim == 2:
+            img = img[..., None]
+        if img.shape[2] == 3:
+            return img
+        if img.shape[2] == 1:
+            return np.repeat(img, 3, 2)
+        raise NotImplementedError('Unknown img format')
+
+    @property
+    def rgb(self):
+        mask = np.repeat(ma.getmaskarray(self.latsCenter)[:, :, None], 3, 2)
+        return ma.masked_array(self.rgb_unmasked, mask=mask)
+
+    # ------------------------------------------------------------------ derived geometry
+    @property
+    def boundingBox(self):
+        """Min/max of the outline (the boundary of the valid-corner mask), widened to the full
+        longitude range when a pole is enclosed (reference mapping.py:694-743).  The
+        reductions and the pole test run on the device (`amt_bbox_stats`)."""
+        if self._boundingBox is None:
+            s = self._deviceStats()
+            if s.n_boundary_corners == 0:
+                raise ValueError('the mapping has no defined coordinates')
+            latMin, latMax, lonMin, lonMax = s.lat_min, s.lat_max, s.lon_min, s.lon_max
+            if s.pole_flags:
+                if latMax < 0:
+                    box = (-90, -180, latMax, 180)
+                else:
+                    box = (latMin, -180, 90, 180)
+            elif lonMax - lonMin > 180:
+                box = (latMin, s.lon_min_pos, latMax, s.lon_max_neg)
+            else:
+                box = (latMin, lonMin, latMax, lonMax)
+            self._boundingBox = BoundingBox(*box)
+        return self._boundingBox
+
+    containsDiscontinuity = property(lambda self: self.boundingBox.containsDiscontinuity)
+    containsPole = property(lambda self: self.boundingBox.containsPole)
+
+    @property
+    def outline(self):
+        """(n,2) [lat, lon] of the boundary nodes of the valid-corner mask, in row-major order
+        (NOT a clockwise polygon walk as in the reference, mapping.py:655-691)."""
+        lats, lons = self.lats, self.lons
+        valid = ~ma.getmaskarray(lats)
+        pad = np.zeros((valid.shape[0] + 2, valid.shape[1] + 2), bool)
+        pad[1:-1, 1:-1] = valid
+        interior = pad[:-2, 1:-1] & pad[2:, 1:-1] & pad[1:-1, :-2] & pad[1:-1, 2:]
+        b = valid & ~interior
+        return np.transpose([lats.data[b], lons.data[b]])
+
+    @property
+    def centroid(self):
+        raise NotImplementedError('polygon centroid needs the ordered outline walk (out of the hot path)')
+
+    @property
+    def isPlateCarree(self):
+        return isPlateCarree(self.lats, self.lons)
+
+    def checkPlateCarree(self):
+        return checkPlateCarree(self.lats, self.lons)
+
+    # ------------------------------------------------------------------ masking
+    def createMasked(self, centerMask):
+        """Copy of this mapping with `centerMask` (True == masked) applied to the centre
+        planes; corners left without any defined neighbour are masked as well."""
+        centerMask = np.ascontiguousarray(centerMask, dtype=np.uint8)
+        assert centerMask.shape == tuple(self.shape)
+        return self._maskedCopy(mask=centerMask)
+
+    def maskedByElevation(self, minElevation=10):
+        """New mapping with data below `minElevation` degrees masked (reference
+        mapping.py:845-864); runs entirely on the device planes."""
+        m = self._maskedCopy(minElevation=float(minElevation))
+        if m._deviceStats().n_valid_centers == 0:
+            raise ValueError('minElevation=' + str(minElevation) + ' would mask all pixels!')
+        return m
+
+    def _maskedCopy(self, mask=None, minElevation=float('nan')):
+        ctx = self.context
+        have_mag = 'mlat_k' in self._planes
+        src = self.devicePlanes(magnetic=have_mag)
+        m = copy.copy(self)
+        m._planes = {k: v.clone() for k, v in src.items()}
+        m._host = {}
+        m._stats = None
+        m._boundingBox = None
+        m._illConditioned = None
+        h, w = self.shape
+        dmask = ctx.to_device(mask.ravel()) if mask is not None else None
+        ctx.apply_center_mask(w, h, m._planes, dmask, minElevation)
+        return m
+
+    def setDirty(self):
+        self._boundingBox = None
+        self._stats = None
+
+    # ------------------------------------------------------------------ invariants
+    def checkGuarantees(self):
+        """Test helper, same assertions as reference mapping.py:362-428."""
+        lats, lons = self.lats, self.lons
+        latsCenter, lonsCenter = self.latsCenter, self.lonsCenter
+        mlat, mlt = self.mLatMlt
+        mlatCenter, mltCenter = self.mLatMltCenter
+        img, elevation = self.img, self.elevation
+        for a in (lats, latsCenter, mlat, elevation):
+            assert not np.any(np.isnan(a))
+        mk, mc = ma.getmaskarray(lats), ma.getmaskarray(latsCenter)
+        assert np.array_equal(mk, ma.getmaskarray(lons))
+        assert np.array_equal(mc, ma.getmaskarray(lonsCenter))
+        pad = np.zeros((mc.shape[0] + 2, mc.shape[1] + 2), bool)
+        pad[1:-1, 1:-1] = ~mc
+        assert np.all(mk | pad[1:, 1:] | pad[1:, :-1] | pad[:-1, :-1] | pad[:-1, 1:])
+        ok = ~mk
+        assert np.all(mc | (ok[:-1, :-1] & ok[1:, :-1] & ok[1:, 1:] & ok[:-1, 1:]))
+        imgMask = ma.getmaskarray(img)
+        imgMask = imgMask.reshape(imgMask.shape[0], imgMask.shape[1], -1)
+        for d in range(imgMask.shape[2]):
+            assert np.array_equal(imgMask[:, :, d], mc)
+        assert np.array_equal(ma.getmaskarray(elevation), mc)
+        assert np.array_equal(ma.getmaskarray(mlatCenter), mc)
+        assert np.array_equal(ma.getmaskarray(mltCenter), mc)
+        assert np.array_equal(ma.getmaskarray(mlat), mk)
+        assert np.array_equal(ma.getmaskarray(mlt), mk)
+
+    # ------------------------------------------------------------------ to be overridden
+    def createResampled(self, lats, lons, latsCenter, lonsCenter, elevation, img):
+        return GenericMapping(lats, lons, latsCenter, lonsCenter, elevation, self.altitude, img,
+                              self.cameraPosGCRS, self.photoTime, self.identifier, metadata=self.metadata,
+                              device=self._device)
+
+
+def checkPlateCarree(lats, lons):
+    """Raise ValueError unless the 2-D coordinate arrays describe a plate-carree grid:
+    latitudes evenly spaced and decreasing, longitudes evenly spaced and increasing
+    (reference mapping.py:931-960)."""
+    if ma.isMaskedArray(lats):
+        lats, lons = lats.data, lons.data
+    if np.any(np.isnan(lats)):
+        raise ValueError('coordinates contains NaNs')
+    lons = np.unwrap(np.deg2rad(lons))
+    if lons[0, -1] - lons[0, 0] <= 0:
+        raise ValueError('longitudes are not monotonically increasing')
+    if lats[0, 0] - lats[-1, 0] <= 0:
+        raise ValueError('latitudes are not monotonically decreasing')
+    eps = 1e-4
+    dLon = np.diff(lons[0])
+    if not np.max(dLon) - np.min(dLon) < eps:
+        raise ValueError('longitudes are not evenly spaced; max delta: {}'.format(np.max(dLon) - np.min(dLon)))
+    dLat = -np.diff(lats[:, 0])
+    if not np.max(dLat) - np.min(dLat) < eps:
+        raise ValueError('latitudes are not evenly spaced; max delta: {}'.format(np.max(dLat) - np.min(dLat)))
+
+
+def isPlateCarree(lats, lons):
+    try:
+        checkPlateCarree(lats, lons)
+    except Exception:
+        return False
+    return True
+
+
+class GenericMapping(BaseMapping):
+    """A mapping built from precalculated coordinate arrays (numpy, masked numpy or device
+    tensors), e.g. the result of `resample()` (reference mapping.py:1233-1310).  The arrays
+    are uploaded once and sanitised on the device."""
+
+    def __init__(self, lats, lons, latsCenter, lonsCenter, elev, alti, img, cameraPosGCRS, photoTime,
+                 identifier, metadata=None, device=None, sanitize=True):
+        h, w = img.shape[0], img.shape[1]
+        assert tuple(lats.shape) == tuple(lons.shape) == (h + 1, w + 1)
+        assert tuple(latsCenter.shape) == tuple(lonsCenter.shape) == (h, w)
+        assert elev is None or tuple(elev.shape) == (h, w)
+        assert img.dtype in (np.uint8, np.uint16)
+        BaseMapping.__init__(self, alti, cameraPosGCRS, photoTime, identifier, metadata, device)
+        self._shape = (h, w)
+        if ma.isMaskedArray(img):
+            imgMask = ma.getmaskarray(img).reshape(h, w, -1)[:, :, 0]
+            img = img.data
+        else:
+            imgMask = None
+        self._imgData = img
+        ctx = self.context
+
+        def up(a):
+            if hasattr(a, 'data_ptr'):          # already a device tensor
+                return a.reshape(-1)
+            if ma.isMaskedArray(a):
+                a = a.astype(np.float64).filled(np.nan)
+            return ctx.to_device(np.asarray(a, dtype=np.float64)).reshape(-1)
+
+        self._planes = dict(lat_k=up(lats), lon_k=up(lons), lat_c=up(latsCenter), lon_c=up(lonsCenter))
+        if elev is not None:
+            self._planes['elev_c'] = up(elev)
+        else:
+            import torch
+            self._planes['elev_c'] = ctx.zeros(h * w, torch.float64)
+        if imgMask is not None and imgMask.any():
+            # reference mapping.py:1077-1081: the image mask is applied to the centre coordinates
+            ctx.apply_center_mask(w, h, self._planes, ctx.to_device(imgMask.astype(np.uint8).ravel()))
+        if sanitize:
+            ctx.sanitize(w, h, self._planes)
+
+    shape = property(lambda self: self._shape)
+    img_unmasked = property(lambda self: self._imgData)
+
+    def _computePlanes(self, ctx, names):
+        # generic geodetic -> MLat/MLT route (reference mapping.py:540-550)
+        if any(n.startswith('ml') for n in names):
+            m = transform.mat_geo_to_sm(transform.date2es(self.photoTime))
+            for suffix in ('k', 'c'):
+                mlat, mlt = ctx.latlon_to_mlatmlt(self._planes['lat_' + suffix], self._planes['lon_' + suffix],
+                                                  self.altitude, wgs84A, wgs84B, m)
+                self._planes['mlat_' + suffix], self._planes['mlt_' + suffix] = mlat, mlt
+        unknown = [n for n in names if n not in self._planes]
+        if unknown:
+            raise KeyError(unknown)
+
+    @staticmethod
+    def fromMapping(mapping):
+        p = mapping.devicePlanes()
+        h, w = mapping.shape
+        return GenericMapping(p['lat_k'].clone().reshape(h + 1, w + 1), p['lon_k'].clone().reshape(h + 1, w + 1),
+                              p['lat_c'].clone().reshape(h, w), p['lon_c'].clone().reshape(h, w),
+                              p['elev_c'].clone().reshape(h, w), mapping.altitude, mapping.img_unmasked,
+                              mapping.cameraPosGCRS, mapping.photoTime, mapping.identifier, mapping.metadata,
+                              device=mapping._device, sanitize=False)
+
+
+class MappingCollection(object):
+    """Mappings of (almost) the same photo time, e.g. a network of all-sky cameras
+    (reference mapping.py:1315-1373)."""
+
+    def __init__(self, mappings, identifier, mayOverlap=True):
+        self._mappings = mappings
+        self._identifier = identifier
+        self._mayOverlap = mayOverlap
+
+    identifier = property(lambda self: self._identifier)
+    mappings = property(lambda self: self._mappings)
+    mayOverlap = property(lambda self: self._mayOverlap)
+    empty = property(lambda self: len(self._mappings) == 0)
+
+    def maskedByElevation(self, minElevation=10):
+        return MappingCollection([m.maskedByElevation(minElevation) for m in self.mappings],
+                                 self.identifier, self.mayOverlap)
+
+    @property
+    def boundingBox(self):
+        return BoundingBox.mergedBoundingBoxes([m.boundingBox for m in self.mappings])
+
+    @property
+    def photoTime(self):
+        times = sorted(m.photoTime for m in self.mappings)
+        return times[len(times) // 2]
+
+    def __len__(self):
+        return len(self._mappings)
+
+
+class _SMMapping(GenericMapping):
+    @property
+    def cameraFootpoint(self):
+        et = transform.date2es(self.photoTime)
+        s = transform.mat_j2000_to_sm(et).dot(np.asarray(self.cameraPosGCRS, dtype=np.float64))
+        mlat = np.rad2deg(np.arctan2(s[2], np.sqrt(s[0] * s[0] + s[1] * s[1])))
+        mlt = transform.smLonToMLT(np.rad2deg(np.arctan2(s[1], s[0])))
+        return Location(mlat, transform.mltToSmLon(mlt))
+
+
+def convertMappingToSM(mapping):
+    """Mapping whose "lat/lon" are solar-magnetic latitude / longitude (reference
+    mapping.py:1519-1547); used by `resampleMLatMLT`."""
+    p = mapping.devicePlanes(magnetic=True)
+    h, w = mapping.shape
+
+    def smlon(mlt):
+        return transform.mltToSmLon(mlt.clone())
+
+    return _SMMapping(p['mlat_k'].clone().reshape(h + 1, w + 1), smlon(p['mlt_k']).reshape(h + 1, w + 1),
+                      p['mlat_c'].clone().reshape(h, w), smlon(p['mlt_c']).reshape(h, w),
+                      p['elev_c'].clone().reshape(h, w), mapping.altitude, mapping.img_unmasked,
+                      mapping.cameraPosGCRS, mapping.photoTime, mapping.identifier, device=mapping._device,
+                      sanitize=False)

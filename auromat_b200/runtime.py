@@ -1,0 +1,196 @@
+"""Per-GPU runtime: one C-ABI context per device, torch tensors as device/pinned memory.
+
+PyTorch is plumbing only (allocator, streams, torch.distributed); every array pass of the
+hot path is one of the CUDA kernels behind `include/auromat_b200.h`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
+
+from . import _lib
+
+_contexts = {}
+_lock = threading.Lock()
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class Context:
+    """Owns an `amt_ctx*` for one CUDA device and wraps the C entry points with torch
+    tensors (device pointers) as arguments."""
+
+    def __init__(self, device: int):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise RuntimeError("auromat_b200 needs a CUDA device (B200, sm_100a); none is visible and "
+                               "there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = int(device)
+        self.torch_device = torch.device("cuda", self.device)
+        handle = C.c_void_p()
+        _lib.check(self.lib.amt_ctx_create(self.device, C.byref(handle)))
+        self.handle = handle
+        self._stats_dev = None
+
+    # ------------------------------------------------------------------ plumbing
+    def stream(self):
+        return C.c_void_p(_torch().cuda.current_stream(self.torch_device).cuda_stream)
+
+    def synchronize(self):
+        _torch().cuda.current_stream(self.torch_device).synchronize()
+
+    def empty(self, shape, dtype):
+        torch = _torch()
+        return torch.empty(shape, dtype=dtype, device=self.torch_device)
+
+    def zeros(self, shape, dtype):
+        torch = _torch()
+        return torch.zeros(shape, dtype=dtype, device=self.torch_device)
+
+    def to_device(self, array, non_blocking=True):
+        """numpy array (or pinned torch CPU tensor) -> device tensor on the current stream."""
+        torch = _torch()
+        if isinstance(array, np.ndarray):
+            if array.dtype == np.uint16:
+                t = torch.from_numpy(np.ascontiguousarray(array).view(np.int16))
+                return t.to(self.torch_device, non_blocking=non_blocking).view(torch.uint16)
+            array = torch.from_numpy(np.ascontiguousarray(array))
+        return array.to(self.torch_device, non_blocking=non_blocking)
+
+    @staticmethod
+    def to_numpy(tensor):
+        torch = _torch()
+        t = tensor.detach()
+        if t.dtype == torch.uint16:
+            return t.view(torch.int16).cpu().numpy().view(np.uint16)
+        return t.cpu().numpy()
+
+    @staticmethod
+    def ptr(tensor):
+        return C.c_void_p(tensor.data_ptr()) if tensor is not None else C.c_void_p(None)
+
+    @property
+    def launch_count(self) -> int:
+        n = C.c_uint64()
+        _lib.check(self.lib.amt_ctx_launch_count(self.handle, C.byref(n)))
+        return n.value
+
+    # ------------------------------------------------------------------ kernels
+    def georef(self, frame: _lib.AmtFrame, planes: dict, stats=None):
+        """planes: name -> device tensor for any subset of amt_georef_out members."""
+        out = _lib.AmtGeorefOut()
+        for name, t in planes.items():
+            setattr(out, "d_" + name, t.data_ptr())
+        _lib.check(self.lib.amt_georef(self.handle, C.byref(frame), C.byref(out), self.ptr(stats), self.stream()))
+
+    def new_stats(self):
+        torch = _torch()
+        return torch.zeros(C.sizeof(_lib.AmtStats), dtype=torch.uint8, device=self.torch_device)
+
+    def sanitize(self, width, height, planes: dict):
+        out = _lib.AmtGeorefOut()
+        for name, t in planes.items():
+            setattr(out, "d_" + name, t.data_ptr())
+        _lib.check(self.lib.amt_sanitize(self.handle, width, height, C.byref(out), self.stream()))
+
+    def bbox_stats(self, width, height, lat_k, lon_k, lat_c, stats, pre: "_lib.AmtGrid | None" = None):
+        _lib.check(self.lib.amt_bbox_stats(self.handle, width, height, self.ptr(lat_k), self.ptr(lon_k),
+                                           self.ptr(lat_c), C.byref(pre) if pre is not None else None,
+                                           self.ptr(stats), self.stream()))
+
+    def apply_center_mask(self, width, height, planes: dict, mask=None, min_elevation=float("nan")):
+        out = _lib.AmtGeorefOut()
+        for name, t in planes.items():
+            setattr(out, "d_" + name, t.data_ptr())
+        _lib.check(self.lib.amt_apply_center_mask(self.handle, width, height, self.ptr(mask),
+                                                  float(min_elevation), C.byref(out), self.stream()))
+
+    def rotate_coords(self, lat, lon, pre: _lib.AmtGrid):
+        _lib.check(self.lib.amt_rotate_coords(self.handle, self.ptr(lat), self.ptr(lon), lat.numel(),
+                                              C.byref(pre), self.stream()))
+
+    def plate_carree_coords(self, nx, ny, lat_hi, lat_lo, lon_lo, lon_hi):
+        torch = _torch()
+        lat_k = torch.empty((ny + 1, nx + 1), dtype=torch.float64, device=self.torch_device)
+        lon_k = torch.empty_like(lat_k)
+        lat_c = torch.empty((ny, nx), dtype=torch.float64, device=self.torch_device)
+        lon_c = torch.empty_like(lat_c)
+        _lib.check(self.lib.amt_plate_carree_coords(self.handle, nx, ny, float(lat_hi), float(lat_lo),
+                                                    float(lon_lo), float(lon_hi), self.ptr(lat_k), self.ptr(lon_k),
+                                                    self.ptr(lat_c), self.ptr(lon_c), self.stream()))
+        return lat_k, lon_k, lat_c, lon_c
+
+    def read_stats(self, stats) -> _lib.AmtStats:
+        raw = stats.cpu().numpy().tobytes()
+        return _lib.AmtStats.from_buffer_copy(raw)
+
+    def latlon_to_mlatmlt(self, lat, lon, altitude, wgs_a, wgs_b, m_geo_sm):
+        torch = _torch()
+        mlat = torch.empty_like(lat)
+        mlt = torch.empty_like(lat)
+        m = (C.c_double * 9)(*np.asarray(m_geo_sm, dtype=np.float64).ravel())
+        _lib.check(self.lib.amt_latlon_to_mlatmlt(self.handle, self.ptr(lat), self.ptr(lon), lat.numel(),
+                                                  float(altitude), float(wgs_a), float(wgs_b), m,
+                                                  self.ptr(mlat), self.ptr(mlt), self.stream()))
+        return mlat, mlt
+
+    def bin_accumulate(self, lat_c, lon_c, side, img, grid: _lib.AmtGrid, count, sums, fsum, near_edge=None):
+        torch = _torch()
+        dtype = {torch.uint8: _lib.AMT_U8, torch.uint16: _lib.AMT_U16}.get(img.dtype)
+        if dtype is None:
+            raise NotImplementedError("image dtype must be uint8 or uint16, got %s" % img.dtype)
+        n = lat_c.numel()
+        channels = img.numel() // n
+        _lib.check(self.lib.amt_bin_accumulate(self.handle, self.ptr(lat_c), self.ptr(lon_c), self.ptr(side),
+                                               self.ptr(img), dtype, channels, n, C.byref(grid), self.ptr(count),
+                                               self.ptr(sums), self.ptr(fsum), self.ptr(near_edge), self.stream()))
+
+    def cell_indices(self, lat_c, lon_c, grid: _lib.AmtGrid):
+        torch = _torch()
+        ix = torch.empty(lat_c.numel(), dtype=torch.int32, device=self.torch_device)
+        iy = torch.empty_like(ix)
+        _lib.check(self.lib.amt_cell_indices(self.handle, self.ptr(lat_c), self.ptr(lon_c), lat_c.numel(),
+                                             C.byref(grid), self.ptr(ix), self.ptr(iy), self.stream()))
+        return ix, iy
+
+    def normalise(self, grid: _lib.AmtGrid, img_dtype, channels, count, sums, fsum):
+        torch = _torch()
+        dtype = {torch.uint8: _lib.AMT_U8, torch.uint16: _lib.AMT_U16}[img_dtype]
+        out_img = torch.empty((grid.ny, grid.nx, channels), dtype=img_dtype, device=self.torch_device)
+        out_mask = torch.empty((grid.ny, grid.nx), dtype=torch.uint8, device=self.torch_device)
+        out_side = torch.empty((grid.ny, grid.nx), dtype=torch.float64, device=self.torch_device) \
+            if fsum is not None else None
+        _lib.check(self.lib.amt_normalise(self.handle, C.byref(grid), dtype, channels, self.ptr(count),
+                                          self.ptr(sums), self.ptr(fsum), self.ptr(out_img), self.ptr(out_mask),
+                                          self.ptr(out_side), self.stream()))
+        return out_img, out_mask, out_side
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.amt_ctx_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def get_context(device=None) -> Context:
+    """The process-wide context of `device` (default: torch's current CUDA device)."""
+    torch = _torch()
+    if device is None:
+        if not torch.cuda.is_available():
+            raise RuntimeError("auromat_b200 needs a CUDA device (B200, sm_100a); none is visible and "
+                               "there is no CPU fallback")
+        device = torch.cuda.current_device()
+    device = int(device)
+    with _lock:
+        ctx = _contexts.get(device)
+        if ctx is None:
+            ctx = _contexts[device] = Context(device)
+        return ctx

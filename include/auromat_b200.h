@@ -1,0 +1,250 @@
+/*
+ * auromat_b200 -- C ABI of the B200 (sm_100a) georeference + regrid hot path.
+ *
+ * The reference (esa/auromat v1.0.8) is pure Python and has no FFI; its boundary for this
+ * path is the Python API `auromat.mapping.spacecraft.getMapping` + `auromat.resample.resample`.
+ * This header declares the flat C entry points a maintainer would bind (ctypes) to replace
+ * the numpy array passes underneath that API.  Each entry point cites the reference
+ * interface it replaces (paths relative to the reference tree).
+ *
+ * Conventions
+ *   - every function returns an `amt_status` (0 == AMT_OK); `amt_last_error()` returns a
+ *     thread-local, human readable message for the last non-zero status;
+ *   - all pointers named `d_*` are DEVICE pointers, all pointers named `h_*` are HOST
+ *     pointers; the library never returns memory it owns except through amt_alloc_* ;
+ *   - all kernels are enqueued on the `stream` argument (a `cudaStream_t` passed as void*,
+ *     NULL == legacy default stream) and the functions do NOT synchronise unless stated;
+ *   - arrays are C-contiguous, row-major, the layout numpy gives the reference's arrays;
+ *   - misses (no ray/ellipsoid intersection) are NaN, exactly as in the reference
+ *     (`numpy.ma.masked_invalid` is applied by the Python wrapper).
+ */
+#ifndef AUROMAT_B200_H
+#define AUROMAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMT_ABI_VERSION 1
+
+typedef enum amt_status {
+    AMT_OK = 0,
+    AMT_ERR_INVALID_ARGUMENT = 1, /* -> ValueError / AssertionError in the wrapper      */
+    AMT_ERR_UNSUPPORTED = 2,      /* -> NotImplementedError (projection, method, dtype)  */
+    AMT_ERR_CUDA = 3,             /* -> RuntimeError with the CUDA error string          */
+    AMT_ERR_NO_DEVICE = 4         /* -> RuntimeError: no CUDA device / wrong arch        */
+} amt_status;
+
+/* ----------------------------------------------------------------------------------------
+ * Per-frame constants.  Everything in here is computed ON THE HOST by the wrapper exactly
+ * as the reference computes it (scalar Python/numpy), once per frame:
+ *   crpix, cd          coordinates/wcs.py:83-90    header CRPIX1/2, CD1_1..CD2_2
+ *   rot                coordinates/wcs.py:135-139  euler_matrix(..., 'rzxz')[:3,:3]
+ *   sip_*              FITS-SIP forward polynomial (reference: astropy fallback, wcs.py:54-56)
+ *   cam                mapping/mapping.py:318      cameraPosGCRS [km]
+ *   inv_axes           coordinates/intersection.py:66  (1/a, 1/a, 1/b) of the inflated ellipsoid,
+ *                      a = wgs84A + altitude, b = wgs84B + altitude (mapping/mapping.py:1497-1500)
+ *   origin_inside      coordinates/intersection.py:239-241
+ *   m_geo              coordinates/transform.py:683-686  mat_j2000_to_geo(et)
+ *   m_sm               coordinates/transform.py:688-691  mat_j2000_to_sm(et)
+ *   wgs_a, wgs_b       coordinates/geodesic.py:20-21  (un-inflated, used by Bowring)
+ * -------------------------------------------------------------------------------------- */
+#define AMT_SIP_MAX_ORDER 9
+#define AMT_SIP_MAX_COEF 55 /* (9+1)(9+2)/2 */
+
+typedef struct amt_frame {
+    int32_t width, height;      /* IMAGEW, IMAGEH                                         */
+    int32_t fast_center;        /* mapping/astrometry.py:24-40 fastCenterCalculation      */
+    int32_t origin_inside;
+    double crpix[2];
+    double cd[4];               /* row-major 2x2                                          */
+    double rot[9];              /* row-major 3x3, native -> celestial                     */
+    double cam[3];
+    double inv_axes[3];
+    double m_geo[9];            /* row-major 3x3                                          */
+    double m_sm[9];
+    double wgs_a, wgs_b;
+    int32_t sip_order_a;        /* 0 == no SIP                                            */
+    int32_t sip_order_b;
+    /* packed triangular: index(p,q) = p*(order+1) - p*(p-1)/2 + q  for p+q <= order      */
+    double sip_a[AMT_SIP_MAX_COEF];
+    double sip_b[AMT_SIP_MAX_COEF];
+} amt_frame;
+
+/* Outputs of the georeference pass; any pointer may be NULL (that plane is not written).
+ * Corner planes have (height+1)*(width+1) doubles, centre planes height*width.
+ * Replaces the lazy array properties of mapping/astrometry.py:108-212:
+ *   lat_k, lon_k   -> lats, lons                 (:138-144)   degrees
+ *   mlat_k, mlt_k  -> mLatMlt                    (:170-183)   degrees / hours
+ *   lat_c, lon_c   -> latsCenter, lonsCenter     (:146-152)
+ *   mlat_c, mlt_c  -> mLatMltCenter              (:185-198)
+ *   elev_c         -> elevation                  (:200-212)   degrees                    */
+typedef struct amt_georef_out {
+    double* d_lat_k;
+    double* d_lon_k;
+    double* d_mlat_k;
+    double* d_mlt_k;
+    double* d_lat_c;
+    double* d_lon_c;
+    double* d_mlat_c;
+    double* d_mlt_c;
+    double* d_elev_c;
+} amt_georef_out;
+
+/* Reductions over the corner planes (mapping/mapping.py:694-743 boundingBox min/max part;
+ * "boundary" = valid corner with an invalid or out-of-array 4-neighbour, i.e. the nodes the
+ * reference's outline (mapping.py:672-681, utils.py:97-139) runs through).               */
+typedef struct amt_stats {
+    double lat_min, lat_max;         /* over boundary corners                             */
+    double lon_min, lon_max;
+    double lon_min_pos, lon_max_neg; /* min over lon>0, max over lon<=0 (discontinuity)    */
+    uint64_t n_valid_corners;
+    uint64_t n_boundary_corners;
+    uint64_t n_valid_centers;
+    uint64_t n_ill_conditioned;      /* rays with tiny discriminant        */
+    uint64_t pole_flags;             /* bit0: a valid pixel quad encloses the north pole,
+                                        bit1: the south pole (replaces the outline/azimuth
+                                        test of mapping.py:705-718, geodesic.py:183-202)   */
+} amt_stats;
+
+/* Plate-carree target grid as seen by the binning kernel.  The wrapper derives these on the
+ * host with the reference's own arithmetic (resample.py:220-241,281-299,330-335):
+ *   x axis = longitude, y axis = latitude (util/histogram.py call at resample.py:337)
+ *   edges_x[i] = fl(fl(i*step_x) + lo_x), edges_x[nx] = hi_x   (numpy.linspace)           */
+typedef enum amt_prerotate {
+    AMT_PRE_NONE = 0,
+    AMT_PRE_WRAP180 = 1,   /* resample.py:203-218  lon := wrap_at_180(lon + 180)           */
+    AMT_PRE_POLE = 2       /* resample.py:176-201  rotatePole(+90 deg about X)             */
+} amt_prerotate;
+
+typedef struct amt_grid {
+    int32_t nx, ny;        /* number of core bins: (nLon-2), (nLat-2)                      */
+    int32_t prerotate;     /* amt_prerotate                                                */
+    int32_t reserved;
+    double lo_x, hi_x, step_x;
+    double lo_y, hi_y, step_y;
+    double round_x, round_y;   /* 10**decimal of util/histogram.py:218-219                 */
+    double altitude;           /* for AMT_PRE_POLE (transform.py:301-322)                  */
+    double wgs_a, wgs_b;
+    double rot[9];             /* rotation_matrix(+90deg, X)[:3,:3] for AMT_PRE_POLE       */
+} amt_grid;
+
+typedef enum amt_dtype { AMT_U8 = 0, AMT_U16 = 1 } amt_dtype;
+
+/* ------------------------------------------------------------------------ context ---- */
+typedef struct amt_ctx amt_ctx;
+
+const char* amt_last_error(void);
+int amt_abi_version(void);
+
+/* Creates a context bound to CUDA device `device` (must be compute capability 10.x).     */
+int amt_ctx_create(int device, amt_ctx** out);
+int amt_ctx_destroy(amt_ctx* ctx);
+int amt_ctx_device(const amt_ctx* ctx, int* device);
+/* Number of kernels this context has launched so far (bench.py `gpu_launches`).           */
+int amt_ctx_launch_count(const amt_ctx* ctx, uint64_t* count);
+
+/* Plain memory helpers so that a C caller does not need the CUDA runtime API.            */
+int amt_alloc_device(amt_ctx* ctx, size_t bytes, void** d_ptr);
+int amt_free_device(amt_ctx* ctx, void* d_ptr);
+int amt_alloc_pinned(amt_ctx* ctx, size_t bytes, void** h_ptr);
+int amt_free_pinned(amt_ctx* ctx, void* h_ptr);
+int amt_copy_h2d(amt_ctx* ctx, void* d_dst, const void* h_src, size_t bytes, void* stream);
+int amt_copy_d2h(amt_ctx* ctx, void* h_dst, const void* d_src, size_t bytes, void* stream);
+int amt_memset_device(amt_ctx* ctx, void* d_ptr, int value, size_t bytes, void* stream);
+int amt_stream_synchronize(amt_ctx* ctx, void* stream);
+
+/* ------------------------------------------------------------------- stage 1 + 2 ---- */
+/* Fused pixel -> WCS(TAN[+SIP]) -> ray -> inflated-ellipsoid intersection -> geodetic
+ * lat/lon, MLat/MLT, elevation, for all corners and all centres of one frame.
+ * Replaces: coordinates/wcs.py:18-157, mapping/mapping.py:1474-1510,
+ * coordinates/intersection.py:58-104, coordinates/transform.py:252-297,324-343,403-430,
+ * mapping/astrometry.py:49-64,86-106,138-212, utils.py:28-46.                             */
+int amt_georef(amt_ctx* ctx, const amt_frame* frame, const amt_georef_out* out,
+               amt_stats* d_stats /* nullable: n_ill_conditioned += ... */, void* stream);
+
+/* Mask sanitisation, in place: planes get NaN where the reference would mask.
+ * Replaces mapping/mapping.py:1063-1125 (`_doSanitize`, afterMasking=False, no image mask):
+ *   corner masked if all of its (<=4) neighbouring centres are missing; centre masked if any
+ *   of its 4 corners is masked; corners once more.  Needs lat_k and lat_c; every non-NULL
+ *   plane of `planes` is updated consistently.                                            */
+int amt_sanitize(amt_ctx* ctx, int32_t width, int32_t height, const amt_georef_out* planes,
+                 void* stream);
+
+/* Bounding-box reductions over the boundary corners (min/max part of
+ * mapping/mapping.py:694-743) plus valid counts.  When `pre` is non-NULL and
+ * pre->prerotate != AMT_PRE_NONE the boundary coordinates are first rotated exactly as
+ * resample.py:176-218 rotates the outline (only prerotate, altitude, wgs_a/b and rot of
+ * `pre` are read).  `d_stats` is a DEVICE amt_stats; n_ill_conditioned is left untouched. */
+int amt_bbox_stats(amt_ctx* ctx, int32_t width, int32_t height, const double* d_lat_k,
+                   const double* d_lon_k, const double* d_lat_c, const amt_grid* pre,
+                   amt_stats* d_stats, void* stream);
+
+/* Apply a centre mask (mapping/mapping.py:845-864 maskedByElevation, :1171-1231 createMasked
+ * followed by `_doSanitize(afterMasking=True)`), in place: a centre becomes NaN if
+ * d_mask[i] != 0 (d_mask nullable) or if !(d_elev_c[i] >= min_elevation) (skipped when
+ * min_elevation is NaN); then every corner whose (<=4) neighbouring centres are all missing
+ * becomes NaN.                                                                             */
+int amt_apply_center_mask(amt_ctx* ctx, int32_t width, int32_t height, const uint8_t* d_mask,
+                          double min_elevation, const amt_georef_out* planes, void* stream);
+
+/* rotatePole (coordinates/transform.py:301-322) or the 180-degree longitude wrap
+ * (resample.py:213,218,276-277) applied in place to `n` (lat, lon) pairs in degrees; only
+ * prerotate, altitude, wgs_a/b and rot of `pre` are read.                                  */
+int amt_rotate_coords(amt_ctx* ctx, double* d_lat, double* d_lon, size_t n, const amt_grid* pre,
+                      void* stream);
+
+/* Coordinates of the plate-carree target grid (resample.py:229-241): writes the 2-D corner
+ * planes (ny+1)x(nx+1) and centre planes ny x nx of the resampled mapping, row 0 = north,
+ * from the snapped node ranges lat: linspace(lat_hi, lat_lo, ny+2), lon: linspace(lon_lo,
+ * lon_hi, nx+2) -- bit-identical to numpy.linspace / meshgrid.  Any output may be NULL.   */
+int amt_plate_carree_coords(amt_ctx* ctx, int32_t nx, int32_t ny, double lat_hi, double lat_lo,
+                            double lon_lo, double lon_hi, double* d_lat_k, double* d_lon_k,
+                            double* d_lat_c, double* d_lon_c, void* stream);
+
+/* Generic (non-astrometry) geodetic -> MLat/MLT route of mapping/mapping.py:540-550 +
+ * coordinates/transform.py:156-178,432-459 for `n` points; lat/lon in degrees.           */
+int amt_latlon_to_mlatmlt(amt_ctx* ctx, const double* d_lat, const double* d_lon, size_t n,
+                          double altitude, double wgs_a, double wgs_b, const double m_geo_sm[9],
+                          double* d_mlat, double* d_mlt, void* stream);
+
+/* ----------------------------------------------------------------------- stage 3 ---- */
+/* Accumulators: `d_count` and `d_sums` are u64 planes of ny*nx cells, row 0 = NORTHERNMOST
+ * latitude row (the reference's flipud, resample.py:349); `d_sums` holds `channels` planes;
+ * `d_fsum` is one f64 plane for the float side channel (elevation) or NULL.
+ * The caller zeroes them (amt_memset_device) -- or keeps accumulating several frames into
+ * the same grid (mosaic).
+ * Replaces resample.py:176-218 (pre-rotation), :315-338 + util/histogram.py:205-262.
+ * `d_img`: height*width*channels interleaved (numpy HWC), dtype u8 or u16.
+ * A centre pixel participates iff its latitude is not NaN (resample.py:316).
+ * `d_near_edge`: optional u64 counter of samples within 1 ulp of a bin edge.              */
+int amt_bin_accumulate(amt_ctx* ctx, const double* d_lat_c, const double* d_lon_c,
+                       const double* d_side, const void* d_img, int32_t dtype, int32_t channels,
+                       size_t n_pixels, const amt_grid* grid, uint64_t* d_count, uint64_t* d_sums,
+                       double* d_fsum, uint64_t* d_near_edge, void* stream);
+
+/* Per-sample core-bin indices (ix, iy), -1 for outliers / NaN: the index computation of
+ * util/histogram.py:205-224 exposed for the bit-exactness tests.                          */
+int amt_cell_indices(amt_ctx* ctx, const double* d_lat_c, const double* d_lon_c, size_t n_pixels,
+                     const amt_grid* grid, int32_t* d_ix, int32_t* d_iy, void* stream);
+
+/* sum / count -> mean; NaN (mask=1) where count == 0; integer images are rounded half-even
+ * and cast back to `dtype` (resample.py:128-136,339-351).
+ * out_img: ny*nx*channels interleaved; out_mask: ny*nx bytes; out_side: ny*nx doubles.   */
+int amt_normalise(amt_ctx* ctx, const amt_grid* grid, int32_t dtype, int32_t channels,
+                  const uint64_t* d_count, const uint64_t* d_sums, const double* d_fsum,
+                  void* d_out_img, uint8_t* d_out_mask, double* d_out_side, void* stream);
+
+/* Fully fused centre chain: pixel -> ray -> intersection -> lat/lon (+elevation) -> bin,
+ * without materialising any per-pixel plane.                 */
+int amt_georef_bin_fused(amt_ctx* ctx, const amt_frame* frame, const void* d_img, int32_t dtype,
+                         int32_t channels, const amt_grid* grid, uint64_t* d_count,
+                         uint64_t* d_sums, double* d_fsum, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUROMAT_B200_H */

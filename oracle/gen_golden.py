@@ -1,0 +1,120 @@
+"""Generates tests/golden/*.npz by running the REFERENCE ITSELF (esa/auromat, imported from
+/root/reference through oracle/ref_shim.py) on seeded synthetic inputs.  Run inside the build
+container only (the reference tree does not exist on the GPU box):
+
+    python oracle/gen_golden.py
+
+The arrays stored are the reference's own outputs; tests compare the oracle restatement
+(bit for bit) and the CUDA path (to the stated tolerances) against them.
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim  # noqa: E402
+from auromat_b200 import synthetic  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def quiet():
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+def reference_frame(ref, hdr, cam, t, fast):
+    """lat/lon/mlat/mlt/elevation through the reference's own functions
+    (mapping/astrometry.py:49-212 call order)."""
+    H, W = hdr['IMAGEH'], hdr['IMAGEW']
+    import auromat.utils as U
+    A = ref.astrometry.BaseAstrometryMapping
+    with quiet():
+        dk = ref.astrometry.pixelDirection(hdr, True)
+        pk = ref.mapping.inflatedEarthIntersection(dk.reshape(-1, 3), cam, 110).reshape(dk.shape)
+        if fast:
+            dc, pc = A._calcCenters(dk), A._calcCenters(pk)
+        else:
+            dc = ref.astrometry.pixelDirection(hdr, False)
+            pc = ref.mapping.inflatedEarthIntersection(dc.reshape(-1, 3), cam, 110).reshape(dc.shape)
+        out = {}
+        la, lo = ref.transform.j2000ToLatLon(pk.reshape(-1, 3), t)
+        out['lats'], out['lons'] = la.reshape(H + 1, W + 1), lo.reshape(H + 1, W + 1)
+        la, lo = ref.transform.j2000ToLatLon(pc.reshape(-1, 3), t)
+        out['latsCenter'], out['lonsCenter'] = la.reshape(H, W), lo.reshape(H, W)
+        a, b = ref.transform.j2000ToMLatMLT(pk.reshape(-1, 3), t)
+        out['mlat'], out['mlt'] = a.reshape(H + 1, W + 1), b.reshape(H + 1, W + 1)
+        a, b = ref.transform.j2000ToMLatMLT(pc.reshape(-1, 3), t)
+        out['mlatCenter'], out['mltCenter'] = a.reshape(H, W), b.reshape(H, W)
+        with np.errstate(invalid='ignore'):
+            iu = U.unitVectors(pc.reshape(-1, 3))
+            al = U.angleBetween((-dc).reshape(-1, 3), iu).reshape(H, W)
+        np.rad2deg(al, al)
+        np.subtract(90, al, al)
+        out['elevation'] = al
+    return out
+
+
+def main():
+    ref = ref_shim.load_reference()
+    os.makedirs(OUT, exist_ok=True)
+    W, H = 133, 89
+    hdr = synthetic.issHeader(W, H)
+    t, cam = synthetic.headerTimeAndCamera(hdr)
+    img = synthetic.issImage(W, H)
+    for fast in (False, True):
+        g = reference_frame(ref, hdr, cam, t, fast)
+        # reference resampling of the reference coordinates (resample.py:159-279)
+        valid = ~np.isnan(g['lats'])
+        latMin, latMax = np.nanmin(g['lats']), np.nanmax(g['lats'])
+        lonMin, lonMax = np.nanmin(g['lons']), np.nanmax(g['lons'])
+        BB = ref.mapping.BoundingBox(latMin, lonMin, latMax, lonMax)
+        cm = np.isnan(g['latsCenter'])
+        imgf = img.astype(np.float64)
+        imgf[cm] = np.nan
+        merged = np.dstack((imgf, g['elevation']))
+        with quiet():
+            r = ref.resample._resample(g['latsCenter'], g['lonsCenter'], 110, merged, None, BB, (9.0, 5.0),
+                                       False, False, 'mean')
+        np.savez_compressed(os.path.join(OUT, "iss_frame_%dx%d_fast%d.npz" % (W, H, int(fast))),
+                            bbox=np.array([latMin, lonMin, latMax, lonMax]), px_per_deg=np.array([9.0, 5.0]),
+                            rs_lats=r[0], rs_lons=r[1], rs_latsCenter=r[2], rs_lonsCenter=r[3], rs_data=r[4], **g)
+    # frame matrices for a few dates (transform.py:683-696), given the ephemeris second
+    ets = np.array([380755615.06, 3.0e8, -1.2e8, 5.5e8])
+    mats = {}
+    for i, et in enumerate(ets):
+        mats['geo%d' % i] = ref.transform.mat_j2000_to_geo(et)
+        mats['sm%d' % i] = ref.transform.mat_j2000_to_sm(et)
+        mats['geosm%d' % i] = ref.transform.mat_geo_to_sm(et)
+    np.savez_compressed(os.path.join(OUT, "frame_matrices.npz"), ets=ets, **mats)
+    # rotatePole + discontinuity/pole resampling on the reference's own test coordinates
+    # (test/resample_test.py:24-68)
+    rng = np.random.default_rng(7)
+    n = 4000
+    lat = rng.uniform(60, 89.9, n)
+    lon = rng.uniform(-180, 180, n)
+    with quiet():
+        rl, ro = ref.transform.rotatePole(np.deg2rad(lat), np.deg2rad(lon), 110, angle=90, axis=[1, 0, 0])
+    np.savez_compressed(os.path.join(OUT, "rotate_pole.npz"), lat=lat, lon=lon, rlat=np.rad2deg(rl), rlon=np.rad2deg(ro))
+    # histogram2d with weights (util/histogram.py) incl. samples exactly on edges
+    x = rng.uniform(-3, 13, 20000)
+    y = rng.uniform(40, 61, 20000)
+    ex = np.linspace(0.3, 10.1, 50)
+    x[:49] = ex[:49]
+    x[49:60] = 10.1
+    y[60:70] = 60.0
+    w1 = rng.integers(0, 256, 20000).astype(np.float64)
+    hs, _, _ = ref.histogram.histogram2d(x, y, bins=(49, 80), range=[[0.3, 10.1], [41.0, 60.0]], weights=[None, w1])
+    np.savez_compressed(os.path.join(OUT, "histogram2d.npz"), x=x, y=y, w=w1, count=hs[0], wsum=hs[1],
+                        bins=np.array([49, 80]), range=np.array([[0.3, 10.1], [41.0, 60.0]]))
+    print("golden vectors written to", OUT)
+
+
+if __name__ == "__main__":
+    main()

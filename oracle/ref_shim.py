@@ -42,6 +42,8 @@ def reference_available() -> bool:
 class _Unit:
     """Minimal astropy.units stand-in: value * unit -> quantity, .to(unit).value."""
 
+    __array_ufunc__ = None      # make ndarray * unit defer to __rmul__
+
     def __init__(self, name, in_deg=None, in_km=None):
         self.name, self.in_deg, self.in_km = name, in_deg, in_km
 
@@ -83,12 +85,21 @@ class _Angle:
         self._deg = v
 
     def wrap_at(self, wrap):
+        # astropy `Angle._wrap_at`: wraps = (angle - (wrap - 360)) // 360; angle -= wraps*360,
+        # followed by two fix-ups for rounding.  (astropy==0.4, pinned by the reference, is
+        # absent here; this is the algorithm of current astropy.)
         w = wrap.value * wrap.unit.in_deg
-        # astropy: wrapped = np.mod(self_angle - wrap_angle, 360) - (360 - wrap_angle)
-        a = self._deg
-        wrapped = np.mod(a - w, 360.0) - (360.0 - w)
+        a = np.array(self._deg, dtype=np.float64, copy=True, ndmin=1)
+        floor_ = w - 360.0
+        with np.errstate(invalid='ignore'):
+            wraps = (a - floor_) // 360.0
+        valid = np.isfinite(wraps) & (wraps != 0)
+        if np.any(valid):
+            a -= wraps * 360.0
+            a[a >= w] -= 360.0
+            a[a < floor_] += 360.0
         out = _Angle.__new__(_Angle)
-        out._deg = wrapped
+        out._deg = a.reshape(np.shape(self._deg))
         return out
 
     @property

@@ -1,0 +1,118 @@
+"""Pins the oracle to the reference itself: runs esa/auromat's own functions (imported from
+/root/reference through oracle/ref_shim.py) and the oracle restatement on the same inputs
+and requires BIT-FOR-BIT equality.  Skipped where the reference tree is not mounted."""
+import contextlib
+import datetime
+import io
+
+import numpy as np
+import pytest
+
+import oracle.auromat_oracle as O
+from auromat_b200 import synthetic
+from oracle import ref_shim
+
+pytestmark = pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree not mounted")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    with contextlib.redirect_stdout(io.StringIO()):
+        return ref_shim.load_reference()
+
+
+def quiet():
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+def bit_equal(a, b):
+    return np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True)
+
+
+@pytest.mark.parametrize("W,H", [(266, 177), (97, 61)])
+def test_stage_functions_bit_for_bit(ref, W, H):
+    hdr = synthetic.issHeader(W, H)
+    t, cam = synthetic.headerTimeAndCamera(hdr)
+    with quiet():
+        rd = ref.astrometry.pixelDirection(hdr, corner=True)
+        rdc = ref.astrometry.pixelDirection(hdr, corner=False)
+        rp = ref.mapping.inflatedEarthIntersection(rd.reshape(-1, 3), cam, 110)
+        rl = ref.transform.j2000ToLatLon(rp, t)
+        rm = ref.transform.j2000ToMLatMLT(rp, t)
+    od, odc = O.pix2dir(hdr, True), O.pix2dir(hdr, False)
+    assert bit_equal(rd, od) and bit_equal(rdc, odc)
+    op = O.inflated_earth_intersection(od.reshape(-1, 3), cam, 110)
+    assert bit_equal(rp, op)
+    ol, om = O.j2000_to_latlon(op, t), O.j2000_to_mlat_mlt(op, t)
+    assert bit_equal(rl[0], ol[0]) and bit_equal(rl[1], ol[1])
+    assert bit_equal(rm[0], om[0]) and bit_equal(rm[1], om[1])
+    assert 0.3 < np.mean(~np.isnan(op[:, 0])) < 0.9
+
+
+def test_matrices_bit_for_bit(ref):
+    for d in (datetime.datetime(2012, 1, 25, 9, 26, 55, 60000), datetime.datetime(2003, 7, 1, 23, 59, 1),
+              datetime.datetime(2019, 12, 31, 0, 0, 0)):
+        et = ref.transform.date2es(d)
+        assert et == O.date2es(d)
+        for n in ('mat_P', 'mat_T1', 'mat_T2', 'mat_T3', 'mat_T4', 'mat_j2000_to_geo', 'mat_j2000_to_sm',
+                  'mat_geo_to_sm'):
+            assert bit_equal(getattr(ref.transform, n)(et), getattr(O, n)(et)), n
+
+
+@pytest.mark.parametrize("mode", ["plain", "discontinuity", "pole"])
+def test_resample_bit_for_bit(ref, mode):
+    rng = np.random.default_rng(3)
+    h, w = 60, 80
+    yy, xx = np.mgrid[0:h + 1, 0:w + 1].astype(float)
+    if mode == "plain":
+        lats, lons = 70 - yy * 0.11 - xx * 0.01, -100 + xx * 0.2 + yy * 0.02
+    elif mode == "discontinuity":
+        lats, lons = 70 - yy * 0.11, 170 + xx * 0.25
+        lons = O.wrap_at_180(lons)
+    else:
+        r = 1 + np.hypot(yy - h / 2, xx - w / 2) * 0.12
+        ang = np.arctan2(yy - h / 2, xx - w / 2)
+        lats, lons = 90 - r, np.rad2deg(ang)
+    latsC = (lats[:-1, :-1] + lats[1:, 1:]) / 2
+    lonsC = lons[:-1, :-1] if mode != "plain" else (lons[:-1, :-1] + lons[1:, 1:]) / 2
+    latsC[:5, :7] = np.nan
+    lonsC = np.where(np.isnan(latsC), np.nan, lonsC)
+    data = np.dstack((rng.integers(0, 256, (h, w, 3)).astype(float), rng.uniform(0, 90, (h, w))))
+    data[np.isnan(latsC)] = np.nan
+    outline = np.transpose([lats.ravel(), lons.ravel()])
+    if mode == "pole":
+        bbox = (float(np.min(lats)), -180.0, 90.0, 180.0)
+    elif mode == "discontinuity":
+        bbox = (float(np.min(lats)), float(np.min(lons[lons > 0])), float(np.max(lats)), float(np.max(lons[lons <= 0])))
+    else:
+        bbox = (float(np.min(lats)), float(np.min(lons)), float(np.max(lats)), float(np.max(lons)))
+    BB = ref.mapping.BoundingBox(*bbox)
+    with quiet():
+        r = ref.resample._resample(latsC.copy(), lonsC.copy(), 110, data.copy(), lambda: outline.copy(), BB,
+                                   (6.0, 3.0), mode == "discontinuity", mode == "pole", 'mean')
+    o = O.resample_grid(latsC.copy(), lonsC.copy(), 110, data.copy(), bbox, (6.0, 3.0),
+                        contains_discontinuity=mode == "discontinuity", contains_pole=mode == "pole",
+                        outline_latlon=outline.copy())
+    for a, b in zip(r, o):
+        assert bit_equal(a, b)
+    assert np.isfinite(o[4][:, :, 0]).sum() > 100
+
+
+def test_sanitize_masks_match_reference(ref):
+    import numpy.ma as ma
+    rng = np.random.default_rng(5)
+    h, w = 40, 50
+    lat_k = rng.uniform(0, 1, (h + 1, w + 1))
+    lat_k[rng.uniform(size=lat_k.shape) < 0.2] = np.nan
+    lat_c = rng.uniform(0, 1, (h, w))
+    lat_c[rng.uniform(size=lat_c.shape) < 0.3] = np.nan
+    lats, lons = ma.masked_invalid(lat_k.copy()), ma.masked_invalid(lat_k.copy())
+    latsC, lonsC = ma.masked_invalid(lat_c.copy()), ma.masked_invalid(lat_c.copy())
+    img = ma.masked_array(np.zeros((h, w, 3), np.uint8), mask=np.zeros((h, w, 3), bool))
+    elev = ma.masked_invalid(lat_c.copy())
+    with quiet():
+        ref.mapping._doSanitize(lats, lons, latsC, lonsC, img, elev)
+    mk, mc = O.sanitize_masks(np.isnan(lat_k), np.isnan(lat_c))
+    assert np.array_equal(ma.getmaskarray(lats), mk)
+    assert np.array_equal(ma.getmaskarray(latsC), mc)
+    assert np.array_equal(ma.getmaskarray(img)[:, :, 0], mc)
