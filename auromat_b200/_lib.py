@@ -37,7 +37,7 @@ class AmtFrame(C.Structure):
 class AmtGeorefOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "d_lat_k", "d_lon_k", "d_mlat_k", "d_mlt_k",
-        "d_lat_c", "d_lon_c", "d_mlat_c", "d_mlt_c", "d_elev_c")]
+        "d_lat_c", "d_lon_c", "d_mlat_c", "d_mlt_c", "d_elev_c", "d_valid_k", "d_valid_c")]
 
 
 class AmtStats(C.Structure):
@@ -80,8 +80,10 @@ SIGNATURES = {
     "amt_stream_synchronize": (C.c_int, [C.c_void_p, C.c_void_p]),
     "amt_georef": (C.c_int, [C.c_void_p, C.POINTER(AmtFrame), C.POINTER(AmtGeorefOut), C.c_void_p, C.c_void_p]),
     "amt_sanitize": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(AmtGeorefOut), C.c_void_p]),
+    "amt_valid_bits": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p]),
     "amt_bbox_stats": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
-                                 C.POINTER(AmtGrid), C.c_void_p, C.c_void_p]),
+                                 C.c_void_p, C.c_int32, C.POINTER(AmtGrid), C.c_void_p, C.c_void_p]),
     "amt_apply_center_mask": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_double,
                                         C.POINTER(AmtGeorefOut), C.c_void_p]),
     "amt_rotate_coords": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(AmtGrid), C.c_void_p]),

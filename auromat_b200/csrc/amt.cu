@@ -166,13 +166,18 @@ struct GeorefParams {
     double sip_b[AMT_SIP_MAX_COEF];
     amt_georef_out o;
     unsigned long long* ill;     // n_ill_conditioned counter (nullable)
-    unsigned int nbk;            // blocks that handle corners (flat kernel)
+    unsigned int corner_rows;    // rows of corners handled by blockIdx.y < corner_rows (points kernel)
 };
 
-// A ray "grazes" when its normalised discriminant q = rootTerm/dDD = 1 - (perpendicular miss
-// distance / ellipsoid radius)^2 is below this: 1 ulp of direction noise then moves the
-// intersection by ~3e-15/sqrt(q) degrees, i.e. more than 1e-9 deg for q < 1e-11.
-constexpr double kIllThreshold = 1e-10;
+// Writes NaN to every requested plane of one point (a ray that misses the ellipsoid).
+__device__ __forceinline__ void emit_nan(size_t i, double* __restrict__ a, double* __restrict__ b,
+                                         double* __restrict__ c, double* __restrict__ d) {
+    const double nan = qnan();
+    if (a) a[i] = nan;
+    if (b) b[i] = nan;
+    if (c) c[i] = nan;
+    if (d) d[i] = nan;
+}
 
 // One intersection point -> all requested outputs at flat index i.
 __device__ __forceinline__ void emit_point(const GeorefParams& p, const double P[3], size_t i,
@@ -192,97 +197,155 @@ __device__ __forceinline__ void emit_point(const GeorefParams& p, const double P
     }
 }
 
+__device__ __forceinline__ void count_grazing(unsigned long long* counter, bool graze, unsigned lane) {
+    if (counter) {
+        const unsigned m = __ballot_sync(0xffffffffu, graze);
+        if (m && lane == 0) atomicAdd(counter, (unsigned long long)__popc(m));
+    }
+}
+
 // fastCenterCalculation == False: corners and centres are independent points
-// (mapping/astrometry.py:49-64,86-106).  Blocks [0, nbk) process corners, the rest centres.
+// (mapping/astrometry.py:49-64,86-106).  2-D launch: blockIdx.y < corner_rows are rows of
+// corners, the remaining rows are rows of centres; a warp covers 32 consecutive x of one row,
+// so its hit ballot is exactly one word of the row-padded validity bitmap.
+// Rays that miss the ellipsoid (reference: NaN rows that propagate through every later
+// pass) leave right after the discriminant test.
 __global__ void __launch_bounds__(256) k_georef_points(const __grid_constant__ GeorefParams p) {
-    const bool corner = blockIdx.x < p.nbk;
-    const int W = p.f.W, H = p.f.H;
+    const bool corner = blockIdx.y < p.corner_rows;
+    const int W = p.f.W;
     const int rowlen = corner ? W + 1 : W;
-    const size_t n = corner ? (size_t)(W + 1) * (H + 1) : (size_t)W * H;
-    const size_t i = (size_t)(corner ? blockIdx.x : blockIdx.x - p.nbk) * blockDim.x + threadIdx.x;
-    bool ill = false;
-    if (i < n) {
-        const int y = (int)(i / rowlen);
-        const int x = (int)(i - (size_t)y * rowlen);
+    const int y = corner ? blockIdx.y : blockIdx.y - p.corner_rows;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    bool graze = false, hit = false;
+    if (x < rowlen) {
+        const size_t i = (size_t)y * rowlen + x;
         // wcs.py:41-44: corner grids start at -0.5
         const double px = corner ? (double)x - 0.5 : (double)x;
         const double py = corner ? (double)y - 0.5 : (double)y;
         double dir[3], P[3];
         pix2dir(p.f, p.sip_a, p.sip_b, px, py, dir);
-        const double q = intersect(p.f, dir, P);
-        ill = q >= 0.0 && q < kIllThreshold;
+        hit = intersect(p.f, dir, P, graze);
         if (corner) {
-            emit_point(p, P, i, p.o.d_lat_k, p.o.d_lon_k, p.o.d_mlat_k, p.o.d_mlt_k);
+            if (hit) emit_point(p, P, i, p.o.d_lat_k, p.o.d_lon_k, p.o.d_mlat_k, p.o.d_mlt_k);
+            else emit_nan(i, p.o.d_lat_k, p.o.d_lon_k, p.o.d_mlat_k, p.o.d_mlt_k);
         } else {
-            emit_point(p, P, i, p.o.d_lat_c, p.o.d_lon_c, p.o.d_mlat_c, p.o.d_mlt_c);
-            if (p.o.d_elev_c) p.o.d_elev_c[i] = elevation_deg(dir, P);
+            if (hit) {
+                emit_point(p, P, i, p.o.d_lat_c, p.o.d_lon_c, p.o.d_mlat_c, p.o.d_mlt_c);
+                if (p.o.d_elev_c) p.o.d_elev_c[i] = elevation_deg(dir, P);
+            } else {
+                emit_nan(i, p.o.d_lat_c, p.o.d_lon_c, p.o.d_mlat_c, p.o.d_mlt_c);
+                if (p.o.d_elev_c) p.o.d_elev_c[i] = qnan();
+            }
         }
     }
-    if (p.ill) {
-        const unsigned m = __ballot_sync(0xffffffffu, ill);
-        if (m && (threadIdx.x & 31) == 0) atomicAdd(p.ill, (unsigned long long)__popc(m));
-    }
+    __syncwarp();
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    uint32_t* bits = corner ? p.o.d_valid_k : p.o.d_valid_c;
+    const int wpr = (rowlen + 31) >> 5;
+    if (bits && lane == 0 && (x >> 5) < wpr) bits[(size_t)y * wpr + (x >> 5)] = m;
+    count_grazing(p.ill, graze, lane);
 }
 
 // fastCenterCalculation == True: a CTA evaluates a (TH+1)x(TW+1) patch of corner rays into
 // shared memory, then derives each centre from the mean of its 4 corner intersection points
 // and (un-normalised) directions: mapping/astrometry.py:154-160 (`_calcCenters`).
 constexpr int TW = 32, TH = 8;
+
+// one corner ray of the tile: direction + intersection into shared memory, outputs if owned
+__device__ __forceinline__ bool tile_corner(const GeorefParams& p, double (*sP)[TH + 1][TW + 1],
+                                            double (*sD)[TH + 1][TW + 1], int x0, int y0, int cx, int cy,
+                                            bool& graze) {
+    const int W = p.f.W, H = p.f.H;
+    const int x = x0 + cx, y = y0 + cy;
+    bool hit = false;
+    if (x <= W && y <= H) {
+        double dir[3], P[3];
+        bool g;
+        pix2dir(p.f, p.sip_a, p.sip_b, (double)x - 0.5, (double)y - 0.5, dir);
+        hit = intersect(p.f, dir, P, g);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { sP[k][cy][cx] = hit ? P[k] : qnan(); sD[k][cy][cx] = dir[k]; }
+        // each corner is owned by exactly one tile for the global outputs / counters
+        const bool own = (cx < TW || x == W) && (cy < TH || y == H);
+        if (own) {
+            graze |= g;
+            const size_t i = (size_t)y * (W + 1) + x;
+            if (hit) emit_point(p, P, i, p.o.d_lat_k, p.o.d_lon_k, p.o.d_mlat_k, p.o.d_mlt_k);
+            else emit_nan(i, p.o.d_lat_k, p.o.d_lon_k, p.o.d_mlat_k, p.o.d_mlt_k);
+        } else {
+            hit = false;     // not ours: do not publish the bit
+        }
+    }
+    return hit;
+}
+
 __global__ void __launch_bounds__(TW* TH) k_georef_tiles(const __grid_constant__ GeorefParams p) {
     __shared__ double sP[3][TH + 1][TW + 1];
     __shared__ double sD[3][TH + 1][TW + 1];
     const int W = p.f.W, H = p.f.H;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-    const int tid = threadIdx.y * TW + threadIdx.x;
-    bool ill = false;
-    for (int c = tid; c < (TW + 1) * (TH + 1); c += TW * TH) {
-        const int cy = c / (TW + 1), cx = c - cy * (TW + 1);
-        const int x = x0 + cx, y = y0 + cy;
-        if (x <= W && y <= H) {
-            double dir[3], P[3];
-            pix2dir(p.f, p.sip_a, p.sip_b, (double)x - 0.5, (double)y - 0.5, dir);
-            const double q = intersect(p.f, dir, P);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { sP[k][cy][cx] = P[k]; sD[k][cy][cx] = dir[k]; }
-            // each corner is owned by exactly one tile for the global outputs / counters
-            const bool own = (cx < TW || x == W) && (cy < TH || y == H);
-            if (own) {
-                ill |= q >= 0.0 && q < kIllThreshold;
-                const size_t i = (size_t)y * (W + 1) + x;
-                emit_point(p, P, i, p.o.d_lat_k, p.o.d_lon_k, p.o.d_mlat_k, p.o.d_mlt_k);
-            }
-        }
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int tid = ty * TW + tx;
+    const int wpr_k = (W + 1 + 31) >> 5, wpr_c = (W + 31) >> 5;
+    bool graze = false;
+    // main 32x8 block of corners: one warp per row == one bitmap word
+    {
+        const bool hit = tile_corner(p, sP, sD, x0, y0, tx, ty, graze);
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (p.o.d_valid_k && tx == 0 && y0 + ty <= H && (x0 >> 5) < wpr_k)
+            p.o.d_valid_k[(size_t)(y0 + ty) * wpr_k + (x0 >> 5)] = m;
+    }
+    // halo row cy == TH (warp 0) and halo column cx == TW (warp 1, lanes 0..TH)
+    if (ty == 0) {
+        const bool hit = tile_corner(p, sP, sD, x0, y0, tx, TH, graze);
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        // owned only when this is the last tile row (y0 + TH == H)
+        if (p.o.d_valid_k && tx == 0 && y0 + TH == H && (x0 >> 5) < wpr_k)
+            p.o.d_valid_k[(size_t)H * wpr_k + (x0 >> 5)] = m;
+    } else if (ty == 1) {
+        bool hit = false;
+        if (tx <= TH) hit = tile_corner(p, sP, sD, x0, y0, TW, tx, graze);
+        // owned only when x0 + TW == W: then bit 0 of a word of its own (W % 32 == 0)
+        if (p.o.d_valid_k && tx <= TH && x0 + TW == W && y0 + tx <= H && (tx < TH || y0 + TH == H))
+            p.o.d_valid_k[(size_t)(y0 + tx) * wpr_k + (W >> 5)] = hit ? 1u : 0u;
     }
     __syncthreads();
-    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    const int x = x0 + tx, y = y0 + ty;
+    bool chit = false;
     if (x < W && y < H) {
-        const int cx = threadIdx.x, cy = threadIdx.y;
         double P[3], dir[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             // corners[:-1,:-1] + corners[:-1,1:]; += corners[1:,1:]; += corners[1:,:-1]; /= 4
-            double s = sP[k][cy][cx] + sP[k][cy][cx + 1];
-            s = s + sP[k][cy + 1][cx + 1];
-            s = s + sP[k][cy + 1][cx];
-            P[k] = s / 4.0;
-            double d = sD[k][cy][cx] + sD[k][cy][cx + 1];
-            d = d + sD[k][cy + 1][cx + 1];
-            d = d + sD[k][cy + 1][cx];
-            dir[k] = d / 4.0;
+            double s = sP[k][ty][tx] + sP[k][ty][tx + 1];
+            s = s + sP[k][ty + 1][tx + 1];
+            s = s + sP[k][ty + 1][tx];
+            P[k] = s * 0.25;
+            double d = sD[k][ty][tx] + sD[k][ty][tx + 1];
+            d = d + sD[k][ty + 1][tx + 1];
+            d = d + sD[k][ty + 1][tx];
+            dir[k] = d * 0.25;
         }
         const size_t i = (size_t)y * W + x;
-        emit_point(p, P, i, p.o.d_lat_c, p.o.d_lon_c, p.o.d_mlat_c, p.o.d_mlt_c);
-        if (p.o.d_elev_c) p.o.d_elev_c[i] = elevation_deg(dir, P);
+        chit = P[0] == P[0];                        // all four corner rays hit
+        if (chit) {
+            emit_point(p, P, i, p.o.d_lat_c, p.o.d_lon_c, p.o.d_mlat_c, p.o.d_mlt_c);
+            if (p.o.d_elev_c) p.o.d_elev_c[i] = elevation_deg(dir, P);
+        } else {
+            emit_nan(i, p.o.d_lat_c, p.o.d_lon_c, p.o.d_mlat_c, p.o.d_mlt_c);
+            if (p.o.d_elev_c) p.o.d_elev_c[i] = qnan();
+        }
     }
-    if (p.ill) {
-        const unsigned m = __ballot_sync(0xffffffffu, ill);
-        if (m && (tid & 31) == 0) atomicAdd(p.ill, (unsigned long long)__popc(m));
-    }
+    __syncwarp();
+    const unsigned mc = __ballot_sync(0xffffffffu, chit);
+    if (p.o.d_valid_c && tx == 0 && y < H && (x0 >> 5) < wpr_c) p.o.d_valid_c[(size_t)y * wpr_c + (x0 >> 5)] = mc;
+    count_grazing(p.ill, graze, tid & 31);
 }
 
 static int fill_frame(const amt_frame* fr, GeorefParams& p) {
     CHECK_ARG(fr->width > 0 && fr->height > 0, "amt_frame: width/height must be positive");
-    CHECK_ARG((long long)(fr->width + 1) * (fr->height + 1) < (1LL << 40), "amt_frame: frame too large");
+    CHECK_ARG((long long)(fr->width + 1) * (fr->height + 1) < (1LL << 31), "amt_frame: frame too large");
     CHECK_ARG(fr->sip_order_a >= 0 && fr->sip_order_a <= AMT_SIP_MAX_ORDER &&
               fr->sip_order_b >= 0 && fr->sip_order_b <= AMT_SIP_MAX_ORDER, "amt_frame: SIP order out of range");
     FrameC& f = p.f;
@@ -309,6 +372,7 @@ static int fill_frame(const amt_frame* fr, GeorefParams& p) {
     volatile double num = aa - bb;
     volatile double e2 = num / aa;
     f.a = a; f.b = b;
+    f.b_over_a = b / a;
     f.e2a = e2 * a;
     f.d = num / b;
     f.sip_oa = fr->sip_order_a; f.sip_ob = fr->sip_order_b;
@@ -333,14 +397,14 @@ extern "C" int amt_georef(amt_ctx* ctx, const amt_frame* frame, const amt_georef
         dim3 grid((W + TW) / TW, (H + TH) / TH);   // covers x<=W, y<=H
         k_georef_tiles<<<grid, dim3(TW, TH), 0, st>>>(p);
     } else {
-        const size_t nk = (size_t)(W + 1) * (H + 1), nc = (size_t)W * H;
-        const bool want_k = out->d_lat_k || out->d_lon_k || out->d_mlat_k || out->d_mlt_k;
-        const bool want_c = out->d_lat_c || out->d_lon_c || out->d_mlat_c || out->d_mlt_c || out->d_elev_c;
-        const unsigned nbk = want_k ? (unsigned)((nk + 255) / 256) : 0;
-        const unsigned nbc = want_c ? (unsigned)((nc + 255) / 256) : 0;
-        p.nbk = nbk;
-        if (nbk + nbc == 0) return AMT_OK;
-        k_georef_points<<<nbk + nbc, 256, 0, st>>>(p);
+        const bool want_k = out->d_lat_k || out->d_lon_k || out->d_mlat_k || out->d_mlt_k || out->d_valid_k;
+        const bool want_c = out->d_lat_c || out->d_lon_c || out->d_mlat_c || out->d_mlt_c || out->d_elev_c ||
+                            out->d_valid_c;
+        p.corner_rows = want_k ? H + 1 : 0;
+        const unsigned rows = p.corner_rows + (want_c ? H : 0);
+        if (rows == 0) return AMT_OK;
+        dim3 grid(((want_k ? W + 1 : W) + 255) / 256, rows);
+        k_georef_points<<<grid, 256, 0, st>>>(p);
     }
     LAUNCH_CHECK(ctx);
     return AMT_OK;
@@ -385,13 +449,18 @@ __device__ __forceinline__ void prerotate(const GridC& g, double& la, double& lo
         double G[3], R[3], l2, o2;
         geodetic2ecef(g.a, g.e2, la * kDeg2Rad, lo * kDeg2Rad, g.altitude, G[0], G[1], G[2]);
         mat3(g.rot, G, R);
-        bowring(g.a, g.b, g.e2a, g.d, R[0], R[1], R[2], l2, o2);
+        bowring_ref(g.a, g.b, g.e2a, g.d, R[0], R[1], R[2], l2, o2);
         la = l2 * kRad2Deg;
         lo = o2 * kRad2Deg;
     }
 }
 
 // ============================================================== sanitize + bbox stats
+// Validity bitmaps: one bit per corner / centre, rows padded to whole 32-bit words
+// (words per row: wpr_k = ceil((W+1)/32), wpr_c = ceil(W/32)); padding bits are 0.  The
+// georeference kernels emit them for free (warp ballots); all mask logic of
+// mapping/mapping.py:1063-1125 and the outline/bounding-box reductions of :655-743 then run
+// on these ~1.5 MB bitmaps (L2 resident) instead of re-reading the 96 MB coordinate planes.
 __device__ __forceinline__ unsigned long long dkey(double d) {       // order-preserving key
     const unsigned long long b = (unsigned long long)__double_as_longlong(d);
     return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
@@ -430,35 +499,47 @@ __global__ void k_stats_final(const StatKeys* s, amt_stats* out) {
 
 __device__ __forceinline__ bool isnan_d(double v) { return !(v == v); }
 
-// _doSanitize step 1 (mapping.py:1082-1093): corner masked if itself NaN or all (<=4)
-// neighbouring centres are missing.  Writes a byte mask.
-__global__ void k_sanitize_corner_mask(int W, int H, const double* __restrict__ lat_k,
-                                       const double* __restrict__ lat_c, unsigned char* __restrict__ mk) {
-    const size_t n = (size_t)(W + 1) * (H + 1);
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int y = (int)(i / (W + 1)), x = (int)(i - (size_t)y * (W + 1));
-    bool all_missing = true;
-#pragma unroll
-    for (int dy = -1; dy <= 0; ++dy)
-#pragma unroll
-        for (int dx = -1; dx <= 0; ++dx) {
-            const int cy = y + dy, cx = x + dx;
-            if (cy >= 0 && cy < H && cx >= 0 && cx < W) all_missing &= isnan_d(lat_c[(size_t)cy * W + cx]);
-        }
-    mk[i] = (isnan_d(lat_k[i]) || all_missing) ? 1 : 0;
+struct Bits {                 // a row-padded bitmap
+    const unsigned* w;
+    int wpr, rows;
+    __device__ __forceinline__ unsigned at(int y, int i) const {
+        return (y < 0 || y >= rows || i < 0 || i >= wpr) ? 0u : w[(size_t)y * wpr + i];
+    }
+    // bit x of the result = bit (x-1) / (x+1) of row y
+    __device__ __forceinline__ unsigned from_left(int y, int i) const { return (at(y, i) << 1) | (at(y, i - 1) >> 31); }
+    __device__ __forceinline__ unsigned from_right(int y, int i) const { return (at(y, i) >> 1) | (at(y, i + 1) << 31); }
+};
+
+// bitmaps from NaN-marked planes (generic mappings, after masking)
+__global__ void __launch_bounds__(256) k_valid_bits(int W, int H, const double* __restrict__ lat_k,
+                                                    const double* __restrict__ lat_c, unsigned* __restrict__ bk,
+                                                    unsigned* __restrict__ bc, int wpr_k, int wpr_c) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool corner = (int)blockIdx.y <= H;
+    const int y = corner ? blockIdx.y : blockIdx.y - (H + 1);
+    const int rowlen = corner ? W + 1 : W;
+    const double* src = corner ? lat_k : lat_c;
+    const bool v = x < rowlen && !isnan_d(src[(size_t)y * rowlen + x]);
+    const unsigned m = __ballot_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && (x >> 5) < (corner ? wpr_k : wpr_c))
+        (corner ? bk : bc)[(size_t)y * (corner ? wpr_k : wpr_c) + (x >> 5)] = m;
 }
 
-// step 2 (mapping.py:1095-1104): centre masked if any of its 4 corners is masked.
-__global__ void k_sanitize_centers(int W, int H, const unsigned char* __restrict__ mk, amt_georef_out o) {
-    const size_t n = (size_t)W * H;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int y = (int)(i / W), x = (int)(i - (size_t)y * W);
-    const size_t k = (size_t)y * (W + 1) + x;
-    const bool any = mk[k] | mk[k + 1] | mk[k + W + 1] | mk[k + W + 2];
-    if (any) {
-        const double nan = qnan();
+// step 1 of _doSanitize (mapping.py:1082-1093): a corner stays valid only if at least one of
+// its (<=4) neighbouring centres is valid.  One thread per corner word.
+__global__ void k_bits_corner_rule(int H, Bits K, Bits C, unsigned* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (i >= K.wpr || y > H) return;
+    const unsigned anyc = C.from_left(y - 1, i) | C.at(y - 1, i) | C.from_left(y, i) | C.at(y, i);
+    out[(size_t)y * K.wpr + i] = K.at(y, i) & anyc;
+}
+
+__device__ __forceinline__ void nan_centers(const amt_georef_out& o, size_t base, unsigned bits) {
+    const double nan = qnan();
+    while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const size_t i = base + b;
         if (o.d_lat_c) o.d_lat_c[i] = nan;
         if (o.d_lon_c) o.d_lon_c[i] = nan;
         if (o.d_mlat_c) o.d_mlat_c[i] = nan;
@@ -466,24 +547,12 @@ __global__ void k_sanitize_centers(int W, int H, const unsigned char* __restrict
         if (o.d_elev_c) o.d_elev_c[i] = nan;
     }
 }
-
-// step 3 (mapping.py:1106-1117): corners again, using the updated centre mask.
-__global__ void k_sanitize_corners(int W, int H, const unsigned char* __restrict__ mk,
-                                   const double* __restrict__ lat_c, amt_georef_out o) {
-    const size_t n = (size_t)(W + 1) * (H + 1);
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int y = (int)(i / (W + 1)), x = (int)(i - (size_t)y * (W + 1));
-    bool all_missing = true;
-#pragma unroll
-    for (int dy = -1; dy <= 0; ++dy)
-#pragma unroll
-        for (int dx = -1; dx <= 0; ++dx) {
-            const int cy = y + dy, cx = x + dx;
-            if (cy >= 0 && cy < H && cx >= 0 && cx < W) all_missing &= isnan_d(lat_c[(size_t)cy * W + cx]);
-        }
-    if ((mk && mk[i]) || all_missing) {
-        const double nan = qnan();
+__device__ __forceinline__ void nan_corners(const amt_georef_out& o, size_t base, unsigned bits) {
+    const double nan = qnan();
+    while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const size_t i = base + b;
         if (o.d_lat_k) o.d_lat_k[i] = nan;
         if (o.d_lon_k) o.d_lon_k[i] = nan;
         if (o.d_mlat_k) o.d_mlat_k[i] = nan;
@@ -491,109 +560,169 @@ __global__ void k_sanitize_corners(int W, int H, const unsigned char* __restrict
     }
 }
 
-__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o); v = t < v ? t : v; }
-    return v;
-}
-__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
-    return v;
+// step 2 (mapping.py:1095-1104): a centre stays valid only if all 4 corners are valid (K1);
+// newly masked centres get NaN in every centre plane.  One thread per centre word.
+__global__ void k_bits_center_rule(int W, int H, Bits K1, unsigned* __restrict__ cbits, int wpr_c, amt_georef_out o) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (i >= wpr_c || y >= H) return;
+    const unsigned allk = K1.at(y, i) & K1.from_right(y, i) & K1.at(y + 1, i) & K1.from_right(y + 1, i);
+    const unsigned c0 = cbits[(size_t)y * wpr_c + i];
+    const unsigned c1 = c0 & allk;
+    if (c1 != c0) {
+        cbits[(size_t)y * wpr_c + i] = c1;
+        nan_centers(o, (size_t)y * W + 32 * i, c0 & ~c1);
+    }
 }
 
-// bbox min/max over the boundary corners + valid counts (mapping.py:694-703,729-737).
-// Blocks [0,nbk) scan corners, the rest count valid centres.
-__global__ void __launch_bounds__(256) k_stats(int W, int H, unsigned nbk, const double* __restrict__ lat_k,
-                                               const double* __restrict__ lon_k,
-                                               const double* __restrict__ lat_c, const __grid_constant__ GridC g,
-                                               StatKeys* s) {
-    const int lane = threadIdx.x & 31;
-    if (blockIdx.x >= nbk) {
-        const size_t n = (size_t)W * H;
-        const size_t i = (size_t)(blockIdx.x - nbk) * blockDim.x + threadIdx.x;
-        const bool v = i < n && !isnan_d(lat_c[i]);
-        const unsigned m = __ballot_sync(0xffffffffu, v);
-        if (m && lane == 0) atomicAdd(&s->n_valid_c, (unsigned long long)__popc(m));
-        if (v) {
-            // Pole test: the longitudes of the 4 corners of a valid pixel wind once around
-            // (+-360 deg) iff the quad encloses a pole.
-            const int y = (int)(i / W), x = (int)(i - (size_t)y * W);
-            const size_t k = (size_t)y * (W + 1) + x;
-            const double l0 = lon_k[k], l1 = lon_k[k + 1], l2 = lon_k[k + W + 2], l3 = lon_k[k + W + 1];
-            double w = 0.0;
-            const double dl[4] = {l1 - l0, l2 - l1, l3 - l2, l0 - l3};
+// step 3 (mapping.py:1106-1117): corners once more with the updated centres; corners that
+// lost validity since the original bitmap K0 get NaN.  Writes the final bitmap over K0.
+__global__ void k_bits_corner_final(int W, int H, Bits K1, Bits C1, unsigned* __restrict__ k0, amt_georef_out o) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (i >= K1.wpr || y > H) return;
+    const unsigned anyc = C1.from_left(y - 1, i) | C1.at(y - 1, i) | C1.from_left(y, i) | C1.at(y, i);
+    const unsigned k2 = K1.at(y, i) & anyc;
+    const unsigned old = k0[(size_t)y * K1.wpr + i];
+    if (k2 != old) {
+        k0[(size_t)y * K1.wpr + i] = k2;
+        nan_corners(o, (size_t)y * (W + 1) + 32 * i, old & ~k2);
+    }
+}
+
+__device__ __forceinline__ unsigned long long umin64(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
+__device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
+
+// Bounding box over the outline (valid corners with an invalid / out-of-array 4-neighbour,
+// mapping.py:672-703,729-737) + valid counts, from the bitmaps.  Grid-stride over words,
+// block-level reduction, one set of atomics per block.
+__global__ void __launch_bounds__(256) k_stats_bits(int W, int H, Bits K, Bits C, const double* __restrict__ lat_k,
+                                                    const double* __restrict__ lon_k,
+                                                    const __grid_constant__ GridC g, StatKeys* s) {
+    unsigned long long mn_la = ~0ULL, mx_la = 0ULL, mn_lo = ~0ULL, mx_lo = 0ULL, mn_pos = ~0ULL, mx_neg = 0ULL;
+    unsigned nvk = 0, nb = 0, nvc = 0;
+    const int nwk = K.wpr * (H + 1);
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nwk; t += gridDim.x * blockDim.x) {
+        const int y = t / K.wpr, i = t - y * K.wpr;
+        const unsigned v = K.w[t];
+        if (!v) continue;
+        nvk += __popc(v);
+        const unsigned interior = v & K.from_left(y, i) & K.from_right(y, i) & K.at(y - 1, i) & K.at(y + 1, i);
+        unsigned b = v & ~interior;
+        nb += __popc(b);
+        while (b) {
+            const int bit = __ffs(b) - 1;
+            b &= b - 1;
+            const size_t idx = (size_t)y * (W + 1) + 32 * i + bit;
+            double la = lat_k[idx], lo = lon_k[idx];
+            if (g.prerotate != AMT_PRE_NONE) prerotate(g, la, lo);
+            const unsigned long long kla = dkey(la), klo = dkey(lo);
+            mn_la = umin64(mn_la, kla); mx_la = umax64(mx_la, kla);
+            mn_lo = umin64(mn_lo, klo); mx_lo = umax64(mx_lo, klo);
+            if (lo > 0.0) mn_pos = umin64(mn_pos, klo); else mx_neg = umax64(mx_neg, klo);
+        }
+    }
+    const int nwc = C.wpr * H;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nwc; t += gridDim.x * blockDim.x) nvc += __popc(C.w[t]);
+
+    __shared__ unsigned long long sh[6][8];
+    __shared__ unsigned shc[3][8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                double d = dl[q];
-                if (d > 180.0) d -= 360.0;
-                if (d <= -180.0) d += 360.0;
-                w += d;
-            }
-            if (fabs(w) > 180.0) atomicOr(&s->pole_flags, lat_k[k] > 0.0 ? 1u : 2u);
-        }
-        return;
+    for (int o = 16; o; o >>= 1) {
+        mn_la = umin64(mn_la, __shfl_xor_sync(0xffffffffu, mn_la, o));
+        mx_la = umax64(mx_la, __shfl_xor_sync(0xffffffffu, mx_la, o));
+        mn_lo = umin64(mn_lo, __shfl_xor_sync(0xffffffffu, mn_lo, o));
+        mx_lo = umax64(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, o));
+        mn_pos = umin64(mn_pos, __shfl_xor_sync(0xffffffffu, mn_pos, o));
+        mx_neg = umax64(mx_neg, __shfl_xor_sync(0xffffffffu, mx_neg, o));
+        nvk += __shfl_xor_sync(0xffffffffu, nvk, o);
+        nb += __shfl_xor_sync(0xffffffffu, nb, o);
+        nvc += __shfl_xor_sync(0xffffffffu, nvc, o);
     }
-    const size_t n = (size_t)(W + 1) * (H + 1);
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = false, boundary = false;
-    double la = 0, lo = 0;
-    if (i < n) {
-        la = lat_k[i];
-        valid = !isnan_d(la);
-        if (valid) {
-            lo = lon_k[i];
-            const int y = (int)(i / (W + 1)), x = (int)(i - (size_t)y * (W + 1));
-            boundary = x == 0 || y == 0 || x == W || y == H;
-            if (!boundary)
-                boundary = isnan_d(lat_k[i - 1]) || isnan_d(lat_k[i + 1]) ||
-                           isnan_d(lat_k[i - (W + 1)]) || isnan_d(lat_k[i + (W + 1)]);
-        }
-    }
-    const unsigned mv = __ballot_sync(0xffffffffu, valid);
-    const unsigned mb = __ballot_sync(0xffffffffu, boundary);
-    if (mv && lane == 0) atomicAdd(&s->n_valid_k, (unsigned long long)__popc(mv));
-    if (!mb) return;
-    if (boundary && g.prerotate != AMT_PRE_NONE) prerotate(g, la, lo);
-    unsigned long long kmin_la = boundary ? dkey(la) : ~0ULL, kmax_la = boundary ? dkey(la) : 0ULL;
-    unsigned long long kmin_lo = boundary ? dkey(lo) : ~0ULL, kmax_lo = boundary ? dkey(lo) : 0ULL;
-    unsigned long long kmin_pos = (boundary && lo > 0.0) ? dkey(lo) : ~0ULL;
-    unsigned long long kmax_neg = (boundary && !(lo > 0.0)) ? dkey(lo) : 0ULL;
-    kmin_la = warp_min_u64(kmin_la); kmax_la = warp_max_u64(kmax_la);
-    kmin_lo = warp_min_u64(kmin_lo); kmax_lo = warp_max_u64(kmax_lo);
-    kmin_pos = warp_min_u64(kmin_pos); kmax_neg = warp_max_u64(kmax_neg);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (lane == 0) {
-        atomicAdd(&s->n_boundary, (unsigned long long)__popc(mb));
-        atomicMin(&s->lat_min, kmin_la); atomicMax(&s->lat_max, kmax_la);
-        atomicMin(&s->lon_min, kmin_lo); atomicMax(&s->lon_max, kmax_lo);
-        if (kmin_pos != ~0ULL) atomicMin(&s->lon_min_pos, kmin_pos);
-        if (kmax_neg != 0ULL) atomicMax(&s->lon_max_neg, kmax_neg);
+        sh[0][warp] = mn_la; sh[1][warp] = mx_la; sh[2][warp] = mn_lo; sh[3][warp] = mx_lo;
+        sh[4][warp] = mn_pos; sh[5][warp] = mx_neg;
+        shc[0][warp] = nvk; shc[1][warp] = nb; shc[2][warp] = nvc;
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) {
+            sh[0][0] = umin64(sh[0][0], sh[0][w]); sh[1][0] = umax64(sh[1][0], sh[1][w]);
+            sh[2][0] = umin64(sh[2][0], sh[2][w]); sh[3][0] = umax64(sh[3][0], sh[3][w]);
+            sh[4][0] = umin64(sh[4][0], sh[4][w]); sh[5][0] = umax64(sh[5][0], sh[5][w]);
+            shc[0][0] += shc[0][w]; shc[1][0] += shc[1][w]; shc[2][0] += shc[2][w];
+        }
+        if (shc[0][0]) atomicAdd(&s->n_valid_k, (unsigned long long)shc[0][0]);
+        if (shc[2][0]) atomicAdd(&s->n_valid_c, (unsigned long long)shc[2][0]);
+        if (shc[1][0]) {
+            atomicAdd(&s->n_boundary, (unsigned long long)shc[1][0]);
+            atomicMin(&s->lat_min, sh[0][0]); atomicMax(&s->lat_max, sh[1][0]);
+            atomicMin(&s->lon_min, sh[2][0]); atomicMax(&s->lon_max, sh[3][0]);
+            if (sh[4][0] != ~0ULL) atomicMin(&s->lon_min_pos, sh[4][0]);
+            if (sh[5][0] != 0ULL) atomicMax(&s->lon_max_neg, sh[5][0]);
+        }
+    }
+}
+
+// Pole test for mappings without a camera model (GenericMapping): the longitudes of the 4
+// corners of a valid pixel wind once around (+-360 deg) iff the quad encloses a pole.
+// Replaces the outline / azimuth-sum test of mapping.py:705-718, geodesic.py:112-202.
+__global__ void __launch_bounds__(256) k_pole_test(int W, int H, Bits C, const double* __restrict__ lat_k,
+                                                   const double* __restrict__ lon_k, StatKeys* s) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W || y >= H) return;
+    if (!((C.at(y, x >> 5) >> (x & 31)) & 1u)) return;
+    const size_t k = (size_t)y * (W + 1) + x;
+    const double l0 = lon_k[k], l1 = lon_k[k + 1], l2 = lon_k[k + W + 2], l3 = lon_k[k + W + 1];
+    const double dl[4] = {l1 - l0, l2 - l1, l3 - l2, l0 - l3};
+    double w = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        double d = dl[q];
+        if (d > 180.0) d -= 360.0;
+        if (d <= -180.0) d += 360.0;
+        w += d;
+    }
+    if (fabs(w) > 180.0) atomicOr(&s->pole_flags, lat_k[k] > 0.0 ? 1u : 2u);
+}
+
+static inline int wpr_of(int n) { return (n + 31) / 32; }
+
+extern "C" int amt_valid_bits(amt_ctx* ctx, int32_t W, int32_t H, const double* d_lat_k, const double* d_lat_c,
+                              uint32_t* d_valid_k, uint32_t* d_valid_c, void* stream) {
+    ENTER(ctx);
+    CHECK_ARG(W > 0 && H > 0 && d_lat_k && d_lat_c && d_valid_k && d_valid_c, "amt_valid_bits: bad arguments");
+    dim3 grid((W + 1 + 255) / 256, 2 * H + 1);
+    k_valid_bits<<<grid, 256, 0, (cudaStream_t)stream>>>(W, H, d_lat_k, d_lat_c, d_valid_k, d_valid_c,
+                                                          wpr_of(W + 1), wpr_of(W));
+    LAUNCH_CHECK(ctx);
+    return AMT_OK;
 }
 
 extern "C" int amt_sanitize(amt_ctx* ctx, int32_t W, int32_t H, const amt_georef_out* planes, void* stream) {
     ENTER(ctx);
     CHECK_ARG(planes && W > 0 && H > 0, "amt_sanitize: bad arguments");
-    CHECK_ARG(planes->d_lat_k && planes->d_lat_c, "amt_sanitize: lat_k and lat_c planes are required");
+    CHECK_ARG(planes->d_valid_k && planes->d_valid_c, "amt_sanitize: validity bitmaps are required");
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t nk = (size_t)(W + 1) * (H + 1), nc = (size_t)W * H;
-    int rc = ensure_scratch(ctx, nk);
+    const int wk = wpr_of(W + 1), wc = wpr_of(W);
+    int rc = ensure_scratch(ctx, (size_t)wk * (H + 1) * 4);
     if (rc) return rc;
-    unsigned char* mk = (unsigned char*)ctx->scratch;
-    const unsigned nbk = (unsigned)((nk + 255) / 256), nbc = (unsigned)((nc + 255) / 256);
-    k_sanitize_corner_mask<<<nbk, 256, 0, st>>>(W, H, planes->d_lat_k, planes->d_lat_c, mk);
+    unsigned* k1 = (unsigned*)ctx->scratch;
+    Bits K0{planes->d_valid_k, wk, H + 1}, C{planes->d_valid_c, wc, H}, K1{k1, wk, H + 1};
+    dim3 gk((wk + 127) / 128, H + 1), gc((wc + 127) / 128, H);
+    k_bits_corner_rule<<<gk, 128, 0, st>>>(H, K0, C, k1);
     LAUNCH_CHECK(ctx);
-    k_sanitize_centers<<<nbc, 256, 0, st>>>(W, H, mk, *planes);
+    k_bits_center_rule<<<gc, 128, 0, st>>>(W, H, K1, planes->d_valid_c, wc, *planes);
     LAUNCH_CHECK(ctx);
-    k_sanitize_corners<<<nbk, 256, 0, st>>>(W, H, mk, planes->d_lat_c, *planes);
+    k_bits_corner_final<<<gk, 128, 0, st>>>(W, H, K1, C, planes->d_valid_k, *planes);
     LAUNCH_CHECK(ctx);
     return AMT_OK;
 }
 
 extern "C" int amt_bbox_stats(amt_ctx* ctx, int32_t W, int32_t H, const double* d_lat_k, const double* d_lon_k,
-                              const double* d_lat_c, const amt_grid* pre, amt_stats* d_stats, void* stream) {
+                              const uint32_t* d_valid_k, const uint32_t* d_valid_c, int32_t pole_test,
+                              const amt_grid* pre, amt_stats* d_stats, void* stream) {
     ENTER(ctx);
-    CHECK_ARG(W > 0 && H > 0 && d_lat_k && d_lon_k && d_stats, "amt_bbox_stats: bad arguments");
+    CHECK_ARG(W > 0 && H > 0 && d_lat_k && d_lon_k && d_valid_k && d_valid_c && d_stats, "amt_bbox_stats: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     GridC g;
     memset(&g, 0, sizeof g);
@@ -601,50 +730,70 @@ extern "C" int amt_bbox_stats(amt_ctx* ctx, int32_t W, int32_t H, const double* 
         int rc = fill_grid(pre, g, true);
         if (rc) return rc;
     }
-    const size_t nk = (size_t)(W + 1) * (H + 1), nc = (size_t)W * H;
-    // the key block lives behind the sanitize mask in the scratch arena
-    const size_t off = (nk + 255) / 256 * 256;
+    const int wk = wpr_of(W + 1), wc = wpr_of(W);
+    // the key block lives behind the sanitize scratch bitmap
+    const size_t off = ((size_t)wk * (H + 1) * 4 + 255) / 256 * 256;
     int rc = ensure_scratch(ctx, off + sizeof(StatKeys));
     if (rc) return rc;
     StatKeys* keys = (StatKeys*)((unsigned char*)ctx->scratch + off);
-    const unsigned nbk = (unsigned)((nk + 255) / 256), nbc = d_lat_c ? (unsigned)((nc + 255) / 256) : 0;
+    Bits K{d_valid_k, wk, H + 1}, C{d_valid_c, wc, H};
     k_stats_init<<<1, 1, 0, st>>>(keys);
     LAUNCH_CHECK(ctx);
-    k_stats<<<nbk + nbc, 256, 0, st>>>(W, H, nbk, d_lat_k, d_lon_k, d_lat_c, g, keys);
+    const int words = wk * (H + 1);
+    const int blocks = max(1, min(ctx->sm_count * 4, (words + 255) / 256));
+    k_stats_bits<<<blocks, 256, 0, st>>>(W, H, K, C, d_lat_k, d_lon_k, g, keys);
     LAUNCH_CHECK(ctx);
+    if (pole_test) {
+        dim3 grid((W + 255) / 256, H);
+        k_pole_test<<<grid, 256, 0, st>>>(W, H, C, d_lat_k, d_lon_k, keys);
+        LAUNCH_CHECK(ctx);
+    }
     k_stats_final<<<1, 1, 0, st>>>(keys, d_stats);
     LAUNCH_CHECK(ctx);
     return AMT_OK;
 }
 
 // createMasked / maskedByElevation (mapping.py:845-864,1171-1231) on the device planes.
-__global__ void k_apply_center_mask(size_t n, const unsigned char* __restrict__ mask, double min_elev,
-                                    amt_georef_out o) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    bool m = mask && mask[i];
-    if (min_elev == min_elev) m |= !(o.d_elev_c[i] >= min_elev);   // (elevation < min).filled(True)
-    if (m) {
-        const double nan = qnan();
-        if (o.d_lat_c) o.d_lat_c[i] = nan;
-        if (o.d_lon_c) o.d_lon_c[i] = nan;
-        if (o.d_mlat_c) o.d_mlat_c[i] = nan;
-        if (o.d_mlt_c) o.d_mlt_c[i] = nan;
-        if (o.d_elev_c) o.d_elev_c[i] = nan;
+__global__ void __launch_bounds__(256) k_apply_center_mask(int W, int H, const unsigned char* __restrict__ mask,
+                                                           double min_elev, unsigned* __restrict__ cbits, int wpr_c,
+                                                           amt_georef_out o) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    bool keep = false;
+    if (x < W) {
+        const size_t i = (size_t)y * W + x;
+        keep = (cbits[(size_t)y * wpr_c + (x >> 5)] >> (x & 31)) & 1u;
+        bool m = mask && mask[i];
+        if (keep && min_elev == min_elev) m |= !(o.d_elev_c[i] >= min_elev);   // (elevation < min).filled(True)
+        if (keep && m) {
+            keep = false;
+            const double nan = qnan();
+            if (o.d_lat_c) o.d_lat_c[i] = nan;
+            if (o.d_lon_c) o.d_lon_c[i] = nan;
+            if (o.d_mlat_c) o.d_mlat_c[i] = nan;
+            if (o.d_mlt_c) o.d_mlt_c[i] = nan;
+            if (o.d_elev_c) o.d_elev_c[i] = nan;
+        }
     }
+    __syncwarp();
+    const unsigned b = __ballot_sync(0xffffffffu, keep);
+    if ((threadIdx.x & 31) == 0 && (x >> 5) < wpr_c) cbits[(size_t)y * wpr_c + (x >> 5)] = b;
 }
 
 extern "C" int amt_apply_center_mask(amt_ctx* ctx, int32_t W, int32_t H, const uint8_t* d_mask,
                                      double min_elevation, const amt_georef_out* planes, void* stream) {
     ENTER(ctx);
     CHECK_ARG(planes && W > 0 && H > 0, "amt_apply_center_mask: bad arguments");
-    CHECK_ARG(planes->d_lat_k && planes->d_lat_c, "amt_apply_center_mask: lat_k and lat_c planes are required");
+    CHECK_ARG(planes->d_valid_k && planes->d_valid_c, "amt_apply_center_mask: validity bitmaps are required");
     CHECK_ARG(!(min_elevation == min_elevation) || planes->d_elev_c, "amt_apply_center_mask: elevation plane required");
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t nk = (size_t)(W + 1) * (H + 1), nc = (size_t)W * H;
-    k_apply_center_mask<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(nc, d_mask, min_elevation, *planes);
+    const int wk = wpr_of(W + 1), wc = wpr_of(W);
+    dim3 grid((W + 255) / 256, H);
+    k_apply_center_mask<<<grid, 256, 0, st>>>(W, H, d_mask, min_elevation, planes->d_valid_c, wc, *planes);
     LAUNCH_CHECK(ctx);
-    k_sanitize_corners<<<(unsigned)((nk + 255) / 256), 256, 0, st>>>(W, H, nullptr, planes->d_lat_c, *planes);
+    // afterMasking=True: only "corner needs a valid neighbouring centre" (mapping.py:1082-1093)
+    Bits K{planes->d_valid_k, wk, H + 1}, C{planes->d_valid_c, wc, H};
+    dim3 gk((wk + 127) / 128, H + 1);
+    k_bits_corner_final<<<gk, 128, 0, st>>>(W, H, K, C, planes->d_valid_k, *planes);
     LAUNCH_CHECK(ctx);
     return AMT_OK;
 }

@@ -1,0 +1,152 @@
+// FP64 building blocks for the georeference kernels: reciprocal / division / (r)sqrt from the
+// MUFU seed + Newton/Goldschmidt steps, and a table-driven atan2.
+//
+// Why not libm: ncu on the first version of k_georef_points (profiles/r01_*) showed 1280
+// issued instructions per point of which only ~400 were FP64 math -- CUDA's atan2/atan/acos
+// spend most of their instructions on special-case handling and on materialising polynomial
+// coefficients with UMOV/IMAD.MOV.  The functions below keep their constants in __constant__
+// memory (used as direct c[][] operands), have no slow paths (inputs are finite, non-denormal
+// coordinates in km / ratios) and are accurate to <= 2 ulp, i.e. ~1e-14 degrees after the
+// whole chain against a 1e-9 degree parity budget.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace amt {
+
+__device__ __forceinline__ double mufu_rcp(double a) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    return r;
+}
+__device__ __forceinline__ double mufu_rsqrt(double a) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    return r;
+}
+
+// 1/a to ~1 ulp: ~20-bit seed, two Newton steps (4 DFMA).
+__device__ __forceinline__ double rcp_nr(double a) {
+    double r = mufu_rcp(a);
+    double e = fma(-a, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-a, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
+// n/a to <= 1 ulp given r ~ 1/a (one residual correction, 1 DMUL + 2 DFMA).
+__device__ __forceinline__ double div_with_rcp(double n, double a, double r) {
+    double q = n * r;
+    const double e = fma(-a, q, n);
+    return fma(e, r, q);
+}
+__device__ __forceinline__ double div_fast(double n, double a) { return div_with_rcp(n, a, rcp_nr(a)); }
+
+// Goldschmidt: g -> sqrt(a), h -> 0.5/sqrt(a).  Two coupled steps from the ~20-bit seed.
+__device__ __forceinline__ void sqrt_rsqrt(double a, double& sq, double& half_rsq) {
+    const double y = mufu_rsqrt(a);
+    double g = a * y;
+    double h = 0.5 * y;
+    double r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    // one residual step on g brings sqrt to <= 1 ulp
+    const double e = fma(-g, g, a);
+    sq = fma(e, h, g);
+    half_rsq = h;
+}
+__device__ __forceinline__ double sqrt_fast(double a) {
+    double s, h;
+    sqrt_rsqrt(a, s, h);
+    return s;
+}
+// 1/sqrt(a) to ~1 ulp (no residual step on g needed).
+__device__ __forceinline__ double rsqrt_fast(double a) {
+    const double y = mufu_rsqrt(a);
+    double g = a * y;
+    double h = 0.5 * y;
+    double r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-g, h, 0.5);
+    h = fma(h, r, h);
+    return h + h;
+}
+
+// atan(i/32), i = 0..32
+__constant__ double c_atan_tab[33] = {
+    0, 0.031239833430268277, 0.06241880999595735,
+    0.09347678115858947, 0.12435499454676144, 0.15499674192394097,
+    0.18534794999569476, 0.21535769969773805, 0.24497866312686414,
+    0.27416745111965879, 0.30288486837497142, 0.3310960767041321,
+    0.35877067027057225, 0.38588266939807375, 0.41241044159738732,
+    0.43833655985795783, 0.46364760900080609, 0.48833395105640554,
+    0.51238946031073773, 0.5358112379604637, 0.55859931534356244,
+    0.58075635356767041, 0.60228734613496415, 0.6231993299340659,
+    0.64350110879328437, 0.66320299270609329, 0.68231655487474807,
+    0.70085440788445019, 0.71882999962162453, 0.7362574289814281,
+    0.75315128096219441, 0.7695264804056583, 0.78539816339744828,
+};
+
+// atan(mn/mx) for 0 <= mn <= mx, mx > 0: pick c = i/32 nearest to mn/mx from the MUFU
+// reciprocal seed, then atan(mn/mx) = atan(c) + atan(t), t = (mn - c*mx)/(mx + c*mn),
+// |t| <= 1/64 + 2^-19, where the degree-9 odd Taylor polynomial is exact to 1e-21.
+__device__ __forceinline__ double atan_ratio(double mn, double mx) {
+    const double q = mn * mufu_rcp(mx);
+    // round-to-nearest-integer of 32*q via the 2^52+2^51 trick; the integer sits in the low word
+    const double magic = 6755399441055744.0;
+    const double qi = fma(q, 32.0, magic);
+    int i = __double2loint(qi);
+    i = min(max(i, 0), 32);                      // also keeps NaN inputs inside the table
+    const double c = (qi - magic) * 0.03125;     // == i/32 exactly (q is in [0, 1])
+    const double num = fma(-c, mx, mn);
+    const double den = fma(c, mn, mx);
+    const double t = div_fast(num, den);
+    const double s = t * t;
+    double p = 1.0 / 9.0;
+    p = fma(p, s, -1.0 / 7.0);
+    p = fma(p, s, 1.0 / 5.0);
+    p = fma(p, s, -1.0 / 3.0);
+    const double ts = t * s;
+    return c_atan_tab[i] + fma(ts, p, t);
+}
+
+constexpr double kPi = 3.141592653589793;
+constexpr double kHalfPi = 1.5707963267948966;
+
+// atan2(y, x), any quadrant, finite inputs, not both zero.
+__device__ __forceinline__ double atan2_fast(double y, double x) {
+    const double a = fabs(y), b = fabs(x);
+    const bool swap = a > b;
+    double r = atan_ratio(swap ? b : a, swap ? a : b);
+    if (swap) r = kHalfPi - r;
+    if (x < 0.0) r = kPi - r;
+    return copysign(r, y);
+}
+
+// atan2(y, x) for x >= 0 (result in [-pi/2, pi/2]); also serves atan(y/x).
+__device__ __forceinline__ double atan2_posx(double y, double x) {
+    const double a = fabs(y);
+    const bool swap = a > x;
+    double r = atan_ratio(swap ? x : a, swap ? a : x);
+    if (swap) r = kHalfPi - r;
+    return copysign(r, y);
+}
+
+// acos(d) for d in [-1, 1] via atan2(sqrt((1-d)(1+d)), d); (1-d) is exact for d >= 0.5.
+__device__ __forceinline__ double acos_fast(double d) {
+    const double w = (1.0 - d) * (1.0 + d);
+    const double s = w > 0.0 ? sqrt_fast(w) : 0.0;
+    const double a = fabs(d);
+    const bool swap = s > a;
+    if (s == 0.0) return d < 0.0 ? kPi : 0.0;
+    double r = atan_ratio(swap ? a : s, swap ? s : a);
+    if (swap) r = kHalfPi - r;
+    if (d < 0.0) r = kPi - r;
+    return r;
+}
+
+}  // namespace amt

@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "../../include/auromat_b200.h"
+#include "amt_fastmath.cuh"
 
 namespace amt {
 
@@ -31,6 +32,7 @@ struct FrameC {
     double m_geo[9];
     double m_sm[9];
     double a, b, e2a, d;    // Bowring constants        transform.py:254-255,290
+    double b_over_a;
     int sip_oa, sip_ob;
 };
 
@@ -40,14 +42,13 @@ struct FrameC {
 // back to Cartesian via sin/cos; the composition is the algebraic identity
 //     (cos t cos p, cos t sin p, sin t) = (-y, x, 180/pi) / sqrt(x^2 + y^2 + (180/pi)^2)
 // with p = atan2(x,-y), t = atan((180/pi)/r), which we evaluate directly: no transcendental
-// call, <= 2 ulp from the reference's value (tested against the oracle to 1e-9 deg after
-// the full chain).
+// call, <= 2 ulp from the reference's value.
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void sip_distort(const double* __restrict__ ca, int oa,
                                             const double* __restrict__ cb, int ob,
                                             double& u, double& v) {
     // f(u,v) = sum_{p+q<=order} C_pq u^p v^q, Horner in v inside Horner in u, highest power
-    // first (same fixed order as oracle/_sip_poly).
+    // first (same fixed order as oracle/_sip_poly; no FMA so that both sides round alike).
     double fu = 0.0, fv = 0.0;
     for (int pass = 0; pass < 2; ++pass) {
         const double* c = pass == 0 ? ca : cb;
@@ -73,56 +74,79 @@ __device__ __forceinline__ void pix2dir(const FrameC& f, const double* __restric
     double v = (py - f.crpix1) + 1.0;
     if (f.sip_oa | f.sip_ob) sip_distort(sip_a, f.sip_oa, sip_b, f.sip_ob, u, v);
     // wcs.py:102  xy = CD . pxy
-    const double x = f.cd[0] * u + f.cd[1] * v;
-    const double y = f.cd[2] * u + f.cd[3] * v;
+    const double x = fma(f.cd[0], u, f.cd[1] * v);
+    const double y = fma(f.cd[2], u, f.cd[3] * v);
     // wcs.py:111-144 collapsed (see header comment)
     const double K = 180.0 / 3.141592653589793;
-    const double n2 = (x * x + y * y) + K * K;
-    const double inv = 1.0 / sqrt(n2);
+    const double inv = rsqrt_fast(fma(x, x, fma(y, y, K * K)));
     const double l = -y * inv, m = x * inv, n = K * inv;
     // wcs.py:142  lmnrot = R . lmn
-    dir[0] = (f.rot[0] * l + f.rot[1] * m) + f.rot[2] * n;
-    dir[1] = (f.rot[3] * l + f.rot[4] * m) + f.rot[5] * n;
-    dir[2] = (f.rot[6] * l + f.rot[7] * m) + f.rot[8] * n;
+    dir[0] = fma(f.rot[2], n, fma(f.rot[1], m, f.rot[0] * l));
+    dir[1] = fma(f.rot[5], n, fma(f.rot[4], m, f.rot[3] * l));
+    dir[2] = fma(f.rot[8], n, fma(f.rot[7], m, f.rot[6] * l));
 }
 
 // ---------------------------------------------------------------------------------------
 // Stage 2a: directed ray / inflated-ellipsoid intersection in the J2000 frame.
-// coordinates/intersection.py:58-104, operation for operation (this block is the
-// ill-conditioned one for grazing rays, so no re-association and no FMA).
-// Returns the normalised discriminant rootTerm/dDD for conditioning diagnostics.
+// coordinates/intersection.py:58-104, operation for operation: this is the one
+// ill-conditioned block of the path (grazing rays: the discriminant cancels), so it keeps
+// the reference's order of IEEE operations -- no re-association, no FMA, IEEE sqrt and
+// divide.  Returns false when the ray misses (reference: NaN row).
+// `graze` is set when the normalised discriminant rootTerm/dDD is below kGrazeThreshold.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ double intersect(const FrameC& f, const double dir[3], double P[3]) {
+constexpr double kGrazeThreshold = 1e-10;
+
+__device__ __forceinline__ bool intersect(const FrameC& f, const double dir[3], double P[3], bool& graze) {
     const double D0 = dir[0] * f.rad[0], D1 = dir[1] * f.rad[1], D2 = dir[2] * f.rad[2];
     const double dDO = (D0 * f.otr[0] + D1 * f.otr[1]) + D2 * f.otr[2];
     const double dDD = (D0 * D0 + D1 * D1) + D2 * D2;
     double rt = dDO * dDO;
     rt = rt - f.oDO * dDD;
     rt = rt + dDD;
-    const double root = sqrt(rt);                    // NaN when the line misses
+    graze = rt >= 0.0 && rt < kGrazeThreshold * dDD;
+    if (!(rt >= 0.0)) return false;                  // sqrt of a negative -> NaN row
+    const double root = sqrt(rt);
     double t = f.origin_inside ? dDO + root : dDO - root;
-    if (t < 0.0) t = qnan();                         // intersection.py:50-56 (behind the camera)
+    if (!(t >= 0.0)) return false;                   // intersection.py:50-56 (behind the camera)
     t = t / dDD;
     P[0] = dir[0] * t + f.cam[0];                    // res = direction*dMin - (-lineOrigin)
     P[1] = dir[1] * t + f.cam[1];
     P[2] = dir[2] * t + f.cam[2];
-    return rt / dDD;
+    return true;
 }
 
 __device__ __forceinline__ void mat3(const double* __restrict__ M, const double v[3], double o[3]) {
-    o[0] = (M[0] * v[0] + M[1] * v[1]) + M[2] * v[2];
-    o[1] = (M[3] * v[0] + M[4] * v[1]) + M[5] * v[2];
-    o[2] = (M[6] * v[0] + M[7] * v[1]) + M[8] * v[2];
+    o[0] = fma(M[2], v[2], fma(M[1], v[1], M[0] * v[0]));
+    o[1] = fma(M[5], v[2], fma(M[4], v[1], M[3] * v[0]));
+    o[2] = fma(M[8], v[2], fma(M[7], v[1], M[6] * v[0]));
 }
 
 // ---------------------------------------------------------------------------------------
-// Stage 2b: ECEF -> geodetic, single-iteration Bowring 1985.
-// coordinates/transform.py:252-297 (`_ecef2GeodeticOptimized_np`).  Output in radians.
-// `cu3 **= 3` of the reference is libm pow(c,3); we use c*c*c (<= 1 ulp apart; the term it
-// feeds is scaled by e^2 ~ 0.7 %, so the effect on lat is < 1e-18 rad).
+// Stage 2b: ECEF -> geodetic, single-iteration Bowring 1985 (coordinates/transform.py:252-297).
+//   p = sqrt(x^2+y^2), r = sqrt(p^2+z^2), tu = b z (1 + d/r)/(a p), cu3 = (1+tu^2)^(-3/2),
+//   lat = atan((z + d cu3 tu^3)/(p - e^2 a cu3)), lon = atan2(y, x)
+// evaluated with one Goldschmidt (sqrt, 1/sqrt) pair per root, no division besides the two
+// inside the arctangents:  tu = (b/a) z (r + d) (1/r)(1/p).  Output in radians.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void bowring(double a, double b, double e2a, double d,
+__device__ __forceinline__ void bowring(double a, double b_over_a, double e2a, double d,
                                         double x, double y, double z, double& lat, double& lon) {
+    const double p2 = fma(x, x, y * y);
+    double p, hp, r, hr;
+    sqrt_rsqrt(p2, p, hp);                       // hp = 0.5/p
+    sqrt_rsqrt(fma(z, z, p2), r, hr);            // hr = 0.5/r
+    const double tu = ((b_over_a * z) * (r + d)) * ((hp + hp) * (hr + hr));
+    const double c = rsqrt_fast(fma(tu, tu, 1.0));
+    const double cu3 = (c * c) * c;
+    const double su3 = (tu * cu3) * (tu * tu);
+    lat = atan2_posx(fma(d, su3, z), fma(-e2a, cu3, p));
+    lon = atan2_fast(y, x);
+    (void)a;
+}
+
+// Reference-order Bowring with libm, used by the (cold) rotatePole path where the result
+// feeds a bit-exact binning comparison against numpy.
+__device__ __forceinline__ void bowring_ref(double a, double b, double e2a, double d,
+                                            double x, double y, double z, double& lat, double& lon) {
     const double p2 = x * x + y * y;
     const double p = sqrt(p2);
     const double r = sqrt(p2 + z * z);
@@ -158,22 +182,20 @@ __device__ __forceinline__ void geodetic2ecef(double a, double e2, double lat, d
 
 // SM Cartesian -> (MLat deg, MLT h): transform.py:104-127 + :419-430 + :373-386.
 __device__ __forceinline__ void sm_to_mlat_mlt(const double S[3], double& mlat, double& mlt) {
-    const double s = sqrt(S[0] * S[0] + S[1] * S[1]);
-    const double smlon = atan2(S[1], S[0]) * kRad2Deg;
-    mlat = atan2(S[2], s) * kRad2Deg;
-    mlt = smlon * (24.0 / 360.0) + 12.0;
+    const double s = sqrt_fast(fma(S[0], S[0], S[1] * S[1]));
+    const double smlon = atan2_fast(S[1], S[0]) * kRad2Deg;
+    mlat = atan2_posx(S[2], s) * kRad2Deg;
+    mlt = fma(smlon, 24.0 / 360.0, 12.0);
 }
 
 // elevation, mapping/astrometry.py:200-212 + utils.py:28-46; `dir` need not be unit
 // (fast centres use the un-normalised mean of four corner directions, astrometry.py:61-62).
 __device__ __forceinline__ double elevation_deg(const double dir[3], const double P[3]) {
-    const double len = sqrt((P[0] * P[0] + P[1] * P[1]) + P[2] * P[2]);
-    const double u0 = P[0] / len, u1 = P[1] / len, u2 = P[2] / len;
-    double dot = ((-dir[0]) * u0 + (-dir[1]) * u1) + (-dir[2]) * u2;
-    // np.clip(dot, -1, 1): NaN propagates
-    if (dot < -1.0) dot = -1.0;
-    if (dot > 1.0) dot = 1.0;
-    return 90.0 - acos(dot) * kRad2Deg;
+    const double inv_len = rsqrt_fast(fma(P[2], P[2], fma(P[1], P[1], P[0] * P[0])));
+    double dot = -fma(dir[2], P[2], fma(dir[1], P[1], dir[0] * P[0])) * inv_len;
+    // np.clip(dot, -1, 1)
+    dot = fmin(fmax(dot, -1.0), 1.0);
+    return fma(-acos_fast(dot), kRad2Deg, 90.0);
 }
 
 // One J2000 intersection point -> lat/lon [deg] (+ MLat/MLT).  transform.py:324-343,403-430.
@@ -181,7 +203,7 @@ __device__ __forceinline__ void point_to_geo(const FrameC& f, const double P[3],
     double G[3];
     mat3(f.m_geo, P, G);
     double la, lo;
-    bowring(f.a, f.b, f.e2a, f.d, G[0], G[1], G[2], la, lo);
+    bowring(f.a, f.b_over_a, f.e2a, f.d, G[0], G[1], G[2], la, lo);
     lat = la * kRad2Deg;
     lon = lo * kRad2Deg;
 }

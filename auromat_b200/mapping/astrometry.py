@@ -59,6 +59,8 @@ class BaseAstrometryMapping(BaseMapping):
             want |= {'lat_k', 'lon_k', 'lat_c', 'lon_c', 'elev_c'}
         fresh = {n: ctx.empty(nk if n in CORNER_PLANES else nc, torch.float64)
                  for n in want if n not in self._planes}
+        # the hit bitmaps are (re)written by every launch; sanitisation then starts from them
+        fresh['valid_k'], fresh['valid_c'] = ctx.new_bitmaps(w, h)
         if self._illConditioned is None:
             self._illConditioned = ctx.new_stats()
             stats = self._illConditioned
@@ -69,6 +71,66 @@ class BaseAstrometryMapping(BaseMapping):
         if self._sanitize:
             ctx.sanitize(w, h, self._planes)
         self.isSanitized = True
+
+    # ---- pole containment: exact geometric test instead of the reference's outline walk ----
+    _poleTestOnDevice = False
+
+    def _poleFlags(self):
+        """bit0 / bit1: the geographic north / south pole (at the mapping altitude) is seen by
+        a valid pixel.  The pole point is projected through the inverse WCS; replaces the
+        azimuth-sum test on a 50-point convex outline (reference mapping.py:705-718)."""
+        from ..coordinates import transform
+        from ..coordinates.geodesic import wgs84A, wgs84B
+        fr = self.frameConstants
+        h, w = self.shape
+        a, b = wgs84A + self.altitude, wgs84B + self.altitude
+        cam = np.asarray(self.cameraPosGCRS, dtype=np.float64)
+        mgeo = np.array(fr.m_geo[:]).reshape(3, 3)
+        rot = np.array(fr.rot[:]).reshape(3, 3)
+        cd = np.array(fr.cd[:]).reshape(2, 2)
+        inside = bool(fr.origin_inside)
+        flags = 0
+        for bit, sign in ((1, 1.0), (2, -1.0)):
+            P = mgeo.T.dot(np.array([0.0, 0.0, sign * b]))
+            d = P - cam
+            normal = P / np.array([a * a, a * a, b * b])
+            if (np.dot(d, normal) >= 0) != inside:      # far side of the ellipsoid
+                continue
+            lmn = rot.T.dot(d / np.linalg.norm(d))
+            if lmn[2] <= 0:
+                continue
+            K = 180.0 / np.pi
+            xy = np.array([K * lmn[1] / lmn[2], -K * lmn[0] / lmn[2]])
+            uv = np.linalg.solve(cd, xy)
+            if fr.sip_order_a or fr.sip_order_b:
+                uv = self._invertSip(uv)
+            px, py = uv[0] + fr.crpix[0] - 1, uv[1] + fr.crpix[1] - 1
+            if -0.5 <= px <= w - 0.5 and -0.5 <= py <= h - 0.5:
+                ix = min(max(int(np.floor(px + 0.5)), 0), w - 1)
+                iy = min(max(int(np.floor(py + 0.5)), 0), h - 1)
+                lat = float(self.devicePlanes()['lat_c'][iy * w + ix].item())
+                if lat == lat:
+                    flags |= bit
+        return flags
+
+    def _invertSip(self, target):
+        """Solve (u,v) + (f,g)(u,v) = target by fixed-point iteration (|distortion| << 1)."""
+        fr = self.frameConstants
+
+        def poly(packed, order, u, v):
+            acc = 0.0
+            for p in range(order, -1, -1):
+                base = p * (order + 1) - (p * (p - 1)) // 2
+                inner = 0.0
+                for q in range(order - p, -1, -1):
+                    inner = inner * v + packed[base + q]
+                acc = acc * u + inner
+            return acc
+        u, v = target
+        for _ in range(30):
+            u = target[0] - poly(fr.sip_a, fr.sip_order_a, u, v)
+            v = target[1] - poly(fr.sip_b, fr.sip_order_b, u, v)
+        return np.array([u, v])
 
     @property
     def illConditionedCount(self):

@@ -155,6 +155,13 @@ class BaseMapping(object):
     def _computePlanes(self, ctx, names):
         raise NotImplementedError
 
+    # Pole containment: by default the per-pixel longitude winding test on the device;
+    # mappings with a camera model override `_poleFlags` with an exact geometric test.
+    _poleTestOnDevice = True
+
+    def _poleFlags(self):
+        return 0
+
     def _ensurePlanes(self, names):
         missing = [n for n in names if n not in self._planes]
         if missing:
@@ -197,8 +204,10 @@ class BaseMapping(object):
             p = self.devicePlanes()
             h, w = self.shape
             st = ctx.new_stats()
-            ctx.bbox_stats(w, h, p['lat_k'], p['lon_k'], p['lat_c'], st)
+            ctx.bbox_stats(w, h, p, st, pole_test=self._poleTestOnDevice)
             s = ctx.read_stats(st)
+            if not self._poleTestOnDevice:
+                s.pole_flags = self._poleFlags()
             if getattr(self, '_illConditioned', None) is not None:
                 s.n_ill_conditioned = int(ctx.read_stats(self._illConditioned).n_ill_conditioned)
             self._stats = s
@@ -346,8 +355,8 @@ class BaseMapping(object):
 
     def _maskedCopy(self, mask=None, minElevation=float('nan')):
         ctx = self.context
-        have_mag = 'mlat_k' in self._planes
-        src = self.devicePlanes(magnetic=have_mag)
+        # all planes are materialised first: a later georeference launch would not know the mask
+        src = self.devicePlanes(magnetic=True)
         m = copy.copy(self)
         m._planes = {k: v.clone() for k, v in src.items()}
         m._host = {}
@@ -450,24 +459,44 @@ class GenericMapping(BaseMapping):
         self._imgData = img
         ctx = self.context
 
-        def up(a):
+        # The coordinate values handed in stay available as the `.data` of the masked arrays
+        # (the reference's sanitisation only touches masks); the device planes carry NaN
+        # wherever the sanitised mask is set.
+        self._raw = {}
+
+        def up(name, a):
             if hasattr(a, 'data_ptr'):          # already a device tensor
-                return a.reshape(-1)
+                self._raw[name] = a.reshape(-1)
+                return a.reshape(-1).clone()
             if ma.isMaskedArray(a):
                 a = a.astype(np.float64).filled(np.nan)
-            return ctx.to_device(np.asarray(a, dtype=np.float64)).reshape(-1)
+            a = np.asarray(a, dtype=np.float64)
+            self._raw[name] = a
+            return ctx.to_device(a).reshape(-1)
 
-        self._planes = dict(lat_k=up(lats), lon_k=up(lons), lat_c=up(latsCenter), lon_c=up(lonsCenter))
+        self._planes = dict(lat_k=up('lat_k', lats), lon_k=up('lon_k', lons), lat_c=up('lat_c', latsCenter),
+                            lon_c=up('lon_c', lonsCenter))
         if elev is not None:
-            self._planes['elev_c'] = up(elev)
+            self._planes['elev_c'] = up('elev_c', elev)
         else:
             import torch
             self._planes['elev_c'] = ctx.zeros(h * w, torch.float64)
+        ctx.valid_bits(w, h, self._planes)
         if imgMask is not None and imgMask.any():
             # reference mapping.py:1077-1081: the image mask is applied to the centre coordinates
             ctx.apply_center_mask(w, h, self._planes, ctx.to_device(imgMask.astype(np.uint8).ravel()))
         if sanitize:
             ctx.sanitize(w, h, self._planes)
+
+    def _download(self, name):
+        if name not in self._host:
+            masked = BaseMapping._download(self, name)
+            raw = self._raw.get(name)
+            if raw is not None:
+                data = self.context.to_numpy(raw) if hasattr(raw, 'data_ptr') else raw
+                data = np.asarray(data, dtype=np.float64).reshape(masked.shape)
+                self._host[name] = ma.masked_array(data, mask=ma.getmaskarray(masked) | np.isnan(data))
+        return self._host[name]
 
     shape = property(lambda self: self._shape)
     img_unmasked = property(lambda self: self._imgData)

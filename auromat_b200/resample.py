@@ -190,7 +190,7 @@ def resampleToDevice(mapping, pxPerDeg=25, arcsecPerPx=None, containsPole=None):
         p = mapping.devicePlanes()
         h, w = mapping.shape
         st = ctx.new_stats()
-        ctx.bbox_stats(w, h, p['lat_k'], p['lon_k'], None, st, _preRotation(mode, mapping.altitude))
+        ctx.bbox_stats(w, h, p, st, pre=_preRotation(mode, mapping.altitude))
         s = ctx.read_stats(st)
         lonMin, lonMax = s.lon_min, s.lon_max
         if mode == _lib.AMT_PRE_POLE:

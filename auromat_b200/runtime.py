@@ -99,9 +99,29 @@ class Context:
             setattr(out, "d_" + name, t.data_ptr())
         _lib.check(self.lib.amt_sanitize(self.handle, width, height, C.byref(out), self.stream()))
 
-    def bbox_stats(self, width, height, lat_k, lon_k, lat_c, stats, pre: "_lib.AmtGrid | None" = None):
-        _lib.check(self.lib.amt_bbox_stats(self.handle, width, height, self.ptr(lat_k), self.ptr(lon_k),
-                                           self.ptr(lat_c), C.byref(pre) if pre is not None else None,
+    @staticmethod
+    def bitmap_words(width, height):
+        """(#words of the corner bitmap, #words of the centre bitmap), rows padded to 32 bits."""
+        return (height + 1) * ((width + 1 + 31) // 32), height * ((width + 31) // 32)
+
+    def new_bitmaps(self, width, height):
+        torch = _torch()
+        nk, nc = self.bitmap_words(width, height)
+        return (torch.empty(nk, dtype=torch.int32, device=self.torch_device),
+                torch.empty(nc, dtype=torch.int32, device=self.torch_device))
+
+    def valid_bits(self, width, height, planes: dict):
+        """Build the validity bitmaps of NaN-marked planes into planes['valid_k'/'valid_c']."""
+        planes['valid_k'], planes['valid_c'] = self.new_bitmaps(width, height)
+        _lib.check(self.lib.amt_valid_bits(self.handle, width, height, self.ptr(planes['lat_k']),
+                                           self.ptr(planes['lat_c']), self.ptr(planes['valid_k']),
+                                           self.ptr(planes['valid_c']), self.stream()))
+
+    def bbox_stats(self, width, height, planes: dict, stats, pole_test=False, pre: "_lib.AmtGrid | None" = None):
+        _lib.check(self.lib.amt_bbox_stats(self.handle, width, height, self.ptr(planes['lat_k']),
+                                           self.ptr(planes['lon_k']), self.ptr(planes['valid_k']),
+                                           self.ptr(planes['valid_c']), 1 if pole_test else 0,
+                                           C.byref(pre) if pre is not None else None,
                                            self.ptr(stats), self.stream()))
 
     def apply_center_mask(self, width, height, planes: dict, mask=None, min_elevation=float("nan")):

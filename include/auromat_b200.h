@@ -92,6 +92,12 @@ typedef struct amt_georef_out {
     double* d_mlat_c;
     double* d_mlt_c;
     double* d_elev_c;
+    /* validity bitmaps, 1 bit per corner / centre (1 == defined), rows padded to 32-bit words:
+     * (height+1) x ceil((width+1)/32) and height x ceil(width/32) words; padding bits are 0.
+     * Written by amt_georef (ballots of the ray hit test), consumed and updated by
+     * amt_sanitize, amt_apply_center_mask; read by amt_bbox_stats.                        */
+    uint32_t* d_valid_k;
+    uint32_t* d_valid_c;
 } amt_georef_out;
 
 /* Reductions over the corner planes (mapping/mapping.py:694-743 boundingBox min/max part;
@@ -166,22 +172,29 @@ int amt_stream_synchronize(amt_ctx* ctx, void* stream);
 int amt_georef(amt_ctx* ctx, const amt_frame* frame, const amt_georef_out* out,
                amt_stats* d_stats /* nullable: n_ill_conditioned += ... */, void* stream);
 
-/* Mask sanitisation, in place: planes get NaN where the reference would mask.
- * Replaces mapping/mapping.py:1063-1125 (`_doSanitize`, afterMasking=False, no image mask):
- *   corner masked if all of its (<=4) neighbouring centres are missing; centre masked if any
- *   of its 4 corners is masked; corners once more.  Needs lat_k and lat_c; every non-NULL
- *   plane of `planes` is updated consistently.                                            */
+/* Validity bitmaps from NaN-marked latitude planes (mappings that were not produced by
+ * amt_georef: uploaded arrays, resampled grids).                                          */
+int amt_valid_bits(amt_ctx* ctx, int32_t width, int32_t height, const double* d_lat_k,
+                   const double* d_lat_c, uint32_t* d_valid_k, uint32_t* d_valid_c, void* stream);
+
+/* Mask sanitisation, in place: planes get NaN where the reference would mask, the bitmaps
+ * are updated.  Replaces mapping/mapping.py:1063-1125 (`_doSanitize`, afterMasking=False, no
+ * image mask): corner masked if all of its (<=4) neighbouring centres are missing; centre
+ * masked if any of its 4 corners is masked; corners once more.  The stencils run on the
+ * bitmaps; only newly masked elements of the planes are touched.                          */
 int amt_sanitize(amt_ctx* ctx, int32_t width, int32_t height, const amt_georef_out* planes,
                  void* stream);
 
-/* Bounding-box reductions over the boundary corners (min/max part of
- * mapping/mapping.py:694-743) plus valid counts.  When `pre` is non-NULL and
- * pre->prerotate != AMT_PRE_NONE the boundary coordinates are first rotated exactly as
- * resample.py:176-218 rotates the outline (only prerotate, altitude, wgs_a/b and rot of
- * `pre` are read).  `d_stats` is a DEVICE amt_stats; n_ill_conditioned is left untouched. */
+/* Bounding-box reductions over the outline = valid corners with an invalid or out-of-array
+ * 4-neighbour (min/max part of mapping/mapping.py:694-743) plus valid counts.  When `pre` is
+ * non-NULL and pre->prerotate != AMT_PRE_NONE the outline coordinates are first rotated
+ * exactly as resample.py:176-218 rotates the outline (only prerotate, altitude, wgs_a/b and
+ * rot of `pre` are read).  pole_test != 0 additionally runs the per-pixel longitude winding
+ * test (one pass over lon_k).  `d_stats` is a DEVICE amt_stats; n_ill_conditioned is left
+ * untouched.                                                                              */
 int amt_bbox_stats(amt_ctx* ctx, int32_t width, int32_t height, const double* d_lat_k,
-                   const double* d_lon_k, const double* d_lat_c, const amt_grid* pre,
-                   amt_stats* d_stats, void* stream);
+                   const double* d_lon_k, const uint32_t* d_valid_k, const uint32_t* d_valid_c,
+                   int32_t pole_test, const amt_grid* pre, amt_stats* d_stats, void* stream);
 
 /* Apply a centre mask (mapping/mapping.py:845-864 maskedByElevation, :1171-1231 createMasked
  * followed by `_doSanitize(afterMasking=True)`), in place: a centre becomes NaN if

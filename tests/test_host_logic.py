@@ -1,0 +1,220 @@
+"""CPU tests of the product's host side: per-frame constants, grid derivation, header parsing,
+bounding boxes, and that the C-ABI library loads and exports every declared symbol.
+No kernel is launched here."""
+import ctypes
+import datetime
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle.auromat_oracle as O
+from auromat_b200 import _lib, fits, synthetic
+from auromat_b200.coordinates import geodesic, igrf, transform, wcs
+from auromat_b200.mapping.mapping import BoundingBox, wrapAt180
+from auromat_b200 import resample as R
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    header = open(os.path.join(ROOT, "include", "auromat_b200.h")).read()
+    declared = set(re.findall(r"\b(amt_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(built_lib)
+    for name in sorted(declared):
+        assert hasattr(lib, name), "missing export: " + name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    loaded = _lib.load()
+    assert loaded.amt_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    # sizes implied by include/auromat_b200.h (natural alignment, no packing)
+    assert ctypes.sizeof(_lib.AmtFrame) == 4 * 4 + 8 * (2 + 4 + 9 + 3 + 3 + 9 + 9 + 2) + 2 * 4 + 8 * 2 * 55
+    assert ctypes.sizeof(_lib.AmtGeorefOut) == 11 * 8
+    assert ctypes.sizeof(_lib.AmtStats) == 6 * 8 + 5 * 8
+    assert ctypes.sizeof(_lib.AmtGrid) == 4 * 4 + 8 * (6 + 2 + 3 + 9)
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    from auromat_b200.mapping.spacecraft import getMapping
+    m = getMapping(synthetic.issImage(32, 24), synthetic.issHeader(32, 24), identifier='x')
+    with pytest.raises(RuntimeError):
+        m.lats                              # no CPU fallback
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "auromat_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+@pytest.mark.parametrize("date", [datetime.datetime(2012, 1, 25, 9, 26, 55, 60000),
+                                  datetime.datetime(2003, 7, 1, 23, 59, 1),
+                                  datetime.datetime(1999, 12, 31, 12, 0, 0)])
+def test_frame_matrices_bit_equal_to_oracle(date):
+    et = transform.date2es(date)
+    assert et == O.date2es(date)
+    for name in ('mat_P', 'mat_T1', 'mat_T2', 'mat_T3', 'mat_T4', 'mat_j2000_to_geo', 'mat_j2000_to_sm',
+                 'mat_geo_to_sm'):
+        assert np.array_equal(getattr(transform, name)(et), getattr(O, name)(et)), name
+
+
+def test_igrf_and_constants():
+    assert geodesic.wgs84A == O.WGS84_A and geodesic.wgs84B == O.WGS84_B
+    assert igrf.IGRF_DEFINED_UNTIL_YEAR == 2020
+    with pytest.raises(ValueError):
+        transform.mat_j2000_to_sm(transform.date2es(datetime.datetime(2020, 6, 1)))
+    et = transform.date2es(datetime.datetime(2012, 1, 25))
+    assert transform.mag_lat(et) == O.mag_lat(et) and transform.mag_lon(et) == O.mag_lon(et)
+
+
+def test_frame_constants():
+    hdr = synthetic.issHeader(133, 89, sipOrder=3)
+    t, cam = synthetic.headerTimeAndCamera(hdr)
+    fr = wcs.frameConstants(hdr, cam, t, 110, fastCenterCalculation=True)
+    assert (fr.width, fr.height, fr.fast_center, fr.origin_inside) == (133, 89, 1, 0)
+    assert np.array_equal(np.array(fr.rot[:]).reshape(3, 3), O.tan_native_rotation(hdr))
+    et = O.date2es(t)
+    assert np.array_equal(np.array(fr.m_geo[:]).reshape(3, 3), O.mat_j2000_to_geo(et))
+    assert np.array_equal(np.array(fr.m_sm[:]).reshape(3, 3), O.mat_j2000_to_sm(et))
+    a, b = O.WGS84_A + 110, O.WGS84_B + 110
+    assert list(fr.inv_axes[:]) == [1 / a, 1 / a, 1 / b]
+    oa, A, ob, B = O.sip_coefficients(hdr)
+    assert (fr.sip_order_a, fr.sip_order_b) == (3, 3)
+    for (p, q), v in A.items():
+        assert fr.sip_a[p * 4 - (p * (p - 1)) // 2 + q] == v
+    with pytest.raises(NotImplementedError):
+        bad = dict(hdr)
+        bad['CTYPE1'] = 'RA---SIN'
+        wcs.frameConstants(bad, cam, t, 110)
+
+
+def test_fixed_grid_equals_reference_arithmetic():
+    rng = np.random.default_rng(0)
+    for k in range(400):
+        ppd = (rng.uniform(1, 400), rng.uniform(1, 400)) if k % 3 else (36.0, float(rng.integers(1, 50)))
+        la = np.sort(rng.uniform(-89, 89, 2))
+        lo = np.sort(rng.uniform(-179, 179, 2))
+        a = R.fixedGrid(ppd, la[0], la[1], lo[0], lo[1])
+        b = O.fixed_grid(ppd, la[0], la[1], lo[0], lo[1])
+        assert tuple(a) == tuple(b)
+    # bounds that sit exactly on grid nodes, and the argmax wrap-around corner cases
+    assert tuple(R.fixedGrid((4, 4), 10.0, 20.25, -30.0, -10.5)) == tuple(O.fixed_grid((4, 4), 10.0, 20.25, -30.0, -10.5))
+    assert tuple(R.fixedGrid((2, 2), -90.0, 90.0, -180.0, 180.0)) == tuple(O.fixed_grid((2, 2), -90.0, 90.0, -180.0, 180.0))
+
+
+def test_target_grid_matches_histogram_range():
+    """The amt_grid handed to the kernels equals the bins/range the reference passes to
+    histogram2d (resample.py:330-337) and its rounding decimals (histogram.py:215-219)."""
+    ppd = (36.0, 20.7)
+    latMin, latMax, lonMin, lonMax = 47.9, 61.3, -111.6, -91.9
+    g, info = R.targetGrid(ppd, latMin, latMax, lonMin, lonMax)
+    nLat, nLon, a, b, c, d = O.fixed_grid(ppd, latMin, latMax, lonMin, lonMax)
+    latSC, latStep = np.linspace(b, a, num=nLat, retstep=True)
+    lonSC, lonStep = np.linspace(c, d, num=nLon, retstep=True)
+    latSC, lonSC = latSC[1:-1], lonSC[1:-1]
+    assert (g.nx, g.ny) == (len(lonSC), len(latSC))
+    assert (g.lo_x, g.hi_x) == (lonSC[0] - lonStep / 2, lonSC[-1] + lonStep / 2)
+    assert (g.lo_y, g.hi_y) == (latSC[-1] + latStep / 2, latSC[0] - latStep / 2)
+    ex = np.linspace(g.lo_x, g.hi_x, g.nx + 1)
+    assert g.step_x == (ex[-1] - ex[0]) / g.nx
+    assert g.round_x == 10.0 ** (int(-np.log10(np.diff(ex).min())) + 6)
+    ey = np.linspace(g.lo_y, g.hi_y, g.ny + 1)
+    assert g.round_y == 10.0 ** (int(-np.log10(np.diff(ey).min())) + 6)
+    with pytest.raises(AssertionError):
+        R.targetGrid((0, 1), 0, 1, 0, 1)
+
+
+def test_plate_carree_resolution():
+    bb = BoundingBox(47.9, -111.6, 61.3, -91.9)
+    lat, lon = R.plateCarreeResolution(bb, 100)
+    olat, olon = O.plate_carree_resolution((47.9, -111.6, 61.3, -91.9), 100)
+    assert (lat, lon) == (olat, olon)
+    assert lat == 1 / (100 * (1.0 / 3600.0))
+    assert 19 < lon < 22           # cos(54.6 deg) * 36 px/deg
+    # spans the date line
+    lat2, lon2 = R.plateCarreeResolution(BoundingBox(60, 170, 70, -170), 100)
+    assert 12 < lon2 < 19
+
+
+def test_wrap_at_180():
+    x = np.array([-540.0, -180.0, -179.9, 0.0, 179.9, 180.0, 190.0, 359.0, 360.0, 725.0, np.nan])
+    w = wrapAt180(x)
+    assert np.array_equal(w[:-1], [-180.0, -180.0, -179.9, 0.0, 179.9, -180.0, -170.0, -1.0, 0.0, 5.0])
+    assert np.isnan(w[-1])
+    assert np.array_equal(w, O.wrap_at_180(x), equal_nan=True)
+    assert wrapAt180(190.0) == -170.0
+
+
+def test_bounding_box():
+    bb = BoundingBox(10, 170, 20, -170)
+    assert bb.containsDiscontinuity and not bb.containsPole
+    assert BoundingBox(60, -180, 90, 180).containsPole
+    with pytest.raises(AssertionError):
+        BoundingBox(0, -190, 1, 0)
+    m = BoundingBox.mergedBoundingBoxes([BoundingBox(10, 160, 20, 175), BoundingBox(5, -178, 15, -170)])
+    assert (m.latSouth, m.lonWest, m.latNorth, m.lonEast) == (5, 160, 20, -170)
+    m = BoundingBox.mergedBoundingBoxes([BoundingBox(0, -10, 1, 10), BoundingBox(0, 5, 2, 30)])
+    assert (m.lonWest, m.lonEast) == (-10, 30)
+    m = BoundingBox.minimumBoundingBox([(1, 2), (3, 4), (-1, 3)])
+    assert (m.latSouth, m.lonWest, m.latNorth, m.lonEast) == (-1, 2, 3, 4)
+    assert BoundingBox(1, 2, 3, 4) == BoundingBox(1, 2, 3, 4)
+
+
+def _card(key, value, comment=''):
+    if isinstance(value, str):
+        v = "'%-8s'" % value
+        s = "%-8s= %-20s" % (key, v)
+    elif isinstance(value, bool):
+        s = "%-8s= %20s" % (key, 'T' if value else 'F')
+    else:
+        s = "%-8s= %20s" % (key, repr(value))
+    if comment:
+        s += " / " + comment
+    return s[:80].ljust(80)
+
+
+def test_fits_header_reader(tmp_path):
+    hdr = synthetic.issHeader()
+    cards = [_card('SIMPLE', True, 'conforms to FITS standard'), _card('BITPIX', 8), _card('NAXIS', 0)]
+    cards += [_card(k, v, 'x') for k, v in hdr.items()]
+    cards.append("COMMENT this is ignored".ljust(80))
+    cards.append(_card('NORADID', '25544'))
+    cards.append("END".ljust(80))
+    raw = "".join(cards)
+    raw = raw.ljust((len(raw) + 2879) // 2880 * 2880)
+    p = tmp_path / "frame.wcs"
+    p.write_bytes(raw.encode('ascii'))
+    h = fits.readHeader(str(p))
+    for k, v in hdr.items():
+        assert h[k] == v, k
+    assert fits.getNoradId(h) == 25544
+    assert fits.getPhotoTime(h) == datetime.datetime(2012, 1, 25, 9, 27, 8, 60000)
+    pos, date, delta = fits.getShiftedSpacecraftPosition(h)
+    assert date == datetime.datetime(2012, 1, 25, 9, 26, 55, 60000) and delta.total_seconds() == -13.0
+    assert np.array_equal(pos, [hdr['POSXSHIF'], hdr['POSYSHIF'], hdr['POSZSHIF']])
+    assert fits.getSpacecraftPosition(h) == (None, None)
+    from auromat_b200.mapping.spacecraft import _prepareMappingParams
+    header, photoTime, original, cam = _prepareMappingParams(str(p))
+    assert photoTime == date and original == fits.getPhotoTime(h) and np.array_equal(cam, pos)
+    # timeshift without TLE data cannot be honoured (reference spacecraft.py:441-462)
+    with pytest.raises(ValueError):
+        _prepareMappingParams(h, timeshift=datetime.timedelta(seconds=1))
+
+
+def test_synthetic_sequence():
+    hs = synthetic.sequenceHeaders(5, 133, 89)
+    r = [np.linalg.norm([h['POSXSHIF'], h['POSYSHIF'], h['POSZSHIF']]) for h in hs]
+    assert np.allclose(r, r[0])
+    assert hs[1]['CRVAL1'] - hs[0]['CRVAL1'] == pytest.approx(0.05)
+    t0, _ = synthetic.headerTimeAndCamera(hs[0])
+    t4, _ = synthetic.headerTimeAndCamera(hs[4])
+    assert (t4 - t0).total_seconds() == 4
