@@ -17,6 +17,7 @@ AMT_SIP_MAX_ORDER = 9
 AMT_SIP_MAX_COEF = 55
 AMT_U8, AMT_U16 = 0, 1
 AMT_PRE_NONE, AMT_PRE_WRAP180, AMT_PRE_POLE = 0, 1, 2
+AMT_MODEL_WCS, AMT_MODEL_ALLSKY = 0, 1
 
 c_double_p = C.POINTER(C.c_double)
 
@@ -31,6 +32,9 @@ class AmtFrame(C.Structure):
         ("wgs_a", C.c_double), ("wgs_b", C.c_double),
         ("sip_order_a", C.c_int32), ("sip_order_b", C.c_int32),
         ("sip_a", C.c_double * AMT_SIP_MAX_COEF), ("sip_b", C.c_double * AMT_SIP_MAX_COEF),
+        ("model", C.c_int32), ("reserved", C.c_int32),
+        ("allsky_xc", C.c_double), ("allsky_yc", C.c_double), ("allsky_k", C.c_double),
+        ("allsky_rotation", C.c_double),
     ]
 
 

@@ -23,15 +23,17 @@ Z = (0.0, 0.0, -1.0)
 
 def rotation_matrix(angle, direction):
     """3x3 rotation about `direction` by `angle` rad (Rodrigues form; reference
-    coordinates/transformations.py:295-336, upper-left block)."""
+    coordinates/transformations.py:295-336, upper-left block).  Scalar arithmetic in the
+    reference's order: R = diag(cos) + outer(d,d)*(1-cos) + skew(d*sin)."""
     sina, cosa = math.sin(angle), math.cos(angle)
-    d = np.array(direction, dtype=np.float64)
-    d /= math.sqrt(np.dot(d, d))
-    R = np.diag([cosa, cosa, cosa])
-    R += np.outer(d, d) * (1.0 - cosa)
-    d *= sina
-    R += np.array([[0.0, -d[2], d[1]], [d[2], 0.0, -d[0]], [-d[1], d[0], 0.0]])
-    return R
+    dx, dy, dz = (float(v) for v in direction)
+    n = math.sqrt(dx * dx + dy * dy + dz * dz)
+    dx, dy, dz = dx / n, dy / n, dz / n
+    omc = 1.0 - cosa
+    sx, sy, sz = dx * sina, dy * sina, dz * sina
+    return np.array([[cosa + (dx * dx) * omc + 0.0, 0.0 + (dx * dy) * omc + -sz, 0.0 + (dx * dz) * omc + sy],
+                     [0.0 + (dy * dx) * omc + sz, cosa + (dy * dy) * omc + 0.0, 0.0 + (dy * dz) * omc + -sx],
+                     [0.0 + (dz * dx) * omc + -sy, 0.0 + (dz * dy) * omc + sx, cosa + (dz * dz) * omc + 0.0]])
 
 
 def euler_matrix_rzxz(ai, aj, ak):
@@ -158,6 +160,20 @@ def mat_j2000_to_sm(et):
 
 def mat_geo_to_sm(et):
     return mat_T4(et).dot(mat_T3(et)).dot(mat_T2(et)).dot(mat_T1(et).T)
+
+
+def frameMatrices(et):
+    """(J2000->GEO, J2000->SM, GEO->SM) for one ephemeris second, every primitive rotation
+    evaluated once.  Bit-identical to mat_j2000_to_geo / mat_j2000_to_sm / mat_geo_to_sm."""
+    P, T1, T2 = mat_P(et), mat_T1(et), mat_T2(et)
+    lat, lon = mag_lat(et), mag_lon(et)
+    Qg = [math.cos(lat) * math.cos(lon), math.cos(lat) * math.sin(lon), math.sin(lat)]
+    Qe = np.dot(np.dot(T2, T1.T), Qg)
+    T3 = rotation_matrix(-math.atan2(np.deg2rad(Qe[1]), np.deg2rad(Qe[2])), X)
+    mu = math.atan2(np.deg2rad(Qe[0]), np.deg2rad(math.sqrt(Qe[1] * Qe[1] + Qe[2] * Qe[2])))
+    T4 = rotation_matrix(-mu, Y)
+    T432 = T4.dot(T3).dot(T2)
+    return np.dot(T1, P), T432.dot(P), T432.dot(T1.T)
 
 
 # ---- scalar helpers used by the mapping objects (single points; not the per-pixel path) ----

@@ -66,8 +66,9 @@ def frameConstants(header, cameraPosGCRS, photoTime, altitude, fastCenterCalcula
     x, y, z = cam
     fr.origin_inside = 1 if (x / a) ** 2 + (y / a) ** 2 + (z / b) ** 2 < 1 else 0   # intersection.py:239-241
     et = transform.date2es(photoTime)
-    fr.m_geo[:] = transform.mat_j2000_to_geo(et).ravel().tolist()
-    fr.m_sm[:] = transform.mat_j2000_to_sm(et).ravel().tolist()
+    m_geo, m_sm, _ = transform.frameMatrices(et)
+    fr.m_geo[:] = m_geo.ravel().tolist()
+    fr.m_sm[:] = m_sm.ravel().tolist()
     fr.wgs_a, fr.wgs_b = wgs84A, wgs84B
     if str(header['CTYPE1']).endswith('-SIP'):
         fr.sip_order_a, pa = _sipPacked(header, 'A')

@@ -222,8 +222,9 @@ __global__ void __launch_bounds__(256) k_georef_points(const __grid_constant__ G
         // wcs.py:41-44: corner grids start at -0.5
         const double px = corner ? (double)x - 0.5 : (double)x;
         const double py = corner ? (double)y - 0.5 : (double)y;
-        double dir[3], P[3];
-        pix2dir(p.f, p.sip_a, p.sip_b, px, py, dir);
+        double dir[3], P[3], cam_el = 0.0;
+        if (p.f.model == AMT_MODEL_ALLSKY) cam_el = pix2dir_allsky(p.f, px, py, dir);
+        else pix2dir(p.f, p.sip_a, p.sip_b, px, py, dir);
         hit = intersect(p.f, dir, P, graze);
         if (corner) {
             if (hit) emit_point(p, P, i, p.o.d_lat_k, p.o.d_lon_k, p.o.d_mlat_k, p.o.d_mlt_k);
@@ -231,7 +232,8 @@ __global__ void __launch_bounds__(256) k_georef_points(const __grid_constant__ G
         } else {
             if (hit) {
                 emit_point(p, P, i, p.o.d_lat_c, p.o.d_lon_c, p.o.d_mlat_c, p.o.d_mlt_c);
-                if (p.o.d_elev_c) p.o.d_elev_c[i] = elevation_deg(dir, P);
+                if (p.o.d_elev_c)
+                    p.o.d_elev_c[i] = p.f.model == AMT_MODEL_ALLSKY ? cam_el : elevation_deg(dir, P);
             } else {
                 emit_nan(i, p.o.d_lat_c, p.o.d_lon_c, p.o.d_mlat_c, p.o.d_mlt_c);
                 if (p.o.d_elev_c) p.o.d_elev_c[i] = qnan();
@@ -376,6 +378,11 @@ static int fill_frame(const amt_frame* fr, GeorefParams& p) {
     f.e2a = e2 * a;
     f.d = num / b;
     f.sip_oa = fr->sip_order_a; f.sip_ob = fr->sip_order_b;
+    CHECK_ARG(fr->model == AMT_MODEL_WCS || fr->model == AMT_MODEL_ALLSKY, "amt_frame: unknown camera model");
+    CHECK_ARG(fr->model == AMT_MODEL_WCS || (fr->allsky_k > 0 && !fr->fast_center),
+              "amt_frame: all-sky model needs k > 0 and fast_center == 0");
+    f.model = fr->model;
+    f.as_xc = fr->allsky_xc; f.as_yc = fr->allsky_yc; f.as_k = fr->allsky_k; f.as_rot = fr->allsky_rotation;
     memcpy(p.sip_a, fr->sip_a, sizeof p.sip_a);
     memcpy(p.sip_b, fr->sip_b, sizeof p.sip_b);
     return AMT_OK;

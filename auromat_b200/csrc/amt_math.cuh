@@ -34,6 +34,8 @@ struct FrameC {
     double a, b, e2a, d;    // Bowring constants        transform.py:254-255,290
     double b_over_a;
     int sip_oa, sip_ob;
+    int model;
+    double as_xc, as_yc, as_k, as_rot;   // all-sky fisheye model (mapping/miracle.py:314-347)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -84,6 +86,51 @@ __device__ __forceinline__ void pix2dir(const FrameC& f, const double* __restric
     dir[0] = fma(f.rot[2], n, fma(f.rot[1], m, f.rot[0] * l));
     dir[1] = fma(f.rot[5], n, fma(f.rot[4], m, f.rot[3] * l));
     dir[2] = fma(f.rot[8], n, fma(f.rot[7], m, f.rot[6] * l));
+}
+
+// numpy floor_divide / remainder for doubles (npy_divmod), used by the astropy-style wrap
+__device__ __forceinline__ double np_floor_divide(double a, double b) {
+    double mod = fmod(a, b);
+    double div = (a - mod) / b;
+    if (mod != 0.0 && ((b < 0.0) != (mod < 0.0))) div -= 1.0;
+    if (div != 0.0) {
+        double fl = floor(div);
+        if (div - fl > 0.5) fl += 1.0;
+        return fl;
+    }
+    return copysign(0.0, a / b);
+}
+
+// All-sky fisheye camera (mapping/miracle.py:314-347 calculateAzEl, :240-258 direction):
+// (row, col) -> azimuth / elevation -> local Cartesian -> ECEF via `rot`.  `px, py` follow
+// this file's convention (pixel centres at integers); the reference counts corners at
+// integers, hence the +0.5.  Cold path (small frames): plain libm in the reference's order.
+__device__ __forceinline__ double pix2dir_allsky(const FrameC& f, double px, double py, double dir[3]) {
+    const double v0 = (py + 0.5) - f.as_xc;           // "X is vertical" (cal.txt)
+    const double v1 = (px + 0.5) - f.as_yc;
+    double az = atan2(v1, -v0);                       // signedAngleBetween(vecs, [-1, 0])
+    az = az - f.as_rot;
+    // Angle(az rad).wrap_at(360 deg): az - floor(az / 2pi) * 2pi, then to degrees
+    const double two_pi = 6.283185307179586;
+    const double wraps = np_floor_divide(az, two_pi);
+    if (wraps == wraps && wraps != 0.0 && !isinf(wraps)) {
+        az = az - wraps * two_pi;
+        if (az >= two_pi) az -= two_pi;
+        if (az < 0.0) az += two_pi;
+    }
+    const double az_deg = az * kRad2Deg;
+    const double dist = sqrt(v0 * v0 + v1 * v1);
+    const double el_deg = 90.0 - (dist / f.as_k) * kRad2Deg;
+    const double el = el_deg * kDeg2Rad;
+    const double azp = (-(az_deg - 180.0)) * kDeg2Rad;
+    double se, ce, sa, ca;
+    sincos(el, &se, &ce);
+    sincos(azp, &sa, &ca);
+    const double l = ce * ca, m = ce * sa, n = se;    // spherical_to_cartesian(1, el, az)
+    dir[0] = (f.rot[0] * l + f.rot[1] * m) + f.rot[2] * n;
+    dir[1] = (f.rot[3] * l + f.rot[4] * m) + f.rot[5] * n;
+    dir[2] = (f.rot[6] * l + f.rot[7] * m) + f.rot[8] * n;
+    return el_deg;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -259,19 +306,6 @@ __device__ __forceinline__ int bin_index(double x, double lo, double hi, double 
         near = (next_down(x) <= e0) || (next_up(x) >= e1);
     }
     return k;
-}
-
-// numpy floor_divide / remainder for doubles (npy_divmod), used by the astropy-style wrap
-__device__ __forceinline__ double np_floor_divide(double a, double b) {
-    double mod = fmod(a, b);
-    double div = (a - mod) / b;
-    if (mod != 0.0 && ((b < 0.0) != (mod < 0.0))) div -= 1.0;
-    if (div != 0.0) {
-        double fl = floor(div);
-        if (div - fl > 0.5) fl += 1.0;
-        return fl;
-    }
-    return copysign(0.0, a / b);
 }
 
 // Angle(x deg).wrap_at(180 deg).degree (astropy `_wrap_at`): x - floor((x+180)/360)*360

@@ -1,0 +1,135 @@
+"""Multi-GPU use of the path: one process per GPU (torchrun), `torch.distributed` for plumbing.
+
+* Image sequences shard by frame -- frames are independent (reference
+  `mapping/spacecraft.py:308-332`), so rank r takes frames r, r+N, r+2N, ... and there is NO
+  data-path collective.
+* Multi-camera mosaics (a `MappingCollection` of all-sky stations on one common plate-carree
+  grid; "all resamplings are aligned to the same global grid", reference `resample.py:220-221`)
+  have exactly one exchange step: every rank bins its stations into private sum/count grids
+  and the grids are summed with ONE all-reduce (NCCL over NVLink on GPUs; gloo in the CPU
+  tests).  Counts and integer channel sums are int64, so the reduction is exact and
+  independent of the reduction order; only the float side channel (elevation) is summed in
+  floating point.
+"""
+from __future__ import annotations
+
+import numpy as np
+import numpy.ma as ma
+
+from . import _lib
+from .mapping.mapping import BoundingBox, GenericMapping
+
+
+def worldInfo():
+    """(rank, world_size) of the default process group, (0, 1) when not initialised."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except ImportError:
+        pass
+    return 0, 1
+
+
+def shardIndices(n, rank=None, world=None):
+    """Indices of the frames of an n-frame sequence owned by `rank`: i with i mod world == rank."""
+    if rank is None or world is None:
+        rank, world = worldInfo()
+    return list(range(rank, n, world))
+
+
+def shardSequence(items, rank=None, world=None):
+    items = list(items)
+    return [items[i] for i in shardIndices(len(items), rank, world)]
+
+
+def gatherBoundingBoxes(localBoxes, group=None):
+    """All ranks' bounding boxes (list of BoundingBox), via all_gather_object."""
+    import torch.distributed as dist
+    rank, world = worldInfo()
+    local = [(b.latSouth, b.lonWest, b.latNorth, b.lonEast) for b in localBoxes]
+    if world == 1:
+        gathered = [local]
+    else:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, local, group=group)
+    return [BoundingBox(*t) for part in gathered for t in part]
+
+
+def allreduceGrids(acc, group=None):
+    """Sum the accumulator tensor(s) over all ranks, in place.  `acc` is the int64 tensor
+    holding count | channel sums, or a list of tensors (the float64 side sums separately)."""
+    import torch.distributed as dist
+    _, world = worldInfo()
+    if world == 1:
+        return acc
+    for t in (acc if isinstance(acc, (list, tuple)) else [acc]):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return acc
+
+
+class MosaicAccumulator(object):
+    """Sum / count grids of a common plate-carree target grid on one device.
+
+    grid: `amt_grid` from `resample.targetGrid`; channels: image channels; the layout of the
+    int64 accumulator is count | sums[channels] (planes of ny*nx cells, row 0 = north), the
+    float64 accumulator holds the elevation sums."""
+
+    def __init__(self, grid, info, channels, imgDtype, context):
+        import torch
+        self.grid, self.info, self.channels, self.imgDtype, self.ctx = grid, info, channels, imgDtype, context
+        self.cells = grid.nx * grid.ny
+        self.acc = context.zeros((1 + channels) * self.cells, torch.int64)
+        self.fsum = context.zeros(self.cells, torch.float64)
+
+    count = property(lambda self: self.acc[:self.cells])
+    sums = property(lambda self: self.acc[self.cells:])
+
+    def add(self, mapping):
+        """Bin one mapping into the grids (`amt_bin_accumulate`)."""
+        p = mapping.devicePlanes()
+        img = mapping.deviceImage()
+        assert img.shape[2] == self.channels
+        self.ctx.bin_accumulate(p['lat_c'], p['lon_c'], p['elev_c'], img, self.grid, self.count, self.sums, self.fsum)
+
+    def allreduce(self, group=None):
+        allreduceGrids([self.acc, self.fsum], group)
+
+    def finalise(self, template):
+        """Normalise and wrap the mosaic as a GenericMapping (metadata from `template`)."""
+        ctx, g, info = self.ctx, self.grid, self.info
+        outImg, outMask, outElev = ctx.normalise(g, self.imgDtype, self.channels, self.count, self.sums, self.fsum)
+        lat_k, lon_k, lat_c, lon_c = ctx.plate_carree_coords(g.nx, g.ny, info['latMaxInGrid'], info['latMinInGrid'],
+                                                             info['lonMinInGrid'], info['lonMaxInGrid'])
+        img = ctx.to_numpy(outImg)
+        mask = ctx.to_numpy(outMask).astype(bool)
+        img = ma.masked_array(img, mask=np.repeat(mask[:, :, None], img.shape[2], 2))
+        return GenericMapping(lat_k, lon_k, lat_c, lon_c, outElev, template.altitude, img, template.cameraPosGCRS,
+                              template.photoTime, 'mosaic', device=ctx.device)
+
+
+def mosaic(mappings, pxPerDeg, group=None):
+    """Compose the mappings held by ALL ranks (each rank passes its own subset) into one
+    mean-binned mosaic on a common grid; every rank returns the full mosaic mapping.
+
+    Steps: all-gather the per-mapping bounding boxes -> common `fixedGrid` on every rank ->
+    local binning -> one all-reduce of the sum/count grids -> normalise."""
+    from .resample import targetGrid
+    mappings = list(mappings)
+    assert mappings, 'every rank needs at least one mapping'
+    try:
+        _, _ = pxPerDeg
+    except TypeError:
+        pxPerDeg = (pxPerDeg, pxPerDeg)
+    boxes = gatherBoundingBoxes([m.boundingBox for m in mappings], group)
+    bb = BoundingBox.mergedBoundingBoxes(boxes)
+    if bb.containsDiscontinuity:
+        raise NotImplementedError('mosaics across the date line / poles need a common pre-rotation')
+    grid, info = targetGrid(pxPerDeg, bb.latSouth, bb.latNorth, bb.lonWest, bb.lonEast)
+    m0 = mappings[0]
+    img0 = m0.deviceImage()
+    acc = MosaicAccumulator(grid, info, img0.shape[2], img0.dtype, m0.context)
+    for m in mappings:
+        acc.add(m)
+    acc.allreduce(group)
+    return acc.finalise(m0), acc

@@ -72,7 +72,17 @@ typedef struct amt_frame {
     /* packed triangular: index(p,q) = p*(order+1) - p*(p-1)/2 + q  for p+q <= order      */
     double sip_a[AMT_SIP_MAX_COEF];
     double sip_b[AMT_SIP_MAX_COEF];
+    /* Camera model.  AMT_MODEL_WCS: everything above.  AMT_MODEL_ALLSKY: ground-based fisheye
+     * all-sky imager (mapping/miracle.py:240-258,314-347): zenith at (row, col) = (xc, yc) in
+     * pixels, zenith distance z = d/k [rad], image rotation [rad]; `rot` then is
+     * R_lon * R_lat (local -> ECEF, :249-252), `cam` the station in ECEF [km], `m_geo` the
+     * identity, and the elevation plane receives the camera elevation angle 90 - z.         */
+    int32_t model;
+    int32_t reserved;
+    double allsky_xc, allsky_yc, allsky_k, allsky_rotation;
 } amt_frame;
+
+enum { AMT_MODEL_WCS = 0, AMT_MODEL_ALLSKY = 1 };
 
 /* Outputs of the georeference pass; any pointer may be NULL (that plane is not written).
  * Corner planes have (height+1)*(width+1) doubles, centre planes height*width.

@@ -61,6 +61,51 @@ def reference_frame(ref, hdr, cam, t, fast):
     return out
 
 
+def load_miracle():
+    """Import the reference's mapping/miracle.py with ONE in-memory patch:
+    `np.indices(...)` -> `.astype(float)`, because `ind += 0.5` on the integer index array
+    (miracle.py:328-332) raises on numpy >= 1.10 (and silently truncated before that)."""
+    import importlib.util
+    path = os.path.join(ref_shim.REFERENCE_ROOT, 'auromat/mapping/miracle.py')
+    src = open(path).read()
+    old = 'ind = np.indices((w_, w_))'
+    assert old in src
+    src = src.replace(old, old + '.astype(float)')
+    spec = importlib.util.spec_from_loader('auromat.mapping.miracle', loader=None, origin=path)
+    mod = importlib.util.module_from_spec(spec)
+    mod.__file__ = path
+    sys.modules['auromat.mapping.miracle'] = mod
+    exec(compile(src, path, 'exec'), mod.__dict__)
+    return mod
+
+
+def reference_allsky(ref, mir, cal, width, t, altitude=110):
+    """lat/lon (corners, centres) and camera elevation through the reference's MIRACLEMapping
+    methods (miracle.py:196-258,314-347), bypassing its file-based constructor."""
+    class _M(mir.MIRACLEMapping.__mro__[1]):
+        def createMasked(self, m):
+            pass
+    m = object.__new__(_M)
+    m._calData, m._simple, m._img, m._altitude, m._photoTime = cal, False, None, altitude, t
+    m._img_unmasked = np.zeros((width, width, 3), np.uint8)
+    m.cameraPosGEO = list(ref.transform.geodetic2EcefZero(np.deg2rad(cal.lat), np.deg2rad(cal.lon)))
+    with quiet():
+        lats, lons = m._calculateLatsLons(center=False)
+        latc, lonc = m._calculateLatsLons(center=True)
+        _, el = m.calculateAzEl(center=True)
+    return dict(lats=lats, lons=lons, latsCenter=latc, lonsCenter=lonc, elevation=np.asarray(el))
+
+
+def allsky_golden(ref):
+    import datetime
+    mir = load_miracle()
+    # the SOD row of the reference's test/resources/cal.txt
+    cal = mir.CalibrationData('SOD', 2011.5, 2012.5, 67.42, 26.39, 219.3, 244.2, 155.81, 0.14373, None)
+    g = reference_allsky(ref, mir, cal, 96, datetime.datetime(2012, 3, 4, 17, 19, 0))
+    np.savez_compressed(os.path.join(OUT, "allsky_SOD_96.npz"),
+                        cal=np.array([cal.lat, cal.lon, cal.xc, cal.yc, cal.k, cal.rotation]), **g)
+
+
 def main():
     ref = ref_shim.load_reference()
     os.makedirs(OUT, exist_ok=True)
@@ -113,6 +158,7 @@ def main():
     hs, _, _ = ref.histogram.histogram2d(x, y, bins=(49, 80), range=[[0.3, 10.1], [41.0, 60.0]], weights=[None, w1])
     np.savez_compressed(os.path.join(OUT, "histogram2d.npz"), x=x, y=y, w=w1, count=hs[0], wsum=hs[1],
                         bins=np.array([49, 80]), range=np.array([[0.3, 10.1], [41.0, 60.0]]))
+    allsky_golden(ref)
     print("golden vectors written to", OUT)
 
 

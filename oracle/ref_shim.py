@@ -78,34 +78,40 @@ _m = _Unit("m", in_km=1e-3)
 
 
 class _Angle:
-    """astropy.coordinates.Angle stand-in: Angle(q).wrap_at(w).degree."""
+    """astropy.coordinates.Angle stand-in: Angle(q).wrap_at(w).degree.  Like astropy, the
+    value is kept in the unit it was given in and wrapped in that unit (`Angle._wrap_at`:
+    wraps = (angle - (wrap - 360deg)) // 360deg; angle -= wraps*360deg; two rounding
+    fix-ups); `.degree` converts at the end.  astropy==0.4, pinned by the reference, is
+    absent here; this is the algorithm of current astropy."""
 
     def __init__(self, q):
-        v = np.asarray(q.value, dtype=np.float64) * q.unit.in_deg
-        self._deg = v
+        self._v = np.asarray(q.value, dtype=np.float64)
+        self._unit = q.unit
 
     def wrap_at(self, wrap):
-        # astropy `Angle._wrap_at`: wraps = (angle - (wrap - 360)) // 360; angle -= wraps*360,
-        # followed by two fix-ups for rounding.  (astropy==0.4, pinned by the reference, is
-        # absent here; this is the algorithm of current astropy.)
-        w = wrap.value * wrap.unit.in_deg
-        a = np.array(self._deg, dtype=np.float64, copy=True, ndmin=1)
-        floor_ = w - 360.0
+        to_native = wrap.unit.in_deg / self._unit.in_deg
+        w = wrap.value * to_native
+        a360 = 360.0 * (1.0 / self._unit.in_deg) if self._unit is not _deg else 360.0
+        if self._unit is _rad:
+            a360 = 360.0 * (math.pi / 180.0)
+        a = np.array(self._v, dtype=np.float64, copy=True, ndmin=1)
+        floor_ = w - a360
         with np.errstate(invalid='ignore'):
-            wraps = (a - floor_) // 360.0
+            wraps = (a - floor_) // a360
         valid = np.isfinite(wraps) & (wraps != 0)
         if np.any(valid):
-            a -= wraps * 360.0
-            a[a >= w] -= 360.0
-            a[a < floor_] += 360.0
+            a -= wraps * a360
+            a[a >= w] -= a360
+            a[a < floor_] += a360
         out = _Angle.__new__(_Angle)
-        out._deg = a.reshape(np.shape(self._deg))
+        out._v = a.reshape(np.shape(self._v))
+        out._unit = self._unit
         return out
 
     @property
     def degree(self):
-        d = self._deg
-        return d if d.ndim else float(d)
+        d = self._v if self._unit is _deg else self._v * self._unit.in_deg
+        return d if np.ndim(d) else float(d)
 
 
 class _Time:

@@ -490,3 +490,96 @@ def test_full_size_sampled_rows_vs_oracle(env, full_frame):
         assert np.sum(np.isnan(a) != np.isnan(b)) <= 2 * (nrow + 1)    # sanitised limb pixels only
         assert np.max(np.abs(a[both] - b[both])) <= tol
     assert W == 4256
+
+
+# --------------------------------------------------------------- all-sky stations + mosaic
+def _stations(n, seed=2):
+    from auromat_b200.mapping.allsky import CalibrationData
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n):
+        out.append(CalibrationData('S%02d' % i, 2011.5, 2012.5, float(rng.uniform(55, 70)),
+                                   float(rng.uniform(-160, -60)), 256.0 + float(rng.uniform(-20, 20)),
+                                   256.0 + float(rng.uniform(-20, 20)), 155.81, float(rng.uniform(-0.2, 0.2)), None))
+    return out
+
+
+def test_allsky_vs_oracle_and_reference_golden(env):
+    import datetime
+    import oracle.auromat_oracle as O
+    from auromat_b200.mapping.allsky import AllSkyMapping, CalibrationData
+    t = datetime.datetime(2012, 3, 4, 17, 19, 0)
+    g = np.load(os.path.join(GOLDEN, "allsky_SOD_96.npz"))
+    lat, lon, xc, yc, k, rot = g['cal']
+    cal = CalibrationData('SOD', 2011.5, 2012.5, lat, lon, xc, yc, k, rot, None)
+    img = np.zeros((96, 96, 1), np.uint16)
+    m = AllSkyMapping(cal, img, t, 110, sanitize=False)
+    for name, arr in (('lats', m.lats), ('lons', m.lons), ('latsCenter', m.latsCenter),
+                      ('lonsCenter', m.lonsCenter), ('elevation', m.elevation)):
+        a = arr.filled(np.nan)
+        assert np.array_equal(np.isnan(a), np.isnan(g[name])), name
+        d = np.abs(a - g[name])
+        if name.startswith('lon'):
+            d = np.minimum(d, 360 - d)
+        assert np.nanmax(d) <= TOL_DEG, (name, np.nanmax(d))
+    # larger frame against the oracle, incl. the generic MLat/MLT route
+    cal2 = _stations(1)[0]
+    w = 256
+    m2 = AllSkyMapping(cal2, np.zeros((w, w, 1), np.uint16), t, 110, sanitize=False)
+    s = w / 512
+    o = O.allsky_georeference(w, cal2.xc * s, cal2.yc * s, cal2.k * s, cal2.rotation, cal2.lat, cal2.lon, 110)
+    for name, arr in (('lats', m2.lats), ('latsCenter', m2.latsCenter), ('lonsCenter', m2.lonsCenter),
+                      ('elevation', m2.elevation)):
+        d = np.abs(arr.filled(np.nan) - o[name])
+        assert np.nanmax(np.minimum(d, 360 - d)) <= TOL_DEG, name
+    omlat, omlt = O.latlon_to_mlat_mlt(o['latsCenter'], o['lonsCenter'], 110, t)
+    mlat, mlt = m2.mLatMltCenter
+    assert np.nanmax(np.abs(mlat.filled(np.nan) - omlat)) <= TOL_DEG
+    d = np.abs(mlt.filled(np.nan) - omlt)
+    assert np.nanmax(np.minimum(d, 24 - d)) <= TOL_DEG / 15
+
+
+def test_mosaic_single_process_vs_oracle(env):
+    """Config-5 style: several all-sky stations binned into ONE common grid; the serial oracle
+    is the sum of per-station histogram2d outputs, then one division."""
+    import datetime
+    import oracle.auromat_oracle as O
+    from auromat_b200 import parallel
+    from auromat_b200.mapping.allsky import getMappingCollection
+    t = datetime.datetime(2012, 3, 4, 17, 19, 0)
+    cals = _stations(6)
+    rng = np.random.default_rng(9)
+    w = 128
+    imgs = [rng.integers(0, 65536, (w, w, 1), dtype=np.uint16) for _ in cals]
+    coll = getMappingCollection(imgs, cals, t, 110, minElevation=1)
+    assert len(coll) == 6
+    mosaic, acc = parallel.mosaic(coll.mappings, pxPerDeg=(20, 20))
+    grid = acc.grid
+    cnt = acc.count.cpu().numpy().reshape(grid.ny, grid.nx)
+    sums = acc.sums.cpu().numpy().reshape(grid.ny, grid.nx)
+    bins, rng_ = (grid.nx, grid.ny), [[grid.lo_x, grid.hi_x], [grid.lo_y, grid.hi_y]]
+    tc = np.zeros((grid.ny, grid.nx))
+    ts = np.zeros((grid.ny, grid.nx))
+    te = np.zeros((grid.ny, grid.nx))
+    for m, im in zip(coll.mappings, imgs):
+        la, lo = m.latsCenter.filled(np.nan).ravel(), m.lonsCenter.filled(np.nan).ravel()
+        ok = ~np.isnan(la)
+        e = m.elevation.filled(np.nan).ravel()
+        c, s, ee = O.histogram2d_weighted(lo[ok], la[ok], bins, rng_, [None, im.reshape(-1)[ok].astype(float), e[ok]])
+        tc += c.T[::-1]
+        ts += s.T[::-1]
+        te += ee.T[::-1]
+    assert np.array_equal(cnt, tc) and np.array_equal(sums, ts)
+    assert tc.sum() > 30000 and (tc > 0).mean() > 0.02
+    with np.errstate(invalid='ignore', divide='ignore'):
+        mean = np.round(ts / tc)
+    got = mosaic.img
+    assert np.array_equal(ma.getmaskarray(got)[:, :, 0], tc == 0)
+    assert np.array_equal(got.filled(0)[:, :, 0][tc > 0], mean[tc > 0].astype(np.uint16))
+    ge = mosaic.elevation.filled(np.nan)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        assert np.nanmax(np.abs(ge - te / tc) / (te / tc)) < 1e-6
+    mosaic.checkPlateCarree()
+    # maskedByElevation(1) of every station really removed the below-horizon fisheye corners
+    for m in coll.mappings:
+        assert m.elevation.min() >= 1

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(built_lib):
 
 def test_struct_layouts_match_header():
     # sizes implied by include/auromat_b200.h (natural alignment, no packing)
-    assert ctypes.sizeof(_lib.AmtFrame) == 4 * 4 + 8 * (2 + 4 + 9 + 3 + 3 + 9 + 9 + 2) + 2 * 4 + 8 * 2 * 55
+    assert ctypes.sizeof(_lib.AmtFrame) == 4 * 4 + 8 * (2 + 4 + 9 + 3 + 3 + 9 + 9 + 2) + 2 * 4 + 8 * 2 * 55 + 2 * 4 + 4 * 8
     assert ctypes.sizeof(_lib.AmtGeorefOut) == 11 * 8
     assert ctypes.sizeof(_lib.AmtStats) == 6 * 8 + 5 * 8
     assert ctypes.sizeof(_lib.AmtGrid) == 4 * 4 + 8 * (6 + 2 + 3 + 9)
@@ -65,6 +65,12 @@ def test_frame_matrices_bit_equal_to_oracle(date):
     for name in ('mat_P', 'mat_T1', 'mat_T2', 'mat_T3', 'mat_T4', 'mat_j2000_to_geo', 'mat_j2000_to_sm',
                  'mat_geo_to_sm'):
         assert np.array_equal(getattr(transform, name)(et), getattr(O, name)(et)), name
+    geo, sm, geosm = transform.frameMatrices(et)
+    assert np.array_equal(geo, O.mat_j2000_to_geo(et))
+    assert np.array_equal(sm, O.mat_j2000_to_sm(et))
+    assert np.array_equal(geosm, O.mat_geo_to_sm(et))
+    for ang, axis in ((0.3, [1, 0, 0]), (-2.1, [0, 0, -1]), (1e-3, [0, 1, 0]), (2.5, [-1, 0, 0])):
+        assert np.array_equal(transform.rotation_matrix(ang, axis), O.rotation_matrix3(ang, axis))
 
 
 def test_igrf_and_constants():

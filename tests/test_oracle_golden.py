@@ -146,3 +146,14 @@ def test_vincenty_a12_sanity():
     assert abs(O.vincenty_a12(0, 0, 0, 10) - 10 / (1 - 1 / 298.257223563) * (1 - 1 / 298.257223563)) < 0.05
     a = O.vincenty_a12(55, -111, 55, -92)
     assert 10.8 < a < 10.95       # 19 deg of longitude at 55N ~ 10.87 deg of arc
+
+
+def test_allsky_matches_reference_golden():
+    """mapping/miracle.py model (reference outputs with the documented np.indices patch)."""
+    g = np.load(os.path.join(GOLDEN, "allsky_SOD_96.npz"))
+    lat, lon, xc, yc, k, rot = g['cal']
+    s = 96 / 512
+    o = O.allsky_georeference(96, xc * s, yc * s, k * s, rot, lat, lon, 110)
+    for name in ('lats', 'lons', 'latsCenter', 'lonsCenter', 'elevation'):
+        assert np.array_equal(np.isnan(o[name]), np.isnan(g[name]))
+        assert np.nanmax(np.abs(o[name] - g[name])) <= TOL_DEG, name

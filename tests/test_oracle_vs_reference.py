@@ -116,3 +116,16 @@ def test_sanitize_masks_match_reference(ref):
     assert np.array_equal(ma.getmaskarray(lats), mk)
     assert np.array_equal(ma.getmaskarray(latsC), mc)
     assert np.array_equal(ma.getmaskarray(img)[:, :, 0], mc)
+
+
+def test_allsky_model_bit_for_bit(ref):
+    import datetime
+    import oracle.gen_golden as G
+    mir = G.load_miracle()
+    cal = mir.CalibrationData('KEV', 2011.5, 2012.5, 69.76, 27.01, 249.5, 273.8, 154.59, 0.07049, None)
+    w = 64
+    g = G.reference_allsky(ref, mir, cal, w, datetime.datetime(2012, 3, 4, 17, 19, 0))
+    s = w / 512
+    o = O.allsky_georeference(w, cal.xc * s, cal.yc * s, cal.k * s, cal.rotation, cal.lat, cal.lon, 110)
+    for name in ('lats', 'lons', 'latsCenter', 'lonsCenter', 'elevation'):
+        assert bit_equal(g[name], o[name]), name
