@@ -1,0 +1,95 @@
+"""Summarise ncu output into small text files for profiles/ (run in the build container).
+
+    python scripts/ncu_summary.py report gpurun_out/prof.ncu-rep  > profiles/rNN_kernel.txt
+    python scripts/ncu_summary.py launches gpurun_out/launches.csv > profiles/rNN_launches.txt
+"""
+import collections
+import csv
+import io
+import subprocess
+import sys
+
+KEYS = [
+    'gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread',
+    'launch__occupancy_limit_registers', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+    'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+    'lts__t_bytes.sum', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+    'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active',
+    'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
+    'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active',
+    'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
+    'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active',
+    'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
+    'smsp__issue_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
+    'smsp__sass_thread_inst_executed_op_dfma_pred_on.sum', 'smsp__sass_thread_inst_executed_op_dmul_pred_on.sum',
+    'smsp__sass_thread_inst_executed_op_dadd_pred_on.sum',
+    'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio',
+    'l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_st.sum',
+    'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum',
+    'l1tex__t_set_accesses_pipe_lsu_mem_global_op_red.sum', 'lts__t_sectors_op_red.sum', 'lts__t_sectors_op_atom.sum',
+]
+
+
+def ncu(args):
+    return subprocess.run(['ncu'] + args, capture_output=True, text=True).stdout
+
+
+def report(path):
+    raw = list(csv.reader(io.StringIO(ncu(['-i', path, '--page', 'raw', '--csv']))))
+    hdr, units = raw[0], raw[1]
+    for row in raw[2:]:
+        name = row[hdr.index('Kernel Name')]
+        print('== kernel:', name)
+        for h, u, v in zip(hdr, units, row):
+            if h in KEYS:
+                print('  %-82s %18s %s' % (h, v, u))
+    src = list(csv.reader(io.StringIO(ncu(['-i', path, '--page', 'source', '--csv']))))
+    # one table per kernel; take the first
+    try:
+        h = src[1]
+        si, ei = h.index('Source'), h.index('Instructions Executed')
+        agg, tot = collections.Counter(), 0
+        for r in src[2:]:
+            if len(r) <= ei:
+                break
+            try:
+                n = int(float(r[ei]))
+            except ValueError:
+                continue
+            toks = r[si].split()
+            if not toks:
+                continue
+            op = (toks[1] if toks[0].startswith('@') else toks[0]).split('.')[0]
+            agg[op] += n
+            tot += n
+        print('== executed warp instructions by SASS opcode (first kernel): total %d' % tot)
+        for k, v in agg.most_common(24):
+            print('  %-10s %14d %5.1f%%' % (k, v, 100.0 * v / tot))
+    except Exception as e:  # pragma: no cover
+        print('source page unavailable:', e)
+
+
+def launches(path):
+    rows = [r for r in csv.reader(open(path)) if len(r) > 5]
+    hdr = rows[0]
+    ki, vi = hdr.index('Kernel Name'), hdr.index('Metric Value')
+    agg = collections.OrderedDict()
+    for r in rows[1:]:
+        try:
+            v = float(r[vi].replace(',', ''))
+        except ValueError:
+            continue
+        agg.setdefault(r[ki], []).append(v)
+    tot = sum(sum(v) for v in agg.values())
+    print('%-72s %5s %12s %12s %7s' % ('kernel', 'n', 'avg_us', 'total_us', 'share'))
+    for k, v in agg.items():
+        print('%-72s %5d %12.1f %12.1f %6.1f%%' % (k[:72], len(v), sum(v) / len(v) / 1e3, sum(v) / 1e3, 100 * sum(v) / tot))
+
+
+if __name__ == '__main__':
+    {'report': report, 'launches': launches}[sys.argv[1]](sys.argv[2])
