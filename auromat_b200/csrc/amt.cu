@@ -204,49 +204,95 @@ __device__ __forceinline__ void count_grazing(unsigned long long* counter, bool 
     }
 }
 
-// fastCenterCalculation == False: corners and centres are independent points
-// (mapping/astrometry.py:49-64,86-106).  2-D launch: blockIdx.y < corner_rows are rows of
-// corners, the remaining rows are rows of centres; a warp covers 32 consecutive x of one row,
-// so its hit ballot is exactly one word of the row-padded validity bitmap.
-// Rays that miss the ellipsoid (reference: NaN rows that propagate through every later
-// pass) leave right after the discriminant test.
-__global__ void __launch_bounds__(256) k_georef_points(const __grid_constant__ GeorefParams p) {
-    const bool corner = blockIdx.y < p.corner_rows;
-    const int W = p.f.W;
-    const int rowlen = corner ? W + 1 : W;
-    const int y = corner ? blockIdx.y : blockIdx.y - p.corner_rows;
+// fastCenterCalculation == False: corners and centres are independent rays
+// (mapping/astrometry.py:49-64,86-106).  One thread per pixel evaluates BOTH the corner
+// (x-0.5, y-0.5) and the centre (x, y): two independent FP64 dependency chains per thread
+// (ILP for the Newton / polynomial sequences) that share the per-frame constants.  Launch:
+// (W+1) x (H+1) threads, a warp covers 32 consecutive x of one row, so its two hit ballots are
+// exactly one word each of the row-padded validity bitmaps.
+// Rays that miss the ellipsoid (reference: NaN rows that propagate through every later pass)
+// cost only the direction + discriminant: a warp whose rays all miss leaves right there.
+template <bool WANT_K, bool WANT_C>
+#ifndef AMT_GEOREF_MINBLOCKS
+#define AMT_GEOREF_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(256, AMT_GEOREF_MINBLOCKS) k_georef_points(const __grid_constant__ GeorefParams p) {
+    const int W = p.f.W, H = p.f.H;
+    const int y = blockIdx.y;
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    bool graze = false, hit = false;
-    if (x < rowlen) {
-        const size_t i = (size_t)y * rowlen + x;
+    const bool in_k = WANT_K && x <= W;
+    const bool in_c = WANT_C && x < W && y < H;
+    bool graze_k = false, graze_c = false, hit_k = false, hit_c = false;
+    double dk[3], Pk[3], dc[3], Pc[3], cam_el = 0.0;
+    const double nan = qnan();
+    if (in_k | in_c) {
         // wcs.py:41-44: corner grids start at -0.5
-        const double px = corner ? (double)x - 0.5 : (double)x;
-        const double py = corner ? (double)y - 0.5 : (double)y;
-        double dir[3], P[3], cam_el = 0.0;
-        if (p.f.model == AMT_MODEL_ALLSKY) cam_el = pix2dir_allsky(p.f, px, py, dir);
-        else pix2dir(p.f, p.sip_a, p.sip_b, px, py, dir);
-        hit = intersect(p.f, dir, P, graze);
-        if (corner) {
-            if (hit) emit_point(p, P, i, p.o.d_lat_k, p.o.d_lon_k, p.o.d_mlat_k, p.o.d_mlt_k);
-            else emit_nan(i, p.o.d_lat_k, p.o.d_lon_k, p.o.d_mlat_k, p.o.d_mlt_k);
+        const double fx = (double)x, fy = (double)y;
+        if (p.f.model == AMT_MODEL_ALLSKY) {
+            if (WANT_K) pix2dir_allsky(p.f, fx - 0.5, fy - 0.5, dk);
+            if (WANT_C) cam_el = pix2dir_allsky(p.f, fx, fy, dc);
         } else {
-            if (hit) {
-                emit_point(p, P, i, p.o.d_lat_c, p.o.d_lon_c, p.o.d_mlat_c, p.o.d_mlt_c);
-                if (p.o.d_elev_c)
-                    p.o.d_elev_c[i] = p.f.model == AMT_MODEL_ALLSKY ? cam_el : elevation_deg(dir, P);
-            } else {
-                emit_nan(i, p.o.d_lat_c, p.o.d_lon_c, p.o.d_mlat_c, p.o.d_mlt_c);
-                if (p.o.d_elev_c) p.o.d_elev_c[i] = qnan();
-            }
+            if (WANT_K) pix2dir<false>(p.f, p.sip_a, p.sip_b, fx - 0.5, fy - 0.5, dk);
+            if (WANT_C) pix2dir<false>(p.f, p.sip_a, p.sip_b, fx, fy, dc);
+        }
+        if (WANT_K) hit_k = intersect(p.f, dk, Pk, graze_k) && in_k;
+        if (WANT_C) hit_c = intersect(p.f, dc, Pc, graze_c) && in_c;
+        graze_k &= in_k;
+        graze_c &= in_c;
+    }
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned mk = __ballot_sync(0xffffffffu, hit_k), mc = __ballot_sync(0xffffffffu, hit_c);
+    if (lane == 0) {
+        const int wk = (W + 1 + 31) >> 5, wc = (W + 31) >> 5;
+        if (WANT_K && p.o.d_valid_k && (x >> 5) < wk) p.o.d_valid_k[(size_t)y * wk + (x >> 5)] = mk;
+        if (WANT_C && p.o.d_valid_c && y < H && (x >> 5) < wc) p.o.d_valid_c[(size_t)y * wc + (x >> 5)] = mc;
+    }
+    count_grazing(p.ill, graze_k | graze_c, lane);
+    const size_t ik = (size_t)y * (W + 1) + x, ic = (size_t)y * W + x;
+    if ((mk | mc) == 0) {                    // the whole warp looks at space
+        if (in_k) emit_nan(ik, p.o.d_lat_k, p.o.d_lon_k, p.o.d_mlat_k, p.o.d_mlt_k);
+        if (in_c) {
+            emit_nan(ic, p.o.d_lat_c, p.o.d_lon_c, p.o.d_mlat_c, p.o.d_mlt_c);
+            if (p.o.d_elev_c) p.o.d_elev_c[ic] = nan;
+        }
+        return;
+    }
+    // Both chains run unconditionally from here (a missed ray carries NaN through the
+    // arithmetic, exactly like the reference's NaN rows); only the stores are predicated.
+    if (!hit_k) Pk[0] = Pk[1] = Pk[2] = nan;
+    if (!hit_c) Pc[0] = Pc[1] = Pc[2] = nan;
+    const bool geo = p.o.d_lat_k || p.o.d_lon_k || p.o.d_lat_c || p.o.d_lon_c;
+    const bool mag = p.o.d_mlat_k || p.o.d_mlt_k || p.o.d_mlat_c || p.o.d_mlt_c;
+    if (geo) {
+        double la_k, lo_k, la_c, lo_c;
+        if (WANT_K) point_to_geo(p.f, Pk, la_k, lo_k);
+        if (WANT_C) point_to_geo(p.f, Pc, la_c, lo_c);
+        if (WANT_K && in_k) {
+            if (p.o.d_lat_k) p.o.d_lat_k[ik] = la_k;
+            if (p.o.d_lon_k) p.o.d_lon_k[ik] = lo_k;
+        }
+        if (WANT_C && in_c) {
+            if (p.o.d_lat_c) p.o.d_lat_c[ic] = la_c;
+            if (p.o.d_lon_c) p.o.d_lon_c[ic] = lo_c;
         }
     }
-    __syncwarp();
-    const unsigned lane = threadIdx.x & 31;
-    const unsigned m = __ballot_sync(0xffffffffu, hit);
-    uint32_t* bits = corner ? p.o.d_valid_k : p.o.d_valid_c;
-    const int wpr = (rowlen + 31) >> 5;
-    if (bits && lane == 0 && (x >> 5) < wpr) bits[(size_t)y * wpr + (x >> 5)] = m;
-    count_grazing(p.ill, graze, lane);
+    if (mag) {
+        double ml_k, mt_k, ml_c, mt_c;
+        if (WANT_K) point_to_mag(p.f, Pk, ml_k, mt_k);
+        if (WANT_C) point_to_mag(p.f, Pc, ml_c, mt_c);
+        if (WANT_K && in_k) {
+            if (p.o.d_mlat_k) p.o.d_mlat_k[ik] = ml_k;
+            if (p.o.d_mlt_k) p.o.d_mlt_k[ik] = mt_k;
+        }
+        if (WANT_C && in_c) {
+            if (p.o.d_mlat_c) p.o.d_mlat_c[ic] = ml_c;
+            if (p.o.d_mlt_c) p.o.d_mlt_c[ic] = mt_c;
+        }
+    }
+    if (WANT_C && in_c && p.o.d_elev_c) {
+        double e = p.f.model == AMT_MODEL_ALLSKY ? cam_el : elevation_deg<false>(dc, Pc);
+        p.o.d_elev_c[ic] = hit_c ? e : nan;
+    }
 }
 
 // fastCenterCalculation == True: a CTA evaluates a (TH+1)x(TW+1) patch of corner rays into
@@ -264,7 +310,7 @@ __device__ __forceinline__ bool tile_corner(const GeorefParams& p, double (*sP)[
     if (x <= W && y <= H) {
         double dir[3], P[3];
         bool g;
-        pix2dir(p.f, p.sip_a, p.sip_b, (double)x - 0.5, (double)y - 0.5, dir);
+        pix2dir<true>(p.f, p.sip_a, p.sip_b, (double)x - 0.5, (double)y - 0.5, dir);
         hit = intersect(p.f, dir, P, g);
 #pragma unroll
         for (int k = 0; k < 3; ++k) { sP[k][cy][cx] = hit ? P[k] : qnan(); sD[k][cy][cx] = dir[k]; }
@@ -333,7 +379,7 @@ __global__ void __launch_bounds__(TW* TH) k_georef_tiles(const __grid_constant__
         chit = P[0] == P[0];                        // all four corner rays hit
         if (chit) {
             emit_point(p, P, i, p.o.d_lat_c, p.o.d_lon_c, p.o.d_mlat_c, p.o.d_mlt_c);
-            if (p.o.d_elev_c) p.o.d_elev_c[i] = elevation_deg(dir, P);
+            if (p.o.d_elev_c) p.o.d_elev_c[i] = elevation_deg<true>(dir, P);
         } else {
             emit_nan(i, p.o.d_lat_c, p.o.d_lon_c, p.o.d_mlat_c, p.o.d_mlt_c);
             if (p.o.d_elev_c) p.o.d_elev_c[i] = qnan();
@@ -407,11 +453,11 @@ extern "C" int amt_georef(amt_ctx* ctx, const amt_frame* frame, const amt_georef
         const bool want_k = out->d_lat_k || out->d_lon_k || out->d_mlat_k || out->d_mlt_k || out->d_valid_k;
         const bool want_c = out->d_lat_c || out->d_lon_c || out->d_mlat_c || out->d_mlt_c || out->d_elev_c ||
                             out->d_valid_c;
-        p.corner_rows = want_k ? H + 1 : 0;
-        const unsigned rows = p.corner_rows + (want_c ? H : 0);
-        if (rows == 0) return AMT_OK;
-        dim3 grid(((want_k ? W + 1 : W) + 255) / 256, rows);
-        k_georef_points<<<grid, 256, 0, st>>>(p);
+        if (!want_k && !want_c) return AMT_OK;
+        dim3 grid((W + 1 + 255) / 256, want_k ? H + 1 : H);
+        if (want_k && want_c) k_georef_points<true, true><<<grid, 256, 0, st>>>(p);
+        else if (want_k) k_georef_points<true, false><<<grid, 256, 0, st>>>(p);
+        else k_georef_points<false, true><<<grid, 256, 0, st>>>(p);
     }
     LAUNCH_CHECK(ctx);
     return AMT_OK;
@@ -919,13 +965,24 @@ __device__ __forceinline__ int cell_of(const GridC& g, double la, double lo, int
     return (g.ny - 1 - iy) * g.nx + ix;               // flipud, resample.py:349
 }
 
-// Accumulate one warp's samples: consecutive lanes that hit the same cell form a run; a
-// segmented warp scan sums each run and only its last lane issues the atomics.
-template <int C>
+// Accumulate one warp's samples.  Consecutive lanes that hit the same cell form a run
+// (neighbouring pixels land in the same ~100"/px cell); run sums come from ONE unsegmented
+// warp prefix scan (run sum = prefix[tail] - prefix[head-1]) over the channels packed into
+// 64-bit words, and only the last lane of a run issues the atomics.
+template <typename T, int C>
+struct Packed {
+    static constexpr int BITS = sizeof(T) == 1 ? 16 : 21;      // 32*255 < 2^16, 32*65535 < 2^21
+    static constexpr int PER = 64 / BITS;
+    static constexpr int NW = (C + PER - 1) / PER;
+    static constexpr unsigned long long MASK = (1ULL << BITS) - 1;
+};
+
+template <typename T, int C>
 __device__ __forceinline__ void warp_accumulate(int cell, const unsigned (&val)[C], double side, bool has_side,
                                                 unsigned long long* __restrict__ count,
                                                 unsigned long long* __restrict__ sums,
                                                 double* __restrict__ fsum, size_t plane) {
+    using P = Packed<T, C>;
     const unsigned lane = threadIdx.x & 31;
     const int prev = __shfl_up_sync(0xffffffffu, cell, 1);
     const bool head = lane == 0 || prev != cell;
@@ -934,30 +991,63 @@ __device__ __forceinline__ void warp_accumulate(int cell, const unsigned (&val)[
     const int start = 31 - __clz(heads & le);         // first lane of my run
     const int next = __shfl_down_sync(0xffffffffu, cell, 1);
     const bool tail = lane == 31 || next != cell;
-    unsigned v[C];
+    unsigned long long w[P::NW];
 #pragma unroll
-    for (int c = 0; c < C; ++c) v[c] = val[c];
+    for (int k = 0; k < P::NW; ++k) w[k] = 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) w[c / P::PER] |= (unsigned long long)val[c] << ((c % P::PER) * P::BITS);
+    // a NaN side value (possible only for hand-made mappings) must stay inside its own cell:
+    // then the side channel of this warp falls back to one atomic per sample
+    const bool side_direct = has_side && __ballot_sync(0xffffffffu, cell >= 0 && side != side) != 0;
+    if (side_direct) {
+        if (cell >= 0) atomicAdd(&fsum[cell], side);
+        has_side = false;
+    }
     double s = side;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        const bool take = (int)lane - d >= start;
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-            const unsigned t = __shfl_up_sync(0xffffffffu, v[c], d);
-            if (take) v[c] += t;
+        for (int k = 0; k < P::NW; ++k) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, w[k], d);
+            if (lane >= d) w[k] += t;
         }
         if (has_side) {
             const double t = __shfl_up_sync(0xffffffffu, s, d);
-            if (take) s += t;
+            if (lane >= d) s += t;
         }
     }
+    // prefix just before my run
+    const int before = start > 0 ? start - 1 : 0;
+    unsigned long long wb[P::NW];
+#pragma unroll
+    for (int k = 0; k < P::NW; ++k) {
+        wb[k] = __shfl_sync(0xffffffffu, w[k], before);
+        if (start == 0) wb[k] = 0;
+    }
+    double sb = has_side ? __shfl_sync(0xffffffffu, s, before) : 0.0;
+    if (start == 0) sb = 0.0;
+#ifdef AMT_EXP_NOATOMIC
+    if (tail && cell >= 0 && count[cell] == 0x123456789ULL) {
+#else
     if (tail && cell >= 0) {
+#endif
         atomicAdd(&count[cell], (unsigned long long)(lane - start + 1));
 #pragma unroll
-        for (int c = 0; c < C; ++c) atomicAdd(&sums[(size_t)c * plane + cell], (unsigned long long)v[c]);
-        if (has_side) atomicAdd(&fsum[cell], s);
+        for (int c = 0; c < C; ++c) {
+            const unsigned long long run = ((w[c / P::PER] - wb[c / P::PER]) >> ((c % P::PER) * P::BITS)) & P::MASK;
+            atomicAdd(&sums[(size_t)c * plane + cell], run);
+        }
+        if (has_side) atomicAdd(&fsum[cell], s - sb);
     }
 }
+
+// Each warp bins kBinSeg consecutive segments of 32 pixels; all global loads of the segments
+// are issued before any dependent work (memory-level parallelism: the kernel is bound by load
+// latency / HBM, not by arithmetic).
+#ifndef AMT_BIN_SEG
+#define AMT_BIN_SEG 2
+#endif
+constexpr int kBinSeg = AMT_BIN_SEG;
 
 template <typename T, int C, bool NEAR>
 __global__ void __launch_bounds__(256) k_bin(const double* __restrict__ lat, const double* __restrict__ lon,
@@ -965,26 +1055,41 @@ __global__ void __launch_bounds__(256) k_bin(const double* __restrict__ lat, con
                                              const __grid_constant__ GridC g, unsigned long long* __restrict__ count,
                                              unsigned long long* __restrict__ sums, double* __restrict__ fsum,
                                              unsigned long long* __restrict__ near_counter) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int cell = -1, ix, iy;
-    bool near = false;
-    unsigned val[C];
+    const unsigned lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t base = warp * (32 * kBinSeg) + lane;
+    double la[kBinSeg], lo[kBinSeg], sd[kBinSeg];
+    unsigned val[kBinSeg][C];
 #pragma unroll
-    for (int c = 0; c < C; ++c) val[c] = 0;
-    double s = 0.0;
-    if (i < n) {
-        cell = cell_of<NEAR>(g, lat[i], lon[i], ix, iy, near);
-        if (cell >= 0) {
+    for (int k = 0; k < kBinSeg; ++k) {
+        const size_t i = base + 32 * k;
+        const bool in = i < n;
+        la[k] = in ? lat[i] : qnan();
+        lo[k] = in ? lon[i] : 0.0;
+        sd[k] = (in && side) ? side[i] : 0.0;
 #pragma unroll
-            for (int c = 0; c < C; ++c) val[c] = img[i * C + c];
-            if (side) s = side[i];
+        for (int c = 0; c < C; ++c) val[k][c] = in ? (unsigned)img[i * C + c] : 0u;
+    }
+    bool near_any = false;
+#pragma unroll
+    for (int k = 0; k < kBinSeg; ++k) {
+        int cell = -1, ix, iy;
+        bool near = false;
+        if (la[k] == la[k]) cell = cell_of<NEAR>(g, la[k], lo[k], ix, iy, near);
+        near_any |= near;
+        if (NEAR) {
+            const unsigned m = __ballot_sync(0xffffffffu, near);
+            if (m && lane == 0) atomicAdd(near_counter, (unsigned long long)__popc(m));
         }
+        if (__ballot_sync(0xffffffffu, cell >= 0) == 0) continue;   // nothing of this segment lands in the grid
+        if (cell < 0) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) val[k][c] = 0;
+            sd[k] = 0.0;
+        }
+        warp_accumulate<T, C>(cell, val[k], sd[k], side != nullptr, count, sums, fsum, (size_t)g.nx * g.ny);
     }
-    warp_accumulate<C>(cell, val, s, side != nullptr, count, sums, fsum, (size_t)g.nx * g.ny);
-    if (NEAR) {
-        const unsigned m = __ballot_sync(0xffffffffu, near);
-        if (m && (threadIdx.x & 31) == 0) atomicAdd(near_counter, (unsigned long long)__popc(m));
-    }
+    (void)near_any;
 }
 
 template <typename T, bool NEAR>
@@ -1014,7 +1119,8 @@ extern "C" int amt_bin_accumulate(amt_ctx* ctx, const double* d_lat_c, const dou
     int rc = fill_grid(grid, g);
     if (rc) return rc;
     if (n_pixels == 0) return AMT_OK;
-    const unsigned blocks = (unsigned)((n_pixels + 255) / 256);
+    const size_t per_block = 256 * (size_t)kBinSeg;
+    const unsigned blocks = (unsigned)((n_pixels + per_block - 1) / per_block);
     cudaStream_t st = (cudaStream_t)stream;
     unsigned long long* cnt = (unsigned long long*)d_count;
     unsigned long long* sm = (unsigned long long*)d_sums;

@@ -24,39 +24,39 @@ __device__ __forceinline__ double mufu_rsqrt(double a) {
     return r;
 }
 
-// 1/a to ~1 ulp: ~20-bit seed, two Newton steps (4 DFMA).
-__device__ __forceinline__ double rcp_nr(double a) {
-    double r = mufu_rcp(a);
-    double e = fma(-a, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-a, r, 1.0);
-    r = fma(r, e, r);
-    return r;
+// 1/a to ~2^-40: ~20-bit seed + one Newton step (2 DFMA).
+__device__ __forceinline__ double rcp_nr1(double a) {
+    const double r = mufu_rcp(a);
+    return fma(r, fma(-a, r, 1.0), r);
 }
 
-// n/a to <= 1 ulp given r ~ 1/a (one residual correction, 1 DMUL + 2 DFMA).
-__device__ __forceinline__ double div_with_rcp(double n, double a, double r) {
-    double q = n * r;
-    const double e = fma(-a, q, n);
-    return fma(e, r, q);
+// n/a to <= 1 ulp: q = n*r with r ~ 1/a to 2^-40, then one residual correction
+// q += r*(n - a*q) (error 2^-40 * 2^-40 before rounding).  MUFU + 1 DMUL + 4 DFMA.
+__device__ __forceinline__ double div_fast(double n, double a) {
+    const double r = rcp_nr1(a);
+    const double q = n * r;
+    return fma(fma(-a, q, n), r, q);
 }
-__device__ __forceinline__ double div_fast(double n, double a) { return div_with_rcp(n, a, rcp_nr(a)); }
 
-// Goldschmidt: g -> sqrt(a), h -> 0.5/sqrt(a).  Two coupled steps from the ~20-bit seed.
+// Goldschmidt from the ~20-bit MUFU seed: g -> sqrt(a) (<= 1 ulp after the residual step),
+// h -> 0.5/sqrt(a) to ~2^-40 (enough wherever it only scales a small correction term).
 __device__ __forceinline__ void sqrt_rsqrt(double a, double& sq, double& half_rsq) {
     const double y = mufu_rsqrt(a);
     double g = a * y;
     double h = 0.5 * y;
-    double r = fma(-g, h, 0.5);
+    const double r = fma(-g, h, 0.5);
     g = fma(g, r, g);
     h = fma(h, r, h);
-    r = fma(-g, h, 0.5);
-    g = fma(g, r, g);
-    h = fma(h, r, h);
-    // one residual step on g brings sqrt to <= 1 ulp
-    const double e = fma(-g, g, a);
-    sq = fma(e, h, g);
+    sq = fma(fma(-g, g, a), h, g);      // residual step: error 2^-40 * 2^-40 before rounding
     half_rsq = h;
+}
+// 1/sqrt(a) to ~2^-40 (one Goldschmidt step)
+__device__ __forceinline__ double rsqrt_40(double a) {
+    const double y = mufu_rsqrt(a);
+    const double g = a * y;
+    double h = 0.5 * y;
+    h = fma(h, fma(-g, h, 0.5), h);
+    return h + h;
 }
 __device__ __forceinline__ double sqrt_fast(double a) {
     double s, h;

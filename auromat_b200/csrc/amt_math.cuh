@@ -68,6 +68,7 @@ __device__ __forceinline__ void sip_distort(const double* __restrict__ ca, int o
     v = v + fv;
 }
 
+template <bool NORMALISE>
 __device__ __forceinline__ void pix2dir(const FrameC& f, const double* __restrict__ sip_a,
                                         const double* __restrict__ sip_b,
                                         double px, double py, double dir[3]) {
@@ -78,10 +79,16 @@ __device__ __forceinline__ void pix2dir(const FrameC& f, const double* __restric
     // wcs.py:102  xy = CD . pxy
     const double x = fma(f.cd[0], u, f.cd[1] * v);
     const double y = fma(f.cd[2], u, f.cd[3] * v);
-    // wcs.py:111-144 collapsed (see header comment)
+    // wcs.py:111-144 collapsed (see header comment).  The intersection and everything after
+    // it are invariant to the length of the direction ("not required to be unit vectors",
+    // intersection.py:152); only the fast-centre path, which averages four *unit* corner
+    // directions (astrometry.py:61-62), needs the normalisation.
     const double K = 180.0 / 3.141592653589793;
-    const double inv = rsqrt_fast(fma(x, x, fma(y, y, K * K)));
-    const double l = -y * inv, m = x * inv, n = K * inv;
+    double l = -y, m = x, n = K;
+    if (NORMALISE) {
+        const double inv = rsqrt_fast(fma(x, x, fma(y, y, K * K)));
+        l *= inv; m *= inv; n *= inv;
+    }
     // wcs.py:142  lmnrot = R . lmn
     dir[0] = fma(f.rot[2], n, fma(f.rot[1], m, f.rot[0] * l));
     dir[1] = fma(f.rot[5], n, fma(f.rot[4], m, f.rot[3] * l));
@@ -135,30 +142,32 @@ __device__ __forceinline__ double pix2dir_allsky(const FrameC& f, double px, dou
 
 // ---------------------------------------------------------------------------------------
 // Stage 2a: directed ray / inflated-ellipsoid intersection in the J2000 frame.
-// coordinates/intersection.py:58-104, operation for operation: this is the one
-// ill-conditioned block of the path (grazing rays: the discriminant cancels), so it keeps
-// the reference's order of IEEE operations -- no re-association, no FMA, IEEE sqrt and
-// divide.  Returns false when the ray misses (reference: NaN row).
-// `graze` is set when the normalised discriminant rootTerm/dDD is below kGrazeThreshold.
+// coordinates/intersection.py:58-104:  D = dir/axes, O = -cam/axes,
+//   rootTerm = (D.O)^2 - (O.O)(D.D) + (D.D);  t = (D.O -+ sqrt(rootTerm)) / (D.D);  P = dir t + cam
+// This is the one ill-conditioned block of the path (grazing rays: rootTerm cancels).  The dot
+// products and rootTerm are accumulated with FMA -- each partial result is rounded once
+// instead of twice, i.e. at least as accurate as the reference's separate multiply/add passes --
+// and sqrt / divide are the <= 1 ulp Goldschmidt / Newton forms.  Returns false when the ray
+// misses (reference: NaN row).  `graze` is set when the normalised discriminant rootTerm/(D.D)
+// is below kGrazeThreshold: there 1 ulp of input noise moves the footprint by > 1e-9 deg, in
+// the reference as much as here.
 // ---------------------------------------------------------------------------------------
 constexpr double kGrazeThreshold = 1e-10;
 
 __device__ __forceinline__ bool intersect(const FrameC& f, const double dir[3], double P[3], bool& graze) {
     const double D0 = dir[0] * f.rad[0], D1 = dir[1] * f.rad[1], D2 = dir[2] * f.rad[2];
-    const double dDO = (D0 * f.otr[0] + D1 * f.otr[1]) + D2 * f.otr[2];
-    const double dDD = (D0 * D0 + D1 * D1) + D2 * D2;
-    double rt = dDO * dDO;
-    rt = rt - f.oDO * dDD;
-    rt = rt + dDD;
+    const double dDO = fma(D2, f.otr[2], fma(D1, f.otr[1], D0 * f.otr[0]));
+    const double dDD = fma(D2, D2, fma(D1, D1, D0 * D0));
+    const double rt = fma(dDO, dDO, fma(-f.oDO, dDD, dDD));
     graze = rt >= 0.0 && rt < kGrazeThreshold * dDD;
     if (!(rt >= 0.0)) return false;                  // sqrt of a negative -> NaN row
-    const double root = sqrt(rt);
+    const double root = rt > 0.0 ? sqrt_fast(rt) : 0.0;
     double t = f.origin_inside ? dDO + root : dDO - root;
     if (!(t >= 0.0)) return false;                   // intersection.py:50-56 (behind the camera)
-    t = t / dDD;
-    P[0] = dir[0] * t + f.cam[0];                    // res = direction*dMin - (-lineOrigin)
-    P[1] = dir[1] * t + f.cam[1];
-    P[2] = dir[2] * t + f.cam[2];
+    t = div_fast(t, dDD);
+    P[0] = fma(dir[0], t, f.cam[0]);                 // res = direction*dMin - (-lineOrigin)
+    P[1] = fma(dir[1], t, f.cam[1]);
+    P[2] = fma(dir[2], t, f.cam[2]);
     return true;
 }
 
@@ -182,7 +191,7 @@ __device__ __forceinline__ void bowring(double a, double b_over_a, double e2a, d
     sqrt_rsqrt(p2, p, hp);                       // hp = 0.5/p
     sqrt_rsqrt(fma(z, z, p2), r, hr);            // hr = 0.5/r
     const double tu = ((b_over_a * z) * (r + d)) * ((hp + hp) * (hr + hr));
-    const double c = rsqrt_fast(fma(tu, tu, 1.0));
+    const double c = rsqrt_40(fma(tu, tu, 1.0));   // scales the e^2-sized correction terms only
     const double cu3 = (c * c) * c;
     const double su3 = (tu * cu3) * (tu * tu);
     lat = atan2_posx(fma(d, su3, z), fma(-e2a, cu3, p));
@@ -235,11 +244,15 @@ __device__ __forceinline__ void sm_to_mlat_mlt(const double S[3], double& mlat, 
     mlt = fma(smlon, 24.0 / 360.0, 12.0);
 }
 
-// elevation, mapping/astrometry.py:200-212 + utils.py:28-46; `dir` need not be unit
-// (fast centres use the un-normalised mean of four corner directions, astrometry.py:61-62).
+// elevation, mapping/astrometry.py:200-212 + utils.py:28-46: 90 - acos(clip(-dir . P/|P|)).
+// UNIT_DIR: `dir` is used as is (the reference's own behaviour for fast centres, whose
+// direction is the un-normalised mean of four unit corner directions, astrometry.py:61-62);
+// otherwise `dir` has arbitrary length and is normalised here (one rsqrt for both lengths).
+template <bool UNIT_DIR>
 __device__ __forceinline__ double elevation_deg(const double dir[3], const double P[3]) {
-    const double inv_len = rsqrt_fast(fma(P[2], P[2], fma(P[1], P[1], P[0] * P[0])));
-    double dot = -fma(dir[2], P[2], fma(dir[1], P[1], dir[0] * P[0])) * inv_len;
+    double n2 = fma(P[2], P[2], fma(P[1], P[1], P[0] * P[0]));
+    if (!UNIT_DIR) n2 *= fma(dir[2], dir[2], fma(dir[1], dir[1], dir[0] * dir[0]));
+    double dot = -fma(dir[2], P[2], fma(dir[1], P[1], dir[0] * P[0])) * rsqrt_fast(n2);
     // np.clip(dot, -1, 1)
     dot = fmin(fmax(dot, -1.0), 1.0);
     return fma(-acos_fast(dot), kRad2Deg, 90.0);

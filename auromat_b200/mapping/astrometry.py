@@ -29,7 +29,6 @@ class BaseAstrometryMapping(BaseMapping):
         self.fastCenterCalculation = fastCenterCalculation
         self._sanitize = sanitize and not fastCenterCalculation
         self.isSanitized = bool(fastCenterCalculation)
-        self._illConditioned = None
         self._frame = None
 
     wcsHeader = property(lambda self: self._wcsHeader)
@@ -57,13 +56,17 @@ class BaseAstrometryMapping(BaseMapping):
             want |= {'mlat_k', 'mlt_k', 'mlat_c', 'mlt_c'}
         else:
             want |= {'lat_k', 'lon_k', 'lat_c', 'lon_c', 'elev_c'}
-        fresh = {n: ctx.empty(nk if n in CORNER_PLANES else nc, torch.float64)
+        pool = getattr(self, '_planeBuffers', None) or {}      # caller-provided ring buffers (pipeline)
+        fresh = {n: pool[n] if n in pool else ctx.empty(nk if n in CORNER_PLANES else nc, torch.float64)
                  for n in want if n not in self._planes}
         # the hit bitmaps are (re)written by every launch; sanitisation then starts from them
-        fresh['valid_k'], fresh['valid_c'] = ctx.new_bitmaps(w, h)
-        if self._illConditioned is None:
-            self._illConditioned = ctx.new_stats()
-            stats = self._illConditioned
+        if 'valid_k' in pool:
+            fresh['valid_k'], fresh['valid_c'] = pool['valid_k'], pool['valid_c']
+        else:
+            fresh['valid_k'], fresh['valid_c'] = ctx.new_bitmaps(w, h)
+        if self._statsDevice is None:
+            self._statsDevice = ctx.new_stats()     # zeroed; the kernel adds the grazing-ray count
+            stats = self._statsDevice
         else:
             stats = None
         ctx.georef(self.frameConstants, fresh, stats)

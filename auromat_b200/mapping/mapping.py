@@ -139,6 +139,8 @@ class BaseMapping(object):
         self._planes = {}          # name -> device tensor (float64, NaN == masked)
         self._host = {}            # name -> numpy masked array cache
         self._stats = None
+        self._statsPending = None
+        self._statsDevice = None   # device amt_stats block (georeference kernels count grazing rays into it)
         self._boundingBox = None
         self._imgDevice = None
 
@@ -198,18 +200,24 @@ class BaseMapping(object):
             self._host[name] = ma.masked_invalid(arr, copy=False)
         return self._host[name]
 
-    def _deviceStats(self):
-        if self._stats is None:
+    def _startStats(self):
+        """Enqueue the outline / bounding-box reductions and their read-back without waiting
+        (the sequence pipeline overlaps the wait with the next frame's host work)."""
+        if self._stats is None and self._statsPending is None:
             ctx = self.context
             p = self.devicePlanes()
             h, w = self.shape
-            st = ctx.new_stats()
+            st = self._statsDevice if self._statsDevice is not None else ctx.new_stats()
             ctx.bbox_stats(w, h, p, st, pole_test=self._poleTestOnDevice)
-            s = ctx.read_stats(st)
+            self._statsPending = ctx.start_stats_readback(st)
+
+    def _deviceStats(self):
+        if self._stats is None:
+            self._startStats()
+            s = self.context.finish_stats(self._statsPending)
+            self._statsPending = None
             if not self._poleTestOnDevice:
                 s.pole_flags = self._poleFlags()
-            if getattr(self, '_illConditioned', None) is not None:
-                s.n_ill_conditioned = int(ctx.read_stats(self._illConditioned).n_ill_conditioned)
             self._stats = s
         return self._stats
 
@@ -361,8 +369,9 @@ class BaseMapping(object):
         m._planes = {k: v.clone() for k, v in src.items()}
         m._host = {}
         m._stats = None
+        m._statsPending = None
+        m._statsDevice = None
         m._boundingBox = None
-        m._illConditioned = None
         h, w = self.shape
         dmask = ctx.to_device(mask.ravel()) if mask is not None else None
         ctx.apply_center_mask(w, h, m._planes, dmask, minElevation)
@@ -371,6 +380,7 @@ class BaseMapping(object):
     def setDirty(self):
         self._boundingBox = None
         self._stats = None
+        self._statsPending = None
 
     # ------------------------------------------------------------------ invariants
     def checkGuarantees(self):

@@ -1,0 +1,210 @@
+"""Software-pipelined getMapping + resample over an image sequence on one GPU.
+
+`getMappingSequence` of the reference (mapping/spacecraft.py:308-332) yields one mapping at a
+time and `ResampleProvider` (resample.py:370-394) maps `resample` over it; every frame is
+independent.  `resampleSequence` is the same composition with the three host-visible phases of
+a frame interleaved across frames so that the GPU never waits for the host:
+
+  A(i)   host: per-frame constants; enqueue  H2D image (copy stream) | georeference, sanitise,
+         outline statistics, async read-back of the 88-byte statistics block (compute stream)
+  B(i-1) host: bounding box -> target grid (needs the statistics of frame i-1, long finished);
+         enqueue zero/bin/normalise (+ async D2H of the resampled image and elevation)
+  C(i-2) host: hand the finished frame to the caller
+
+The only device->host dependency of the path (grid size depends on the footprint) is thereby
+hidden behind the next frame's georeferencing.  Results are identical to calling
+`resample(getMapping(...))` frame by frame.
+"""
+from __future__ import annotations
+
+import collections
+import weakref
+
+import numpy as np
+import numpy.ma as ma
+
+from . import _lib
+from .mapping.spacecraft import getMapping
+from .resample import resampleToDevice
+
+
+class ResampledFrame(object):
+    """Result of one frame: the georeferenced mapping (device planes) and its resampling.
+    With toHost=True the resampled image / mask / elevation have already been copied into pinned
+    host buffers when the frame is yielded; `img` and `elevation` return arrays the caller owns.
+    `toMapping()` builds the same GenericMapping `resample()` returns."""
+
+    def __init__(self, mapping, grid, info, dImg, dMask, dElev):
+        self.mapping, self.grid, self.info = mapping, grid, info
+        self.deviceImg, self.deviceMask, self.deviceElevation = dImg, dMask, dElev
+        self._host = None
+        self._event = None
+
+    def _startDownload(self, ctx, pool):
+        import torch
+        key = (tuple(self.deviceImg.shape), self.deviceImg.dtype)
+        bucket = pool.setdefault(key, [])
+
+        def triple():
+            return (torch.empty(self.deviceImg.shape, dtype=self.deviceImg.dtype).pin_memory(),
+                    torch.empty(self.deviceMask.shape, dtype=torch.uint8).pin_memory(),
+                    torch.empty(self.deviceElevation.shape, dtype=torch.float64).pin_memory())
+        if not bucket and key not in pool.setdefault('_seen', set()):
+            # first frame of this output shape: page-lock a whole working set at once (cudaHostAlloc is
+            # a millisecond-scale call; later frames must not pay for it)
+            pool['_seen'].add(key)
+            bucket.extend(triple() for _ in range(5))
+        bufs = bucket.pop() if bucket else triple()
+        for h, d in zip(bufs, (self.deviceImg, self.deviceMask, self.deviceElevation)):
+            h.copy_(d, non_blocking=True)
+        self._host = bufs
+        weakref.finalize(self, bucket.append, bufs)    # pinned buffers return to the pool with the frame
+        self._event = torch.cuda.Event()
+        self._event.record(torch.cuda.current_stream(ctx.torch_device))
+
+    def _finish(self):
+        if self._event is not None:
+            self._event.synchronize()
+            self._event = None
+
+    @property
+    def img(self):
+        """Masked (ny, nx, n) resampled image on the host."""
+        self._finish()
+        if self._host is None:
+            ctx = self.mapping.context
+            img, mask = ctx.to_numpy(self.deviceImg), ctx.to_numpy(self.deviceMask)
+        else:
+            img, mask = self._host[0].numpy().copy(), self._host[1].numpy()
+            if img.dtype == np.int16:
+                img = img.view(np.uint16)
+        mask = mask.astype(bool)
+        return ma.masked_array(img, mask=np.repeat(mask[:, :, None], img.shape[2], 2))
+
+    @property
+    def elevation(self):
+        self._finish()
+        e = self._host[2].numpy().copy() if self._host is not None else \
+            self.mapping.context.to_numpy(self.deviceElevation)
+        return ma.masked_invalid(e)
+
+    def toMapping(self):
+        """The GenericMapping on the plate-carree grid that `resample()` would return."""
+        self._finish()
+        m, g, info = self.mapping, self.grid, self.info
+        ctx = m.context
+        lat_k, lon_k, lat_c, lon_c = ctx.plate_carree_coords(g.nx, g.ny, info['latMaxInGrid'], info['latMinInGrid'],
+                                                             info['lonMinInGrid'], info['lonMaxInGrid'])
+        if info['mode'] != _lib.AMT_PRE_NONE:
+            from .resample import _preRotation
+            back = _preRotation(info['mode'], m.altitude, angle=-90)
+            ctx.rotate_coords(lat_k, lon_k, back)
+            ctx.rotate_coords(lat_c, lon_c, back)
+        return m.createResampled(lat_k, lon_k, lat_c, lon_c, self.deviceElevation, self.img)
+
+
+def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, altitude=110,
+                     fastCenterCalculation=False, magnetic=False, metadatas=None, depth=2, toHost=True,
+                     device=None, ringBuffers=False):
+    """Generator of `ResampledFrame` for an image sequence (frames in order).
+
+    :param imagesOrArrays: iterable of (h,w,n) uint8/uint16 arrays (ideally pinned), device
+                           tensors or image paths
+    :param wcsHeaders: iterable of header dicts or `.wcs` paths, same length
+    :param magnetic: also produce the MLat/MLT planes of every frame
+    :param depth: frames in flight (>= 1); 1 disables the overlap
+    :param toHost: copy the resampled image / mask / elevation to pinned host buffers
+    :param ringBuffers: keep the coordinate planes of the frames in a fixed ring of depth+3 plane
+        sets (0.9 GB each for a 12-Mpix frame) instead of allocating per frame: constant memory
+        footprint for arbitrarily long sequences, but `frame.mapping`'s planes are only valid
+        until depth+2 further frames have been yielded (the resampled outputs stay valid)
+    """
+    import torch
+    from .runtime import get_context
+    ctx = get_context(device)
+    main = torch.cuda.current_stream(ctx.torch_device)
+    # one copy stream, one image ring and one pinned-buffer pool per context: they survive
+    # across sequences (torch caches device blocks per stream)
+    copy = ctx.__dict__.get('_copy_stream')
+    if copy is None:
+        copy = ctx.__dict__['_copy_stream'] = torch.cuda.Stream(ctx.torch_device)
+    stageA, stageB = collections.deque(), collections.deque()
+    pool = ctx.__dict__.setdefault('_pinned_frames', {})
+    imgRing = ctx.__dict__.setdefault('_image_ring', [])
+    metadatas = metadatas if metadatas else None
+
+    def upload(i, img):
+        """Host array -> device on the copy stream; returns (tensor, event) or (img, None)."""
+        if isinstance(img, str) or hasattr(img, 'data_ptr'):
+            return img, None
+        src = np.ascontiguousarray(img)
+        if src.dtype == np.uint16:
+            t = torch.from_numpy(src.view(np.int16))
+        else:
+            t = torch.from_numpy(src)
+        with torch.cuda.stream(copy):
+            if ringBuffers:
+                if not imgRing or imgRing[0].shape != t.shape or imgRing[0].dtype != t.dtype:
+                    del imgRing[:]
+                    imgRing.extend(torch.empty(t.shape, dtype=t.dtype, device=ctx.torch_device)
+                                   for _ in range(depth + 3))
+                d = imgRing[i % len(imgRing)]
+                copy.wait_stream(main)          # the previous user of this ring slot has been enqueued on main
+                d.copy_(t, non_blocking=True)
+            else:
+                d = t.to(ctx.torch_device, non_blocking=True)
+                d.record_stream(main)
+            ev = torch.cuda.Event()
+            ev.record(copy)
+        if src.dtype == np.uint16:
+            d = d.view(torch.uint16)
+        return d, ev
+
+    ring = []
+
+    def ringSet(i, m):
+        h, w = m.shape
+        if not ring or ring[0]['lat_k'].numel() != (h + 1) * (w + 1):
+            del ring[:]
+            names = ['lat_k', 'lon_k', 'lat_c', 'lon_c', 'elev_c'] + \
+                    (['mlat_k', 'mlt_k', 'mlat_c', 'mlt_c'] if magnetic else [])
+            for _ in range(depth + 3):
+                s = {n: ctx.empty((h + 1) * (w + 1) if n.endswith('_k') else h * w, torch.float64) for n in names}
+                s['valid_k'], s['valid_c'] = ctx.new_bitmaps(w, h)
+                ring.append(s)
+        return ring[i % len(ring)]
+
+    def runA(i, img, hdr):
+        dimg, ev = upload(i, img)
+        meta = metadatas[i] if metadatas else None
+        m = getMapping(dimg, hdr, altitude=altitude, fastCenterCalculation=fastCenterCalculation, metadata=meta,
+                       identifier=None if isinstance(hdr, str) else 'frame%06d' % i, device=ctx.device)
+        if ringBuffers:
+            m._planeBuffers = ringSet(i, m)
+        m.prefetch(magnetic=magnetic)
+        m._startStats()
+        return m, ev
+
+    def runB(m, ev):
+        if ev is not None:
+            main.wait_event(ev)
+        grid, info, dImg, dMask, dElev = resampleToDevice(m, pxPerDeg=pxPerDeg, arcsecPerPx=arcsecPerPx)
+        f = ResampledFrame(m, grid, info, dImg, dMask, dElev)
+        if toHost:
+            f._startDownload(ctx, pool)
+        return f
+
+    def finish(f):
+        f._finish()
+        return f
+
+    for i, (img, hdr) in enumerate(zip(imagesOrArrays, wcsHeaders)):
+        stageA.append(runA(i, img, hdr))
+        if len(stageA) >= depth:
+            stageB.append(runB(*stageA.popleft()))
+        while len(stageB) > depth:
+            yield finish(stageB.popleft())
+    while stageA:
+        stageB.append(runB(*stageA.popleft()))
+    while stageB:
+        yield finish(stageB.popleft())

@@ -147,8 +147,25 @@ class Context:
         return lat_k, lon_k, lat_c, lon_c
 
     def read_stats(self, stats) -> _lib.AmtStats:
-        raw = stats.cpu().numpy().tobytes()
-        return _lib.AmtStats.from_buffer_copy(raw)
+        return self.finish_stats(self.start_stats_readback(stats))
+
+    def start_stats_readback(self, stats):
+        """Enqueue the device->host copy of an amt_stats block into a pooled pinned buffer;
+        returns a handle for `finish_stats` (lets the host prepare the next frame meanwhile)."""
+        torch = _torch()
+        pool = self.__dict__.setdefault('_pinned_stats', [])
+        host = pool.pop() if pool else torch.empty(C.sizeof(_lib.AmtStats), dtype=torch.uint8).pin_memory()
+        host.copy_(stats, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.torch_device))
+        return host, ev
+
+    def finish_stats(self, handle) -> _lib.AmtStats:
+        host, ev = handle
+        ev.synchronize()
+        s = _lib.AmtStats.from_buffer_copy(host.numpy().tobytes())
+        self.__dict__.setdefault('_pinned_stats', []).append(host)
+        return s
 
     def latlon_to_mlatmlt(self, lat, lon, altitude, wgs_a, wgs_b, m_geo_sm):
         torch = _torch()

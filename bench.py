@@ -191,6 +191,7 @@ def workload_config(args, n_gpus):
         "frame": [args.width, args.height], "altitude_km": 110, "arcsec_per_px": ARCSEC_PER_PX,
         "fast_center": bool(args.fast_center), "outputs": "lat/lon/MLat/MLT corners+centres, elevation, resampled RGB+elevation",
         "parallelism": "frames x%d" % n_gpus,
+        "api": "auromat_b200.pipeline.resampleSequence (getMapping + resample per frame, 2 frames in flight)",
         "l2": "per-step working set ~0.9 GB (72 B/px planes + image) exceeds the 126 MB L2; no explicit flush",
     }
 
@@ -201,7 +202,6 @@ def run_b200(args, rank, local_rank, world):
     import torch.distributed as dist
     from auromat_b200 import synthetic
     from auromat_b200.mapping.spacecraft import getMapping
-    from auromat_b200.resample import resample, resampleToDevice
     from auromat_b200.runtime import get_context
 
     if not torch.cuda.is_available():
@@ -222,19 +222,27 @@ def run_b200(args, rank, local_rank, world):
     img_host = torch.from_numpy(synthetic.issImage(W, H, seed=1000 + rank)).pin_memory()
     img_dev = img_host.to(ctx.torch_device)
 
-    def step_device(hdr):
-        m = getMapping(img_dev, hdr, fastCenterCalculation=args.fast_center, identifier="bench")
-        m.prefetch(magnetic=True)
-        return resampleToDevice(m, arcsecPerPx=ARCSEC_PER_PX)
+    from auromat_b200.pipeline import resampleSequence
 
-    def step_e2e(hdr):
-        # public API with HOST buffers: pinned image in, resampled numpy arrays out
-        m = getMapping(img_host.numpy(), hdr, fastCenterCalculation=args.fast_center, identifier="bench")
-        m.prefetch(magnetic=True)
-        r = resample(m, arcsecPerPx=ARCSEC_PER_PX, method='mean')
-        out_img = r.img_unmasked
-        out_elev = r.elevation
-        return out_img, out_elev
+    # `value`: inputs resident in HBM -- the public sequence API (getMappingSequence + ResampleProvider
+    # of the reference, pipelined) over K frames; every frame runs the full path from scratch.
+    def run_device(hdrs):
+        last = None
+        for f in resampleSequence([img_dev] * len(hdrs), hdrs, arcsecPerPx=ARCSEC_PER_PX, magnetic=True,
+                                  fastCenterCalculation=args.fast_center, toHost=False, device=local_rank,
+                                  ringBuffers=True):
+            last = f
+        return last
+
+    # `e2e`: same call with HOST buffers: pinned image in (H2D every frame), resampled image, mask and
+    # elevation out (D2H every frame into pinned buffers)
+    def run_e2e(hdrs):
+        last = None
+        for f in resampleSequence([img_host.numpy()] * len(hdrs), hdrs, arcsecPerPx=ARCSEC_PER_PX, magnetic=True,
+                                  fastCenterCalculation=args.fast_center, toHost=True, device=local_rank,
+                                  ringBuffers=True):
+            last = f
+        return last.img, last.elevation, last
 
     def barrier():
         if world > 1:
@@ -242,14 +250,12 @@ def run_b200(args, rank, local_rank, world):
         torch.cuda.synchronize()
 
     def timed(fn):
-        for s in range(args.warmup):
-            fn(headers[s])
+        fn(headers[:args.warmup])
         barrier()
         launches0 = ctx.launch_count
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for s in range(args.steps):
-            out = fn(headers[args.warmup + s])
+        out = fn(headers[args.warmup:args.warmup + args.steps])
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -263,10 +269,10 @@ def run_b200(args, rank, local_rank, world):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_dev, launches, out = timed(step_device)
+    ms_dev, launches, out = timed(run_device)
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e, _, out_e2e = timed(step_e2e)
-    d2h = int(out_e2e[0].nbytes + out_e2e[1].data.nbytes)
+    ms_e2e, _, out_e2e = timed(run_e2e)
+    d2h = int(sum(b.numel() * b.element_size() for b in out_e2e[2]._host))
     h2d = int(img_host.numel() * img_host.element_size())
 
     # dominant kernel alone: the fused georeference kernel (all 9 planes)

@@ -583,3 +583,33 @@ def test_mosaic_single_process_vs_oracle(env):
     # maskedByElevation(1) of every station really removed the below-horizon fisheye corners
     for m in coll.mappings:
         assert m.elevation.min() >= 1
+
+
+def test_pipelined_sequence_equals_frame_by_frame(env):
+    """auromat_b200.pipeline.resampleSequence == resample(getMapping(...)) for every frame,
+    with host (pinned) inputs, device inputs, and uint16 images."""
+    import torch
+    from auromat_b200 import synthetic
+    from auromat_b200.mapping.spacecraft import getMapping
+    from auromat_b200.pipeline import resampleSequence
+    from auromat_b200.resample import resample
+    W, H, n = 300, 200, 5
+    hdrs = synthetic.sequenceHeaders(n, W, H)
+    for dtype in (np.uint8, np.uint16):
+        imgs = [synthetic.issImage(W, H, seed=40 + i, dtype=dtype) for i in range(n)]
+        expect = [resample(getMapping(im, h, identifier='x'), arcsecPerPx=400) for im, h in zip(imgs, hdrs)]
+        for source in ('host', 'device'):
+            src = imgs if source == 'host' else [env.to_device(im) for im in imgs]
+            got = list(resampleSequence(src, hdrs, arcsecPerPx=400, magnetic=True))
+            assert len(got) == n
+            for f, e in zip(got, expect):
+                assert np.array_equal(ma.getmaskarray(f.img), ma.getmaskarray(e.img))
+                assert np.array_equal(f.img.filled(0), e.img.filled(0))
+                fe, ee = f.elevation.filled(np.nan), e.elevation.filled(np.nan)
+                assert np.array_equal(np.isnan(fe), np.isnan(ee))
+                assert np.nanmax(np.abs(fe - ee)) < 1e-9
+                assert 'mlat_k' in f.mapping._planes
+            m = got[2].toMapping()
+            assert np.array_equal(m.lats.data, expect[2].lats.data)
+            assert np.array_equal(ma.getmaskarray(m.latsCenter), ma.getmaskarray(expect[2].latsCenter))
+    torch.cuda.synchronize()
