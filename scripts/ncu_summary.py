@@ -48,15 +48,28 @@ def report(path):
         for h, u, v in zip(hdr, units, row):
             if h in KEYS:
                 print('  %-82s %18s %s' % (h, v, u))
-    src = list(csv.reader(io.StringIO(ncu(['-i', path, '--page', 'source', '--csv']))))
-    # one table per kernel; take the first
-    try:
-        h = src[1]
-        si, ei = h.index('Source'), h.index('Instructions Executed')
+    text = ncu(['-i', path, '--page', 'source', '--csv'])
+    # the source page is one CSV table per kernel, each introduced by a "Kernel Name" row
+    tables, cur = [], None
+    for r in csv.reader(io.StringIO(text)):
+        if r and r[0] == 'Kernel Name':
+            cur = {'name': r[1], 'rows': []}
+            tables.append(cur)
+        elif cur is not None:
+            cur['rows'].append(r)
+    for t in tables:
+        rows = t['rows']
+        if not rows:
+            continue
+        h = rows[0]
+        try:
+            si, ei = h.index('Source'), h.index('Instructions Executed')
+        except ValueError:
+            continue
         agg, tot = collections.Counter(), 0
-        for r in src[2:]:
+        for r in rows[1:]:
             if len(r) <= ei:
-                break
+                continue
             try:
                 n = int(float(r[ei]))
             except ValueError:
@@ -67,11 +80,9 @@ def report(path):
             op = (toks[1] if toks[0].startswith('@') else toks[0]).split('.')[0]
             agg[op] += n
             tot += n
-        print('== executed warp instructions by SASS opcode (first kernel): total %d' % tot)
-        for k, v in agg.most_common(24):
-            print('  %-10s %14d %5.1f%%' % (k, v, 100.0 * v / tot))
-    except Exception as e:  # pragma: no cover
-        print('source page unavailable:', e)
+        print('== executed warp instructions by SASS opcode: %s: total %d' % (t['name'][:60], tot))
+        for k, v in agg.most_common(22):
+            print('  %-10s %14d %5.1f%%' % (k, v, 100.0 * v / max(tot, 1)))
 
 
 def launches(path):

@@ -224,3 +224,24 @@ def test_synthetic_sequence():
     t0, _ = synthetic.headerTimeAndCamera(hs[0])
     t4, _ = synthetic.headerTimeAndCamera(hs[4])
     assert (t4 - t0).total_seconds() == 4
+
+
+def test_target_grid_round_scale_randomised():
+    """The analytic shortcut for `decimal` (histogram.py:215-219) equals the numpy evaluation."""
+    rng = np.random.default_rng(4)
+    for _ in range(200):
+        ppd = (float(rng.uniform(0.5, 400)), float(rng.uniform(0.5, 400)))
+        la = np.sort(rng.uniform(-80, 80, 2))
+        lo = np.sort(rng.uniform(-170, 170, 2))
+        if la[1] - la[0] < 3 / ppd[0] or lo[1] - lo[0] < 3 / ppd[1]:
+            continue
+        g, info = R.targetGrid(ppd, la[0], la[1], lo[0], lo[1])
+        ex = np.linspace(g.lo_x, g.hi_x, g.nx + 1)
+        ey = np.linspace(g.lo_y, g.hi_y, g.ny + 1)
+        assert g.round_x == 10.0 ** (int(-np.log10(np.diff(ex).min())) + 6)
+        assert g.round_y == 10.0 ** (int(-np.log10(np.diff(ey).min())) + 6)
+        assert g.step_x == (ex[-1] - ex[0]) / g.nx and g.step_y == (ey[-1] - ey[0]) / g.ny
+    # power-of-ten steps take the exact path
+    g, _ = R.targetGrid((10, 10), 10.0, 20.0, 30.0, 50.0)
+    ex = np.linspace(g.lo_x, g.hi_x, g.nx + 1)
+    assert g.round_x == 10.0 ** (int(-np.log10(np.diff(ex).min())) + 6)
