@@ -95,6 +95,8 @@ SIGNATURES = {
                                           C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "amt_latlon_to_mlatmlt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_double,
                                         C.c_double, c_double_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "amt_sm_to_latlon": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, c_double_p, C.c_double, C.c_double,
+                                   C.c_void_p]),
     "amt_bin_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                      C.c_int32, C.c_size_t, C.POINTER(AmtGrid), C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -222,6 +222,16 @@ __global__ void __launch_bounds__(256, AMT_GEOREF_MINBLOCKS) k_georef_points(con
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in_k = WANT_K && x <= W;
     const bool in_c = WANT_C && x < W && y < H;
+    // per-frame SIP coefficients: constant bank -> shared memory once per CTA (uniform branch)
+    __shared__ double s_sip[2 * AMT_SIP_MAX_COEF];
+    if (p.f.sip_oa | p.f.sip_ob) {
+        if (threadIdx.x < 2 * AMT_SIP_MAX_COEF)
+            s_sip[threadIdx.x] = threadIdx.x < AMT_SIP_MAX_COEF ? p.sip_a[threadIdx.x]
+                                                                : p.sip_b[threadIdx.x - AMT_SIP_MAX_COEF];
+        __syncthreads();
+    }
+    const double* sip_a = s_sip;
+    const double* sip_b = s_sip + AMT_SIP_MAX_COEF;
     bool graze_k = false, graze_c = false, hit_k = false, hit_c = false;
     double dk[3], Pk[3], dc[3], Pc[3], cam_el = 0.0;
     const double nan = qnan();
@@ -232,8 +242,8 @@ __global__ void __launch_bounds__(256, AMT_GEOREF_MINBLOCKS) k_georef_points(con
             if (WANT_K) pix2dir_allsky(p.f, fx - 0.5, fy - 0.5, dk);
             if (WANT_C) cam_el = pix2dir_allsky(p.f, fx, fy, dc);
         } else {
-            if (WANT_K) pix2dir<false>(p.f, p.sip_a, p.sip_b, fx - 0.5, fy - 0.5, dk);
-            if (WANT_C) pix2dir<false>(p.f, p.sip_a, p.sip_b, fx, fy, dc);
+            if (WANT_K) pix2dir<false>(p.f, sip_a, sip_b, fx - 0.5, fy - 0.5, dk);
+            if (WANT_C) pix2dir<false>(p.f, sip_a, sip_b, fx, fy, dc);
         }
         if (WANT_K) hit_k = intersect(p.f, dk, Pk, graze_k) && in_k;
         if (WANT_C) hit_c = intersect(p.f, dc, Pc, graze_c) && in_c;
@@ -301,7 +311,8 @@ __global__ void __launch_bounds__(256, AMT_GEOREF_MINBLOCKS) k_georef_points(con
 constexpr int TW = 32, TH = 8;
 
 // one corner ray of the tile: direction + intersection into shared memory, outputs if owned
-__device__ __forceinline__ bool tile_corner(const GeorefParams& p, double (*sP)[TH + 1][TW + 1],
+__device__ __forceinline__ bool tile_corner(const GeorefParams& p, const double* sip_a, const double* sip_b,
+                                            double (*sP)[TH + 1][TW + 1],
                                             double (*sD)[TH + 1][TW + 1], int x0, int y0, int cx, int cy,
                                             bool& graze) {
     const int W = p.f.W, H = p.f.H;
@@ -310,7 +321,7 @@ __device__ __forceinline__ bool tile_corner(const GeorefParams& p, double (*sP)[
     if (x <= W && y <= H) {
         double dir[3], P[3];
         bool g;
-        pix2dir<true>(p.f, p.sip_a, p.sip_b, (double)x - 0.5, (double)y - 0.5, dir);
+        pix2dir<true>(p.f, sip_a, sip_b, (double)x - 0.5, (double)y - 0.5, dir);
         hit = intersect(p.f, dir, P, g);
 #pragma unroll
         for (int k = 0; k < 3; ++k) { sP[k][cy][cx] = hit ? P[k] : qnan(); sD[k][cy][cx] = dir[k]; }
@@ -331,29 +342,37 @@ __device__ __forceinline__ bool tile_corner(const GeorefParams& p, double (*sP)[
 __global__ void __launch_bounds__(TW* TH) k_georef_tiles(const __grid_constant__ GeorefParams p) {
     __shared__ double sP[3][TH + 1][TW + 1];
     __shared__ double sD[3][TH + 1][TW + 1];
+    __shared__ double s_sip[2 * AMT_SIP_MAX_COEF];
     const int W = p.f.W, H = p.f.H;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int tid = ty * TW + tx;
+    if (p.f.sip_oa | p.f.sip_ob) {
+        if (tid < 2 * AMT_SIP_MAX_COEF)
+            s_sip[tid] = tid < AMT_SIP_MAX_COEF ? p.sip_a[tid] : p.sip_b[tid - AMT_SIP_MAX_COEF];
+        __syncthreads();
+    }
+    const double* sip_a = s_sip;
+    const double* sip_b = s_sip + AMT_SIP_MAX_COEF;
     const int wpr_k = (W + 1 + 31) >> 5, wpr_c = (W + 31) >> 5;
     bool graze = false;
     // main 32x8 block of corners: one warp per row == one bitmap word
     {
-        const bool hit = tile_corner(p, sP, sD, x0, y0, tx, ty, graze);
+        const bool hit = tile_corner(p, sip_a, sip_b, sP, sD, x0, y0, tx, ty, graze);
         const unsigned m = __ballot_sync(0xffffffffu, hit);
         if (p.o.d_valid_k && tx == 0 && y0 + ty <= H && (x0 >> 5) < wpr_k)
             p.o.d_valid_k[(size_t)(y0 + ty) * wpr_k + (x0 >> 5)] = m;
     }
     // halo row cy == TH (warp 0) and halo column cx == TW (warp 1, lanes 0..TH)
     if (ty == 0) {
-        const bool hit = tile_corner(p, sP, sD, x0, y0, tx, TH, graze);
+        const bool hit = tile_corner(p, sip_a, sip_b, sP, sD, x0, y0, tx, TH, graze);
         const unsigned m = __ballot_sync(0xffffffffu, hit);
         // owned only when this is the last tile row (y0 + TH == H)
         if (p.o.d_valid_k && tx == 0 && y0 + TH == H && (x0 >> 5) < wpr_k)
             p.o.d_valid_k[(size_t)H * wpr_k + (x0 >> 5)] = m;
     } else if (ty == 1) {
         bool hit = false;
-        if (tx <= TH) hit = tile_corner(p, sP, sD, x0, y0, TW, tx, graze);
+        if (tx <= TH) hit = tile_corner(p, sip_a, sip_b, sP, sD, x0, y0, TW, tx, graze);
         // owned only when x0 + TW == W: then bit 0 of a word of its own (W % 32 == 0)
         if (p.o.d_valid_k && tx <= TH && x0 + TW == W && y0 + tx <= H && (tx < TH || y0 + TH == H))
             p.o.d_valid_k[(size_t)(y0 + tx) * wpr_k + (W >> 5)] = hit ? 1u : 0u;
@@ -945,6 +964,45 @@ extern "C" int amt_latlon_to_mlatmlt(amt_ctx* ctx, const double* d_lat, const do
     const double e2 = num / aa;
     k_latlon_to_mlatmlt<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         d_lat, d_lon, n, altitude, wgs_a, e2, fm, d_mlat, d_mlt);
+    LAUNCH_CHECK(ctx);
+    return AMT_OK;
+}
+
+// smToLatLon (transform.py:461-485): spherical_to_cartesian(1, lat, lon) -> sm_to_geo (the
+// transpose of mat_geo_to_sm) -> ecef2Geodetic -> degrees.  Reference order, libm (cold path).
+__global__ void k_sm_to_latlon(double* __restrict__ lat, double* __restrict__ lon, size_t n, FrameC fm,
+                               double a, double b, double e2a, double d) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double la = lat[i] * kDeg2Rad, lo = lon[i] * kDeg2Rad;
+    double sl, cl, so, co;
+    sincos(la, &sl, &cl);
+    sincos(lo, &so, &co);
+    const double S[3] = {(cl * 1.0) * co, (cl * 1.0) * so, sl * 1.0};
+    // reverse transform: mat.T . v
+    const double* M = fm.m_sm;
+    const double G0 = (M[0] * S[0] + M[3] * S[1]) + M[6] * S[2];
+    const double G1 = (M[1] * S[0] + M[4] * S[1]) + M[7] * S[2];
+    const double G2 = (M[2] * S[0] + M[5] * S[1]) + M[8] * S[2];
+    double l2, o2;
+    bowring_ref(a, b, e2a, d, G0, G1, G2, l2, o2);
+    lat[i] = l2 * kRad2Deg;
+    lon[i] = o2 * kRad2Deg;
+}
+
+extern "C" int amt_sm_to_latlon(amt_ctx* ctx, double* d_lat, double* d_lon, size_t n, const double m_geo_sm[9],
+                                double wgs_a, double wgs_b, void* stream) {
+    ENTER(ctx);
+    CHECK_ARG(d_lat && d_lon && m_geo_sm, "amt_sm_to_latlon: NULL argument");
+    if (n == 0) return AMT_OK;
+    FrameC fm;
+    memset(&fm, 0, sizeof fm);
+    memcpy(fm.m_sm, m_geo_sm, sizeof fm.m_sm);
+    volatile double aa = wgs_a * wgs_a, bb = wgs_b * wgs_b;
+    volatile double num = aa - bb;
+    volatile double e2 = num / aa;
+    k_sm_to_latlon<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_lat, d_lon, n, fm, wgs_a, wgs_b,
+                                                                               e2 * wgs_a, num / wgs_b);
     LAUNCH_CHECK(ctx);
     return AMT_OK;
 }

@@ -46,24 +46,47 @@ struct FrameC {
 // with p = atan2(x,-y), t = atan((180/pi)/r), which we evaluate directly: no transcendental
 // call, <= 2 ulp from the reference's value.
 // ---------------------------------------------------------------------------------------
+// f(u,v) = sum_{p+q<=order} C_pq u^p v^q, Horner in v inside Horner in u, highest power first
+// (the fixed evaluation order of oracle/_sip_poly; plain multiply + add so that both sides
+// round alike).  Coefficients: packed triangular, index(p,q) = p*(order+1) - p*(p-1)/2 + q,
+// staged in shared memory by the kernel (every lane reads the same word: broadcast).
+template <int ORDER>
+__device__ __forceinline__ double sip_poly_fixed(const double* __restrict__ c, double u, double v) {
+    double acc = 0.0;
+#pragma unroll
+    for (int p = ORDER; p >= 0; --p) {
+        const int base = p * (ORDER + 1) - (p * (p - 1)) / 2;
+        double inner = 0.0;
+#pragma unroll
+        for (int q = ORDER - p; q >= 0; --q) inner = inner * v + c[base + q];
+        acc = acc * u + inner;
+    }
+    return acc;
+}
+
+__device__ __forceinline__ double sip_poly(const double* __restrict__ c, int order, double u, double v) {
+    switch (order) {
+        case 2: return sip_poly_fixed<2>(c, u, v);
+        case 3: return sip_poly_fixed<3>(c, u, v);
+        case 4: return sip_poly_fixed<4>(c, u, v);
+        case 5: return sip_poly_fixed<5>(c, u, v);
+        default: break;
+    }
+    double acc = 0.0;
+    for (int p = order; p >= 0; --p) {
+        const int base = p * (order + 1) - (p * (p - 1)) / 2;
+        double inner = 0.0;
+        for (int q = order - p; q >= 0; --q) inner = inner * v + c[base + q];
+        acc = acc * u + inner;
+    }
+    return acc;
+}
+
 __device__ __forceinline__ void sip_distort(const double* __restrict__ ca, int oa,
                                             const double* __restrict__ cb, int ob,
                                             double& u, double& v) {
-    // f(u,v) = sum_{p+q<=order} C_pq u^p v^q, Horner in v inside Horner in u, highest power
-    // first (same fixed order as oracle/_sip_poly; no FMA so that both sides round alike).
-    double fu = 0.0, fv = 0.0;
-    for (int pass = 0; pass < 2; ++pass) {
-        const double* c = pass == 0 ? ca : cb;
-        const int order = pass == 0 ? oa : ob;
-        double acc = 0.0;
-        for (int p = order; p >= 0; --p) {
-            const int base = p * (order + 1) - (p * (p - 1)) / 2;
-            double inner = 0.0;
-            for (int q = order - p; q >= 0; --q) inner = inner * v + c[base + q];
-            acc = acc * u + inner;
-        }
-        if (pass == 0) fu = acc; else fv = acc;
-    }
+    const double fu = sip_poly(ca, oa, u, v);
+    const double fv = sip_poly(cb, ob, u, v);
     u = u + fu;
     v = v + fv;
 }
@@ -297,28 +320,38 @@ template <bool NEAR>
 __device__ __forceinline__ int bin_index(double x, double lo, double hi, double step, double inv_step,
                                          int n, double round_scale, bool& near) {
     near = false;
+    if (x >= lo && x < hi) {
+        // common case, branch-free: floor guess, then one correction step against the true
+        // numpy edges e(k) = fl(fl(k*step) + lo), e(n) = hi
+        double kd = floor(__dmul_rn(__dsub_rn(x, lo), inv_step));
+        kd = fmin(fmax(kd, 0.0), (double)(n - 1));
+        const double e0 = __dadd_rn(__dmul_rn(kd, step), lo);
+        const double k1 = kd + 1.0;
+        const double e1 = k1 >= (double)n ? hi : __dadd_rn(__dmul_rn(k1, step), lo);
+        int k = (int)kd;
+        k += (x >= e1) ? 1 : 0;
+        k -= (x < e0) ? 1 : 0;
+        k = min(max(k, 0), n - 1);
+        // One correction step is exact: (x - lo)*inv_step carries a relative error of a few ulp,
+        // i.e. an absolute error <= n * 4e-16 << 1 for any grid that fits in memory, so the
+        // floor guess is the true cell or its direct neighbour; numpy's edges differ from
+        // lo + k*step by ulps only.
+        if (NEAR) {
+            const double f0 = edge_at(lo, hi, step, n, k), f1 = edge_at(lo, hi, step, n, k + 1);
+            near = (next_down(x) <= f0) || (next_up(x) >= f1);
+        }
+        return k;
+    }
     if (!(x == x)) return -1;                        // NaN sorts last -> outlier
     if (x < lo) {
         if (NEAR) near = next_up(x) >= lo;
         return -1;
     }
-    if (x >= hi) {
-        // util/histogram.py:215-224: np.around(x, decimal) == np.around(hi, decimal)
-        const double rx = rint(__dmul_rn(x, round_scale)) / round_scale;
-        const double rh = rint(__dmul_rn(hi, round_scale)) / round_scale;
-        if (NEAR) near = next_down(x) <= hi;
-        return rx == rh ? n - 1 : -1;
-    }
-    const double g = floor(__dmul_rn(__dsub_rn(x, lo), inv_step));
-    int k = g < 0.0 ? 0 : (g > (double)(n - 1) ? n - 1 : (int)g);
-    // fix up against the true numpy edges: want edges[k] <= x < edges[k+1]
-    while (k > 0 && edge_at(lo, hi, step, n, k) > x) --k;
-    while (k < n - 1 && edge_at(lo, hi, step, n, k + 1) <= x) ++k;
-    if (NEAR) {
-        const double e0 = edge_at(lo, hi, step, n, k), e1 = edge_at(lo, hi, step, n, k + 1);
-        near = (next_down(x) <= e0) || (next_up(x) >= e1);
-    }
-    return k;
+    // x >= hi -- util/histogram.py:215-224: np.around(x, decimal) == np.around(hi, decimal)
+    const double rx = rint(__dmul_rn(x, round_scale)) / round_scale;
+    const double rh = rint(__dmul_rn(hi, round_scale)) / round_scale;
+    if (NEAR) near = next_down(x) <= hi;
+    return rx == rh ? n - 1 : -1;
 }
 
 // Angle(x deg).wrap_at(180 deg).degree (astropy `_wrap_at`): x - floor((x+180)/360)*360

@@ -589,3 +589,28 @@ def convertMappingToSM(mapping):
                       p['elev_c'].clone().reshape(h, w), mapping.altitude, mapping.img_unmasked,
                       mapping.cameraPosGCRS, mapping.photoTime, mapping.identifier, device=mapping._device,
                       sanitize=False)
+
+
+def convertSMMappingToGeo(mapping):
+    """Inverse of `convertMappingToSM` (reference mapping.py:1549-1559): the SM "lat/lon" planes
+    of a (resampled) SM mapping back to geodetic coordinates, on the device (`amt_sm_to_latlon`)."""
+    ctx = mapping.context
+    p = mapping.devicePlanes()
+    h, w = mapping.shape
+    m = transform.mat_geo_to_sm(transform.date2es(mapping.photoTime))
+    # the reference converts the `.data` of the SM grids (defined everywhere on a resampled grid)
+    raw = getattr(mapping, '_raw', {})
+    out = {}
+    for suffix in ('k', 'c'):
+        la = raw.get('lat_' + suffix)
+        lo = raw.get('lon_' + suffix)
+        la = ctx.to_device(np.asarray(la, dtype=np.float64).ravel()) if la is not None and not hasattr(la, 'data_ptr') \
+            else (la.clone() if la is not None else p['lat_' + suffix].clone())
+        lo = ctx.to_device(np.asarray(lo, dtype=np.float64).ravel()) if lo is not None and not hasattr(lo, 'data_ptr') \
+            else (lo.clone() if lo is not None else p['lon_' + suffix].clone())
+        ctx.sm_to_latlon(la, lo, m, wgs84A, wgs84B)
+        out['lat_' + suffix], out['lon_' + suffix] = la, lo
+    return GenericMapping(out['lat_k'].reshape(h + 1, w + 1), out['lon_k'].reshape(h + 1, w + 1),
+                          out['lat_c'].reshape(h, w), out['lon_c'].reshape(h, w),
+                          mapping.elevation, mapping.altitude, mapping.img, mapping.cameraPosGCRS,
+                          mapping.photoTime, mapping.identifier, device=mapping._device)

@@ -60,6 +60,34 @@ class BaseSpacecraftMapping(BaseAstrometryMapping):
 
     originalPhotoTime = property(lambda self: self._originalPhotoTime)
 
+    @property
+    def intersectsEarth(self):
+        """Boolean (h,w) array: does the ray of a pixel centre hit the (un-inflated) WGS84 Earth?
+        Reference spacecraft.py:508-521 -> intersection.py:165-199,229-237; here the hit ballots
+        of the georeference kernel for altitude 0 (no coordinate plane is written)."""
+        if 'intersectsEarth' not in self._host:
+            from ..coordinates.wcs import frameConstants
+            ctx = self.context
+            h, w = self.shape
+            fr = frameConstants(self.wcsHeader, self.cameraPosGCRS, self.photoTime, 0.0, False)
+            _, bits = ctx.new_bitmaps(w, h)
+            ctx.georef(fr, {'valid_c': bits})
+            words = ctx.to_numpy(bits).view(np.uint32).reshape(h, (w + 31) // 32)
+            unpacked = (words[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1
+            self._host['intersectsEarth'] = unpacked.reshape(h, -1)[:, :w].astype(bool)
+        return self._host['intersectsEarth']
+
+    def isConsistent(self, starPxCoords=None):
+        """Plausibility of timestamp + astrometric solution (reference spacecraft.py:523-555)."""
+        hit = self.intersectsEarth
+        if np.all(hit) or not np.any(hit):
+            return False
+        if starPxCoords is not None:
+            starPxCoords = np.asarray(starPxCoords)
+            if np.any(hit[starPxCoords[:, 1], starPxCoords[:, 0]]):
+                return False
+        return True
+
 
 class ArraySpacecraftMapping(BaseSpacecraftMapping):
     """Spacecraft mapping of an in-memory uint8/uint16 image array (h,w,n)."""

@@ -177,6 +177,12 @@ class Context:
                                                   self.ptr(mlat), self.ptr(mlt), self.stream()))
         return mlat, mlt
 
+    def sm_to_latlon(self, lat, lon, m_geo_sm, wgs_a, wgs_b):
+        """In place: solar-magnetic (lat, lon) degrees -> geodetic degrees."""
+        m = (C.c_double * 9)(*np.asarray(m_geo_sm, dtype=np.float64).ravel())
+        _lib.check(self.lib.amt_sm_to_latlon(self.handle, self.ptr(lat), self.ptr(lon), lat.numel(), m,
+                                             float(wgs_a), float(wgs_b), self.stream()))
+
     def bin_accumulate(self, lat_c, lon_c, side, img, grid: _lib.AmtGrid, count, sums, fsum, near_edge=None):
         torch = _torch()
         dtype = {torch.uint8: _lib.AMT_U8, torch.uint16: _lib.AMT_U16}.get(img.dtype)

@@ -234,6 +234,12 @@ int amt_latlon_to_mlatmlt(amt_ctx* ctx, const double* d_lat, const double* d_lon
                           double altitude, double wgs_a, double wgs_b, const double m_geo_sm[9],
                           double* d_mlat, double* d_mlt, void* stream);
 
+/* Solar-magnetic (lat, lon) in degrees -> geodetic (lat, lon) in degrees, in place:
+ * coordinates/transform.py:461-485 `smToLatLon` (unit vector -> M_geo_sm^T -> Bowring), used by
+ * `convertSMMappingToGeo` (mapping/mapping.py:1549-1559) after `resampleMLatMLT`.            */
+int amt_sm_to_latlon(amt_ctx* ctx, double* d_lat, double* d_lon, size_t n, const double m_geo_sm[9],
+                     double wgs_a, double wgs_b, void* stream);
+
 /* ----------------------------------------------------------------------- stage 3 ---- */
 /* Accumulators: `d_count` and `d_sums` are u64 planes of ny*nx cells, row 0 = NORTHERNMOST
  * latitude row (the reference's flipud, resample.py:349); `d_sums` holds `channels` planes;

@@ -613,3 +613,56 @@ def test_pipelined_sequence_equals_frame_by_frame(env):
             assert np.array_equal(m.lats.data, expect[2].lats.data)
             assert np.array_equal(ma.getmaskarray(m.latsCenter), ma.getmaskarray(expect[2].latsCenter))
     torch.cuda.synchronize()
+
+
+def test_intersects_earth_and_consistency(env):
+    """BaseSpacecraftMapping.intersectsEarth / isConsistent (reference spacecraft.py:508-555,
+    intersection.py:165-199) from the hit ballots of the georeference kernel."""
+    import oracle.auromat_oracle as O
+    from auromat_b200 import synthetic
+    from auromat_b200.mapping.spacecraft import getMapping
+    hdr = synthetic.issHeader(532, 354)
+    t, cam = synthetic.headerTimeAndCamera(hdr)
+    m = getMapping(synthetic.issImage(532, 354), hdr, identifier='t')
+    d = O.pix2dir(hdr, corner=False)
+    expect = O.ellipsoid_line_intersects(O.WGS84_A, O.WGS84_B, cam, d.reshape(-1, 3)).reshape(354, 532)
+    got = m.intersectsEarth
+    assert got.shape == expect.shape and got.dtype == bool
+    assert np.sum(got != expect) <= 2            # knife-edge rays only
+    assert 0.3 < got.mean() < 0.8
+    # the un-inflated Earth is hit by fewer rays than the 110 km shell
+    assert got.sum() < (~ma.getmaskarray(getMapping(synthetic.issImage(532, 354), hdr, identifier='t',
+                                                    nosanitize=True).latsCenter)).sum()
+    assert m.isConsistent()
+    stars_on_earth = np.argwhere(got)[:3][:, ::-1]
+    assert not m.isConsistent(stars_on_earth)
+    assert m.isConsistent(np.argwhere(~got)[:3][:, ::-1])
+
+
+def test_sm_roundtrip_and_resample_mlat_mlt(env):
+    """convertMappingToSM / resample / convertSMMappingToGeo (reference mapping.py:1519-1559,
+    resample.py:63-71, transform.py:461-485)."""
+    import oracle.auromat_oracle as O
+    from auromat_b200 import synthetic
+    from auromat_b200.mapping.mapping import convertMappingToSM, convertSMMappingToGeo
+    from auromat_b200.mapping.spacecraft import getMapping
+    from auromat_b200.resample import resampleMLatMLT
+    hdr = synthetic.issHeader(300, 200)
+    t, cam = synthetic.headerTimeAndCamera(hdr)
+    m = getMapping(synthetic.issImage(300, 200), hdr, fastCenterCalculation=True, identifier='t')
+    sm = convertMappingToSM(m)
+    mlat, mlt = m.mLatMlt
+    assert np.array_equal(sm.lats.filled(np.nan), mlat.filled(np.nan), equal_nan=True)
+    smlon = O.mlt_to_smlon(mlt.filled(np.nan))
+    assert np.nanmax(np.abs(sm.lons.filled(np.nan) - smlon)) < 1e-12
+    # smToLatLon on the device against the oracle
+    geo = convertSMMappingToGeo(sm)
+    ok = ~np.isnan(mlat.filled(np.nan))
+    olat, olon = O.sm_to_latlon(mlat.filled(np.nan)[ok], smlon[ok], t)
+    assert np.max(np.abs(geo.lats.data[ok] - olat)) <= TOL_DEG
+    d = np.abs(geo.lons.data[ok] - olon)
+    assert np.max(np.minimum(d, 360 - d)) <= TOL_DEG
+    r = resampleMLatMLT(m, arcsecPerPx=400, method='mean')
+    assert not r.isPlateCarree                       # regular in SM, not in geodetic coordinates
+    assert r.img.shape[2] == 3 and (~ma.getmaskarray(r.img)).sum() > 1000
+    r.checkGuarantees()
