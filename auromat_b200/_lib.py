@@ -104,8 +104,11 @@ SIGNATURES = {
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "amt_normalise": (C.c_int, [C.c_void_p, C.POINTER(AmtGrid), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "amt_georef_bin_fused": (C.c_int, [C.c_void_p, C.POINTER(AmtFrame), C.c_void_p, C.c_int32, C.c_int32,
-                                       C.POINTER(AmtGrid), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "amt_bbox_stats_frame": (C.c_int, [C.c_void_p, C.POINTER(AmtFrame), C.c_void_p, C.c_void_p,
+                                       C.POINTER(AmtGrid), C.c_void_p, C.c_void_p]),
+    "amt_georef_bin_fused": (C.c_int, [C.c_void_p, C.POINTER(AmtFrame), C.c_void_p, C.c_void_p, C.c_int32,
+                                       C.c_int32, C.POINTER(AmtGrid), C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]),
 }
 
 _lib = None

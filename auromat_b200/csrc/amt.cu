@@ -666,9 +666,12 @@ __device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsig
 // Bounding box over the outline (valid corners with an invalid / out-of-array 4-neighbour,
 // mapping.py:672-703,729-737) + valid counts, from the bitmaps.  Grid-stride over words,
 // block-level reduction, one set of atomics per block.
+// outline coordinates either from the planes or (lat_k == NULL) recomputed from the frame model
+// for the few outline nodes -- the plane-free (fused) resampling path
 __global__ void __launch_bounds__(256) k_stats_bits(int W, int H, Bits K, Bits C, const double* __restrict__ lat_k,
                                                     const double* __restrict__ lon_k,
-                                                    const __grid_constant__ GridC g, StatKeys* s) {
+                                                    const __grid_constant__ GridC g, StatKeys* s,
+                                                    const GeorefParams* __restrict__ frame) {
     unsigned long long mn_la = ~0ULL, mx_la = 0ULL, mn_lo = ~0ULL, mx_lo = 0ULL, mn_pos = ~0ULL, mx_neg = 0ULL;
     unsigned nvk = 0, nb = 0, nvc = 0;
     const int nwk = K.wpr * (H + 1);
@@ -684,7 +687,17 @@ __global__ void __launch_bounds__(256) k_stats_bits(int W, int H, Bits K, Bits C
             const int bit = __ffs(b) - 1;
             b &= b - 1;
             const size_t idx = (size_t)y * (W + 1) + 32 * i + bit;
-            double la = lat_k[idx], lo = lon_k[idx];
+            double la, lo;
+            if (lat_k) {
+                la = lat_k[idx];
+                lo = lon_k[idx];
+            } else {
+                double dir[3], P[3];
+                bool gz;
+                pix2dir<false>(frame->f, frame->sip_a, frame->sip_b, (double)(32 * i + bit) - 0.5, (double)y - 0.5, dir);
+                intersect(frame->f, dir, P, gz);
+                point_to_geo(frame->f, P, la, lo);
+            }
             if (g.prerotate != AMT_PRE_NONE) prerotate(g, la, lo);
             const unsigned long long kla = dkey(la), klo = dkey(lo);
             mn_la = umin64(mn_la, kla); mx_la = umax64(mx_la, kla);
@@ -790,6 +803,44 @@ extern "C" int amt_sanitize(amt_ctx* ctx, int32_t W, int32_t H, const amt_georef
     return AMT_OK;
 }
 
+extern "C" int amt_bbox_stats_frame(amt_ctx* ctx, const amt_frame* frame, const uint32_t* d_valid_k,
+                                    const uint32_t* d_valid_c, const amt_grid* pre, amt_stats* d_stats,
+                                    void* stream) {
+    ENTER(ctx);
+    CHECK_ARG(frame && d_valid_k && d_valid_c && d_stats, "amt_bbox_stats_frame: bad arguments");
+    CHECK_ARG(frame->model == AMT_MODEL_WCS, "amt_bbox_stats_frame: WCS frames only");
+    cudaStream_t st = (cudaStream_t)stream;
+    GeorefParams p;
+    memset(&p, 0, sizeof p);
+    int rc = fill_frame(frame, p);
+    if (rc) return rc;
+    GridC g;
+    memset(&g, 0, sizeof g);
+    if (pre) {
+        rc = fill_grid(pre, g, true);
+        if (rc) return rc;
+    }
+    const int W = frame->width, H = frame->height;
+    const int wk = wpr_of(W + 1), wc = wpr_of(W);
+    const size_t off = ((size_t)wk * (H + 1) * 4 + 255) / 256 * 256;
+    const size_t off2 = off + 256;
+    rc = ensure_scratch(ctx, off2 + sizeof(GeorefParams));
+    if (rc) return rc;
+    StatKeys* keys = (StatKeys*)((unsigned char*)ctx->scratch + off);
+    GeorefParams* dp = (GeorefParams*)((unsigned char*)ctx->scratch + off2);
+    CUDA_TRY(cudaMemcpyAsync(dp, &p, sizeof p, cudaMemcpyHostToDevice, st));
+    Bits K{d_valid_k, wk, H + 1}, C{d_valid_c, wc, H};
+    k_stats_init<<<1, 1, 0, st>>>(keys);
+    LAUNCH_CHECK(ctx);
+    const int words = wk * (H + 1);
+    const int blocks = max(1, min(ctx->sm_count * 4, (words + 255) / 256));
+    k_stats_bits<<<blocks, 256, 0, st>>>(W, H, K, C, nullptr, nullptr, g, keys, dp);
+    LAUNCH_CHECK(ctx);
+    k_stats_final<<<1, 1, 0, st>>>(keys, d_stats);
+    LAUNCH_CHECK(ctx);
+    return AMT_OK;
+}
+
 extern "C" int amt_bbox_stats(amt_ctx* ctx, int32_t W, int32_t H, const double* d_lat_k, const double* d_lon_k,
                               const uint32_t* d_valid_k, const uint32_t* d_valid_c, int32_t pole_test,
                               const amt_grid* pre, amt_stats* d_stats, void* stream) {
@@ -813,7 +864,7 @@ extern "C" int amt_bbox_stats(amt_ctx* ctx, int32_t W, int32_t H, const double* 
     LAUNCH_CHECK(ctx);
     const int words = wk * (H + 1);
     const int blocks = max(1, min(ctx->sm_count * 4, (words + 255) / 256));
-    k_stats_bits<<<blocks, 256, 0, st>>>(W, H, K, C, d_lat_k, d_lon_k, g, keys);
+    k_stats_bits<<<blocks, 256, 0, st>>>(W, H, K, C, d_lat_k, d_lon_k, g, keys, nullptr);
     LAUNCH_CHECK(ctx);
     if (pole_test) {
         dim3 grid((W + 255) / 256, H);
@@ -1262,10 +1313,96 @@ extern "C" int amt_normalise(amt_ctx* ctx, const amt_grid* grid, int32_t dtype, 
     return AMT_OK;
 }
 
-extern "C" int amt_georef_bin_fused(amt_ctx* ctx, const amt_frame* frame, const void* d_img, int32_t dtype,
-                                    int32_t channels, const amt_grid* grid, uint64_t* d_count,
-                                    uint64_t* d_sums, double* d_fsum, void* stream) {
-    (void)ctx; (void)frame; (void)d_img; (void)dtype; (void)channels; (void)grid; (void)d_count; (void)d_sums;
-    (void)d_fsum; (void)stream;
-    return set_err(AMT_ERR_UNSUPPORTED, "amt_georef_bin_fused: not built yet");
+// Fully fused centre chain: pixel -> ray -> intersection -> lat/lon + elevation -> cell ->
+// run-aggregated accumulation, for the centres whose bit is set in the (sanitised) validity
+// bitmap.  No coordinate plane is read or written: 3 B/pixel of image in, the grids out.
+template <typename T, int C>
+__global__ void __launch_bounds__(256) k_georef_bin_fused(const __grid_constant__ GeorefParams p,
+                                                          const uint32_t* __restrict__ valid_c,
+                                                          const T* __restrict__ img, const __grid_constant__ GridC g,
+                                                          unsigned long long* __restrict__ count,
+                                                          unsigned long long* __restrict__ sums,
+                                                          double* __restrict__ fsum) {
+    const int W = p.f.W;
+    const int y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ double s_sip[2 * AMT_SIP_MAX_COEF];
+    if (p.f.sip_oa | p.f.sip_ob) {
+        if (threadIdx.x < 2 * AMT_SIP_MAX_COEF)
+            s_sip[threadIdx.x] = threadIdx.x < AMT_SIP_MAX_COEF ? p.sip_a[threadIdx.x]
+                                                                : p.sip_b[threadIdx.x - AMT_SIP_MAX_COEF];
+        __syncthreads();
+    }
+    const int wc = (W + 31) >> 5;
+    const unsigned word = (x >> 5) < wc ? valid_c[(size_t)y * wc + (x >> 5)] : 0u;
+    if (word == 0) return;                                 // warp-uniform: nothing valid in this word
+    const bool valid = (word >> (x & 31)) & 1u;
+    int cell = -1;
+    unsigned val[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) val[c] = 0;
+    double side = 0.0;
+    if (valid) {
+        double dir[3], P[3];
+        bool gz;
+        pix2dir<false>(p.f, s_sip, s_sip + AMT_SIP_MAX_COEF, (double)x, (double)y, dir);
+        if (intersect(p.f, dir, P, gz)) {
+            double la, lo;
+            point_to_geo(p.f, P, la, lo);
+            int ix, iy;
+            bool near;
+            cell = cell_of<false>(g, la, lo, ix, iy, near);
+            if (cell >= 0) {
+                const size_t i = (size_t)y * W + x;
+#pragma unroll
+                for (int c = 0; c < C; ++c) val[c] = img[i * C + c];
+                if (fsum) side = elevation_deg<false>(dir, P);
+            }
+        }
+    }
+    if (__ballot_sync(0xffffffffu, cell >= 0) == 0) return;
+    warp_accumulate<T, C>(cell, val, side, fsum != nullptr, count, sums, fsum, (size_t)g.nx * g.ny);
+}
+
+template <typename T>
+static void launch_fused(int channels, dim3 grid, cudaStream_t st, const GeorefParams& p, const uint32_t* vc,
+                         const void* img, const GridC& g, unsigned long long* count, unsigned long long* sums,
+                         double* fsum) {
+    const T* im = (const T*)img;
+    switch (channels) {
+        case 1: k_georef_bin_fused<T, 1><<<grid, 256, 0, st>>>(p, vc, im, g, count, sums, fsum); break;
+        case 2: k_georef_bin_fused<T, 2><<<grid, 256, 0, st>>>(p, vc, im, g, count, sums, fsum); break;
+        case 3: k_georef_bin_fused<T, 3><<<grid, 256, 0, st>>>(p, vc, im, g, count, sums, fsum); break;
+        case 4: k_georef_bin_fused<T, 4><<<grid, 256, 0, st>>>(p, vc, im, g, count, sums, fsum); break;
+    }
+}
+
+extern "C" int amt_georef_bin_fused(amt_ctx* ctx, const amt_frame* frame, const uint32_t* d_valid_c,
+                                    const void* d_img, int32_t dtype, int32_t channels, const amt_grid* grid,
+                                    uint64_t* d_count, uint64_t* d_sums, double* d_fsum, void* stream) {
+    ENTER(ctx);
+    CHECK_ARG(frame && d_valid_c && d_img && grid && d_count && d_sums, "amt_georef_bin_fused: NULL argument");
+    CHECK_ARG(channels >= 1 && channels <= 4, "amt_georef_bin_fused: channels must be 1..4");
+    if (frame->model != AMT_MODEL_WCS || frame->fast_center)
+        return set_err(AMT_ERR_UNSUPPORTED, "amt_georef_bin_fused: WCS frames with fast_center == 0 only "
+                                            "(fast centres need the corner intersection points)");
+    if (dtype != AMT_U8 && dtype != AMT_U16)
+        return set_err(AMT_ERR_UNSUPPORTED, "amt_georef_bin_fused: image dtype must be uint8 or uint16");
+    GeorefParams p;
+    memset(&p, 0, sizeof p);
+    int rc = fill_frame(frame, p);
+    if (rc) return rc;
+    GridC g;
+    rc = fill_grid(grid, g);
+    if (rc) return rc;
+    dim3 lg((frame->width + 255) / 256, frame->height);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == AMT_U8)
+        launch_fused<unsigned char>(channels, lg, st, p, d_valid_c, d_img, g, (unsigned long long*)d_count,
+                                    (unsigned long long*)d_sums, d_fsum);
+    else
+        launch_fused<unsigned short>(channels, lg, st, p, d_valid_c, d_img, g, (unsigned long long*)d_count,
+                                     (unsigned long long*)d_sums, d_fsum);
+    LAUNCH_CHECK(ctx);
+    return AMT_OK;
 }

@@ -75,6 +75,39 @@ class BaseAstrometryMapping(BaseMapping):
             ctx.sanitize(w, h, self._planes)
         self.isSanitized = True
 
+    # ---- plane-free (fused) resampling: hit bitmaps + outline statistics only ----
+    def _ensureHitBitmaps(self):
+        """Validity bitmaps of this frame without any coordinate plane: ray hit ballots
+        (direction + discriminant per ray) followed by the sanitisation stencils."""
+        if 'valid_k' not in self._planes:
+            ctx = self.context
+            h, w = self.shape
+            bits = {}
+            bits['valid_k'], bits['valid_c'] = ctx.new_bitmaps(w, h)
+            if self._statsDevice is None:
+                self._statsDevice = ctx.new_stats()
+            ctx.georef(self.frameConstants, bits, self._statsDevice)
+            if self._sanitize:
+                ctx.sanitize(w, h, bits)
+            self._planes.update(bits)
+        return self._planes['valid_k'], self._planes['valid_c']
+
+    def _startStats(self):
+        if 'lat_k' in self._planes or self.fastCenterCalculation or not getattr(self, '_planeFree', False):
+            return BaseMapping._startStats(self)
+        if self._stats is None and self._statsPending is None:
+            ctx = self.context
+            vk, vc = self._ensureHitBitmaps()
+            ctx.bbox_stats_frame(self.frameConstants, vk, vc, self._statsDevice)
+            self._statsPending = ctx.start_stats_readback(self._statsDevice)
+
+    def setPlaneFree(self, flag=True):
+        """Let `boundingBox` / `resample` work from the hit bitmaps and the frame model alone
+        (`amt_bbox_stats_frame`, `amt_georef_bin_fused`) as long as no coordinate array has
+        been asked for.  Not available with fastCenterCalculation."""
+        self._planeFree = bool(flag) and not self.fastCenterCalculation
+        return self
+
     # ---- pole containment: exact geometric test instead of the reference's outline walk ----
     _poleTestOnDevice = False
 
@@ -111,8 +144,13 @@ class BaseAstrometryMapping(BaseMapping):
             if -0.5 <= px <= w - 0.5 and -0.5 <= py <= h - 0.5:
                 ix = min(max(int(np.floor(px + 0.5)), 0), w - 1)
                 iy = min(max(int(np.floor(py + 0.5)), 0), h - 1)
-                lat = float(self.devicePlanes()['lat_c'][iy * w + ix].item())
-                if lat == lat:
+                if 'lat_c' in self._planes or not getattr(self, '_planeFree', False):
+                    lat = float(self.devicePlanes()['lat_c'][iy * w + ix].item())
+                    valid = lat == lat
+                else:
+                    word = int(self._ensureHitBitmaps()[1][iy * ((w + 31) // 32) + ix // 32].item()) & 0xffffffff
+                    valid = bool((word >> (ix % 32)) & 1)
+                if valid:
                     flags |= bit
         return flags
 

@@ -110,7 +110,7 @@ class ResampledFrame(object):
 
 def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, altitude=110,
                      fastCenterCalculation=False, magnetic=False, metadatas=None, depth=2, toHost=True,
-                     device=None, ringBuffers=False):
+                     device=None, ringBuffers=False, coordinates=True):
     """Generator of `ResampledFrame` for an image sequence (frames in order).
 
     :param imagesOrArrays: iterable of (h,w,n) uint8/uint16 arrays (ideally pinned), device
@@ -119,6 +119,10 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
     :param magnetic: also produce the MLat/MLT planes of every frame
     :param depth: frames in flight (>= 1); 1 disables the overlap
     :param toHost: copy the resampled image / mask / elevation to pinned host buffers
+    :param coordinates: False = plane-free mode: only the resampling is wanted, the per-pixel
+        coordinate planes are never written (hit bitmaps -> outline statistics -> fused
+        georeference+binning kernel); `frame.mapping` computes them lazily if asked.  Ignored
+        (treated as True) with fastCenterCalculation or magnetic=True.
     :param ringBuffers: keep the coordinate planes of the frames in a fixed ring of depth+3 plane
         sets (0.9 GB each for a 12-Mpix frame) instead of allocating per frame: constant memory
         footprint for arbitrarily long sequences, but `frame.mapping`'s planes are only valid
@@ -184,6 +188,10 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
         meta = metadatas[i] if metadatas else None
         m = getMapping(dimg, hdr, altitude=altitude, fastCenterCalculation=fastCenterCalculation, metadata=meta,
                        identifier=None if isinstance(hdr, str) else 'frame%06d' % i, device=ctx.device)
+        if not coordinates and not magnetic and not fastCenterCalculation:
+            m.setPlaneFree(True)
+            m._startStats()
+            return m, ev
         if ringBuffers:
             m._planeBuffers = ringSet(i, m)
         m.prefetch(magnetic=magnetic)

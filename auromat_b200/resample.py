@@ -192,12 +192,16 @@ def resampleToDevice(mapping, pxPerDeg=25, arcsecPerPx=None, containsPole=None):
         mode = _lib.AMT_PRE_POLE
     elif mapping.containsDiscontinuity:
         mode = _lib.AMT_PRE_WRAP180
+    planeFree = getattr(mapping, '_planeFree', False) and 'lat_c' not in mapping._planes
     if mode != _lib.AMT_PRE_NONE:
         # min/max of the rotated outline (reference resample.py:176-216)
-        p = mapping.devicePlanes()
         h, w = mapping.shape
         st = ctx.new_stats()
-        ctx.bbox_stats(w, h, p, st, pre=_preRotation(mode, mapping.altitude))
+        if planeFree:
+            vk, vc = mapping._ensureHitBitmaps()
+            ctx.bbox_stats_frame(mapping.frameConstants, vk, vc, st, pre=_preRotation(mode, mapping.altitude))
+        else:
+            ctx.bbox_stats(w, h, mapping.devicePlanes(), st, pre=_preRotation(mode, mapping.altitude))
         s = ctx.read_stats(st)
         lonMin, lonMax = s.lon_min, s.lon_max
         if mode == _lib.AMT_PRE_POLE:
@@ -212,7 +216,11 @@ def resampleToDevice(mapping, pxPerDeg=25, arcsecPerPx=None, containsPole=None):
     count = acc[:cells]
     sums = acc[cells:(1 + channels) * cells]
     fsum = acc[(1 + channels) * cells:].view(torch.float64)
-    binMappingInto(mapping, grid, count, sums, fsum)
+    if planeFree:
+        # fused centre chain + binning: no coordinate plane is materialised
+        ctx.georef_bin_fused(mapping.frameConstants, mapping._ensureHitBitmaps()[1], img, grid, count, sums, fsum)
+    else:
+        binMappingInto(mapping, grid, count, sums, fsum)
     outImg, outMask, outElev = ctx.normalise(grid, img.dtype, channels, count, sums, fsum)
     info['count'] = count
     return grid, info, outImg, outMask, outElev

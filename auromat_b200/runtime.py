@@ -124,6 +124,21 @@ class Context:
                                            C.byref(pre) if pre is not None else None,
                                            self.ptr(stats), self.stream()))
 
+    def bbox_stats_frame(self, frame: _lib.AmtFrame, valid_k, valid_c, stats, pre: "_lib.AmtGrid | None" = None):
+        _lib.check(self.lib.amt_bbox_stats_frame(self.handle, C.byref(frame), self.ptr(valid_k), self.ptr(valid_c),
+                                                 C.byref(pre) if pre is not None else None, self.ptr(stats),
+                                                 self.stream()))
+
+    def georef_bin_fused(self, frame: _lib.AmtFrame, valid_c, img, grid: _lib.AmtGrid, count, sums, fsum):
+        torch = _torch()
+        dtype = {torch.uint8: _lib.AMT_U8, torch.uint16: _lib.AMT_U16}.get(img.dtype)
+        if dtype is None:
+            raise NotImplementedError("image dtype must be uint8 or uint16, got %s" % img.dtype)
+        channels = img.numel() // (frame.width * frame.height)
+        _lib.check(self.lib.amt_georef_bin_fused(self.handle, C.byref(frame), self.ptr(valid_c), self.ptr(img), dtype,
+                                                 channels, C.byref(grid), self.ptr(count), self.ptr(sums),
+                                                 self.ptr(fsum), self.stream()))
+
     def apply_center_mask(self, width, height, planes: dict, mask=None, min_elevation=float("nan")):
         out = _lib.AmtGeorefOut()
         for name, t in planes.items():

@@ -267,11 +267,20 @@ int amt_normalise(amt_ctx* ctx, const amt_grid* grid, int32_t dtype, int32_t cha
                   const uint64_t* d_count, const uint64_t* d_sums, const double* d_fsum,
                   void* d_out_img, uint8_t* d_out_mask, double* d_out_side, void* stream);
 
-/* Fully fused centre chain: pixel -> ray -> intersection -> lat/lon (+elevation) -> bin,
- * without materialising any per-pixel plane.                 */
-int amt_georef_bin_fused(amt_ctx* ctx, const amt_frame* frame, const void* d_img, int32_t dtype,
-                         int32_t channels, const amt_grid* grid, uint64_t* d_count,
-                         uint64_t* d_sums, double* d_fsum, void* stream);
+/* Plane-free resampling, three calls:
+ *   1. amt_georef with only d_valid_k / d_valid_c set: hit ballots of all corner and centre
+ *      rays (direction + discriminant only), then amt_sanitize on the bitmaps;
+ *   2. amt_bbox_stats_frame: outline min/max with the outline coordinates recomputed from the
+ *      frame model for the few outline nodes (no planes) -> the host derives the grid;
+ *   3. amt_georef_bin_fused: pixel -> ray -> intersection -> lat/lon (+elevation) -> cell ->
+ *      accumulate for every centre whose bit is set; 3 B/pixel of image in, the grids out.
+ * fast_center frames are not supported (their centres need the corner intersection points). */
+int amt_bbox_stats_frame(amt_ctx* ctx, const amt_frame* frame, const uint32_t* d_valid_k,
+                         const uint32_t* d_valid_c, const amt_grid* pre, amt_stats* d_stats,
+                         void* stream);
+int amt_georef_bin_fused(amt_ctx* ctx, const amt_frame* frame, const uint32_t* d_valid_c,
+                         const void* d_img, int32_t dtype, int32_t channels, const amt_grid* grid,
+                         uint64_t* d_count, uint64_t* d_sums, double* d_fsum, void* stream);
 
 #ifdef __cplusplus
 }

@@ -666,3 +666,86 @@ def test_sm_roundtrip_and_resample_mlat_mlt(env):
     assert not r.isPlateCarree                       # regular in SM, not in geodetic coordinates
     assert r.img.shape[2] == 3 and (~ma.getmaskarray(r.img)).sum() > 1000
     r.checkGuarantees()
+
+
+@pytest.mark.parametrize("W,H", [(1, 1), (2, 3), (31, 5), (32, 8), (33, 9), (64, 16), (65, 17), (257, 3)])
+@pytest.mark.parametrize("fast", [False, True])
+def test_ragged_and_tiny_frames(env, W, H, fast):
+    """Frames smaller than a warp / tile, and sizes on and beside the 32-pixel word and 32x8
+    tile boundaries: coordinates, masks and bitmaps against the oracle."""
+    import oracle.auromat_oracle as O
+    from auromat_b200 import synthetic
+    from auromat_b200.mapping.spacecraft import getMapping
+    hdr = synthetic.issHeader(W, H)
+    # shift the reference pixel so that the tiny frame straddles the limb (mixed hit / miss)
+    hdr['CRPIX2'] = hdr['CRPIX2'] - 0.18 * H
+    img = synthetic.issImage(W, H)
+    m = getMapping(img, hdr, fastCenterCalculation=fast, identifier='t')
+    with quiet():
+        g = oracle_frame(hdr, fast)
+    assert_coords_close(gpu_arrays(m), g, allow=m.illConditionedCount)
+    p = m.devicePlanes()
+    wk, wc = (W + 1 + 31) // 32, (W + 31) // 32
+    bk = p['valid_k'].cpu().numpy().view(np.uint32).reshape(H + 1, wk)
+    bc = p['valid_c'].cpu().numpy().view(np.uint32).reshape(H, wc)
+    unpack = lambda b, n: ((b[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(b.shape[0], -1)
+    assert np.array_equal(unpack(bk, W + 1)[:, :W + 1].astype(bool), ~np.isnan(g['lats']))
+    assert np.array_equal(unpack(bc, W)[:, :W].astype(bool), ~np.isnan(g['latsCenter']))
+    assert not unpack(bk, W + 1)[:, W + 1:].any() and not unpack(bc, W)[:, W:].any()    # padding bits stay 0
+    if (~np.isnan(g['latsCenter'])).any():
+        m.checkGuarantees()
+
+
+@pytest.mark.parametrize("channels", [1, 2, 4])
+def test_channel_counts_and_gray_images(env, channels):
+    """1-, 2- and 4-channel uint16 images through binning and normalisation."""
+    import oracle.auromat_oracle as O
+    from auromat_b200 import synthetic
+    from auromat_b200.mapping.spacecraft import getMapping
+    from auromat_b200.resample import resample
+    W, H = 200, 130
+    hdr = synthetic.issHeader(W, H)
+    rng = np.random.default_rng(channels)
+    img = rng.integers(0, 65536, (H, W, channels), dtype=np.uint16)
+    m = getMapping(img, hdr, fastCenterCalculation=True, identifier='t')
+    r = resample(m, pxPerDeg=(9.0, 5.0))
+    geo = {k: v.filled(np.nan) for k, v in gpu_arrays(m).items()}
+    o = O.resample_frame(geo, img, 110, px_per_deg=(9.0, 5.0))
+    assert r.img.shape == o['img'].shape and r.img.dtype == np.uint16
+    assert np.array_equal(ma.getmaskarray(r.img), o['img_mask'])
+    assert np.array_equal(r.img.filled(0), np.where(o['img_mask'], 0, o['img']))
+
+
+@pytest.mark.parametrize("sip", [0, 3])
+def test_plane_free_fused_path_equals_materialised(env, sip):
+    """amt_bbox_stats_frame + amt_georef_bin_fused (no coordinate planes) give the same
+    bounding box, grid, counts, integer sums and means as georeference -> planes -> binning."""
+    import torch
+    from auromat_b200 import synthetic
+    from auromat_b200.mapping.spacecraft import getMapping
+    from auromat_b200.pipeline import resampleSequence
+    from auromat_b200.resample import resampleToDevice
+    W, H = 532, 354
+    hdr = synthetic.issHeader(W, H, sipOrder=sip)
+    img = synthetic.issImage(W, H)
+    a = getMapping(img, hdr, identifier='a')
+    b = getMapping(img, hdr, identifier='b').setPlaneFree(True)
+    ga, ia, imgA, maskA, elevA = resampleToDevice(a, arcsecPerPx=100)
+    gb, ib, imgB, maskB, elevB = resampleToDevice(b, arcsecPerPx=100)
+    assert 'lat_c' not in b._planes and 'lat_k' not in b._planes          # nothing was materialised
+    assert a.boundingBox == b.boundingBox
+    assert (ga.nx, ga.ny, ga.lo_x, ga.hi_x, ga.lo_y, ga.hi_y) == (gb.nx, gb.ny, gb.lo_x, gb.hi_x, gb.lo_y, gb.hi_y)
+    assert torch.equal(ia['count'], ib['count'])
+    assert torch.equal(imgA, imgB) and torch.equal(maskA, maskB)
+    ea, eb = elevA.cpu().numpy(), elevB.cpu().numpy()
+    assert np.array_equal(np.isnan(ea), np.isnan(eb))
+    assert np.nanmax(np.abs(ea - eb)) < 1e-9
+    s = b._deviceStats()
+    assert (s.n_valid_corners, s.n_valid_centers) == (a._deviceStats().n_valid_corners, a._deviceStats().n_valid_centers)
+    # coordinates are still available lazily
+    assert np.array_equal(b.latsCenter.filled(np.nan), a.latsCenter.filled(np.nan), equal_nan=True)
+    # the sequence API in plane-free mode
+    frames = list(resampleSequence([img] * 3, [hdr] * 3, arcsecPerPx=100, coordinates=False))
+    for f in frames:
+        assert np.array_equal(f.img.filled(0), imgA.cpu().numpy() * ~maskA.cpu().numpy().astype(bool)[:, :, None])
+        assert 'lat_c' not in f.mapping._planes
