@@ -1135,11 +1135,7 @@ __device__ __forceinline__ void warp_accumulate(int cell, const unsigned (&val)[
     }
     double sb = has_side ? __shfl_sync(0xffffffffu, s, before) : 0.0;
     if (start == 0) sb = 0.0;
-#ifdef AMT_EXP_NOATOMIC
-    if (tail && cell >= 0 && count[cell] == 0x123456789ULL) {
-#else
     if (tail && cell >= 0) {
-#endif
         atomicAdd(&count[cell], (unsigned long long)(lane - start + 1));
 #pragma unroll
         for (int c = 0; c < C; ++c) {

@@ -91,25 +91,42 @@ __constant__ double c_atan_tab[33] = {
     0.75315128096219441, 0.7695264804056583, 0.78539816339744828,
 };
 
+// Constants whose low mantissa word is non-zero cannot be instruction immediates; kept in
+// constant memory they become direct c[bank][offset] operands of DFMA/DADD/DMUL instead of two
+// UMOV / IMAD.MOV each (the polynomial coefficients alone were 14 of the 54 instructions of the
+// first version of atan2_fast).
+__constant__ double c_fm[8] = {
+    1.0 / 9.0, -1.0 / 7.0, 1.0 / 5.0, -1.0 / 3.0,      // atan Taylor coefficients
+    1.5707963267948966, 3.141592653589793,             // pi/2, pi
+    57.29577951308232, 0.017453292519943295,           // 180/pi, pi/180
+};
+#define AMT_C_HALF_PI c_fm[4]
+#define AMT_C_PI c_fm[5]
+
+__device__ __forceinline__ double fabs_bits(double x) {        // |x| on the integer pipe, not the FP64 pipe
+    return __hiloint2double(__double2hiint(x) & 0x7fffffff, __double2loint(x));
+}
+
 // atan(mn/mx) for 0 <= mn <= mx, mx > 0: pick c = i/32 nearest to mn/mx from the MUFU
 // reciprocal seed, then atan(mn/mx) = atan(c) + atan(t), t = (mn - c*mx)/(mx + c*mn),
 // |t| <= 1/64 + 2^-19, where the degree-9 odd Taylor polynomial is exact to 1e-21.
 __device__ __forceinline__ double atan_ratio(double mn, double mx) {
     const double q = mn * mufu_rcp(mx);
-    // round-to-nearest-integer of 32*q via the 2^52+2^51 trick; the integer sits in the low word
-    const double magic = 6755399441055744.0;
-    const double qi = fma(q, 32.0, magic);
+    // q + 1.5*2^47 has an ulp of exactly 1/32: the sum IS q rounded to a multiple of 1/32,
+    // and its low mantissa word is the integer 32*c
+    const double magic = 211106232532992.0;      // 1.5 * 2^47
+    const double qi = q + magic;
     int i = __double2loint(qi);
     i = min(max(i, 0), 32);                      // also keeps NaN inputs inside the table
-    const double c = (qi - magic) * 0.03125;     // == i/32 exactly (q is in [0, 1])
+    const double c = qi - magic;                 // == i/32 exactly (q is in [0, 1])
     const double num = fma(-c, mx, mn);
     const double den = fma(c, mn, mx);
     const double t = div_fast(num, den);
     const double s = t * t;
-    double p = 1.0 / 9.0;
-    p = fma(p, s, -1.0 / 7.0);
-    p = fma(p, s, 1.0 / 5.0);
-    p = fma(p, s, -1.0 / 3.0);
+    double p = c_fm[0];
+    p = fma(p, s, c_fm[1]);
+    p = fma(p, s, c_fm[2]);
+    p = fma(p, s, c_fm[3]);
     const double ts = t * s;
     return c_atan_tab[i] + fma(ts, p, t);
 }
@@ -119,20 +136,20 @@ constexpr double kHalfPi = 1.5707963267948966;
 
 // atan2(y, x), any quadrant, finite inputs, not both zero.
 __device__ __forceinline__ double atan2_fast(double y, double x) {
-    const double a = fabs(y), b = fabs(x);
+    const double a = fabs_bits(y), b = fabs_bits(x);
     const bool swap = a > b;
     double r = atan_ratio(swap ? b : a, swap ? a : b);
-    if (swap) r = kHalfPi - r;
-    if (x < 0.0) r = kPi - r;
+    if (swap) r = AMT_C_HALF_PI - r;
+    if (x < 0.0) r = AMT_C_PI - r;
     return copysign(r, y);
 }
 
 // atan2(y, x) for x >= 0 (result in [-pi/2, pi/2]); also serves atan(y/x).
 __device__ __forceinline__ double atan2_posx(double y, double x) {
-    const double a = fabs(y);
+    const double a = fabs_bits(y);
     const bool swap = a > x;
     double r = atan_ratio(swap ? x : a, swap ? a : x);
-    if (swap) r = kHalfPi - r;
+    if (swap) r = AMT_C_HALF_PI - r;
     return copysign(r, y);
 }
 
@@ -140,12 +157,12 @@ __device__ __forceinline__ double atan2_posx(double y, double x) {
 __device__ __forceinline__ double acos_fast(double d) {
     const double w = (1.0 - d) * (1.0 + d);
     const double s = w > 0.0 ? sqrt_fast(w) : 0.0;
-    const double a = fabs(d);
+    const double a = fabs_bits(d);
     const bool swap = s > a;
     if (s == 0.0) return d < 0.0 ? kPi : 0.0;
     double r = atan_ratio(swap ? a : s, swap ? s : a);
-    if (swap) r = kHalfPi - r;
-    if (d < 0.0) r = kPi - r;
+    if (swap) r = AMT_C_HALF_PI - r;
+    if (d < 0.0) r = AMT_C_PI - r;
     return r;
 }
 

@@ -337,7 +337,11 @@ def run_b200(args, rank, local_rank, world):
         "roofline": {
             "kernel": "k_georef_tiles" if args.fast_center else "k_georef_points",
             "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": achieved / peaks["hbm_gbs"], "peak_kind": peak_kind, "traffic": None,
+            "frac": achieved / peaks["hbm_gbs"], "peak_kind": peak_kind,
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel for this frame size from the
+            # ncu --set full capture in profiles/r01_georef_bin_v3_ncu.txt (writes only; part of the
+            # last planes is still in L2 when the kernel ends, hence < algorithmic bytes)
+            "traffic": 811.3e6 if (W, H) == (4256, 2832) and not args.fast_center else None,
             "kernel_ms": k_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PIXEL_GEOREF * npx,
             "fp64": {"algorithmic_gflops": ALGO_FLOP_PER_PIXEL_GEOREF * npx / (k_ms * 1e-3) / 1e9,
                      "note": "kernel is FP64-pipe bound, see profiles/ for sm__pipe_fp64 utilisation"},
