@@ -217,8 +217,10 @@ def run_b200(args, rank, local_rank, world):
     if world == 1:
         headers = [synthetic.issHeader(W, H)] * total
     else:
-        seq = synthetic.sequenceHeaders(total * world, W, H)
-        headers = [seq[s * world + rank] for s in range(total)]
+        # frames of the configs[3] sequence, frame i -> rank i mod N; a cyclic window of 32 frames keeps
+        # the per-GPU work (fraction of pixels that see the Earth) the same for every N (weak scaling)
+        seq = synthetic.sequenceHeaders(32, W, H)
+        headers = [seq[(s * world + rank) % 32] for s in range(total)]
     img_host = torch.from_numpy(synthetic.issImage(W, H, seed=1000 + rank)).pin_memory()
     img_dev = img_host.to(ctx.torch_device)
 
