@@ -162,11 +162,25 @@ def mat_geo_to_sm(et):
     return mat_T4(et).dot(mat_T3(et)).dot(mat_T2(et)).dot(mat_T1(et).T)
 
 
+_D2R = math.pi / 180.0        # np.deg2rad(x) == x * (pi/180)
+
+
 def frameMatrices(et):
     """(J2000->GEO, J2000->SM, GEO->SM) for one ephemeris second, every primitive rotation
     evaluated once.  Bit-identical to mat_j2000_to_geo / mat_j2000_to_sm / mat_geo_to_sm."""
-    P, T1, T2 = mat_P(et), mat_T1(et), mat_T2(et)
-    lat, lon = mag_lat(et), mag_lon(et)
+    t0 = T0(et)
+    P = rotation_matrix((-1.0 * (0.64062 * t0 + 0.00030 * t0 * t0)) * _D2R, Z)
+    P = np.dot(P, rotation_matrix((0.55675 * t0 - 0.00012 * t0 * t0) * _D2R, Y))
+    P = np.dot(P, rotation_matrix((-1.0 * (0.64062 * t0 + 0.00008 * t0 * t0)) * _D2R, Z))
+    T1 = rotation_matrix((100.461 + 36000.770 * t0 + 360.0 * (H(et) / 24.0)) * _D2R, Z)
+    M = 357.528 + 35999.050 * t0
+    lam = 280.460 + 36000.772 * t0
+    lam = lam + (1.915 - 0.0048 * t0) * math.sin(M * _D2R) + 0.020 * math.sin((2 * M) * _D2R)
+    T2 = np.dot(rotation_matrix(lam * _D2R, Z), rotation_matrix((23.439 - 0.013 * t0) * _D2R, X))
+    idx, fy = _fracYear(et)
+    g01, g11, h11 = calcG01(idx, fy), calcG11(idx, fy), calcH11(idx, fy)
+    lon = math.atan2(h11, g11) + math.pi
+    lat = math.pi / 2 - math.atan((g11 * math.cos(lon) + h11 * math.sin(lon)) / g01)
     Qg = [math.cos(lat) * math.cos(lon), math.cos(lat) * math.sin(lon), math.sin(lat)]
     Qe = np.dot(np.dot(T2, T1.T), Qg)
     T3 = rotation_matrix(-math.atan2(np.deg2rad(Qe[1]), np.deg2rad(Qe[2])), X)

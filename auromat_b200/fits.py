@@ -7,6 +7,7 @@ blocks, terminated by `END`.
 """
 from __future__ import annotations
 
+import functools
 from datetime import datetime, timedelta
 
 import numpy as np
@@ -68,15 +69,20 @@ def getNoradId(header):
     return None if noradId is None else int(noradId)
 
 
+@functools.lru_cache(maxsize=4096)
+def _parseDate(dateobs):
+    try:
+        return datetime.strptime(dateobs, '%Y-%m-%dT%H:%M:%S.%f')
+    except ValueError:
+        return datetime.strptime(dateobs, '%Y-%m-%dT%H:%M:%S')
+
+
 def getPhotoTime(header):
     """DATE-OBS as datetime, or None."""
     dateobs = header.get('DATE-OBS')
     if dateobs is None:
         return None
-    try:
-        return datetime.strptime(dateobs, '%Y-%m-%dT%H:%M:%S.%f')
-    except ValueError:
-        return datetime.strptime(dateobs, '%Y-%m-%dT%H:%M:%S')
+    return _parseDate(dateobs)
 
 
 def getSpacecraftPosition(header):

@@ -211,13 +211,20 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
         f._finish()
         return f
 
-    for i, (img, hdr) in enumerate(zip(imagesOrArrays, wcsHeaders)):
-        stageA.append(runA(i, img, hdr))
-        if len(stageA) >= depth:
+    ctx.pin_stream(True)
+    try:
+        for i, (img, hdr) in enumerate(zip(imagesOrArrays, wcsHeaders)):
+            stageA.append(runA(i, img, hdr))
+            if len(stageA) >= depth:
+                stageB.append(runB(*stageA.popleft()))
+            while len(stageB) > depth:
+                ctx.pin_stream(False)
+                yield finish(stageB.popleft())
+                ctx.pin_stream(True)
+        while stageA:
             stageB.append(runB(*stageA.popleft()))
-        while len(stageB) > depth:
+        ctx.pin_stream(False)
+        while stageB:
             yield finish(stageB.popleft())
-    while stageA:
-        stageB.append(runB(*stageA.popleft()))
-    while stageB:
-        yield finish(stageB.popleft())
+    finally:
+        ctx.pin_stream(False)

@@ -40,7 +40,18 @@ class Context:
 
     # ------------------------------------------------------------------ plumbing
     def stream(self):
+        """The CUDA stream all kernels of this context are enqueued on: torch's current stream
+        of the device (looked up per call unless pinned with `pin_stream`)."""
+        s = self.__dict__.get('_pinned_stream')
+        if s is not None:
+            return s
         return C.c_void_p(_torch().cuda.current_stream(self.torch_device).cuda_stream)
+
+    def pin_stream(self, on=True):
+        """Cache the current stream handle (the sequence pipeline issues ~10 calls per frame on
+        the same stream; the lookup through torch costs a few microseconds each)."""
+        self.__dict__['_pinned_stream'] = \
+            C.c_void_p(_torch().cuda.current_stream(self.torch_device).cuda_stream) if on else None
 
     def synchronize(self):
         _torch().cuda.current_stream(self.torch_device).synchronize()
