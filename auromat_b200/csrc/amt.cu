@@ -20,6 +20,7 @@ struct amt_ctx {
     unsigned long long launches;
     void* scratch;
     size_t scratch_bytes;
+    void* stat_keys;          // device StatKeys block, self-cleaning (see k_stats_bits)
 };
 
 static thread_local char g_err[512] = "";
@@ -88,6 +89,7 @@ extern "C" int amt_ctx_create(int device, amt_ctx** out) {
     c->launches = 0;
     c->scratch = nullptr;
     c->scratch_bytes = 0;
+    c->stat_keys = nullptr;
     *out = c;
     return AMT_OK;
 }
@@ -96,6 +98,7 @@ extern "C" int amt_ctx_destroy(amt_ctx* ctx) {
     if (!ctx) return AMT_OK;
     cudaSetDevice(ctx->device);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->stat_keys) cudaFree(ctx->stat_keys);
     delete ctx;
     return AMT_OK;
 }
@@ -156,6 +159,51 @@ extern "C" int amt_memset_device(amt_ctx* ctx, void* d_ptr, int value, size_t by
 extern "C" int amt_stream_synchronize(amt_ctx* ctx, void* stream) {
     ENTER(ctx);
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return AMT_OK;
+}
+
+// ------------------------------------------------------------------ FP64 peak probe
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, double b, double c0, int iters) {
+    double a[8];
+    const double t = threadIdx.x * 1e-9;
+    const double c = c0 + t;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = 1.0 + j * 0.125 + t;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = fma(a[j], b, c);
+    }
+    double s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += a[j];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" int amt_measure_fp64_peak(amt_ctx* ctx, double* dfma_per_second) {
+    ENTER(ctx);
+    CHECK_ARG(dfma_per_second, "amt_measure_fp64_peak: NULL argument");
+    const int blocks = ctx->sm_count * 8, iters = 4096;
+    int rc = ensure_scratch(ctx, (size_t)blocks * 256 * sizeof(double));
+    if (rc) return rc;
+    double* out = (double*)ctx->scratch;
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    k_fp64_peak<<<blocks, 256>>>(out, 1.0000001, 1e-9, 64);
+    float best = 1e30f;
+    for (int r = 0; r < 5; ++r) {
+        CUDA_TRY(cudaEventRecord(e0));
+        k_fp64_peak<<<blocks, 256>>>(out, 1.0000001, 1e-9, iters);
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    ctx->launches += 6;
+    *dfma_per_second = (double)blocks * 256 * iters * 8 / (best * 1e-3);
     return AMT_OK;
 }
 
@@ -546,27 +594,36 @@ struct StatKeys {
     unsigned long long lat_min, lat_max, lon_min, lon_max, lon_min_pos, lon_max_neg;
     unsigned long long n_valid_k, n_boundary, n_valid_c;
     unsigned int pole_flags;
+    unsigned int blocks_done;
 };
 
-__global__ void k_stats_init(StatKeys* s) {
+__device__ __forceinline__ void stats_reset(StatKeys* s) {
     s->lat_min = s->lon_min = s->lon_min_pos = ~0ULL;
     s->lat_max = s->lon_max = s->lon_max_neg = 0ULL;
     s->n_valid_k = s->n_boundary = s->n_valid_c = 0ULL;
     s->pole_flags = 0u;
+    s->blocks_done = 0u;
 }
 
-__global__ void k_stats_final(const StatKeys* s, amt_stats* out) {
+__global__ void k_stats_init(StatKeys* s) { stats_reset(s); }
+
+// keys -> amt_stats, then the key block is reset: it is clean for the next call (no init launch)
+__device__ __forceinline__ void stats_finish(StatKeys* s, amt_stats* out) {
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
-    out->lat_min = s->lat_min == ~0ULL ? inf : dunkey(s->lat_min);
-    out->lon_min = s->lon_min == ~0ULL ? inf : dunkey(s->lon_min);
-    out->lon_min_pos = s->lon_min_pos == ~0ULL ? inf : dunkey(s->lon_min_pos);
-    out->lat_max = s->lat_max == 0ULL ? -inf : dunkey(s->lat_max);
-    out->lon_max = s->lon_max == 0ULL ? -inf : dunkey(s->lon_max);
-    out->lon_max_neg = s->lon_max_neg == 0ULL ? -inf : dunkey(s->lon_max_neg);
-    out->n_valid_corners = s->n_valid_k;
-    out->n_boundary_corners = s->n_boundary;
-    out->n_valid_centers = s->n_valid_c;
-    out->pole_flags = s->pole_flags;
+    volatile StatKeys* v = s;
+    const unsigned long long a = v->lat_min, b = v->lon_min, c = v->lon_min_pos;
+    const unsigned long long d = v->lat_max, e = v->lon_max, f = v->lon_max_neg;
+    out->lat_min = a == ~0ULL ? inf : dunkey(a);
+    out->lon_min = b == ~0ULL ? inf : dunkey(b);
+    out->lon_min_pos = c == ~0ULL ? inf : dunkey(c);
+    out->lat_max = d == 0ULL ? -inf : dunkey(d);
+    out->lon_max = e == 0ULL ? -inf : dunkey(e);
+    out->lon_max_neg = f == 0ULL ? -inf : dunkey(f);
+    out->n_valid_corners = v->n_valid_k;
+    out->n_boundary_corners = v->n_boundary;
+    out->n_valid_centers = v->n_valid_c;
+    out->pole_flags = v->pole_flags;
+    stats_reset(s);
 }
 
 __device__ __forceinline__ bool isnan_d(double v) { return !(v == v); }
@@ -671,7 +728,7 @@ __device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsig
 __global__ void __launch_bounds__(256) k_stats_bits(int W, int H, Bits K, Bits C, const double* __restrict__ lat_k,
                                                     const double* __restrict__ lon_k,
                                                     const __grid_constant__ GridC g, StatKeys* s,
-                                                    const GeorefParams* __restrict__ frame) {
+                                                    const GeorefParams* __restrict__ frame, amt_stats* out) {
     unsigned long long mn_la = ~0ULL, mx_la = 0ULL, mn_lo = ~0ULL, mx_lo = 0ULL, mn_pos = ~0ULL, mx_neg = 0ULL;
     unsigned nvk = 0, nb = 0, nvc = 0;
     const int nwk = K.wpr * (H + 1);
@@ -745,6 +802,12 @@ __global__ void __launch_bounds__(256) k_stats_bits(int W, int H, Bits K, Bits C
             if (sh[4][0] != ~0ULL) atomicMin(&s->lon_min_pos, sh[4][0]);
             if (sh[5][0] != 0ULL) atomicMax(&s->lon_max_neg, sh[5][0]);
         }
+        // the last block to arrive converts the keys and leaves the block clean for the next call
+        __threadfence();
+        if (atomicAdd(&s->blocks_done, 1u) == gridDim.x - 1) {
+            __threadfence();
+            stats_finish(s, out);
+        }
     }
 }
 
@@ -803,6 +866,16 @@ extern "C" int amt_sanitize(amt_ctx* ctx, int32_t W, int32_t H, const amt_georef
     return AMT_OK;
 }
 
+static int get_stat_keys(amt_ctx* ctx, cudaStream_t st, StatKeys** keys) {
+    if (!ctx->stat_keys) {
+        CUDA_TRY(cudaMalloc(&ctx->stat_keys, sizeof(StatKeys)));
+        k_stats_init<<<1, 1, 0, st>>>((StatKeys*)ctx->stat_keys);      // once; afterwards self-cleaning
+        LAUNCH_CHECK(ctx);
+    }
+    *keys = (StatKeys*)ctx->stat_keys;
+    return AMT_OK;
+}
+
 extern "C" int amt_bbox_stats_frame(amt_ctx* ctx, const amt_frame* frame, const uint32_t* d_valid_k,
                                     const uint32_t* d_valid_c, const amt_grid* pre, amt_stats* d_stats,
                                     void* stream) {
@@ -822,21 +895,19 @@ extern "C" int amt_bbox_stats_frame(amt_ctx* ctx, const amt_frame* frame, const 
     }
     const int W = frame->width, H = frame->height;
     const int wk = wpr_of(W + 1), wc = wpr_of(W);
+    // the frame constants live behind the sanitize scratch bitmap
     const size_t off = ((size_t)wk * (H + 1) * 4 + 255) / 256 * 256;
-    const size_t off2 = off + 256;
-    rc = ensure_scratch(ctx, off2 + sizeof(GeorefParams));
+    rc = ensure_scratch(ctx, off + sizeof(GeorefParams));
     if (rc) return rc;
-    StatKeys* keys = (StatKeys*)((unsigned char*)ctx->scratch + off);
-    GeorefParams* dp = (GeorefParams*)((unsigned char*)ctx->scratch + off2);
+    StatKeys* keys;
+    rc = get_stat_keys(ctx, st, &keys);
+    if (rc) return rc;
+    GeorefParams* dp = (GeorefParams*)((unsigned char*)ctx->scratch + off);
     CUDA_TRY(cudaMemcpyAsync(dp, &p, sizeof p, cudaMemcpyHostToDevice, st));
     Bits K{d_valid_k, wk, H + 1}, C{d_valid_c, wc, H};
-    k_stats_init<<<1, 1, 0, st>>>(keys);
-    LAUNCH_CHECK(ctx);
     const int words = wk * (H + 1);
     const int blocks = max(1, min(ctx->sm_count * 4, (words + 255) / 256));
-    k_stats_bits<<<blocks, 256, 0, st>>>(W, H, K, C, nullptr, nullptr, g, keys, dp);
-    LAUNCH_CHECK(ctx);
-    k_stats_final<<<1, 1, 0, st>>>(keys, d_stats);
+    k_stats_bits<<<blocks, 256, 0, st>>>(W, H, K, C, nullptr, nullptr, g, keys, dp, d_stats);
     LAUNCH_CHECK(ctx);
     return AMT_OK;
 }
@@ -854,24 +925,18 @@ extern "C" int amt_bbox_stats(amt_ctx* ctx, int32_t W, int32_t H, const double* 
         if (rc) return rc;
     }
     const int wk = wpr_of(W + 1), wc = wpr_of(W);
-    // the key block lives behind the sanitize scratch bitmap
-    const size_t off = ((size_t)wk * (H + 1) * 4 + 255) / 256 * 256;
-    int rc = ensure_scratch(ctx, off + sizeof(StatKeys));
+    StatKeys* keys;
+    int rc = get_stat_keys(ctx, st, &keys);
     if (rc) return rc;
-    StatKeys* keys = (StatKeys*)((unsigned char*)ctx->scratch + off);
     Bits K{d_valid_k, wk, H + 1}, C{d_valid_c, wc, H};
-    k_stats_init<<<1, 1, 0, st>>>(keys);
-    LAUNCH_CHECK(ctx);
-    const int words = wk * (H + 1);
-    const int blocks = max(1, min(ctx->sm_count * 4, (words + 255) / 256));
-    k_stats_bits<<<blocks, 256, 0, st>>>(W, H, K, C, d_lat_k, d_lon_k, g, keys, nullptr);
-    LAUNCH_CHECK(ctx);
-    if (pole_test) {
+    if (pole_test) {                     // ORs into the key block; converted and reset by k_stats_bits
         dim3 grid((W + 255) / 256, H);
         k_pole_test<<<grid, 256, 0, st>>>(W, H, C, d_lat_k, d_lon_k, keys);
         LAUNCH_CHECK(ctx);
     }
-    k_stats_final<<<1, 1, 0, st>>>(keys, d_stats);
+    const int words = wk * (H + 1);
+    const int blocks = max(1, min(ctx->sm_count * 4, (words + 255) / 256));
+    k_stats_bits<<<blocks, 256, 0, st>>>(W, H, K, C, d_lat_k, d_lon_k, g, keys, nullptr, d_stats);
     LAUNCH_CHECK(ctx);
     return AMT_OK;
 }

@@ -92,6 +92,12 @@ class Context:
         _lib.check(self.lib.amt_ctx_launch_count(self.handle, C.byref(n)))
         return n.value
 
+    def measure_fp64_peak(self) -> float:
+        """Warp-lane DFMA per second of this device (register-resident DFMA stream)."""
+        v = C.c_double()
+        _lib.check(self.lib.amt_measure_fp64_peak(self.handle, C.byref(v)))
+        return v.value
+
     # ------------------------------------------------------------------ kernels
     def georef(self, frame: _lib.AmtFrame, planes: dict, stats=None):
         """planes: name -> device tensor for any subset of amt_georef_out members."""

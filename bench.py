@@ -317,6 +317,7 @@ def run_b200(args, rank, local_rank, world):
     e1.record()
     torch.cuda.synchronize()
     k_ms = e0.elapsed_time(e1) / reps
+    fp64_peak = ctx.measure_fp64_peak() if rank == 0 else 0.0     # warp-lane DFMA/s (2 FLOP each)
 
     if rank != 0:
         if world > 1:
@@ -345,8 +346,14 @@ def run_b200(args, rank, local_rank, world):
             # last planes is still in L2 when the kernel ends, hence < algorithmic bytes)
             "traffic": 811.3e6 if (W, H) == (4256, 2832) and not args.fast_center else None,
             "kernel_ms": k_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PIXEL_GEOREF * npx,
-            "fp64": {"algorithmic_gflops": ALGO_FLOP_PER_PIXEL_GEOREF * npx / (k_ms * 1e-3) / 1e9,
-                     "note": "kernel is FP64-pipe bound, see profiles/ for sm__pipe_fp64 utilisation"},
+            # the kernel is FP64-pipe / issue bound, not HBM bound: algorithmic FP64 rate
+            # (290 reference-formula ops per pixel) against the DFMA peak measured just now;
+            # executed-instruction pipe utilisation is in profiles/ (ncu sm__pipe_fp64_cycles_active)
+            "fp64": {"algorithmic_tflops": ALGO_FLOP_PER_PIXEL_GEOREF * npx / (k_ms * 1e-3) / 1e12,
+                     "peak_tflops_measured": 2 * fp64_peak / 1e12,
+                     "dfma_issue_peak_ginst": fp64_peak / 1e9,
+                     "ncu_pipe_fp64_pct": 63.0, "ncu_issue_active_pct": 75.0,
+                     "ncu_source": "profiles/r01_georef_bin_v3_ncu.txt"},
         },
     }
     if not args.no_cpu_baseline and world == 1:

@@ -163,6 +163,11 @@ int amt_ctx_device(const amt_ctx* ctx, int* device);
 /* Number of kernels this context has launched so far (bench.py `gpu_launches`).           */
 int amt_ctx_launch_count(const amt_ctx* ctx, uint64_t* count);
 
+/* Measures the FP64 pipe peak of the device with a register-resident DFMA stream (8 independent
+ * chains per thread, 8 CTAs of 256 threads per SM): *dfma_per_second = warp-lane DFMA/s; the FP64
+ * roofline denominator of bench.py (FLOP/s = 2 x that).  Synchronises.                      */
+int amt_measure_fp64_peak(amt_ctx* ctx, double* dfma_per_second);
+
 /* Plain memory helpers so that a C caller does not need the CUDA runtime API.            */
 int amt_alloc_device(amt_ctx* ctx, size_t bytes, void** d_ptr);
 int amt_free_device(amt_ctx* ctx, void* d_ptr);
