@@ -31,6 +31,27 @@ def worldInfo():
     return 0, 1
 
 
+def bindToLocalCpus(device_index):
+    """Pin this process to the CPU cores NVML reports as local to GPU `device_index` (same NUMA
+    node / PCIe root) so that pinned host buffers are allocated next to the GPU and the launch
+    thread does not migrate.  Matters once several ranks stream images over PCIe at the same
+    time.  Returns the affinity set, or None if NVML is unavailable."""
+    try:
+        import os
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        n = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = (cpus & allowed) or allowed
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 def shardIndices(n, rank=None, world=None):
     """Indices of the frames of an n-frame sequence owned by `rank`: i with i mod world == rank."""
     if rank is None or world is None:

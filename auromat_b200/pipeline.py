@@ -153,12 +153,16 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
             t = torch.from_numpy(src)
         with torch.cuda.stream(copy):
             if ringBuffers:
-                if not imgRing or imgRing[0].shape != t.shape or imgRing[0].dtype != t.dtype:
+                if len(imgRing) != ringLen or imgRing[0].shape != t.shape or imgRing[0].dtype != t.dtype:
                     del imgRing[:]
                     imgRing.extend(torch.empty(t.shape, dtype=t.dtype, device=ctx.torch_device)
-                                   for _ in range(depth + 3))
+                                   for _ in range(ringLen))
                 d = imgRing[i % len(imgRing)]
-                copy.wait_stream(main)          # the previous user of this ring slot has been enqueued on main
+                prev = slotDone.get(i % len(imgRing))
+                if prev is not None:
+                    copy.wait_event(prev)       # the frame that used this ring slot has been binned
+                else:
+                    copy.wait_stream(main)
                 d.copy_(t, non_blocking=True)
             else:
                 d = t.to(ctx.torch_device, non_blocking=True)
@@ -170,6 +174,18 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
         return d, ev
 
     ring = []
+    slotDone = {}            # ring slot -> event recorded after the binning of its last user
+    ringLen = depth + 3
+    # With ring buffers the two halves of a frame run on two streams: georeference / sanitise /
+    # statistics of frame i on the caller's stream, zero / bin / normalise / D2H of frame i-1 on a
+    # second one, so that the small kernels and launch gaps of one half hide under the big kernel
+    # of the other.  (Without ring buffers the planes are per-frame allocations of the caller's
+    # stream and everything stays on it.)
+    second = None
+    if ringBuffers:
+        second = ctx.__dict__.get('_second_stream')
+        if second is None:
+            second = ctx.__dict__['_second_stream'] = torch.cuda.Stream(ctx.torch_device)
 
     def ringSet(i, m):
         h, w = m.shape
@@ -177,7 +193,7 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
             del ring[:]
             names = ['lat_k', 'lon_k', 'lat_c', 'lon_c', 'elev_c'] + \
                     (['mlat_k', 'mlt_k', 'mlat_c', 'mlt_c'] if magnetic else [])
-            for _ in range(depth + 3):
+            for _ in range(ringLen):
                 s = {n: ctx.empty((h + 1) * (w + 1) if n.endswith('_k') else h * w, torch.float64) for n in names}
                 s['valid_k'], s['valid_c'] = ctx.new_bitmaps(w, h)
                 ring.append(s)
@@ -191,24 +207,50 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
         if not coordinates and not magnetic and not fastCenterCalculation:
             m.setPlaneFree(True)
             m._startStats()
-            return m, ev
+            return m, ev, i
         if ringBuffers:
+            prev = slotDone.get(i % ringLen)
+            if prev is not None:
+                main.wait_event(prev)           # ring slot free: its previous frame has been binned
             m._planeBuffers = ringSet(i, m)
         m.prefetch(magnetic=magnetic)
         m._startStats()
-        return m, ev
+        return m, ev, i
 
-    def runB(m, ev):
-        if ev is not None:
-            main.wait_event(ev)
-        grid, info, dImg, dMask, dElev = resampleToDevice(m, pxPerDeg=pxPerDeg, arcsecPerPx=arcsecPerPx)
-        f = ResampledFrame(m, grid, info, dImg, dMask, dElev)
-        if toHost:
-            f._startDownload(ctx, pool)
+    def runB(m, ev, i=0):
+        if second is None:
+            if ev is not None:
+                main.wait_event(ev)
+            grid, info, dImg, dMask, dElev = resampleToDevice(m, pxPerDeg=pxPerDeg, arcsecPerPx=arcsecPerPx)
+            f = ResampledFrame(m, grid, info, dImg, dMask, dElev)
+            if toHost:
+                f._startDownload(ctx, pool)
+            return f
+        evA = torch.cuda.Event()
+        evA.record(main)                        # everything of stage A of this frame
+        ctx.pin_stream(False)
+        with torch.cuda.stream(second):
+            ctx.pin_stream(True)
+            second.wait_event(evA)
+            if ev is not None:
+                second.wait_event(ev)
+            grid, info, dImg, dMask, dElev = resampleToDevice(m, pxPerDeg=pxPerDeg, arcsecPerPx=arcsecPerPx)
+            f = ResampledFrame(m, grid, info, dImg, dMask, dElev)
+            if toHost:
+                f._startDownload(ctx, pool)
+            done = torch.cuda.Event()
+            done.record(second)
+            ctx.pin_stream(False)
+        ctx.pin_stream(True)
+        slotDone[i % ringLen] = done
+        f._done = done
         return f
 
     def finish(f):
         f._finish()
+        done = getattr(f, '_done', None)
+        if done is not None:
+            main.wait_event(done)               # the caller's stream sees the finished outputs
         return f
 
     ctx.pin_stream(True)

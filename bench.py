@@ -208,6 +208,8 @@ def run_b200(args, rank, local_rank, world):
         raise SystemExit("bench.py: no CUDA device visible; the B200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        from auromat_b200.parallel import bindToLocalCpus
+        bindToLocalCpus(local_rank)          # NUMA-local pinned buffers and launch thread
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = get_context(local_rank)
     W, H = args.width, args.height

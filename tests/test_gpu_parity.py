@@ -598,9 +598,10 @@ def test_pipelined_sequence_equals_frame_by_frame(env):
     for dtype in (np.uint8, np.uint16):
         imgs = [synthetic.issImage(W, H, seed=40 + i, dtype=dtype) for i in range(n)]
         expect = [resample(getMapping(im, h, identifier='x'), arcsecPerPx=400) for im, h in zip(imgs, hdrs)]
-        for source in ('host', 'device'):
-            src = imgs if source == 'host' else [env.to_device(im) for im in imgs]
-            got = list(resampleSequence(src, hdrs, arcsecPerPx=400, magnetic=True))
+        for source in ('host', 'device', 'host-ring', 'device-ring'):
+            src = imgs if source.startswith('host') else [env.to_device(im) for im in imgs]
+            # ring mode = fixed plane ring + two-stream overlap; few frames, so all stay valid
+            got = list(resampleSequence(src, hdrs, arcsecPerPx=400, magnetic=True, ringBuffers='ring' in source))
             assert len(got) == n
             for f, e in zip(got, expect):
                 assert np.array_equal(ma.getmaskarray(f.img), ma.getmaskarray(e.img))
