@@ -86,3 +86,27 @@ def headerTimeAndCamera(header):
     """(photoTime, cameraPosGCRS) the way `getMapping` derives them from the header."""
     t = datetime.strptime(header['DATE-OBS'], '%Y-%m-%dT%H:%M:%S.%f') + timedelta(seconds=header['DATESHIF'])
     return t, np.array([header['POSXSHIF'], header['POSYSHIF'], header['POSZSHIF']])
+
+
+def issHeaderLookingAt(camLat, camLon, targetLat, targetLon, width=D3S_W, height=D3S_H, camAltitude=400.0,
+                       targetAltitude=110.0):
+    """Synthetic ISS header whose camera sits above (camLat, camLon) at `camAltitude` km and whose
+    boresight (CRVAL) points at the ground point (targetLat, targetLon) at `targetAltitude` km:
+    used to place the pole or the date line inside the footprint."""
+    from .coordinates import transform
+    h = issHeader(width, height)
+    t, _ = headerTimeAndCamera(h)
+    mgeo = transform.mat_j2000_to_geo(transform.date2es(t))
+
+    def ecef(lat, lon, r):
+        la, lo = math.radians(lat), math.radians(lon)
+        return np.array([r * math.cos(la) * math.cos(lo), r * math.cos(la) * math.sin(lo), r * math.sin(la)])
+
+    cam = mgeo.T.dot(ecef(camLat, camLon, 6371.0 + camAltitude))
+    tgt = mgeo.T.dot(ecef(targetLat, targetLon, 6371.0 + targetAltitude))
+    d = tgt - cam
+    d /= np.linalg.norm(d)
+    h['CRVAL1'] = math.degrees(math.atan2(d[1], d[0])) % 360.0
+    h['CRVAL2'] = math.degrees(math.asin(d[2]))
+    h['POSXSHIF'], h['POSYSHIF'], h['POSZSHIF'] = (float(v) for v in cam)
+    return h
