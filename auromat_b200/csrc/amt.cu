@@ -1010,6 +1010,94 @@ extern "C" int amt_rotate_coords(amt_ctx* ctx, double* d_lat, double* d_lon, siz
     return AMT_OK;
 }
 
+// maskedByPolygon (mapping.py:866-917): crossing-number test of every corner against an ordered
+// polygon (utils.py:58-74; x = latitude, y = longitude as in the reference's call), then a
+// centre is masked unless its four corners are all defined and inside.
+constexpr int kPolyChunk = 1024;
+
+__global__ void __launch_bounds__(256) k_polygon_corner_bits(int W, int H, const double* __restrict__ lat_k,
+                                                             const double* __restrict__ lon_k,
+                                                             const double* __restrict__ poly, int n_poly,
+                                                             const __grid_constant__ GridC g,
+                                                             unsigned* __restrict__ inside_bits, int wpr_k,
+                                                             unsigned long long* __restrict__ n_inside) {
+    __shared__ double s_x[kPolyChunk + 1], s_y[kPolyChunk + 1];
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    double tx = qnan(), ty = qnan();
+    if (x <= W) {
+        const size_t i = (size_t)y * (W + 1) + x;
+        tx = lat_k[i];
+        ty = lon_k[i];
+        if (tx == tx && g.prerotate != AMT_PRE_NONE) prerotate(g, tx, ty);
+    }
+    bool inside = false;
+    // edge j runs from vertex j-1 (cyclically) to vertex j; chunks overlap by one vertex
+    for (int base = 0; base < n_poly; base += kPolyChunk) {
+        const int cnt = min(kPolyChunk, n_poly - base);
+        __syncthreads();
+        for (int j = threadIdx.x; j <= cnt; j += blockDim.x) {
+            const int v = (base + j - 1 + n_poly) % n_poly;
+            s_x[j] = poly[2 * v];
+            s_y[j] = poly[2 * v + 1];
+        }
+        __syncthreads();
+        double x0 = s_x[0], y0 = s_y[0];
+        bool f0 = y0 >= ty;
+        for (int j = 1; j <= cnt; ++j) {
+            const double x1 = s_x[j], y1 = s_y[j];
+            const bool f1 = y1 >= ty;
+            if (f0 != f1) {
+                const bool hit = ((y1 - ty) * (x0 - x1) >= (x1 - tx) * (y0 - y1)) == f1;
+                inside ^= hit;
+            }
+            x0 = x1; y0 = y1; f0 = f1;
+        }
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, inside && tx == tx && ty == ty);
+    if ((threadIdx.x & 31) == 0 && (x >> 5) < wpr_k) {
+        inside_bits[(size_t)y * wpr_k + (x >> 5)] = b;
+        if (n_inside && b) atomicAdd(n_inside, (unsigned long long)__popc(b));
+    }
+}
+
+__global__ void __launch_bounds__(256) k_polygon_center_mask(int W, int H, const unsigned* __restrict__ inside_bits,
+                                                             int wpr_k, unsigned char* __restrict__ mask) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    auto bit = [&](int yy, int xx) { return (inside_bits[(size_t)yy * wpr_k + (xx >> 5)] >> (xx & 31)) & 1u; };
+    const unsigned all4 = bit(y, x) & bit(y, x + 1) & bit(y + 1, x) & bit(y + 1, x + 1);
+    mask[(size_t)y * W + x] = all4 ? 0 : 1;
+}
+
+extern "C" int amt_polygon_center_mask(amt_ctx* ctx, int32_t W, int32_t H, const double* d_lat_k,
+                                       const double* d_lon_k, const double* d_polygon, int32_t n_polygon,
+                                       const amt_grid* pre, uint8_t* d_center_mask, uint64_t* d_n_inside,
+                                       void* stream) {
+    ENTER(ctx);
+    CHECK_ARG(W > 0 && H > 0 && d_lat_k && d_lon_k && d_polygon && d_center_mask, "amt_polygon_center_mask: bad arguments");
+    CHECK_ARG(n_polygon >= 3, "amt_polygon_center_mask: a polygon needs at least 3 points");
+    GridC g;
+    memset(&g, 0, sizeof g);
+    if (pre) {
+        int rc = fill_grid(pre, g, true);
+        if (rc) return rc;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int wk = wpr_of(W + 1);
+    int rc = ensure_scratch(ctx, (size_t)wk * (H + 1) * 4);
+    if (rc) return rc;
+    unsigned* bits = (unsigned*)ctx->scratch;
+    if (d_n_inside) CUDA_TRY(cudaMemsetAsync(d_n_inside, 0, sizeof(uint64_t), st));
+    dim3 gk((wk * 32 + 255) / 256, H + 1);
+    k_polygon_corner_bits<<<gk, 256, 0, st>>>(W, H, d_lat_k, d_lon_k, d_polygon, n_polygon, g, bits, wk,
+                                              (unsigned long long*)d_n_inside);
+    LAUNCH_CHECK(ctx);
+    dim3 gc((W + 255) / 256, H);
+    k_polygon_center_mask<<<gc, 256, 0, st>>>(W, H, bits, wk, d_center_mask);
+    LAUNCH_CHECK(ctx);
+    return AMT_OK;
+}
+
 // numpy.linspace(start, stop, num)[i] = fl(fl(i*step) + start), last element == stop
 __device__ __forceinline__ double linspace_at(double start, double stop, double step, int num, int i) {
     return i == num - 1 ? stop : __dadd_rn(__dmul_rn((double)i, step), start);

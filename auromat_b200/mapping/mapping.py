@@ -18,7 +18,8 @@ import numpy as np
 import numpy.ma as ma
 
 from .. import _lib
-from ..coordinates import transform
+from .. import utils as polyutils
+from ..coordinates import geodesic, transform
 from ..coordinates.geodesic import Location, wgs84A, wgs84B
 from ..runtime import get_context
 
@@ -26,6 +27,9 @@ Size = namedtuple('Size', ['width', 'height'])
 MappingProperties = namedtuple('MappingProperties',
                                'altitude cameraPosGCRS boundingBox photoTime '
                                'centroid cameraFootpoint identifier')
+
+PixelScales = namedtuple('PixelScales', ['width', 'height', 'diagonal'])
+PixelScale = namedtuple('PixelScale', ['mean', 'median', 'min', 'max'])
 
 CORNER_PLANES = ('lat_k', 'lon_k', 'mlat_k', 'mlt_k')
 CENTER_PLANES = ('lat_c', 'lon_c', 'mlat_c', 'mlt_c', 'elev_c')
@@ -324,19 +328,91 @@ class BaseMapping(object):
 
     @property
     def outline(self):
-        """(n,2) [lat, lon] of the boundary nodes of the valid-corner mask, in row-major order
-        (NOT a clockwise polygon walk as in the reference, mapping.py:655-691)."""
-        lats, lons = self.lats, self.lons
-        valid = ~ma.getmaskarray(lats)
-        pad = np.zeros((valid.shape[0] + 2, valid.shape[1] + 2), bool)
-        pad[1:-1, 1:-1] = valid
-        interior = pad[:-2, 1:-1] & pad[2:, 1:-1] & pad[1:-1, :-2] & pad[1:-1, 2:]
-        b = valid & ~interior
-        return np.transpose([lats.data[b], lons.data[b]])
+        """The complete outline of this mapping as (n,2) [lat, lon]: the ordered (clockwise in
+        image coordinates) walk around the valid-corner mask; can be concave (reference
+        mapping.py:655-662,672-680)."""
+        return self._fullAndConvexOutlines[0]
+
+    @property
+    def outlineConvexHull(self):
+        """The convex hull (in corner-index space) of the outline, as (m,2) [lat, lon]
+        (reference mapping.py:664-670,682-688)."""
+        return self._fullAndConvexOutlines[1]
+
+    def _validCornerMask(self):
+        """(h+1, w+1) bool array of the defined corners.  Read from the 1-bit validity bitmap on
+        the device when the corner planes are not on the host yet (1.5 MB instead of 2 x 96 MB
+        for a 12-Mpixel frame)."""
+        h, w = self.shape
+        if 'lat_k' in self._host:
+            return ~ma.getmaskarray(self._host['lat_k'])
+        p = self.devicePlanes()
+        if 'valid_k' not in p:
+            self.context.valid_bits(w, h, p)
+        words = self.context.to_numpy(p['valid_k']).view(np.uint32).reshape(h + 1, -1)
+        bits = np.unpackbits(words.view(np.uint8), axis=1, bitorder='little')
+        return bits[:, :w + 1].astype(bool)
+
+    def _gatherCorners(self, xy):
+        """[lat, lon] of the corner nodes xy (n,2) in x,y order."""
+        h, w = self.shape
+        if 'lat_k' in self._host and 'lon_k' in self._host:
+            return np.transpose([self._host['lat_k'].data[xy[:, 1], xy[:, 0]],
+                                 self._host['lon_k'].data[xy[:, 1], xy[:, 0]]])
+        p = self.devicePlanes()
+        idx = self.context.to_device(np.ascontiguousarray(xy[:, 1] * (w + 1) + xy[:, 0], dtype=np.int64))
+        lat = self.context.to_numpy(p['lat_k'].reshape(-1).index_select(0, idx))
+        lon = self.context.to_numpy(p['lon_k'].reshape(-1).index_select(0, idx))
+        return np.transpose([lat, lon])
+
+    @property
+    def _fullAndConvexOutlines(self):
+        if getattr(self, '_outlines', None) is None:
+            outl = polyutils.outline(self._validCornerMask())
+            hull = polyutils.convexHull(outl)
+            both = self._gatherCorners(np.concatenate((outl, hull)))
+            self._outlines = both[:len(outl)], both[len(outl):]
+        return self._outlines
 
     @property
     def centroid(self):
-        raise NotImplementedError('polygon centroid needs the ordered outline walk (out of the hot path)')
+        """The centroid of the outline polygon in the plate-carree projection (reference
+        mapping.py:759-783)."""
+        if getattr(self, '_centroid', None) is None:
+            if self.containsPole:
+                raise NotImplementedError
+            outl = self.outline
+            if self.containsDiscontinuity:
+                outl = np.transpose([outl[:, 0], wrapAt180(outl[:, 1] + 180)])
+                lat, lon = polyutils.polygonCentroid(outl)
+                self._centroid = Location(lat, float(wrapAt180(lon + 180)))
+            else:
+                self._centroid = Location(*polyutils.polygonCentroid(outl))
+        return self._centroid
+
+    @property
+    def arcSecPerPx(self):
+        """Min, max, median and mean angular sizes (arcsec) of the width, height and diagonal of
+        (up to) 1000 evenly sampled pixel polygons (reference mapping.py:785-843)."""
+        if getattr(self, '_pixelScales', None) is None:
+            valid = self._validCornerMask()
+            ok = valid[:-1, :-1] & valid[:-1, 1:] & valid[1:, 1:] & valid[1:, :-1]
+            ys, xs = np.nonzero(ok)
+            polyCount = len(ys)
+            sampleCount = min(polyCount, 1000)
+            sel = np.round(np.linspace(0, polyCount - 1, sampleCount)).astype(int)
+            ys, xs = ys[sel], xs[sel]
+            # polygon vertices 0,1,2 = (y,x), (y,x+1), (y+1,x+1)
+            nodes = np.concatenate((np.transpose([xs, ys]), np.transpose([xs + 1, ys]), np.transpose([xs + 1, ys + 1])))
+            ll = self._gatherCorners(nodes).reshape(3, sampleCount, 2)
+            v0, v1, v2 = ll[0], ll[1], ll[2]
+            scales = []
+            for a, b in ((v0, v1), (v1, v2), (v0, v2)):
+                deg = np.array([geodesic.angularDistance(Location(*p), Location(*q)) for p, q in zip(a, b)])
+                scales.append(PixelScale(mean=float(np.mean(deg)) * 3600.0, median=float(np.median(deg)) * 3600.0,
+                                         min=float(deg.min()) * 3600.0, max=float(deg.max()) * 3600.0))
+            self._pixelScales = PixelScales(width=scales[0], height=scales[1], diagonal=scales[2])
+        return self._pixelScales
 
     @property
     def isPlateCarree(self):
@@ -361,7 +437,39 @@ class BaseMapping(object):
             raise ValueError('minElevation=' + str(minElevation) + ' would mask all pixels!')
         return m
 
-    def _maskedCopy(self, mask=None, minElevation=float('nan')):
+    def maskedByPolygon(self, polygon):
+        """Copy of this mapping where only those pixels are retained whose four corners all lie
+        inside `polygon` (ordered points of an unclosed polygon, [lat, lon]); a previously
+        applied mask is ignored by the reference and kept here (the planes carry it).  Mappings
+        or polygons across the date line / a pole are rotated first, best effort, in the
+        reference's order (mapping.py:866-917).  The inside test runs on the device
+        (`amt_polygon_center_mask`)."""
+        from ..resample import _preRotation
+        ctx = self.context
+        polygon = np.array(polygon, dtype=np.float64)
+        assert polygon.ndim == 2 and polygon.shape[1] == 2 and len(polygon) >= 3
+        polyBoundingBox = BoundingBox.minimumBoundingBox(polygon)
+        polyContainsPole = geodesic.containsOrCrossesPole(polygon)
+        pre = None
+        if self.containsDiscontinuity or polyBoundingBox.containsDiscontinuity:
+            pre = _preRotation(_lib.AMT_PRE_WRAP180, self.altitude)
+        elif self.containsPole or polyContainsPole:
+            pre = _preRotation(_lib.AMT_PRE_POLE, self.altitude)
+        dpoly = ctx.to_device(polygon)
+        if pre is not None:
+            # the polygon goes through the same device routine as the corner coordinates
+            plat, plon = dpoly[:, 0].contiguous(), dpoly[:, 1].contiguous()
+            ctx.rotate_coords(plat, plon, pre)
+            import torch
+            dpoly = torch.stack((plat, plon), dim=1).contiguous()
+        p = self.devicePlanes()
+        h, w = self.shape
+        mask, nInside = ctx.polygon_center_mask(w, h, p['lat_k'], p['lon_k'], dpoly, pre)
+        if int(nInside.item()) == 0:
+            raise ValueError('The given mask would mask all pixels!')
+        return self._maskedCopy(deviceMask=mask)
+
+    def _maskedCopy(self, mask=None, deviceMask=None, minElevation=float('nan')):
         ctx = self.context
         # all planes are materialised first: a later georeference launch would not know the mask
         src = self.devicePlanes(magnetic=True)
@@ -372,13 +480,15 @@ class BaseMapping(object):
         m._statsPending = None
         m._statsDevice = None
         m._boundingBox = None
+        m._outlines = m._centroid = m._pixelScales = None
         h, w = self.shape
-        dmask = ctx.to_device(mask.ravel()) if mask is not None else None
+        dmask = deviceMask if deviceMask is not None else (ctx.to_device(mask.ravel()) if mask is not None else None)
         ctx.apply_center_mask(w, h, m._planes, dmask, minElevation)
         return m
 
     def setDirty(self):
         self._boundingBox = None
+        self._outlines = self._centroid = self._pixelScales = None
         self._stats = None
         self._statsPending = None
 

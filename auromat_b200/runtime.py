@@ -167,6 +167,18 @@ class Context:
         _lib.check(self.lib.amt_rotate_coords(self.handle, self.ptr(lat), self.ptr(lon), lat.numel(),
                                               C.byref(pre), self.stream()))
 
+    def polygon_center_mask(self, width, height, lat_k, lon_k, polygon, pre: "_lib.AmtGrid | None" = None):
+        """(centre mask u8 (h*w), #corners inside) of `amt_polygon_center_mask`; `polygon` is a
+        device tensor (n,2) of (lat, lon), already rotated like `pre` rotates the corners."""
+        torch = _torch()
+        mask = torch.empty(width * height, dtype=torch.uint8, device=self.torch_device)
+        n_inside = torch.zeros(1, dtype=torch.int64, device=self.torch_device)
+        _lib.check(self.lib.amt_polygon_center_mask(self.handle, width, height, self.ptr(lat_k), self.ptr(lon_k),
+                                                    self.ptr(polygon), polygon.shape[0],
+                                                    C.byref(pre) if pre is not None else None, self.ptr(mask),
+                                                    self.ptr(n_inside), self.stream()))
+        return mask, n_inside
+
     def plate_carree_coords(self, nx, ny, lat_hi, lat_lo, lon_lo, lon_hi):
         torch = _torch()
         lat_k = torch.empty((ny + 1, nx + 1), dtype=torch.float64, device=self.torch_device)

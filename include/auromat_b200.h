@@ -225,6 +225,19 @@ int amt_apply_center_mask(amt_ctx* ctx, int32_t width, int32_t height, const uin
 int amt_rotate_coords(amt_ctx* ctx, double* d_lat, double* d_lon, size_t n, const amt_grid* pre,
                       void* stream);
 
+/* maskedByPolygon (mapping/mapping.py:866-917) with the inside test of utils.py:58-74
+ * (matplotlib `Path.contains_points` in the reference; here the crossing-number test with
+ * half-open edges, x = latitude, y = longitude): d_center_mask[y*width+x] = 0 if the four corners
+ * of pixel (x,y) are all defined (not NaN) and inside the ordered, unclosed polygon
+ * d_polygon[n_polygon][2] = (lat, lon) in degrees (DEVICE memory), else 1.  `pre` (nullable)
+ * applies the 180-degree wrap / pole rotation of amt_rotate_coords to the corner coordinates
+ * first; the caller rotates the polygon the same way.  *d_n_inside (nullable, device) receives
+ * the number of corners inside (0 => "the given mask would mask all pixels", :906-907).      */
+int amt_polygon_center_mask(amt_ctx* ctx, int32_t width, int32_t height, const double* d_lat_k,
+                            const double* d_lon_k, const double* d_polygon, int32_t n_polygon,
+                            const amt_grid* pre, uint8_t* d_center_mask, uint64_t* d_n_inside,
+                            void* stream);
+
 /* Coordinates of the plate-carree target grid (resample.py:229-241): writes the 2-D corner
  * planes (ny+1)x(nx+1) and centre planes ny x nx of the resampled mapping, row 0 = north,
  * from the snapped node ranges lat: linspace(lat_hi, lat_lo, ny+2), lon: linspace(lon_lo,

@@ -800,3 +800,81 @@ def test_wcs_frames_over_the_pole_and_the_date_line(env, case):
         d = np.abs(a.data[ok] - b[ok])
         assert np.minimum(d, 360 - d).max() <= 1e-9
     r.checkGuarantees()
+
+
+def test_outline_and_centroid_golden_of_the_reference(env):
+    """The reference's end-to-end known answer (test/outline_test.py:147-158): the centroid of
+    `getMapping(ISS030-E-102170_dc.jpg, ISS030-E-102170_dc.wcs, fastCenterCalculation=True)` is
+    (55.00295889563608, -99.21825084682715) to 6 decimals.  `synthetic.issHeader()` carries exactly the
+    cards of that .wcs file (CRVAL, CRPIX, CD, POS*SHIF, DATE-OBS, DATESHIF; the image content
+    does not enter)."""
+    import oracle.auromat_oracle as O
+    from auromat_b200 import synthetic
+    from auromat_b200.mapping.spacecraft import getMapping
+    m = getMapping(synthetic.issImage(), synthetic.issHeader(), fastCenterCalculation=True, identifier='kat')
+    c = m.centroid
+    np.testing.assert_almost_equal([c.lat, c.lon], [55.00295889563608, -99.21825084682715], decimal=6)
+    outl = m.outline
+    assert 10_000 < len(outl) < 20_000 and not np.isnan(outl).any()
+    # the walk equals the oracle's marching squares on the downloaded corner mask, and the
+    # reference's own centroid formula (unsigned area: orientation matters) gives the golden too
+    valid = ~ma.getmaskarray(m.lats)
+    xy = O.outline_marching_squares(valid)
+    ref = np.transpose([m.lats.data[xy[:, 1], xy[:, 0]], m.lons.data[xy[:, 1], xy[:, 0]]])
+    k = int(np.flatnonzero((ref == outl[0]).all(1))[0])
+    assert np.array_equal(np.roll(ref, -k, axis=0), outl)
+    np.testing.assert_almost_equal(O.polygon_centroid(ref), [55.00295889563608, -99.21825084682715], decimal=6)
+    hull = m.outlineConvexHull
+    assert 3 < len(hull) < len(outl)
+    bb = m.boundingBox
+    assert bb.latSouth == outl[:, 0].min() and bb.latNorth == outl[:, 0].max()
+    assert bb.lonWest == outl[:, 1].min() and bb.lonEast == outl[:, 1].max()
+    p = m.properties
+    assert p.centroid == c and p.boundingBox == bb
+    # pixel scales: ~34 arcsec/px WCS scale seen from 400 km -> sub-degree footprints per pixel
+    s = m.arcSecPerPx
+    assert 0 < s.width.min <= s.width.median <= s.width.max and s.diagonal.mean > s.width.mean
+
+
+@pytest.mark.parametrize("case", ["plain", "dateline"])
+def test_masked_by_polygon_vs_oracle(env, case):
+    import oracle.auromat_oracle as O
+    from auromat_b200 import synthetic
+    from auromat_b200.mapping.spacecraft import getMapping
+    W, H = 133, 89
+    if case == "plain":
+        hdr = synthetic.issHeader(W, H)
+        polygon = [[50.0, -108.0], [58.5, -109.0], [60.0, -100.0], [57.0, -99.0], [58.0, -95.0], [49.0, -96.5]]
+    else:
+        hdr = synthetic.issHeaderLookingAt(52.0, 172.0, 58.0, -179.0, W, H)
+        polygon = [[50.0, 170.0], [64.0, 168.0], [66.0, -172.0], [52.0, -170.0]]
+    m = getMapping(synthetic.issImage(W, H), hdr, identifier=case)
+    assert m.containsDiscontinuity == (case == "dateline")
+    r = m.maskedByPolygon(polygon)
+    omask, _ = O.polygon_center_mask(m.lats.filled(np.nan), m.lons.filled(np.nan), polygon, wrap180=(case == "dateline"))
+    omask |= ma.getmaskarray(m.latsCenter)
+    got = ma.getmaskarray(r.latsCenter)
+    assert np.array_equal(got, omask)
+    assert 0.05 < (~got).mean() < (~ma.getmaskarray(m.latsCenter)).mean()
+    r.checkGuarantees()
+    assert np.array_equal(r.latsCenter.compressed(), m.latsCenter[~omask].compressed())
+    # every retained pixel has its four corners inside the polygon
+    from auromat_b200.utils import pointsInsidePolygon
+    lats, lons = m.lats.filled(np.nan), m.lons.filled(np.nan)
+    if case == "dateline":
+        lons = O.wrap_at_180(lons + 180)
+        polygon = [[a, float(O.wrap_at_180(b + 180))] for a, b in polygon]
+    ins = pointsInsidePolygon(np.transpose([lats.ravel(), lons.ravel()]), polygon).reshape(lats.shape)
+    ys, xs = np.nonzero(~got)
+    assert ins[ys, xs].all() and ins[ys + 1, xs + 1].all() and ins[ys, xs + 1].all() and ins[ys + 1, xs].all()
+    with pytest.raises(ValueError):
+        m.maskedByPolygon([[10.0, 10.0], [11.0, 10.0], [11.0, 11.0]])
+    # a polygon with more vertices than one shared-memory chunk: the outline itself, shrunk towards the centroid
+    if case == "plain":
+        outl, c = m.outline, m.centroid
+        big = np.repeat(outl, 6, axis=0)
+        big = big + (np.array([c.lat, c.lon]) - big) * np.linspace(0.05, 0.06, len(big))[:, None]
+        assert len(big) > 1024
+        r2 = m.maskedByPolygon(big)
+        o2, _ = O.polygon_center_mask(lats, lons, big)
+        assert np.array_equal(ma.getmaskarray(r2.latsCenter), o2 | ma.getmaskarray(m.latsCenter))

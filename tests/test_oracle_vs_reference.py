@@ -129,3 +129,59 @@ def test_allsky_model_bit_for_bit(ref):
     o = O.allsky_georeference(w, cal.xc * s, cal.yc * s, cal.k * s, cal.rotation, cal.lat, cal.lon, 110)
     for name in ('lats', 'lons', 'latsCenter', 'lonsCenter', 'elevation'):
         assert bit_equal(g[name], o[name]), name
+
+
+def test_polygon_helpers_vs_reference(ref):
+    """utils.py polygonArea / polygonCentroid / withoutConsecutiveDuplicates / convexHull run
+    unmodified (convexHull through scipy's Delaunay, which is installed here)."""
+    import sys
+    from auromat_b200 import utils as U
+    R = sys.modules['auromat.utils']
+    rng = np.random.default_rng(5)
+    for n in (3, 7, 40):
+        ang = (np.arange(n) + 0.8 * rng.random(n)) * (2 * np.pi / n)     # origin inside => counter-clockwise
+        poly = np.transpose([np.cos(ang), np.sin(ang)]) * rng.uniform(1, 5, (n, 1)) + [55.0, -99.0]   # CCW, star-shaped
+        assert R.polygonArea(poly) == O.polygon_area(poly)
+        assert R.polygonCentroid(poly) == O.polygon_centroid(poly)
+        np.testing.assert_allclose(U.polygonCentroid(poly), R.polygonCentroid(poly), rtol=0, atol=1e-9)
+        np.testing.assert_allclose(U.polygonArea(poly), R.polygonArea(poly), rtol=1e-12)
+        # the reference divides signed moments by the unsigned area: clockwise input is mirrored
+        # through the origin (restated as is in the oracle; the product is orientation independent)
+        assert R.polygonCentroid(poly[::-1]) == O.polygon_centroid(poly[::-1])
+        np.testing.assert_allclose(R.polygonCentroid(poly[::-1]), -np.array(R.polygonCentroid(poly)), rtol=1e-9)
+        np.testing.assert_allclose(U.polygonCentroid(poly[::-1]), R.polygonCentroid(poly), rtol=0, atol=1e-9)
+    pts = rng.integers(0, 60, (300, 2))
+    with quiet():
+        rh = R.convexHull(pts)
+    # scipy's Delaunay hull may keep points lying exactly on a hull edge; the corner set and its order agree
+    mine = U.convexHull(pts)
+    assert {tuple(p) for p in mine.tolist()} <= {tuple(p) for p in rh.tolist()}
+    assert U.polygonArea(mine) == pytest.approx(R.polygonArea(rh))
+    strict = [p for p in rh.tolist() if tuple(p) in {tuple(q) for q in mine.tolist()}]
+    assert strict == mine.tolist()
+    arr = np.array([[1, 2], [1, 2], [3, 4], [3, 4], [3, 4], [1, 2]])
+    assert np.array_equal(R.withoutConsecutiveDuplicates(arr), U.withoutConsecutiveDuplicates(arr))
+
+
+def test_pole_test_on_the_reference_regression_outlines():
+    """test/geodesic_test.py:57-2171, 2173-2669: real ISS outlines (full, reduced, hulls) that
+    once fooled the pole test; none of them contains a pole.  The arrays are parsed out of the
+    reference's test file."""
+    import re
+    from auromat_b200 import utils as U
+    from auromat_b200.coordinates.geodesic import containsOrCrossesPole
+    src = open('/root/reference/auromat/test/geodesic_test.py').read()
+    arrays = re.findall(r"\n\s+(outline\w+) = (?:np\.array\()?(\[\[.*?\]\])", src, re.S)
+    assert len(arrays) >= 5
+    checked = 0
+    for name, body in arrays:
+        pts = np.array(eval(body), dtype=float)
+        assert pts.ndim == 2 and len(pts) >= 3
+        if name == 'outlineReduced100':
+            # a sub-sampled outline self-intersects (the bug); the reference tests its hulls (:2161-2170)
+            assert not containsOrCrossesPole(U.convexHull(pts[::2])), name + '[::2] hull'
+        else:
+            assert not containsOrCrossesPole(pts), name
+        assert not containsOrCrossesPole(U.convexHull(pts)), name + ' hull'
+        checked += 1
+    assert checked >= 5
