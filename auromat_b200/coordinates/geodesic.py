@@ -112,3 +112,48 @@ def containsOrCrossesPole(points):
     """Whether the polygon of ordered (lat, lon) points contains (sum 0) or crosses (|sum| 180)
     one of the poles (reference geodesic.py:187-202)."""
     return abs(_courseDeltaSum(points)) != 360
+
+
+def destination(location, azimuth, distance):
+    """Location reached from `location` after `distance` metres along the geodesic leaving at
+    `azimuth` degrees (reference geodesic.py:83-94; Vincenty's direct formula here)."""
+    f, a = WGS84_F, WGS84_A_M
+    b = a * (1 - f)
+    alpha1 = math.radians(azimuth)
+    sa1, ca1 = math.sin(alpha1), math.cos(alpha1)
+    tanU1 = (1 - f) * math.tan(math.radians(location.lat))
+    cU1 = 1 / math.sqrt(1 + tanU1 * tanU1)
+    sU1 = tanU1 * cU1
+    sigma1 = math.atan2(tanU1, ca1)
+    sa = cU1 * sa1
+    c2a = 1 - sa * sa
+    u2 = c2a * (a * a - b * b) / (b * b)
+    A = 1 + u2 / 16384 * (4096 + u2 * (-768 + u2 * (320 - 175 * u2)))
+    B = u2 / 1024 * (256 + u2 * (-128 + u2 * (74 - 47 * u2)))
+    sigma = distance / (b * A)
+    for _ in range(200):
+        c2sm = math.cos(2 * sigma1 + sigma)
+        ss, cs = math.sin(sigma), math.cos(sigma)
+        dsig = B * ss * (c2sm + B / 4 * (cs * (-1 + 2 * c2sm ** 2)
+                                         - B / 6 * c2sm * (-3 + 4 * ss ** 2) * (-3 + 4 * c2sm ** 2)))
+        new = distance / (b * A) + dsig
+        done = abs(new - sigma) < 1e-15
+        sigma = new
+        if done:
+            break
+    c2sm = math.cos(2 * sigma1 + sigma)
+    ss, cs = math.sin(sigma), math.cos(sigma)
+    t = sU1 * ss - cU1 * cs * ca1
+    lat2 = math.atan2(sU1 * cs + cU1 * ss * ca1, (1 - f) * math.sqrt(sa * sa + t * t))
+    lam = math.atan2(ss * sa1, cU1 * cs - sU1 * ss * ca1)
+    Cc = f / 16 * c2a * (4 + f * (4 - 3 * c2a))
+    L = lam - (1 - Cc) * f * sa * (sigma + Cc * ss * (c2sm + Cc * cs * (-1 + 2 * c2sm ** 2)))
+    lon2 = (math.radians(location.lon) + L + 3 * math.pi) % (2 * math.pi) - math.pi
+    return Location(math.degrees(lat2), math.degrees(lon2))
+
+
+def intermediate(location1, location2, f=0.5):
+    """Location after travelling the fraction `f` of the geodesic from `location1` to
+    `location2` (reference geodesic.py:96-112)."""
+    _, d, az = _inverse(location1.lat, location1.lon, location2.lat, location2.lon)
+    return destination(location1, az, d * f)

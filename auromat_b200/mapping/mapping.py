@@ -12,6 +12,7 @@ methods consume the device planes directly.
 from __future__ import annotations
 
 import copy
+import warnings
 from collections import namedtuple
 
 import numpy as np
@@ -68,6 +69,41 @@ class BoundingBox(object):
     bottomLeft = property(lambda self: Location(self.latSouth, self.lonWest))
     topRight = property(lambda self: Location(self.latNorth, self.lonEast))
     bottomRight = property(lambda self: Location(self.latSouth, self.lonEast))
+
+    @property
+    def _minSphericalRectangle(self):
+        """(center, size in km) of the smallest spherical rectangle around the box (reference
+        mapping.py:119-172; the size is only meaningful below 180 degrees of longitude)."""
+        if getattr(self, '_rect', None) is None:
+            if self.containsPole:
+                north = self.latNorth == 90
+                center = Location(90 if north else -90, 0)
+                width = geodesic.distance(center, Location(self.latSouth if north else self.latNorth, 0)) * 2
+                height = width
+            else:
+                lonWest, lonEast = self.lonWest, self.lonEast
+                if lonWest > lonEast:
+                    lonEast += 360
+                lonc = float(wrapAt180((lonWest + lonEast) / 2))
+                if lonEast - lonWest > 180:
+                    warnings.warn('The bounding box spans more than 180deg in longitude. '
+                                  'The returned size of the minimum spherical rectangle will be incorrect.')
+                width = geodesic.distance(self.bottomLeft, self.bottomRight)
+                width2 = geodesic.distance(self.topLeft, self.topRight)
+                if width2 > width:      # southern hemisphere
+                    width = width2
+                    wideCenter = geodesic.intermediate(self.bottomLeft, self.bottomRight, 0.5)
+                    dataCenter = Location(self.latNorth, lonc)
+                else:                   # northern hemisphere
+                    wideCenter = geodesic.intermediate(self.topLeft, self.topRight, 0.5)
+                    dataCenter = Location(self.latSouth, lonc)
+                height = geodesic.distance(dataCenter, wideCenter)
+                center = geodesic.intermediate(dataCenter, wideCenter, 0.5)
+            self._rect = center, Size(width / 1000, height / 1000)
+        return self._rect
+
+    center = property(lambda self: self._minSphericalRectangle[0])
+    size = property(lambda self: self._minSphericalRectangle[1])
 
     @property
     def containsDiscontinuity(self):
@@ -683,6 +719,59 @@ class _SMMapping(GenericMapping):
         mlat = np.rad2deg(np.arctan2(s[2], np.sqrt(s[0] * s[0] + s[1] * s[1])))
         mlt = transform.smLonToMLT(np.rad2deg(np.arctan2(s[1], s[0])))
         return Location(mlat, transform.mltToSmLon(mlt))
+
+
+class BaseMappingProvider(object):
+    """Base class of mapping providers (reference mapping.py:1376-1445): `range`, `contains`,
+    `get`, `getById`, `getSequence` are provided by subclasses."""
+
+    def __init__(self, maxTimeOffset):
+        self.maxTimeOffset = maxTimeOffset   # seconds
+
+    @property
+    def range(self):
+        raise NotImplementedError
+
+    def contains(self, date):
+        raise NotImplementedError
+
+    def containsAny(self, dates):
+        return any(self.contains(date) for date in dates)
+
+    def get(self, date):
+        raise NotImplementedError
+
+    def getById(self, identifier):
+        raise NotImplementedError
+
+    def getSequence(self, dateBegin=None, dateEnd=None):
+        raise NotImplementedError
+
+
+def _wrapProvider(provider, fn, name):
+    """Copy of `provider` whose get / getById / getSequence results pass through `fn`."""
+    base = type(provider)
+
+    class Wrapped(base):
+        def get(self, *a, **k):
+            return fn(super(Wrapped, self).get(*a, **k))
+
+        def getById(self, *a, **k):
+            return fn(super(Wrapped, self).getById(*a, **k))
+
+        def getSequence(self, *a, **k):
+            return map(fn, super(Wrapped, self).getSequence(*a, **k))
+
+    Wrapped.__name__ = '%s_extended_with_%s' % (base.__name__, name)
+    wrapped = copy.copy(provider)
+    wrapped.__class__ = Wrapped
+    return wrapped
+
+
+def MaskByElevationProvider(provider, *args, **kw):
+    """Wrap a mapping provider so that every returned mapping is masked by elevation
+    (reference mapping.py:1447-1472); parameters as in `BaseMapping.maskedByElevation`."""
+    return _wrapProvider(provider, lambda m: m.maskedByElevation(*args, **kw), 'MaskingProvider')
 
 
 def convertMappingToSM(mapping):

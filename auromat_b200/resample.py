@@ -273,18 +273,5 @@ def resample(mappingOrCollection, pxPerDeg=25, arcsecPerPx=None, containsPole=No
 def ResampleProvider(provider, **kw):
     """Wrap a mapping provider so that every returned mapping is resampled
     (reference resample.py:370-394)."""
-    resampleFn = partial(resample, **kw)
-
-    class ResamplingProvider(type(provider)):
-        def get(self, *a, **k):
-            return resampleFn(super(ResamplingProvider, self).get(*a, **k))
-
-        def getById(self, *a, **k):
-            return resampleFn(super(ResamplingProvider, self).getById(*a, **k))
-
-        def getSequence(self, *a, **k):
-            return map(resampleFn, super(ResamplingProvider, self).getSequence(*a, **k))
-
-    wrapped = copy.copy(provider)
-    wrapped.__class__ = ResamplingProvider
-    return wrapped
+    from .mapping.mapping import _wrapProvider
+    return _wrapProvider(provider, partial(resample, **kw), 'ResamplingProvider')

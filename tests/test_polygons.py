@@ -105,3 +105,77 @@ def test_contains_or_crosses_pole_known_answers():
     assert abs(geodesic.distance(geodesic.Location(0, 0), geodesic.Location(1, 0)) - 110574.3886) < 1e-3
     assert abs(geodesic.angularDistance(geodesic.Location(50, 10), geodesic.Location(51, 12))
                - O.vincenty_a12(50, 10, 51, 12)) < 1e-12
+
+
+def test_bounding_box_center_and_size_known_answers():
+    """test/boundingbox_test.py:12-47 (geographiclib results, 6 decimals)."""
+    import warnings
+    from numpy.testing import assert_array_almost_equal
+    from auromat_b200.mapping.mapping import BoundingBox
+    bb = BoundingBox(latSouth=-60, lonWest=80, latNorth=-30, lonEast=85)
+    assert_array_almost_equal(bb.center, [-45.03119418083877, 82.5])
+    assert_array_almost_equal(bb.size, [482.39311013217343, 3336.5953086140203])
+    bb = BoundingBox(latSouth=-60.646114098, lonWest=82.7852215499, latNorth=-38.7515567117, lonEast=-178.546517062)
+    assert_array_almost_equal(bb.center, [-54.33647117488648, 132.11935224395])
+    assert_array_almost_equal(bb.size, [8084.704893634039, 3464.8889697347718])
+    bb = BoundingBox(latSouth=60, lonWest=-180, latNorth=90, lonEast=180)
+    assert_array_almost_equal(bb.center, [90, 0])
+    assert_array_almost_equal(bb.size, [6695.78581964, 6695.78581964])
+    bb = BoundingBox(latSouth=-90, lonWest=-180, latNorth=-60, lonEast=180)
+    assert_array_almost_equal(bb.center, [-90, 0])
+    assert_array_almost_equal(bb.size, [6695.78581964, 6695.78581964])
+    bb = BoundingBox(latSouth=50, lonWest=80, latNorth=50, lonEast=80)
+    assert_array_almost_equal(bb.center, [50, 80])
+    assert_array_almost_equal(bb.size, 0)
+    bb1 = BoundingBox(latSouth=-55, lonWest=95, latNorth=-45, lonEast=109)
+    bb2 = BoundingBox(latSouth=44, lonWest=-164, latNorth=74, lonEast=-35)
+    bb = BoundingBox.mergedBoundingBoxes([bb1, bb2])
+    assert [bb.latSouth, bb.latNorth, bb.lonWest, bb.lonEast] == [bb1.latSouth, bb2.latNorth, bb1.lonWest, bb2.lonEast]
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        assert_array_almost_equal(bb.center, [21.136113246, -150])
+
+
+def test_provider_wrappers():
+    """MaskByElevationProvider / ResampleProvider (mapping.py:1447-1472, resample.py:370-394)
+    route get / getById / getSequence through the wrapped operation."""
+    from auromat_b200.mapping.mapping import BaseMappingProvider, MaskByElevationProvider
+    from auromat_b200 import resample as R
+
+    class FakeMapping(object):
+        def __init__(self, i):
+            self.i, self.masked = i, None
+
+        def maskedByElevation(self, minElevation=10):
+            m = FakeMapping(self.i)
+            m.masked = minElevation
+            return m
+
+    class Provider(BaseMappingProvider):
+        def get(self, date):
+            return FakeMapping(date)
+
+        def getById(self, identifier):
+            return FakeMapping(identifier)
+
+        def getSequence(self, dateBegin=None, dateEnd=None):
+            return (FakeMapping(i) for i in range(3))
+
+        def contains(self, date):
+            return date == 1
+
+    p = Provider(maxTimeOffset=5)
+    assert p.containsAny([0, 1]) and not p.containsAny([0, 2])
+    w = MaskByElevationProvider(p, 7)
+    assert w.get(1).masked == 7 and w.getById('x').masked == 7 and [m.masked for m in w.getSequence()] == [7, 7, 7]
+    assert w.maxTimeOffset == 5 and p.get(1).masked is None and isinstance(w, Provider)
+    calls = []
+    orig = R.resample
+    R.resample = lambda m, **kw: calls.append((m.i, kw)) or m
+    try:
+        rp = R.ResampleProvider(p, arcsecPerPx=100)
+        rp.get(4)
+        list(rp.getSequence())
+    finally:
+        R.resample = orig
+    assert calls == [(4, {'arcsecPerPx': 100}), (0, {'arcsecPerPx': 100}), (1, {'arcsecPerPx': 100}), (2, {'arcsecPerPx': 100})]
