@@ -92,6 +92,10 @@ SIGNATURES = {
     "amt_apply_center_mask": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_double,
                                         C.POINTER(AmtGeorefOut), C.c_void_p]),
     "amt_rotate_coords": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(AmtGrid), C.c_void_p]),
+    "amt_reproject": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_double), C.c_double,
+                                C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "amt_corner_means": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p]),
     "amt_polygon_center_mask": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_int32, C.POINTER(AmtGrid), C.c_void_p, C.c_void_p, C.c_void_p]),
     "amt_plate_carree_coords": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double,

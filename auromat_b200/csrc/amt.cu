@@ -1211,6 +1211,90 @@ extern "C" int amt_sm_to_latlon(amt_ctx* ctx, double* d_lat, double* d_lon, size
     return AMT_OK;
 }
 
+// ============================================ ground-based imagers: altitude reprojection
+// themis.py:224-253 `reproject`: corner coordinates calibrated for one emission height are
+// moved to another: geodetic2Ecef(lat, lon, heightRef) - station -> viewing direction ->
+// intersection with the ellipsoid inflated by heightNew -> ecef2Geodetic -> degrees.
+__global__ void __launch_bounds__(256) k_reproject(const double* __restrict__ lat_ref,
+                                                   const double* __restrict__ lon_ref, size_t n,
+                                                   const __grid_constant__ FrameC f, double e2, double h_ref,
+                                                   double* __restrict__ lat_out, double* __restrict__ lon_out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double la = lat_ref[i], lo = lon_ref[i];
+    double ol = qnan(), oo = qnan();
+    if (la == la && lo == lo) {
+        double G[3], P[3];
+        geodetic2ecef(f.a, e2, la * kDeg2Rad, lo * kDeg2Rad, h_ref, G[0], G[1], G[2]);
+        const double dir[3] = {G[0] - f.cam[0], G[1] - f.cam[1], G[2] - f.cam[2]};
+        bool graze;
+        if (intersect(f, dir, P, graze)) {
+            double l2, o2;
+            bowring(f.a, f.b_over_a, f.e2a, f.d, P[0], P[1], P[2], l2, o2);
+            ol = l2 * kRad2Deg;
+            oo = o2 * kRad2Deg;
+        }
+    }
+    lat_out[i] = ol;
+    lon_out[i] = oo;
+}
+
+extern "C" int amt_reproject(amt_ctx* ctx, const double* d_lat_ref, const double* d_lon_ref, size_t n,
+                             const double station_ecef[3], double height_ref, double height_new, double wgs_a,
+                             double wgs_b, double* d_lat_out, double* d_lon_out, void* stream) {
+    ENTER(ctx);
+    CHECK_ARG(d_lat_ref && d_lon_ref && station_ecef && d_lat_out && d_lon_out, "amt_reproject: NULL argument");
+    CHECK_ARG(wgs_a > 0 && wgs_b > 0 && wgs_a + height_new > 0 && wgs_b + height_new > 0, "amt_reproject: bad ellipsoid");
+    if (n == 0) return AMT_OK;
+    amt_frame fr;
+    memset(&fr, 0, sizeof fr);
+    fr.width = fr.height = 1;
+    const double a = wgs_a + height_new, b = wgs_b + height_new;
+    memcpy(fr.cam, station_ecef, sizeof fr.cam);
+    fr.inv_axes[0] = fr.inv_axes[1] = 1.0 / a;
+    fr.inv_axes[2] = 1.0 / b;
+    // intersection.py:239-241 _isInsideEllipsoid
+    const double q0 = station_ecef[0] / a, q1 = station_ecef[1] / a, q2 = station_ecef[2] / b;
+    fr.origin_inside = (q0 * q0 + q1 * q1 + q2 * q2) < 1.0;
+    fr.wgs_a = wgs_a;
+    fr.wgs_b = wgs_b;
+    fr.model = AMT_MODEL_WCS;
+    GeorefParams p;
+    memset(&p, 0, sizeof p);
+    int rc = fill_frame(&fr, p);
+    if (rc) return rc;
+    volatile double aa = wgs_a * wgs_a, bb = wgs_b * wgs_b;
+    volatile double num = aa - bb;
+    const double e2 = num / aa;
+    k_reproject<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_lat_ref, d_lon_ref, n, p.f, e2,
+                                                                              height_ref, d_lat_out, d_lon_out);
+    LAUNCH_CHECK(ctx);
+    return AMT_OK;
+}
+
+// themis.py:425-426 / astrometry.py:154-160: centre = mean of the four corners,
+// ((a + b) + c + d) / 4 in the reference's summation order; NaN if any corner is.
+__global__ void __launch_bounds__(256) k_corner_means(int W, int H, const double* __restrict__ lat_k,
+                                                      const double* __restrict__ lon_k,
+                                                      double* __restrict__ lat_c, double* __restrict__ lon_c) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    const size_t k = (size_t)y * (W + 1) + x, i = (size_t)y * W + x;
+    // lats[:-1,:-1] + lats[1:,:-1] + lats[:-1,1:] + lats[1:,1:]
+    lat_c[i] = (((lat_k[k] + lat_k[k + W + 1]) + lat_k[k + 1]) + lat_k[k + W + 2]) / 4.0;
+    lon_c[i] = (((lon_k[k] + lon_k[k + W + 1]) + lon_k[k + 1]) + lon_k[k + W + 2]) / 4.0;
+}
+
+extern "C" int amt_corner_means(amt_ctx* ctx, int32_t W, int32_t H, const double* d_lat_k, const double* d_lon_k,
+                                double* d_lat_c, double* d_lon_c, void* stream) {
+    ENTER(ctx);
+    CHECK_ARG(W > 0 && H > 0 && d_lat_k && d_lon_k && d_lat_c && d_lon_c, "amt_corner_means: bad arguments");
+    dim3 grid((W + 255) / 256, H);
+    k_corner_means<<<grid, 256, 0, (cudaStream_t)stream>>>(W, H, d_lat_k, d_lon_k, d_lat_c, d_lon_c);
+    LAUNCH_CHECK(ctx);
+    return AMT_OK;
+}
+
 // ================================================================== stage 3: binning
 // Flat cell (row 0 = northernmost) of a centre coordinate, or -1.
 template <bool NEAR>

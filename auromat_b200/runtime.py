@@ -167,6 +167,24 @@ class Context:
         _lib.check(self.lib.amt_rotate_coords(self.handle, self.ptr(lat), self.ptr(lon), lat.numel(),
                                               C.byref(pre), self.stream()))
 
+    def reproject(self, lat_ref, lon_ref, station_ecef, height_ref, height_new, wgs_a, wgs_b):
+        """`amt_reproject` on device tensors; returns new (lat, lon) tensors of the same shape."""
+        torch = _torch()
+        lat_out, lon_out = torch.empty_like(lat_ref), torch.empty_like(lon_ref)
+        ecef = (C.c_double * 3)(*[float(v) for v in station_ecef])
+        _lib.check(self.lib.amt_reproject(self.handle, self.ptr(lat_ref), self.ptr(lon_ref), lat_ref.numel(), ecef,
+                                          float(height_ref), float(height_new), float(wgs_a), float(wgs_b),
+                                          self.ptr(lat_out), self.ptr(lon_out), self.stream()))
+        return lat_out, lon_out
+
+    def corner_means(self, width, height, lat_k, lon_k):
+        torch = _torch()
+        lat_c = torch.empty(width * height, dtype=torch.float64, device=self.torch_device)
+        lon_c = torch.empty_like(lat_c)
+        _lib.check(self.lib.amt_corner_means(self.handle, width, height, self.ptr(lat_k), self.ptr(lon_k),
+                                             self.ptr(lat_c), self.ptr(lon_c), self.stream()))
+        return lat_c, lon_c
+
     def polygon_center_mask(self, width, height, lat_k, lon_k, polygon, pre: "_lib.AmtGrid | None" = None):
         """(centre mask u8 (h*w), #corners inside) of `amt_polygon_center_mask`; `polygon` is a
         device tensor (n,2) of (lat, lon), already rotated like `pre` rotates the corners."""

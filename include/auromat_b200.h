@@ -225,6 +225,21 @@ int amt_apply_center_mask(amt_ctx* ctx, int32_t width, int32_t height, const uin
 int amt_rotate_coords(amt_ctx* ctx, double* d_lat, double* d_lon, size_t n, const amt_grid* pre,
                       void* stream);
 
+/* Altitude reprojection of a ground-based imager's calibrated corner coordinates
+ * (mapping/themis.py:224-253 `reproject`): every (lat, lon) [deg] valid for emission height
+ * `height_ref` [km] is turned into the viewing direction from the station (ECEF position
+ * `station_ecef` [km], = geodetic2EcefZero of the station) and intersected with the WGS84
+ * ellipsoid inflated by `height_new`; result in degrees, NaN for NaN input or a missed ray.   */
+int amt_reproject(amt_ctx* ctx, const double* d_lat_ref, const double* d_lon_ref, size_t n,
+                  const double station_ecef[3], double height_ref, double height_new, double wgs_a,
+                  double wgs_b, double* d_lat_out, double* d_lon_out, void* stream);
+
+/* Centre coordinates as the mean of the four surrounding corners (mapping/themis.py:425-426,
+ * same summation order; mapping/astrometry.py:154-160): corner planes (height+1)x(width+1) ->
+ * centre planes height x width.                                                              */
+int amt_corner_means(amt_ctx* ctx, int32_t width, int32_t height, const double* d_lat_k,
+                     const double* d_lon_k, double* d_lat_c, double* d_lon_c, void* stream);
+
 /* maskedByPolygon (mapping/mapping.py:866-917) with the inside test of utils.py:58-74
  * (matplotlib `Path.contains_points` in the reference; here the crossing-number test with
  * half-open edges, x = latitude, y = longitude): d_center_mask[y*width+x] = 0 if the four corners

@@ -106,6 +106,20 @@ def allsky_golden(ref):
                         cal=np.array([cal.lat, cal.lon, cal.xc, cal.yc, cal.k, cal.rotation]), **g)
 
 
+def themis_golden(ref):
+    """mapping/themis.py:224-253 `reproject` (run unmodified) on the SOD golden's corner
+    coordinates: 110 km -> 90 km and 150 km, as a THEMIS L2 calibration would hold them."""
+    g = np.load(os.path.join(OUT, "allsky_SOD_96.npz"))
+    asi = (float(g['cal'][0]), float(g['cal'][1]))
+    lats, lons = g['lats'][::3, ::3], g['lons'][::3, ::3]
+    out = dict(asi=np.array(asi), lats110=lats, lons110=lons)
+    for hNew in (90.0, 150.0):
+        with quiet():
+            la, lo = ref.themis.reproject(asi, lats, lons, 110.0, hNew)
+        out['lats%d' % hNew], out['lons%d' % hNew] = la, lo
+    np.savez_compressed(os.path.join(OUT, "themis_reproject.npz"), **out)
+
+
 def main():
     ref = ref_shim.load_reference()
     os.makedirs(OUT, exist_ok=True)
@@ -159,6 +173,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "histogram2d.npz"), x=x, y=y, w=w1, count=hs[0], wsum=hs[1],
                         bins=np.array([49, 80]), range=np.array([[0.3, 10.1], [41.0, 60.0]]))
     allsky_golden(ref)
+    themis_golden(ref)
     print("golden vectors written to", OUT)
 
 

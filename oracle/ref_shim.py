@@ -224,6 +224,9 @@ def _install_shims():
     _mod("geographiclib.geodesic", Geodesic=_Geod)
 
     # skimage / matplotlib / exifread stubs
+    # spacepy.pycdf (CDF reader of the THEMIS provider; only the array functions are exercised)
+    sp = _mod("spacepy")
+    sp.pycdf = _mod("spacepy.pycdf")
     sk = _mod("skimage")
     sk.measure = _mod("skimage.measure")
     sk.io = _mod("skimage.io")
@@ -282,11 +285,16 @@ def load_reference():
     auromat.mapping.mapping = mapping
     import auromat.mapping.astrometry as astrometry
     import auromat.resample as resample
+    try:
+        import auromat.mapping.themis as themis
+    except Exception as exc:             # the array functions are optional for the other pins
+        themis = None
+        print("reference themis module not importable:", exc)
 
     ns = types.SimpleNamespace(
         igrf=igrf, transformations=transformations, geodesic=geodesic, transform=transform,
         intersection=intersection, wcs=wcs, mapping=mapping, astrometry=astrometry,
-        resample=resample, histogram=hist,
+        resample=resample, histogram=hist, themis=themis,
     )
     _loaded = ns
     return ns

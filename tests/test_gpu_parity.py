@@ -878,3 +878,64 @@ def test_masked_by_polygon_vs_oracle(env, case):
         r2 = m.maskedByPolygon(big)
         o2, _ = O.polygon_center_mask(lats, lons, big)
         assert np.array_equal(ma.getmaskarray(r2.latsCenter), o2 | ma.getmaskarray(m.latsCenter))
+
+
+def test_themis_reproject_and_mapping(env):
+    """Ground-based THEMIS route (mapping/themis.py): altitude reprojection kernel against the
+    reference's golden and the oracle; `mappingFromCalibration` (reproject -> corner means ->
+    -2500 offset -> sanitise -> elevation mask) against the oracle chain; mosaic-ready."""
+    import datetime
+    import oracle.auromat_oracle as O
+    from auromat_b200.mapping import themis
+    from auromat_b200.resample import resample
+    g = np.load(os.path.join(GOLDEN, "themis_reproject.npz"))
+    asi = tuple(float(v) for v in g['asi'])
+    for h in (90, 150):
+        la, lo = themis.reproject(asi, g['lats110'], g['lons110'], 110.0, float(h))
+        assert np.array_equal(np.isnan(la), np.isnan(g['lats%d' % h]))
+        assert np.nanmax(np.abs(la - g['lats%d' % h])) <= TOL_DEG
+        assert np.nanmax(np.abs(lo - g['lons%d' % h])) <= TOL_DEG
+    # a synthetic L2 calibration: fisheye station model evaluated at three reference heights
+    w = 64
+    cal = dict(xc=w / 2.0, yc=w / 2.0, k=w * 155.81 / 512 * 2, rotation=0.1)
+    heights = np.array([90.0, 110.0, 150.0])
+    ref = [O.allsky_georeference(w, cal['xc'], cal['yc'], cal['k'], cal['rotation'], asi[0], asi[1], altitude=h)
+           for h in heights]
+    latsRef = np.array([r['lats'] for r in ref])
+    lonsRef = np.array([r['lons'] for r in ref])
+    el = ref[0]['elevation'].copy()
+    el[np.isnan(ref[0]['latsCenter'])] = np.nan
+    img = np.random.default_rng(4).integers(2500, 40000, (w, w), dtype=np.uint16)
+    t = datetime.datetime(2012, 2, 4, 7, 56, 26)
+    for alt in (110, 120):
+        m = themis.mappingFromCalibration('atha', asi, el, latsRef, lonsRef, heights, img, t, altitude=alt)
+        assert m.identifier == 'atha.2012.02.04.07.56.26' and m.altitude == alt
+        if alt == 110:
+            olat, olon = latsRef[1], lonsRef[1]
+        else:
+            olat, olon = O.themis_reproject(asi, latsRef[0], lonsRef[0], 90.0, 120.0)
+            # the same rays georeferenced directly at 120 km: equal up to the error of the reference's
+            # single-iteration Bowring inverse at these heights (~1e-6 deg in latitude)
+            direct = O.allsky_georeference(w, cal['xc'], cal['yc'], cal['k'], cal['rotation'], asi[0], asi[1], altitude=120)
+            assert np.nanmax(np.abs(olat - direct['lats'])) < 2e-5 and np.nanmax(np.abs(olon - direct['lons'])) < 2e-5
+        oc_lat, oc_lon = O.themis_corner_means(olat, olon)
+        mk, mc = O.sanitize_masks(np.isnan(olat), np.isnan(oc_lat))
+        with np.errstate(invalid='ignore'):
+            mc2 = mc | ~(el >= 1)
+        mk2, mc2 = O.sanitize_masks(mk, mc2, after_masking=True)
+        assert np.array_equal(ma.getmaskarray(m.latsCenter), mc2)
+        assert np.array_equal(ma.getmaskarray(m.lats), mk2)
+        ok = ~mk2
+        assert np.abs(m.lats.data[ok] - olat[ok]).max() <= TOL_DEG and np.abs(m.lons.data[ok] - olon[ok]).max() <= TOL_DEG
+        okc = ~mc2
+        assert np.abs(m.latsCenter.data[okc] - oc_lat[okc]).max() <= TOL_DEG
+        assert np.abs(m.lonsCenter.data[okc] - oc_lon[okc]).max() <= TOL_DEG
+        assert np.array_equal(m.img_unmasked[:, :, 0], img - np.uint16(2500))
+        m.checkGuarantees()
+        assert m.rgb.shape == (w, w, 3) and m.rgb.dtype == np.uint8
+        r = resample(m, pxPerDeg=8)
+        assert isinstance(r, themis.ThemisMapping) and r.station == 'atha'
+        r.checkGuarantees()
+        r.checkPlateCarree()
+    coll = themis.mappingCollection([m, None], t)
+    assert len(coll.mappings) == 1 and coll.identifier == 'THEMIS.2012.02.04.07.56.26'

@@ -157,3 +157,18 @@ def test_allsky_matches_reference_golden():
     for name in ('lats', 'lons', 'latsCenter', 'lonsCenter', 'elevation'):
         assert np.array_equal(np.isnan(o[name]), np.isnan(g[name]))
         assert np.nanmax(np.abs(o[name] - g[name])) <= TOL_DEG, name
+
+
+def test_themis_reproject_matches_reference_golden():
+    """mapping/themis.py:224-253 run by the reference (oracle/gen_golden.py::themis_golden)."""
+    g = np.load(os.path.join(GOLDEN, "themis_reproject.npz"))
+    asi = tuple(g['asi'])
+    for h in (90, 150):
+        la, lo = O.themis_reproject(asi, g['lats110'], g['lons110'], 110.0, float(h))
+        assert_array_equal(np.isnan(la), np.isnan(g['lats%d' % h]))
+        assert np.nanmax(np.abs(la - g['lats%d' % h])) <= TOL_DEG
+        assert np.nanmax(np.abs(lo - g['lons%d' % h])) <= TOL_DEG
+    # reprojecting to the calibration's own height is the identity up to the error of the
+    # single-iteration Bowring inverse at 110 km height (a few 1e-6 deg, inherent to the reference)
+    la, lo = O.themis_reproject(asi, g['lats110'], g['lons110'], 110.0, 110.0)
+    assert np.nanmax(np.abs(la - g['lats110'])) < 2e-5 and np.nanmax(np.abs(lo - g['lons110'])) < 2e-5

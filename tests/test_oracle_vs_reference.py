@@ -185,3 +185,24 @@ def test_pole_test_on_the_reference_regression_outlines():
         assert not containsOrCrossesPole(U.convexHull(pts)), name + ' hull'
         checked += 1
     assert checked >= 5
+
+
+def test_themis_reproject_bit_for_bit(ref):
+    if ref.themis is None:
+        pytest.skip("reference themis module not importable")
+    rng = np.random.default_rng(0)
+    asi = (62.4, -114.5)
+    lat = asi[0] + rng.uniform(-4, 4, (40, 41))
+    lon = asi[1] + rng.uniform(-8, 8, (40, 41))
+    lat[0, 0] = lon[0, 0] = np.nan
+    for hRef, hNew in ((90.0, 110.0), (150.0, 110.0), (110.0, 0.0)):
+        with quiet():
+            r = ref.themis.reproject(asi, lat, lon, hRef, hNew)
+        o = O.themis_reproject(asi, lat, lon, hRef, hNew)
+        assert bit_equal(r[0], o[0]) and bit_equal(r[1], o[1])
+    with quiet():
+        cam = ref.transform.latLonToJ2000(asi[0], asi[1], 0, datetime.datetime(2012, 2, 4, 7, 56, 26))
+    from auromat_b200.coordinates import transform as T
+    from auromat_b200.mapping.allsky import stationEcef
+    mine = T.mat_j2000_to_geo(T.date2es(datetime.datetime(2012, 2, 4, 7, 56, 26))).T.dot(stationEcef(*asi))
+    np.testing.assert_allclose(mine, np.ravel(cam), rtol=0, atol=1e-9)
