@@ -12,6 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libauromat_b200.so")
 
+ABI_VERSION = 2          # AMT_ABI_VERSION of include/auromat_b200.h
 AMT_OK, AMT_ERR_INVALID_ARGUMENT, AMT_ERR_UNSUPPORTED, AMT_ERR_CUDA, AMT_ERR_NO_DEVICE = range(5)
 AMT_SIP_MAX_ORDER = 9
 AMT_SIP_MAX_COEF = 55
@@ -52,6 +53,7 @@ class AmtStats(C.Structure):
         ("n_valid_corners", C.c_uint64), ("n_boundary_corners", C.c_uint64),
         ("n_valid_centers", C.c_uint64), ("n_ill_conditioned", C.c_uint64),
         ("pole_flags", C.c_uint64),
+        ("row_min_c", C.c_int32), ("row_max_c", C.c_int32), ("col_min_c", C.c_int32), ("col_max_c", C.c_int32),
     ]
 
 
@@ -140,7 +142,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the ABI lost a symbol
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.amt_abi_version() != 1:
+    if lib.amt_abi_version() != ABI_VERSION:
         raise ImportError("auromat_b200: ABI version mismatch")
     _lib = lib
     return lib

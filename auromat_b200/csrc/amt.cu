@@ -595,6 +595,7 @@ struct StatKeys {
     unsigned long long n_valid_k, n_boundary, n_valid_c;
     unsigned int pole_flags;
     unsigned int blocks_done;
+    unsigned int row_min, row_max, col_min, col_max;    // pixel box of the valid centres
 };
 
 __device__ __forceinline__ void stats_reset(StatKeys* s) {
@@ -603,6 +604,8 @@ __device__ __forceinline__ void stats_reset(StatKeys* s) {
     s->n_valid_k = s->n_boundary = s->n_valid_c = 0ULL;
     s->pole_flags = 0u;
     s->blocks_done = 0u;
+    s->row_min = s->col_min = 0xffffffffu;
+    s->row_max = s->col_max = 0u;
 }
 
 __global__ void k_stats_init(StatKeys* s) { stats_reset(s); }
@@ -623,6 +626,12 @@ __device__ __forceinline__ void stats_finish(StatKeys* s, amt_stats* out) {
     out->n_boundary_corners = v->n_boundary;
     out->n_valid_centers = v->n_valid_c;
     out->pole_flags = v->pole_flags;
+    const unsigned r0 = v->row_min, r1 = v->row_max, c0 = v->col_min, c1 = v->col_max;
+    const bool any = r0 != 0xffffffffu;
+    out->row_min_c = any ? (int)r0 : 0;
+    out->row_max_c = any ? (int)r1 : -1;
+    out->col_min_c = any ? (int)c0 : 0;
+    out->col_max_c = any ? (int)c1 : -1;
     stats_reset(s);
 }
 
@@ -763,7 +772,22 @@ __global__ void __launch_bounds__(256) k_stats_bits(int W, int H, Bits K, Bits C
         }
     }
     const int nwc = C.wpr * H;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nwc; t += gridDim.x * blockDim.x) nvc += __popc(C.w[t]);
+    unsigned r_lo = 0xffffffffu, r_hi = 0u, c_lo = 0xffffffffu, c_hi = 0u;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nwc; t += gridDim.x * blockDim.x) {
+        const unsigned v = C.w[t];
+        if (!v) continue;
+        nvc += __popc(v);
+        const unsigned y = t / C.wpr, i = t - y * C.wpr;
+        r_lo = min(r_lo, y); r_hi = max(r_hi, y);
+        c_lo = min(c_lo, 32u * i + (unsigned)(__ffs(v) - 1));
+        c_hi = max(c_hi, 32u * i + (unsigned)(31 - __clz(v)));
+    }
+    r_lo = __reduce_min_sync(0xffffffffu, r_lo); r_hi = __reduce_max_sync(0xffffffffu, r_hi);
+    c_lo = __reduce_min_sync(0xffffffffu, c_lo); c_hi = __reduce_max_sync(0xffffffffu, c_hi);
+    if ((threadIdx.x & 31) == 0 && r_lo != 0xffffffffu) {
+        atomicMin(&s->row_min, r_lo); atomicMax(&s->row_max, r_hi);
+        atomicMin(&s->col_min, c_lo); atomicMax(&s->col_max, c_hi);
+    }
 
     __shared__ unsigned long long sh[6][8];
     __shared__ unsigned shc[3][8];

@@ -110,7 +110,7 @@ class ResampledFrame(object):
 
 def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, altitude=110,
                      fastCenterCalculation=False, magnetic=False, metadatas=None, depth=2, toHost=True,
-                     device=None, ringBuffers=False, coordinates=True):
+                     device=None, ringBuffers=False, coordinates=True, sparseUpload=True, transferStats=None):
     """Generator of `ResampledFrame` for an image sequence (frames in order).
 
     :param imagesOrArrays: iterable of (h,w,n) uint8/uint16 arrays (ideally pinned), device
@@ -123,6 +123,11 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
         coordinate planes are never written (hit bitmaps -> outline statistics -> fused
         georeference+binning kernel); `frame.mapping` computes them lazily if asked.  Ignored
         (treated as True) with fastCenterCalculation or magnetic=True.
+    :param sparseUpload: host images are copied to the device only after the frame has been
+        georeferenced, and only the row range that holds georeferenced pixels (for an ISS limb
+        frame ~60 % of the image): pixels that see no Earth never influence the result.
+        `frame.mapping.img` still is the complete host image.
+    :param transferStats: optional dict that receives `h2d_bytes` (image bytes actually copied)
     :param ringBuffers: keep the coordinate planes of the frames in a fixed ring of depth+3 plane
         sets (0.9 GB each for a 12-Mpix frame) instead of allocating per frame: constant memory
         footprint for arbitrarily long sequences, but `frame.mapping`'s planes are only valid
@@ -141,16 +146,25 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
     pool = ctx.__dict__.setdefault('_pinned_frames', {})
     imgRing = ctx.__dict__.setdefault('_image_ring', [])
     metadatas = metadatas if metadatas else None
+    stats = transferStats if transferStats is not None else {}
+    stats.setdefault('h2d_bytes', 0)
+    trace = stats.get('trace')          # optional list: (tag, frame, timing event) per pipeline phase
 
-    def upload(i, img):
-        """Host array -> device on the copy stream; returns (tensor, event) or (img, None)."""
-        if isinstance(img, str) or hasattr(img, 'data_ptr'):
-            return img, None
+    def mark(tag, i, stream):
+        if trace is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream)
+            trace.append((tag, i, ev))
+
+    def hostTensor(img):
         src = np.ascontiguousarray(img)
-        if src.dtype == np.uint16:
-            t = torch.from_numpy(src.view(np.int16))
-        else:
-            t = torch.from_numpy(src)
+        return torch.from_numpy(src.view(np.int16) if src.dtype == np.uint16 else src), src.dtype
+
+    def upload(i, img, rows=None):
+        """Host array -> device on the copy stream; returns (tensor, event).  `rows` = (first,
+        last) restricts the copy to that row range: rows without a single georeferenced pixel
+        are never read by the binning kernel."""
+        t, dtype = hostTensor(img)
         with torch.cuda.stream(copy):
             if ringBuffers:
                 if len(imgRing) != ringLen or imgRing[0].shape != t.shape or imgRing[0].dtype != t.dtype:
@@ -163,13 +177,26 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
                     copy.wait_event(prev)       # the frame that used this ring slot has been binned
                 else:
                     copy.wait_stream(main)
-                d.copy_(t, non_blocking=True)
             else:
-                d = t.to(ctx.torch_device, non_blocking=True)
+                d = torch.empty(t.shape, dtype=t.dtype, device=ctx.torch_device)
                 d.record_stream(main)
+                if second is not None:
+                    d.record_stream(second)
+            mark('H0', i, copy)
+            if rows is None:
+                d.copy_(t, non_blocking=True)
+                nbytes = t.numel() * t.element_size()
+            else:
+                r0, r1 = rows
+                nbytes = 0
+                if r1 >= r0:
+                    d[r0:r1 + 1].copy_(t[r0:r1 + 1], non_blocking=True)
+                    nbytes = (r1 - r0 + 1) * t[0].numel() * t.element_size()
             ev = torch.cuda.Event()
             ev.record(copy)
-        if src.dtype == np.uint16:
+            mark('H1', i, copy)
+        stats['h2d_bytes'] += nbytes
+        if dtype == np.uint16:
             d = d.view(torch.uint16)
         return d, ev
 
@@ -200,10 +227,20 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
         return ring[i % len(ring)]
 
     def runA(i, img, hdr):
-        dimg, ev = upload(i, img)
+        # Georeferencing needs the header only.  A host image is uploaded in stage B, once the
+        # statistics of the frame tell which rows hold georeferenced pixels (`sparseUpload`), or
+        # right away on the copy stream.
+        ev = None
+        late = sparseUpload and isinstance(img, np.ndarray)
+        if isinstance(img, np.ndarray) and not late:
+            dimg, ev = upload(i, img)
+        else:
+            dimg = img
         meta = metadatas[i] if metadatas else None
         m = getMapping(dimg, hdr, altitude=altitude, fastCenterCalculation=fastCenterCalculation, metadata=meta,
                        identifier=None if isinstance(hdr, str) else 'frame%06d' % i, device=ctx.device)
+        if late:
+            m._lateImage = img
         if not coordinates and not magnetic and not fastCenterCalculation:
             m.setPlaneFree(True)
             m._startStats()
@@ -213,11 +250,26 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
             if prev is not None:
                 main.wait_event(prev)           # ring slot free: its previous frame has been binned
             m._planeBuffers = ringSet(i, m)
+        mark('A0', i, main)
         m.prefetch(magnetic=magnetic)
         m._startStats()
+        mark('A1', i, main)
         return m, ev, i
 
+    def lateUpload(m, i):
+        """Stage B of a frame whose host image has not been uploaded yet: copy the rows that hold
+        at least one valid pixel (known from the outline statistics, already on the host)."""
+        img = m.__dict__.pop('_lateImage', None)
+        if img is None:
+            return None
+        st = m._deviceStats()
+        dimg, ev = upload(i, img, rows=(st.row_min_c, st.row_max_c))
+        m._imgDevice = dimg if dimg.dim() == 3 else dimg[..., None]
+        return ev
+
     def runB(m, ev, i=0):
+        late = lateUpload(m, i)
+        ev = late if late is not None else ev
         if second is None:
             if ev is not None:
                 main.wait_event(ev)
@@ -234,10 +286,13 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
             second.wait_event(evA)
             if ev is not None:
                 second.wait_event(ev)
+            mark('B0', i, second)
             grid, info, dImg, dMask, dElev = resampleToDevice(m, pxPerDeg=pxPerDeg, arcsecPerPx=arcsecPerPx)
             f = ResampledFrame(m, grid, info, dImg, dMask, dElev)
+            mark('B1', i, second)
             if toHost:
                 f._startDownload(ctx, pool)
+            mark('D1', i, second)
             done = torch.cuda.Event()
             done.record(second)
             ctx.pin_stream(False)

@@ -240,12 +240,16 @@ def run_b200(args, rank, local_rank, world):
 
     # `e2e`: same call with HOST buffers: pinned image in (H2D every frame), resampled image, mask and
     # elevation out (D2H every frame into pinned buffers)
+    transfer = {}
+
     def run_e2e(hdrs):
         last = None
+        transfer.clear()
         for f in resampleSequence([img_host.numpy()] * len(hdrs), hdrs, arcsecPerPx=ARCSEC_PER_PX, magnetic=True,
                                   fastCenterCalculation=args.fast_center, toHost=True, device=local_rank,
-                                  ringBuffers=True):
+                                  ringBuffers=True, transferStats=transfer):
             last = f
+        transfer['frames'] = len(hdrs)
         return last.img, last.elevation, last
 
     def barrier():
@@ -259,11 +263,18 @@ def run_b200(args, rank, local_rank, world):
         launches0 = ctx.launch_count
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t_host = time.perf_counter()
         out = fn(headers[args.warmup:args.warmup + args.steps])
+        t_host = time.perf_counter() - t_host
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
         launches = ctx.launch_count - launches0
+        if os.environ.get("AMT_BENCH_RANKLOG"):
+            # per-rank diagnostics (stderr): device time of this rank and the wall time its host loop needed
+            sys.stderr.write("[rank %d] %s: device %.4f ms/step, host loop %.4f ms/step, cpus %d\n" % (
+                rank, getattr(fn, "__name__", "variant"), ms / args.steps, t_host * 1e3 / args.steps,
+                len(os.sched_getaffinity(0))))
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=ctx.torch_device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -300,7 +311,10 @@ def run_b200(args, rank, local_rank, world):
             "fast_center": {"value": args.steps * npx / (ms_fc * 1e-3) / 1e6, "unit": UNIT,
                             "ms_per_step": ms_fc / args.steps, "note": "fastCenterCalculation=True, all 9 planes"},
         }
-    h2d = int(img_host.numel() * img_host.element_size())
+    # image bytes actually copied per frame: only the row range that holds georeferenced pixels is
+    # uploaded (pipeline.resampleSequence(sparseUpload=True)); the complete frame would be h2d_full
+    h2d_full = int(img_host.numel() * img_host.element_size())
+    h2d = int(transfer['h2d_bytes'] // max(1, transfer['frames']))
 
     # dominant kernel alone: the fused georeference kernel (all 9 planes)
     m = getMapping(img_dev, headers[0], fastCenterCalculation=args.fast_center, identifier="roofline")
@@ -335,6 +349,7 @@ def run_b200(args, rank, local_rank, world):
         "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
         "frames_per_s": args.steps * world / (ms_dev * 1e-3),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "h2d_bytes_full_frame": h2d_full,
                 "ms_per_step": ms_e2e / args.steps, "frames_per_s": args.steps * world / (ms_e2e * 1e-3)},
         "gpu_launches": int(launches),
         "variants": variants,

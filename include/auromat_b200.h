@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define AMT_ABI_VERSION 1
+#define AMT_ABI_VERSION 2
 
 typedef enum amt_status {
     AMT_OK = 0,
@@ -124,6 +124,9 @@ typedef struct amt_stats {
     uint64_t pole_flags;             /* bit0: a valid pixel quad encloses the north pole,
                                         bit1: the south pole (replaces the outline/azimuth
                                         test of mapping.py:705-718, geodesic.py:183-202)   */
+    int32_t row_min_c, row_max_c;    /* pixel box of the valid centres (rows / columns that  */
+    int32_t col_min_c, col_max_c;    /* hold at least one defined pixel); max < min if none:
+                                        only these image rows are ever read by the binning   */
 } amt_stats;
 
 /* Plate-carree target grid as seen by the binning kernel.  The wrapper derives these on the

@@ -38,6 +38,9 @@ def test_b200_arm_json_line():
     assert d["gpu_launches"] >= 4 * 5
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
-    assert d["e2e"]["h2d_bytes_per_step"] == 1064 * 708 * 3 and d["e2e"]["d2h_bytes_per_step"] > 0
+    # only the image rows that hold georeferenced pixels are uploaded (pipeline sparseUpload)
+    full = 1064 * 708 * 3
+    assert d["e2e"]["h2d_bytes_full_frame"] == full and 0.4 * full < d["e2e"]["h2d_bytes_per_step"] < 0.8 * full
+    assert d["e2e"]["h2d_bytes_per_step"] % (1064 * 3) == 0 and d["e2e"]["d2h_bytes_per_step"] > 0
     assert d["cpu_baseline"]["cores"] == 1 and d["cpu_baseline"]["value"] > 0
     assert d["value"] > 100 * d["cpu_baseline"]["value"]

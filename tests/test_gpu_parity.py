@@ -598,11 +598,22 @@ def test_pipelined_sequence_equals_frame_by_frame(env):
     for dtype in (np.uint8, np.uint16):
         imgs = [synthetic.issImage(W, H, seed=40 + i, dtype=dtype) for i in range(n)]
         expect = [resample(getMapping(im, h, identifier='x'), arcsecPerPx=400) for im, h in zip(imgs, hdrs)]
-        for source in ('host', 'device', 'host-ring', 'device-ring'):
+        for source in ('host', 'device', 'host-ring', 'device-ring', 'host-full', 'host-ring-full'):
             src = imgs if source.startswith('host') else [env.to_device(im) for im in imgs]
             # ring mode = fixed plane ring + two-stream overlap; few frames, so all stay valid
-            got = list(resampleSequence(src, hdrs, arcsecPerPx=400, magnetic=True, ringBuffers='ring' in source))
+            tr = {}
+            got = list(resampleSequence(src, hdrs, arcsecPerPx=400, magnetic=True, ringBuffers='ring' in source,
+                                        sparseUpload='full' not in source, transferStats=tr))
             assert len(got) == n
+            full = sum(im.nbytes for im in imgs)
+            if source.startswith('host'):
+                # rows without a georeferenced pixel (above the limb, ~40 %) are not uploaded
+                rows = sum(int(f.mapping._deviceStats().row_max_c - f.mapping._deviceStats().row_min_c + 1) for f in got)
+                assert tr['h2d_bytes'] == (full if 'full' in source else rows * imgs[0][0].nbytes)
+                assert 'full' in source or 0.4 * full < tr['h2d_bytes'] < 0.8 * full
+                assert np.array_equal(got[0].mapping.img_unmasked, imgs[0])     # the mapping keeps the complete host image
+            else:
+                assert tr['h2d_bytes'] == 0
             for f, e in zip(got, expect):
                 assert np.array_equal(ma.getmaskarray(f.img), ma.getmaskarray(e.img))
                 assert np.array_equal(f.img.filled(0), e.img.filled(0))
