@@ -260,7 +260,9 @@ __device__ __forceinline__ void count_grazing(unsigned long long* counter, bool 
 // exactly one word each of the row-padded validity bitmaps.
 // Rays that miss the ellipsoid (reference: NaN rows that propagate through every later pass)
 // cost only the direction + discriminant: a warp whose rays all miss leaves right there.
-template <bool WANT_K, bool WANT_C>
+// FULL: all nine planes and both bitmaps are requested (the sequence pipeline with MLat/MLT): no
+// null-pointer tests, 32-bit indices.
+template <bool WANT_K, bool WANT_C, bool FULL>
 #ifndef AMT_GEOREF_MINBLOCKS
 #define AMT_GEOREF_MINBLOCKS 4
 #endif
@@ -302,12 +304,22 @@ __global__ void __launch_bounds__(256, AMT_GEOREF_MINBLOCKS) k_georef_points(con
     const unsigned mk = __ballot_sync(0xffffffffu, hit_k), mc = __ballot_sync(0xffffffffu, hit_c);
     if (lane == 0) {
         const int wk = (W + 1 + 31) >> 5, wc = (W + 31) >> 5;
-        if (WANT_K && p.o.d_valid_k && (x >> 5) < wk) p.o.d_valid_k[(size_t)y * wk + (x >> 5)] = mk;
-        if (WANT_C && p.o.d_valid_c && y < H && (x >> 5) < wc) p.o.d_valid_c[(size_t)y * wc + (x >> 5)] = mc;
+        const unsigned xw = (unsigned)x >> 5;
+        if (WANT_K && (FULL || p.o.d_valid_k) && xw < (unsigned)wk) p.o.d_valid_k[(unsigned)y * wk + xw] = mk;
+        if (WANT_C && (FULL || p.o.d_valid_c) && y < H && xw < (unsigned)wc) p.o.d_valid_c[(unsigned)y * wc + xw] = mc;
     }
     count_grazing(p.ill, graze_k | graze_c, lane);
-    const size_t ik = (size_t)y * (W + 1) + x, ic = (size_t)y * W + x;
+    // fill_frame guarantees (W+1)*(H+1) < 2^31: 32-bit flat indices
+    const unsigned ik = (unsigned)y * (unsigned)(W + 1) + (unsigned)x, ic = (unsigned)y * (unsigned)W + (unsigned)x;
     if ((mk | mc) == 0) {                    // the whole warp looks at space
+        if (FULL) {
+            if (in_k) { p.o.d_lat_k[ik] = nan; p.o.d_lon_k[ik] = nan; p.o.d_mlat_k[ik] = nan; p.o.d_mlt_k[ik] = nan; }
+            if (in_c) {
+                p.o.d_lat_c[ic] = nan; p.o.d_lon_c[ic] = nan; p.o.d_mlat_c[ic] = nan; p.o.d_mlt_c[ic] = nan;
+                p.o.d_elev_c[ic] = nan;
+            }
+            return;
+        }
         if (in_k) emit_nan(ik, p.o.d_lat_k, p.o.d_lon_k, p.o.d_mlat_k, p.o.d_mlt_k);
         if (in_c) {
             emit_nan(ic, p.o.d_lat_c, p.o.d_lon_c, p.o.d_mlat_c, p.o.d_mlt_c);
@@ -319,19 +331,19 @@ __global__ void __launch_bounds__(256, AMT_GEOREF_MINBLOCKS) k_georef_points(con
     // arithmetic, exactly like the reference's NaN rows); only the stores are predicated.
     if (!hit_k) Pk[0] = Pk[1] = Pk[2] = nan;
     if (!hit_c) Pc[0] = Pc[1] = Pc[2] = nan;
-    const bool geo = p.o.d_lat_k || p.o.d_lon_k || p.o.d_lat_c || p.o.d_lon_c;
-    const bool mag = p.o.d_mlat_k || p.o.d_mlt_k || p.o.d_mlat_c || p.o.d_mlt_c;
+    const bool geo = FULL || p.o.d_lat_k || p.o.d_lon_k || p.o.d_lat_c || p.o.d_lon_c;
+    const bool mag = FULL || p.o.d_mlat_k || p.o.d_mlt_k || p.o.d_mlat_c || p.o.d_mlt_c;
     if (geo) {
         double la_k, lo_k, la_c, lo_c;
         if (WANT_K) point_to_geo(p.f, Pk, la_k, lo_k);
         if (WANT_C) point_to_geo(p.f, Pc, la_c, lo_c);
         if (WANT_K && in_k) {
-            if (p.o.d_lat_k) p.o.d_lat_k[ik] = la_k;
-            if (p.o.d_lon_k) p.o.d_lon_k[ik] = lo_k;
+            if (FULL || p.o.d_lat_k) p.o.d_lat_k[ik] = la_k;
+            if (FULL || p.o.d_lon_k) p.o.d_lon_k[ik] = lo_k;
         }
         if (WANT_C && in_c) {
-            if (p.o.d_lat_c) p.o.d_lat_c[ic] = la_c;
-            if (p.o.d_lon_c) p.o.d_lon_c[ic] = lo_c;
+            if (FULL || p.o.d_lat_c) p.o.d_lat_c[ic] = la_c;
+            if (FULL || p.o.d_lon_c) p.o.d_lon_c[ic] = lo_c;
         }
     }
     if (mag) {
@@ -339,15 +351,15 @@ __global__ void __launch_bounds__(256, AMT_GEOREF_MINBLOCKS) k_georef_points(con
         if (WANT_K) point_to_mag(p.f, Pk, ml_k, mt_k);
         if (WANT_C) point_to_mag(p.f, Pc, ml_c, mt_c);
         if (WANT_K && in_k) {
-            if (p.o.d_mlat_k) p.o.d_mlat_k[ik] = ml_k;
-            if (p.o.d_mlt_k) p.o.d_mlt_k[ik] = mt_k;
+            if (FULL || p.o.d_mlat_k) p.o.d_mlat_k[ik] = ml_k;
+            if (FULL || p.o.d_mlt_k) p.o.d_mlt_k[ik] = mt_k;
         }
         if (WANT_C && in_c) {
-            if (p.o.d_mlat_c) p.o.d_mlat_c[ic] = ml_c;
-            if (p.o.d_mlt_c) p.o.d_mlt_c[ic] = mt_c;
+            if (FULL || p.o.d_mlat_c) p.o.d_mlat_c[ic] = ml_c;
+            if (FULL || p.o.d_mlt_c) p.o.d_mlt_c[ic] = mt_c;
         }
     }
-    if (WANT_C && in_c && p.o.d_elev_c) {
+    if (WANT_C && in_c && (FULL || p.o.d_elev_c)) {
         double e = p.f.model == AMT_MODEL_ALLSKY ? cam_el : elevation_deg<false>(dc, Pc);
         p.o.d_elev_c[ic] = hit_c ? e : nan;
     }
@@ -522,9 +534,13 @@ extern "C" int amt_georef(amt_ctx* ctx, const amt_frame* frame, const amt_georef
                             out->d_valid_c;
         if (!want_k && !want_c) return AMT_OK;
         dim3 grid((W + 1 + 255) / 256, want_k ? H + 1 : H);
-        if (want_k && want_c) k_georef_points<true, true><<<grid, 256, 0, st>>>(p);
-        else if (want_k) k_georef_points<true, false><<<grid, 256, 0, st>>>(p);
-        else k_georef_points<false, true><<<grid, 256, 0, st>>>(p);
+        const bool full = out->d_lat_k && out->d_lon_k && out->d_mlat_k && out->d_mlt_k && out->d_valid_k &&
+                          out->d_lat_c && out->d_lon_c && out->d_mlat_c && out->d_mlt_c && out->d_elev_c &&
+                          out->d_valid_c;
+        if (full) k_georef_points<true, true, true><<<grid, 256, 0, st>>>(p);
+        else if (want_k && want_c) k_georef_points<true, true, false><<<grid, 256, 0, st>>>(p);
+        else if (want_k) k_georef_points<true, false, false><<<grid, 256, 0, st>>>(p);
+        else k_georef_points<false, true, false><<<grid, 256, 0, st>>>(p);
     }
     LAUNCH_CHECK(ctx);
     return AMT_OK;
@@ -1336,9 +1352,9 @@ __device__ __forceinline__ int cell_of(const GridC& g, double la, double lo, int
 }
 
 // Accumulate one warp's samples.  Consecutive lanes that hit the same cell form a run
-// (neighbouring pixels land in the same ~100"/px cell); run sums come from ONE unsegmented
-// warp prefix scan (run sum = prefix[tail] - prefix[head-1]) over the channels packed into
-// 64-bit words, and only the last lane of a run issues the atomics.
+// (neighbouring pixels land in the same ~100"/px cell); run sums come from one segmented warp
+// scan over the channels packed into 64-bit words, and only the last lane of a run issues
+// the atomics.
 template <typename T, int C>
 struct Packed {
     static constexpr int BITS = sizeof(T) == 1 ? 16 : 21;      // 32*255 < 2^16, 32*65535 < 2^21
@@ -1373,37 +1389,34 @@ __device__ __forceinline__ void warp_accumulate(int cell, const unsigned (&val)[
         if (cell >= 0) atomicAdd(&fsum[cell], side);
         has_side = false;
     }
+    // Segmented inclusive scan (Kogge-Stone on the position inside the run): after the step of
+    // distance d a lane holds the sum of the last min(2d, off+1) samples of its run.  Runs are
+    // short (a 100"/px cell holds ~3 consecutive 34" pixels), so the loop stops as soon as d
+    // exceeds the longest run of the warp -- typically after 2-3 of the 5 steps.
+    const unsigned off = lane - (unsigned)start;
+    const unsigned maxoff = __reduce_max_sync(0xffffffffu, off);
     double s = side;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
+        if ((unsigned)d > maxoff) break;              // warp-uniform
 #pragma unroll
         for (int k = 0; k < P::NW; ++k) {
             const unsigned long long t = __shfl_up_sync(0xffffffffu, w[k], d);
-            if (lane >= d) w[k] += t;
+            if (off >= (unsigned)d) w[k] += t;
         }
         if (has_side) {
             const double t = __shfl_up_sync(0xffffffffu, s, d);
-            if (lane >= d) s += t;
+            if (off >= (unsigned)d) s += t;
         }
     }
-    // prefix just before my run
-    const int before = start > 0 ? start - 1 : 0;
-    unsigned long long wb[P::NW];
-#pragma unroll
-    for (int k = 0; k < P::NW; ++k) {
-        wb[k] = __shfl_sync(0xffffffffu, w[k], before);
-        if (start == 0) wb[k] = 0;
-    }
-    double sb = has_side ? __shfl_sync(0xffffffffu, s, before) : 0.0;
-    if (start == 0) sb = 0.0;
     if (tail && cell >= 0) {
-        atomicAdd(&count[cell], (unsigned long long)(lane - start + 1));
+        atomicAdd(&count[cell], (unsigned long long)(off + 1));
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            const unsigned long long run = ((w[c / P::PER] - wb[c / P::PER]) >> ((c % P::PER) * P::BITS)) & P::MASK;
+            const unsigned long long run = (w[c / P::PER] >> ((c % P::PER) * P::BITS)) & P::MASK;
             atomicAdd(&sums[(size_t)c * plane + cell], run);
         }
-        if (has_side) atomicAdd(&fsum[cell], s - sb);
+        if (has_side) atomicAdd(&fsum[cell], s);
     }
 }
 

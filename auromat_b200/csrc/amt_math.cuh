@@ -323,12 +323,12 @@ __device__ __forceinline__ int bin_index(double x, double lo, double hi, double 
     if (x >= lo && x < hi) {
         // common case, branch-free: floor guess, then one correction step against the true
         // numpy edges e(k) = fl(fl(k*step) + lo), e(n) = hi
-        double kd = floor(__dmul_rn(__dsub_rn(x, lo), inv_step));
-        kd = fmin(fmax(kd, 0.0), (double)(n - 1));
-        const double e0 = __dadd_rn(__dmul_rn(kd, step), lo);
-        const double k1 = kd + 1.0;
-        const double e1 = k1 >= (double)n ? hi : __dadd_rn(__dmul_rn(k1, step), lo);
+        // lo <= x < hi, so the guess is in 0..n (n only through rounding); no clamp of the double
+        // needed: guess n gives e0 = fl(n*step + lo) ~ hi, e1 = hi, and ends at n-1 below
+        const double kd = floor(__dmul_rn(__dsub_rn(x, lo), inv_step));
         int k = (int)kd;
+        const double e0 = __dadd_rn(__dmul_rn(kd, step), lo);
+        const double e1 = k + 1 >= n ? hi : __dadd_rn(__dmul_rn(kd + 1.0, step), lo);
         k += (x >= e1) ? 1 : 0;
         k -= (x < e0) ? 1 : 0;
         k = min(max(k, 0), n - 1);
