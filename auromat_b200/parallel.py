@@ -108,10 +108,9 @@ class MosaicAccumulator(object):
 
     def add(self, mapping):
         """Bin one mapping into the grids (`amt_bin_accumulate`)."""
-        p = mapping.devicePlanes()
-        img = mapping.deviceImage()
-        assert img.shape[2] == self.channels
-        self.ctx.bin_accumulate(p['lat_c'], p['lon_c'], p['elev_c'], img, self.grid, self.count, self.sums, self.fsum)
+        from .resample import binMappingInto
+        assert mapping.deviceImage().shape[2] == self.channels
+        binMappingInto(mapping, self.grid, self.count, self.sums, self.fsum)
 
     def allreduce(self, group=None):
         allreduceGrids([self.acc, self.fsum], group)

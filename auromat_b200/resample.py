@@ -166,8 +166,17 @@ def binMappingInto(mapping, grid, count, sums, fsum, nearEdge=None):
     ctx = mapping.context
     p = mapping.devicePlanes()
     img = mapping.deviceImage()
-    ctx.bin_accumulate(p['lat_c'], p['lon_c'], p['elev_c'] if fsum is not None else None, img, grid,
-                       count, sums, fsum, nearEdge)
+    h, w = mapping.shape
+    # Only the rows that hold defined pixels are handed to the kernel (the outline statistics
+    # carry the pixel box of the valid centres): an ISS limb frame is ~40 % empty sky.
+    st = mapping._deviceStats()
+    r0, r1 = max(0, st.row_min_c), min(h - 1, st.row_max_c)
+    if r1 < r0:
+        return
+    lo, hi = r0 * w, (r1 + 1) * w
+    flat = lambda t: t.reshape(-1)[lo:hi]
+    ctx.bin_accumulate(flat(p['lat_c']), flat(p['lon_c']), flat(p['elev_c']) if fsum is not None else None,
+                       img[r0:r1 + 1], grid, count, sums, fsum, nearEdge)
 
 
 def resampleToDevice(mapping, pxPerDeg=25, arcsecPerPx=None, containsPole=None):
