@@ -679,15 +679,6 @@ __global__ void __launch_bounds__(256) k_valid_bits(int W, int H, const double* 
         (corner ? bk : bc)[(size_t)y * (corner ? wpr_k : wpr_c) + (x >> 5)] = m;
 }
 
-// step 1 of _doSanitize (mapping.py:1082-1093): a corner stays valid only if at least one of
-// its (<=4) neighbouring centres is valid.  One thread per corner word.
-__global__ void k_bits_corner_rule(int H, Bits K, Bits C, unsigned* __restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (i >= K.wpr || y > H) return;
-    const unsigned anyc = C.from_left(y - 1, i) | C.at(y - 1, i) | C.from_left(y, i) | C.at(y, i);
-    out[(size_t)y * K.wpr + i] = K.at(y, i) & anyc;
-}
-
 __device__ __forceinline__ void nan_centers(const amt_georef_out& o, size_t base, unsigned bits) {
     const double nan = qnan();
     while (bits) {
@@ -714,22 +705,8 @@ __device__ __forceinline__ void nan_corners(const amt_georef_out& o, size_t base
     }
 }
 
-// step 2 (mapping.py:1095-1104): a centre stays valid only if all 4 corners are valid (K1);
-// newly masked centres get NaN in every centre plane.  One thread per centre word.
-__global__ void k_bits_center_rule(int W, int H, Bits K1, unsigned* __restrict__ cbits, int wpr_c, amt_georef_out o) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (i >= wpr_c || y >= H) return;
-    const unsigned allk = K1.at(y, i) & K1.from_right(y, i) & K1.at(y + 1, i) & K1.from_right(y + 1, i);
-    const unsigned c0 = cbits[(size_t)y * wpr_c + i];
-    const unsigned c1 = c0 & allk;
-    if (c1 != c0) {
-        cbits[(size_t)y * wpr_c + i] = c1;
-        nan_centers(o, (size_t)y * W + 32 * i, c0 & ~c1);
-    }
-}
-
-// step 3 (mapping.py:1106-1117): corners once more with the updated centres; corners that
-// lost validity since the original bitmap K0 get NaN.  Writes the final bitmap over K0.
+// Corner rule alone (after masking, mapping.py:1082-1093 with afterMasking=True): a corner stays
+// valid only if one of its neighbouring centres is; corners that lost validity get NaN.
 __global__ void k_bits_corner_final(int W, int H, Bits K1, Bits C1, unsigned* __restrict__ k0, amt_georef_out o) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (i >= K1.wpr || y > H) return;
@@ -739,6 +716,62 @@ __global__ void k_bits_corner_final(int W, int H, Bits K1, Bits C1, unsigned* __
     if (k2 != old) {
         k0[(size_t)y * K1.wpr + i] = k2;
         nan_corners(o, (size_t)y * (W + 1) + 32 * i, old & ~k2);
+    }
+}
+
+// All three steps of _doSanitize (mapping.py:1082-1117) in one launch:
+//   1. a corner stays valid only if at least one of its (<=4) neighbouring centres is valid,
+//   2. a centre stays valid only if all 4 corners are (still) valid,
+//   3. rule 1 once more with the updated centres;
+// elements that lose validity get NaN in every plane.  K0 / C0 are COPIES of the input bitmaps (the
+// results overwrite the originals while neighbouring words are still being read); every thread
+// owns one (row, word) position of both bitmaps and recomputes the intermediate words it needs
+// from the 4 x 4 (C0) / 3 x 3 (K0) neighbourhood -- a few hundred bit operations on an
+// L2-resident 1.5 MB working set instead of two more launches.
+struct SanitizeWords {
+    Bits K0, C0;
+    // step 1: corner valid and one of its neighbouring centres valid
+    __device__ __forceinline__ unsigned k1(int y, int i) const {
+        const unsigned anyc = C0.from_left(y - 1, i) | C0.at(y - 1, i) | C0.from_left(y, i) | C0.at(y, i);
+        return K0.at(y, i) & anyc;
+    }
+};
+
+__global__ void __launch_bounds__(128) k_sanitize_fused(int W, int H, Bits K0, Bits C0, unsigned* __restrict__ kout,
+                                                        unsigned* __restrict__ cout, amt_georef_out o) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (i >= K0.wpr || y > H) return;
+    const SanitizeWords sw{K0, C0};
+    // k1 on rows y-1 .. y+1, words i-1 .. i+1
+    unsigned k1[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) k1[r][c] = sw.k1(y - 1 + r, i - 1 + c);
+    // step 2: c1 on rows y-1 .. y, words i-1 .. i  (all four corners valid in k1)
+    unsigned c1[2][2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const unsigned a = k1[r][c], a_r = (a >> 1) | (k1[r][c + 1] << 31);
+            const unsigned b = k1[r + 1][c], b_r = (b >> 1) | (k1[r + 1][c + 1] << 31);
+            c1[r][c] = C0.at(y - 1 + r, i - 1 + c) & a & a_r & b & b_r;
+        }
+    // step 3: corners once more against the updated centres
+    const unsigned up_l = (c1[0][1] << 1) | (c1[0][0] >> 31), dn_l = (c1[1][1] << 1) | (c1[1][0] >> 31);
+    const unsigned k2 = k1[1][1] & (up_l | c1[0][1] | dn_l | c1[1][1]);
+    const unsigned k_old = K0.at(y, i);
+    if (k2 != k_old) {
+        kout[(size_t)y * K0.wpr + i] = k2;
+        nan_corners(o, (size_t)y * (W + 1) + 32 * i, k_old & ~k2);
+    }
+    if (y < H && i < C0.wpr) {
+        const unsigned c_old = C0.at(y, i), c_new = c1[1][1];
+        if (c_new != c_old) {
+            cout[(size_t)y * C0.wpr + i] = c_new;
+            nan_centers(o, (size_t)y * W + 32 * i, c_old & ~c_new);
+        }
     }
 }
 
@@ -756,35 +789,66 @@ __global__ void __launch_bounds__(256) k_stats_bits(int W, int H, Bits K, Bits C
                                                     const GeorefParams* __restrict__ frame, amt_stats* out) {
     unsigned long long mn_la = ~0ULL, mx_la = 0ULL, mn_lo = ~0ULL, mx_lo = 0ULL, mn_pos = ~0ULL, mx_neg = 0ULL;
     unsigned nvk = 0, nb = 0, nvc = 0;
+    // Each lane classifies one bitmap word (coalesced); the outline nodes of the warp's words are
+    // then handled cooperatively: one word per step with the 32 lanes on its 32 bits (coalesced
+    // coordinate loads), four words in flight per step so that the limb rows -- 32 full outline
+    // words per warp -- cost 8 dependent memory round trips instead of 32.
+    const int lane_ = threadIdx.x & 31;
     const int nwk = K.wpr * (H + 1);
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nwk; t += gridDim.x * blockDim.x) {
-        const int y = t / K.wpr, i = t - y * K.wpr;
-        const unsigned v = K.w[t];
-        if (!v) continue;
-        nvk += __popc(v);
-        const unsigned interior = v & K.from_left(y, i) & K.from_right(y, i) & K.at(y - 1, i) & K.at(y + 1, i);
-        unsigned b = v & ~interior;
-        nb += __popc(b);
-        while (b) {
-            const int bit = __ffs(b) - 1;
-            b &= b - 1;
-            const size_t idx = (size_t)y * (W + 1) + 32 * i + bit;
-            double la, lo;
-            if (lat_k) {
-                la = lat_k[idx];
-                lo = lon_k[idx];
-            } else {
-                double dir[3], P[3];
-                bool gz;
-                pix2dir<false>(frame->f, frame->sip_a, frame->sip_b, (double)(32 * i + bit) - 0.5, (double)y - 0.5, dir);
-                intersect(frame->f, dir, P, gz);
-                point_to_geo(frame->f, P, la, lo);
+    const int t_first = blockIdx.x * blockDim.x + threadIdx.x - lane_;
+    for (int t0 = t_first; t0 < nwk; t0 += gridDim.x * blockDim.x) {        // warp-uniform
+        const int t = t0 + lane_;
+        unsigned b = 0;
+        int y = 0, i = 0;
+        if (t < nwk) {
+            y = t / K.wpr;
+            i = t - y * K.wpr;
+            const unsigned v = K.w[t];
+            if (v) {
+                nvk += __popc(v);
+                const unsigned interior = v & K.from_left(y, i) & K.from_right(y, i) & K.at(y - 1, i) & K.at(y + 1, i);
+                b = v & ~interior;
+                nb += __popc(b);
             }
-            if (g.prerotate != AMT_PRE_NONE) prerotate(g, la, lo);
-            const unsigned long long kla = dkey(la), klo = dkey(lo);
-            mn_la = umin64(mn_la, kla); mx_la = umax64(mx_la, kla);
-            mn_lo = umin64(mn_lo, klo); mx_lo = umax64(mx_lo, klo);
-            if (lo > 0.0) mn_pos = umin64(mn_pos, klo); else mx_neg = umax64(mx_neg, klo);
+        }
+        unsigned act = __ballot_sync(0xffffffffu, b != 0);
+        while (act) {
+            constexpr int Q = 4;
+            bool on[Q];
+            double la[Q], lo[Q];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const int src = act ? __ffs(act) - 1 : 0;
+                const unsigned bb = act ? __shfl_sync(0xffffffffu, b, src) : 0u;
+                const int yy = __shfl_sync(0xffffffffu, y, src), ii = __shfl_sync(0xffffffffu, i, src);
+                act &= act - 1;                                  // 0 stays 0
+                on[q] = (bb >> lane_) & 1u;
+                la[q] = lo[q] = 0.0;
+                if (on[q]) {
+                    const int x = 32 * ii + lane_;
+                    if (lat_k) {
+                        const size_t idx = (size_t)yy * (W + 1) + x;
+                        la[q] = lat_k[idx];
+                        lo[q] = lon_k[idx];
+                    } else {
+                        double dir[3], P[3];
+                        bool gz;
+                        pix2dir<false>(frame->f, frame->sip_a, frame->sip_b, (double)x - 0.5, (double)yy - 0.5, dir);
+                        intersect(frame->f, dir, P, gz);
+                        point_to_geo(frame->f, P, la[q], lo[q]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                if (!on[q]) continue;
+                double a_ = la[q], o_ = lo[q];
+                if (g.prerotate != AMT_PRE_NONE) prerotate(g, a_, o_);
+                const unsigned long long kla = dkey(a_), klo = dkey(o_);
+                mn_la = umin64(mn_la, kla); mx_la = umax64(mx_la, kla);
+                mn_lo = umin64(mn_lo, klo); mx_lo = umax64(mx_lo, klo);
+                if (o_ > 0.0) mn_pos = umin64(mn_pos, klo); else mx_neg = umax64(mx_neg, klo);
+            }
         }
     }
     const int nwc = C.wpr * H;
@@ -800,13 +864,10 @@ __global__ void __launch_bounds__(256) k_stats_bits(int W, int H, Bits K, Bits C
     }
     r_lo = __reduce_min_sync(0xffffffffu, r_lo); r_hi = __reduce_max_sync(0xffffffffu, r_hi);
     c_lo = __reduce_min_sync(0xffffffffu, c_lo); c_hi = __reduce_max_sync(0xffffffffu, c_hi);
-    if ((threadIdx.x & 31) == 0 && r_lo != 0xffffffffu) {
-        atomicMin(&s->row_min, r_lo); atomicMax(&s->row_max, r_hi);
-        atomicMin(&s->col_min, c_lo); atomicMax(&s->col_max, c_hi);
-    }
 
     __shared__ unsigned long long sh[6][8];
     __shared__ unsigned shc[3][8];
+    __shared__ unsigned shr[4][8];
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
         mn_la = umin64(mn_la, __shfl_xor_sync(0xffffffffu, mn_la, o));
@@ -824,6 +885,7 @@ __global__ void __launch_bounds__(256) k_stats_bits(int W, int H, Bits K, Bits C
         sh[0][warp] = mn_la; sh[1][warp] = mx_la; sh[2][warp] = mn_lo; sh[3][warp] = mx_lo;
         sh[4][warp] = mn_pos; sh[5][warp] = mx_neg;
         shc[0][warp] = nvk; shc[1][warp] = nb; shc[2][warp] = nvc;
+        shr[0][warp] = r_lo; shr[1][warp] = r_hi; shr[2][warp] = c_lo; shr[3][warp] = c_hi;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -832,6 +894,12 @@ __global__ void __launch_bounds__(256) k_stats_bits(int W, int H, Bits K, Bits C
             sh[2][0] = umin64(sh[2][0], sh[2][w]); sh[3][0] = umax64(sh[3][0], sh[3][w]);
             sh[4][0] = umin64(sh[4][0], sh[4][w]); sh[5][0] = umax64(sh[5][0], sh[5][w]);
             shc[0][0] += shc[0][w]; shc[1][0] += shc[1][w]; shc[2][0] += shc[2][w];
+            shr[0][0] = min(shr[0][0], shr[0][w]); shr[1][0] = max(shr[1][0], shr[1][w]);
+            shr[2][0] = min(shr[2][0], shr[2][w]); shr[3][0] = max(shr[3][0], shr[3][w]);
+        }
+        if (shr[0][0] != 0xffffffffu) {               // one set of atomics per block (same-address atomics are slow)
+            atomicMin(&s->row_min, shr[0][0]); atomicMax(&s->row_max, shr[1][0]);
+            atomicMin(&s->col_min, shr[2][0]); atomicMax(&s->col_max, shr[3][0]);
         }
         if (shc[0][0]) atomicAdd(&s->n_valid_k, (unsigned long long)shc[0][0]);
         if (shc[2][0]) atomicAdd(&s->n_valid_c, (unsigned long long)shc[2][0]);
@@ -892,16 +960,21 @@ extern "C" int amt_sanitize(amt_ctx* ctx, int32_t W, int32_t H, const amt_georef
     CHECK_ARG(planes->d_valid_k && planes->d_valid_c, "amt_sanitize: validity bitmaps are required");
     cudaStream_t st = (cudaStream_t)stream;
     const int wk = wpr_of(W + 1), wc = wpr_of(W);
-    int rc = ensure_scratch(ctx, (size_t)wk * (H + 1) * 4);
+    const size_t nk = (size_t)wk * (H + 1), nc = (size_t)wc * H;
+    int rc = ensure_scratch(ctx, (nk + nc) * 4);
     if (rc) return rc;
-    unsigned* k1 = (unsigned*)ctx->scratch;
-    Bits K0{planes->d_valid_k, wk, H + 1}, C{planes->d_valid_c, wc, H}, K1{k1, wk, H + 1};
-    dim3 gk((wk + 127) / 128, H + 1), gc((wc + 127) / 128, H);
-    k_bits_corner_rule<<<gk, 128, 0, st>>>(H, K0, C, k1);
-    LAUNCH_CHECK(ctx);
-    k_bits_center_rule<<<gc, 128, 0, st>>>(W, H, K1, planes->d_valid_c, wc, *planes);
-    LAUNCH_CHECK(ctx);
-    k_bits_corner_final<<<gk, 128, 0, st>>>(W, H, K1, C, planes->d_valid_k, *planes);
+    // the kernel reads copies of the input bitmaps and overwrites the originals
+    unsigned* k0 = (unsigned*)ctx->scratch;
+    unsigned* c0 = k0 + nk;
+    if (planes->d_valid_c == planes->d_valid_k + nk) {           // allocated back to back: one copy
+        CUDA_TRY(cudaMemcpyAsync(k0, planes->d_valid_k, (nk + nc) * 4, cudaMemcpyDeviceToDevice, st));
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(k0, planes->d_valid_k, nk * 4, cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(c0, planes->d_valid_c, nc * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    Bits K0{k0, wk, H + 1}, C0{c0, wc, H};
+    dim3 gk((wk + 127) / 128, H + 1);
+    k_sanitize_fused<<<gk, 128, 0, st>>>(W, H, K0, C0, planes->d_valid_k, planes->d_valid_c, *planes);
     LAUNCH_CHECK(ctx);
     return AMT_OK;
 }

@@ -241,6 +241,8 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
                        identifier=None if isinstance(hdr, str) else 'frame%06d' % i, device=ctx.device)
         if late:
             m._lateImage = img
+        elif sparseUpload and isinstance(img, str):
+            m._lateImage = m.img_unmasked        # image file: decoded on the host, uploaded like an array
         if not coordinates and not magnetic and not fastCenterCalculation:
             m.setPlaneFree(True)
             m._startStats()

@@ -124,8 +124,9 @@ class Context:
     def new_bitmaps(self, width, height):
         torch = _torch()
         nk, nc = self.bitmap_words(width, height)
-        return (torch.empty(nk, dtype=torch.int32, device=self.torch_device),
-                torch.empty(nc, dtype=torch.int32, device=self.torch_device))
+        # one allocation, corner words first: amt_sanitize then snapshots both with a single copy
+        buf = torch.empty(nk + nc, dtype=torch.int32, device=self.torch_device)
+        return buf[:nk], buf[nk:]
 
     def valid_bits(self, width, height, planes: dict):
         """Build the validity bitmaps of NaN-marked planes into planes['valid_k'/'valid_c']."""
