@@ -525,6 +525,7 @@ extern "C" int amt_georef(amt_ctx* ctx, const amt_frame* frame, const amt_georef
     p.ill = d_stats ? (unsigned long long*)&d_stats->n_ill_conditioned : nullptr;
     const int W = frame->width, H = frame->height;
     cudaStream_t st = (cudaStream_t)stream;
+    if (d_stats) CUDA_TRY(cudaMemsetAsync(&d_stats->n_ill_conditioned, 0, sizeof(uint64_t), st));
     if (frame->fast_center) {
         dim3 grid((W + TW) / TW, (H + TH) / TH);   // covers x<=W, y<=H
         k_georef_tiles<<<grid, dim3(TW, TH), 0, st>>>(p);

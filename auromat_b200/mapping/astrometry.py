@@ -64,15 +64,17 @@ class BaseAstrometryMapping(BaseMapping):
             fresh['valid_k'], fresh['valid_c'] = pool['valid_k'], pool['valid_c']
         else:
             fresh['valid_k'], fresh['valid_c'] = ctx.new_bitmaps(w, h)
+        # the first launch of a frame counts the grazing rays into the statistics block
         if self._statsDevice is None:
-            self._statsDevice = ctx.new_stats()     # zeroed; the kernel adds the grazing-ray count
-            stats = self._statsDevice
-        else:
-            stats = None
-        ctx.georef(self.frameConstants, fresh, stats)
+            self._statsDevice = ctx.new_stats()
+        stats = None if self._grazingCounted else self._statsDevice
+        self._grazingCounted = True
+        # a ring slot comes with the prebuilt amt_georef_out of all its planes
+        out = pool.get('_out') if len(fresh) == pool.get('_nplanes', -1) and not self._planes else None
+        ctx.georef(self.frameConstants, fresh, stats, out=out)
         self._planes.update(fresh)
         if self._sanitize:
-            ctx.sanitize(w, h, self._planes)
+            ctx.sanitize(w, h, self._planes, out=out)
         self.isSanitized = True
 
     # ---- plane-free (fused) resampling: hit bitmaps + outline statistics only ----
@@ -86,7 +88,8 @@ class BaseAstrometryMapping(BaseMapping):
             bits['valid_k'], bits['valid_c'] = ctx.new_bitmaps(w, h)
             if self._statsDevice is None:
                 self._statsDevice = ctx.new_stats()
-            ctx.georef(self.frameConstants, bits, self._statsDevice)
+            ctx.georef(self.frameConstants, bits, None if self._grazingCounted else self._statsDevice)
+            self._grazingCounted = True
             if self._sanitize:
                 ctx.sanitize(w, h, bits)
             self._planes.update(bits)

@@ -181,6 +181,7 @@ class BaseMapping(object):
         self._stats = None
         self._statsPending = None
         self._statsDevice = None   # device amt_stats block (georeference kernels count grazing rays into it)
+        self._grazingCounted = False
         self._boundingBox = None
         self._imgDevice = None
 

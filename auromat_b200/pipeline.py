@@ -37,35 +37,56 @@ class ResampledFrame(object):
     def __init__(self, mapping, grid, info, dImg, dMask, dElev):
         self.mapping, self.grid, self.info = mapping, grid, info
         self.deviceImg, self.deviceMask, self.deviceElevation = dImg, dMask, dElev
-        self._host = None
+        self._hostFlat = None
         self._event = None
 
-    def _startDownload(self, ctx, pool):
+    def _startDownload(self, ctx, pool, depthHint=2):
         """Async D2H of image | mask | elevation into ONE pooled pinned byte buffer.  Buffers are
         pooled by capacity class (next power of two), not by shape: the grid size changes from
         frame to frame and page-locking (cudaHostAlloc) is a millisecond-scale call."""
         import torch
         parts = (self.deviceImg, self.deviceMask, self.deviceElevation)
-        sizes = [p.numel() * p.element_size() for p in parts]
-        offs = [0]
-        for n in sizes[:-1]:
-            offs.append((offs[-1] + n + 63) // 64 * 64)
-        total = offs[-1] + sizes[-1]
+        flatDev = getattr(self.deviceImg, '_amt_flat', None)      # the three parts are views of one buffer
+        if flatDev is not None:
+            base = flatDev.data_ptr()
+            offs = [p.data_ptr() - base for p in parts]
+            sizes = [p.numel() * p.element_size() for p in parts]
+            total = flatDev.numel()
+        else:
+            sizes = [p.numel() * p.element_size() for p in parts]
+            offs = [0]
+            for n in sizes[:-1]:
+                offs.append((offs[-1] + n + 63) // 64 * 64)
+            total = offs[-1] + sizes[-1]
         cap = 1 << max(16, (total - 1).bit_length())
         bucket = pool.setdefault(cap, [])
         if not bucket and cap not in pool.setdefault('_seen', set()):
             pool['_seen'].add(cap)
-            bucket.extend(torch.empty(cap, dtype=torch.uint8).pin_memory() for _ in range(5))
+            bucket.extend(torch.empty(cap, dtype=torch.uint8).pin_memory() for _ in range(2 * depthHint + 6))
+        if not bucket:
+            pool['grown'] = pool.get('grown', 0) + 1         # page-locking inside a sequence: visible in diagnostics
         flat = bucket.pop() if bucket else torch.empty(cap, dtype=torch.uint8).pin_memory()
-        views = []
-        for p, o, n in zip(parts, offs, sizes):
-            v = flat[o:o + n].view(p.dtype).view(p.shape)
-            v.copy_(p, non_blocking=True)
-            views.append(v)
-        self._host = tuple(views)
+        if flatDev is not None:
+            ctx.copy_d2h(flat.data_ptr(), flatDev.data_ptr(), total, ctx.stream())      # one cudaMemcpyAsync
+        else:
+            for p, o, n in zip(parts, offs, sizes):
+                flat[o:o + n].view(p.dtype).view(p.shape).copy_(p, non_blocking=True)
+        # host views are built on first access
+        self._hostFlat = (flat, offs, sizes, [p.dtype for p in parts], [tuple(p.shape) for p in parts])
         weakref.finalize(self, bucket.append, flat)    # the buffer returns to the pool with the frame
         self._event = torch.cuda.Event()
-        self._event.record(torch.cuda.current_stream(ctx.torch_device))
+        self._event.record()
+
+    @property
+    def _host(self):
+        hf = self.__dict__.get('_hostFlat')
+        if hf is None:
+            return None
+        if '_hostViews' not in self.__dict__:
+            flat, offs, sizes, dtypes, shapes = hf
+            self.__dict__['_hostViews'] = tuple(flat[o:o + n].view(dt).view(sh)
+                                                for o, n, dt, sh in zip(offs, sizes, dtypes, shapes))
+        return self.__dict__['_hostViews']
 
     def _finish(self):
         if self._event is not None:
@@ -156,50 +177,52 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
             ev.record(stream)
             trace.append((tag, i, ev))
 
-    def hostTensor(img):
-        src = np.ascontiguousarray(img)
-        return torch.from_numpy(src.view(np.int16) if src.dtype == np.uint16 else src), src.dtype
-
     def upload(i, img, rows=None):
         """Host array -> device on the copy stream; returns (tensor, event).  `rows` = (first,
         last) restricts the copy to that row range: rows without a single georeferenced pixel
         are never read by the binning kernel."""
-        t, dtype = hostTensor(img)
-        with torch.cuda.stream(copy):
-            if ringBuffers:
-                if len(imgRing) != ringLen or imgRing[0].shape != t.shape or imgRing[0].dtype != t.dtype:
-                    del imgRing[:]
-                    imgRing.extend(torch.empty(t.shape, dtype=t.dtype, device=ctx.torch_device)
+        src = np.ascontiguousarray(img)
+        tdtype = {np.dtype(np.uint8): torch.uint8, np.dtype(np.uint16): torch.int16}[src.dtype]
+        if ringBuffers:
+            if len(imgRing) != ringLen or tuple(imgRing[0].shape) != src.shape or imgRing[0].dtype != tdtype:
+                del imgRing[:]
+                with torch.cuda.stream(copy):
+                    imgRing.extend(torch.empty(src.shape, dtype=tdtype, device=ctx.torch_device)
                                    for _ in range(ringLen))
-                d = imgRing[i % len(imgRing)]
-                prev = slotDone.get(i % len(imgRing))
-                if prev is not None:
-                    copy.wait_event(prev)       # the frame that used this ring slot has been binned
-                else:
-                    copy.wait_stream(main)
+            d = imgRing[i % len(imgRing)]
+            prev = slotDone.get(i % len(imgRing))
+            if prev is not None:
+                copy.wait_event(prev)           # the frame that used this ring slot has been binned
             else:
-                d = torch.empty(t.shape, dtype=t.dtype, device=ctx.torch_device)
-                d.record_stream(main)
-                if second is not None:
-                    d.record_stream(second)
-            mark('H0', i, copy)
-            if rows is None:
-                d.copy_(t, non_blocking=True)
-                nbytes = t.numel() * t.element_size()
-            else:
-                r0, r1 = rows
-                nbytes = 0
-                if r1 >= r0:
-                    d[r0:r1 + 1].copy_(t[r0:r1 + 1], non_blocking=True)
-                    nbytes = (r1 - r0 + 1) * t[0].numel() * t.element_size()
-            ev = torch.cuda.Event()
-            ev.record(copy)
-            mark('H1', i, copy)
+                copy.wait_stream(main)
+        else:
+            with torch.cuda.stream(copy):
+                d = torch.empty(src.shape, dtype=tdtype, device=ctx.torch_device)
+            d.record_stream(main)
+            if second is not None:
+                d.record_stream(second)
+        mark('H0', i, copy)
+        rowBytes = src.strides[0]
+        r0, r1 = (0, src.shape[0] - 1) if rows is None else rows
+        nbytes = max(0, r1 - r0 + 1) * rowBytes
+        if nbytes:
+            # plain cudaMemcpyAsync on the copy stream (pinned source => asynchronous)
+            ctx.copy_h2d(d.data_ptr() + r0 * rowBytes, src.ctypes.data + r0 * rowBytes, nbytes, hCopy)
+        ev = torch.cuda.Event()
+        ev.record(copy)
+        mark('H1', i, copy)
         stats['h2d_bytes'] += nbytes
-        if dtype == np.uint16:
+        keepAlive.append((ev, src))             # the host array must outlive the asynchronous copy
+        while len(keepAlive) > ringLen + 2:
+            keepAlive.popleft()
+        if src.dtype == np.uint16:
             d = d.view(torch.uint16)
         return d, ev
 
+    import ctypes
+    hMain = ctypes.c_void_p(main.cuda_stream)
+    hCopy = ctypes.c_void_p(copy.cuda_stream)
+    keepAlive = collections.deque()
     ring = []
     slotDone = {}            # ring slot -> event recorded after the binning of its last user
     ringLen = depth + 3
@@ -213,6 +236,7 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
         second = ctx.__dict__.get('_second_stream')
         if second is None:
             second = ctx.__dict__['_second_stream'] = torch.cuda.Stream(ctx.torch_device)
+    hSecond = ctypes.c_void_p(second.cuda_stream) if second is not None else None
 
     def ringSet(i, m):
         h, w = m.shape
@@ -223,6 +247,8 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
             for _ in range(ringLen):
                 s = {n: ctx.empty((h + 1) * (w + 1) if n.endswith('_k') else h * w, torch.float64) for n in names}
                 s['valid_k'], s['valid_c'] = ctx.new_bitmaps(w, h)
+                s['_out'], s['_nplanes'] = ctx.out_struct(s), len(s)
+                s['_stats'] = ctx.new_stats()
                 ring.append(s)
         return ring[i % len(ring)]
 
@@ -252,6 +278,7 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
             if prev is not None:
                 main.wait_event(prev)           # ring slot free: its previous frame has been binned
             m._planeBuffers = ringSet(i, m)
+            m._statsDevice = m._planeBuffers['_stats']      # ring-owned statistics block (no per-frame alloc)
         mark('A0', i, main)
         m.prefetch(magnetic=magnetic)
         m._startStats()
@@ -278,13 +305,12 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
             grid, info, dImg, dMask, dElev = resampleToDevice(m, pxPerDeg=pxPerDeg, arcsecPerPx=arcsecPerPx)
             f = ResampledFrame(m, grid, info, dImg, dMask, dElev)
             if toHost:
-                f._startDownload(ctx, pool)
+                f._startDownload(ctx, pool, depth)
             return f
         evA = torch.cuda.Event()
         evA.record(main)                        # everything of stage A of this frame
-        ctx.pin_stream(False)
         with torch.cuda.stream(second):
-            ctx.pin_stream(True)
+            ctx.use_stream(hSecond)
             second.wait_event(evA)
             if ev is not None:
                 second.wait_event(ev)
@@ -293,12 +319,11 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
             f = ResampledFrame(m, grid, info, dImg, dMask, dElev)
             mark('B1', i, second)
             if toHost:
-                f._startDownload(ctx, pool)
+                f._startDownload(ctx, pool, depth)
             mark('D1', i, second)
             done = torch.cuda.Event()
             done.record(second)
-            ctx.pin_stream(False)
-        ctx.pin_stream(True)
+        ctx.use_stream(hMain)
         slotDone[i % ringLen] = done
         f._done = done
         return f
@@ -310,20 +335,20 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
             main.wait_event(done)               # the caller's stream sees the finished outputs
         return f
 
-    ctx.pin_stream(True)
+    ctx.use_stream(hMain)
     try:
         for i, (img, hdr) in enumerate(zip(imagesOrArrays, wcsHeaders)):
             stageA.append(runA(i, img, hdr))
             if len(stageA) >= depth:
                 stageB.append(runB(*stageA.popleft()))
             while len(stageB) > depth:
-                ctx.pin_stream(False)
+                ctx.use_stream(None)
                 yield finish(stageB.popleft())
-                ctx.pin_stream(True)
+                ctx.use_stream(hMain)
         while stageA:
             stageB.append(runB(*stageA.popleft()))
-        ctx.pin_stream(False)
+        ctx.use_stream(None)
         while stageB:
             yield finish(stageB.popleft())
     finally:
-        ctx.pin_stream(False)
+        ctx.use_stream(None)

@@ -53,6 +53,16 @@ class Context:
         self.__dict__['_pinned_stream'] = \
             C.c_void_p(_torch().cuda.current_stream(self.torch_device).cuda_stream) if on else None
 
+    def use_stream(self, handle):
+        """Pin an explicit stream handle (ctypes c_void_p) or None to unpin: no torch lookup."""
+        self.__dict__['_pinned_stream'] = handle
+
+    def copy_h2d(self, d_ptr, h_ptr, nbytes, stream_handle):
+        _lib.check(self.lib.amt_copy_h2d(self.handle, C.c_void_p(d_ptr), C.c_void_p(h_ptr), nbytes, stream_handle))
+
+    def copy_d2h(self, h_ptr, d_ptr, nbytes, stream_handle):
+        _lib.check(self.lib.amt_copy_d2h(self.handle, C.c_void_p(h_ptr), C.c_void_p(d_ptr), nbytes, stream_handle))
+
     def synchronize(self):
         _torch().cuda.current_stream(self.torch_device).synchronize()
 
@@ -99,21 +109,28 @@ class Context:
         return v.value
 
     # ------------------------------------------------------------------ kernels
-    def georef(self, frame: _lib.AmtFrame, planes: dict, stats=None):
-        """planes: name -> device tensor for any subset of amt_georef_out members."""
+    @staticmethod
+    def out_struct(planes: dict):
+        """amt_georef_out of a planes dict (name -> device tensor)."""
         out = _lib.AmtGeorefOut()
         for name, t in planes.items():
             setattr(out, "d_" + name, t.data_ptr())
+        return out
+
+    def georef(self, frame: _lib.AmtFrame, planes: dict, stats=None, out=None):
+        """planes: name -> device tensor for any subset of amt_georef_out members; `out`: the
+        prebuilt amt_georef_out of exactly these planes (plane rings of the sequence pipeline)."""
+        if out is None:
+            out = self.out_struct(planes)
         _lib.check(self.lib.amt_georef(self.handle, C.byref(frame), C.byref(out), self.ptr(stats), self.stream()))
 
     def new_stats(self):
         torch = _torch()
         return torch.zeros(C.sizeof(_lib.AmtStats), dtype=torch.uint8, device=self.torch_device)
 
-    def sanitize(self, width, height, planes: dict):
-        out = _lib.AmtGeorefOut()
-        for name, t in planes.items():
-            setattr(out, "d_" + name, t.data_ptr())
+    def sanitize(self, width, height, planes: dict, out=None):
+        if out is None:
+            out = self.out_struct(planes)
         _lib.check(self.lib.amt_sanitize(self.handle, width, height, C.byref(out), self.stream()))
 
     @staticmethod
@@ -158,9 +175,7 @@ class Context:
                                                  self.ptr(fsum), self.stream()))
 
     def apply_center_mask(self, width, height, planes: dict, mask=None, min_elevation=float("nan")):
-        out = _lib.AmtGeorefOut()
-        for name, t in planes.items():
-            setattr(out, "d_" + name, t.data_ptr())
+        out = self.out_struct(planes)
         _lib.check(self.lib.amt_apply_center_mask(self.handle, width, height, self.ptr(mask),
                                                   float(min_elevation), C.byref(out), self.stream()))
 
@@ -220,7 +235,7 @@ class Context:
         host = pool.pop() if pool else torch.empty(C.sizeof(_lib.AmtStats), dtype=torch.uint8).pin_memory()
         host.copy_(stats, non_blocking=True)
         ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(self.torch_device))
+        ev.record()
         return host, ev
 
     def finish_stats(self, handle) -> _lib.AmtStats:
@@ -268,10 +283,17 @@ class Context:
     def normalise(self, grid: _lib.AmtGrid, img_dtype, channels, count, sums, fsum):
         torch = _torch()
         dtype = {torch.uint8: _lib.AMT_U8, torch.uint16: _lib.AMT_U16}[img_dtype]
-        out_img = torch.empty((grid.ny, grid.nx, channels), dtype=img_dtype, device=self.torch_device)
-        out_mask = torch.empty((grid.ny, grid.nx), dtype=torch.uint8, device=self.torch_device)
-        out_side = torch.empty((grid.ny, grid.nx), dtype=torch.float64, device=self.torch_device) \
-            if fsum is not None else None
+        # one allocation for image | mask | side channel (64-byte aligned parts): the sequence
+        # pipeline brings all three to the host with a single copy
+        cells = grid.ny * grid.nx
+        itemsize = 1 if img_dtype == torch.uint8 else 2
+        o_mask = (cells * channels * itemsize + 63) // 64 * 64
+        o_side = (o_mask + cells + 63) // 64 * 64
+        flat = torch.empty(o_side + (cells * 8 if fsum is not None else 0), dtype=torch.uint8, device=self.torch_device)
+        out_img = flat[:cells * channels * itemsize].view(img_dtype).view(grid.ny, grid.nx, channels)
+        out_mask = flat[o_mask:o_mask + cells].view(grid.ny, grid.nx)
+        out_side = flat[o_side:].view(torch.float64).view(grid.ny, grid.nx) if fsum is not None else None
+        out_img._amt_flat = flat
         _lib.check(self.lib.amt_normalise(self.handle, C.byref(grid), dtype, channels, self.ptr(count),
                                           self.ptr(sums), self.ptr(fsum), self.ptr(out_img), self.ptr(out_mask),
                                           self.ptr(out_side), self.stream()))

@@ -188,7 +188,8 @@ int amt_stream_synchronize(amt_ctx* ctx, void* stream);
  * coordinates/intersection.py:58-104, coordinates/transform.py:252-297,324-343,403-430,
  * mapping/astrometry.py:49-64,86-106,138-212, utils.py:28-46.                             */
 int amt_georef(amt_ctx* ctx, const amt_frame* frame, const amt_georef_out* out,
-               amt_stats* d_stats /* nullable: n_ill_conditioned += ... */, void* stream);
+               amt_stats* d_stats /* nullable: n_ill_conditioned is zeroed, then counted; other
+                                      fields untouched */, void* stream);
 
 /* Validity bitmaps from NaN-marked latitude planes (mappings that were not produced by
  * amt_georef: uploaded arrays, resampled grids).                                          */
