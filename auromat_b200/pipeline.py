@@ -40,7 +40,7 @@ class ResampledFrame(object):
         self._hostFlat = None
         self._event = None
 
-    def _startDownload(self, ctx, pool, depthHint=2):
+    def _startDownload(self, ctx, pool, depthHint=2, stream=None):
         """Async D2H of image | mask | elevation into ONE pooled pinned byte buffer.  Buffers are
         pooled by capacity class (next power of two), not by shape: the grid size changes from
         frame to frame and page-locking (cudaHostAlloc) is a millisecond-scale call."""
@@ -69,13 +69,19 @@ class ResampledFrame(object):
         if flatDev is not None:
             ctx.copy_d2h(flat.data_ptr(), flatDev.data_ptr(), total, ctx.stream())      # one cudaMemcpyAsync
         else:
-            for p, o, n in zip(parts, offs, sizes):
-                flat[o:o + n].view(p.dtype).view(p.shape).copy_(p, non_blocking=True)
+            with torch.cuda.stream(stream if stream is not None else torch.cuda.current_stream(ctx.torch_device)):
+                for p, o, n in zip(parts, offs, sizes):
+                    flat[o:o + n].view(p.dtype).view(p.shape).copy_(p, non_blocking=True)
         # host views are built on first access
         self._hostFlat = (flat, offs, sizes, [p.dtype for p in parts], [tuple(p.shape) for p in parts])
         weakref.finalize(self, bucket.append, flat)    # the buffer returns to the pool with the frame
         self._event = torch.cuda.Event()
-        self._event.record()
+        if stream is not None:
+            for p in (flatDev,) if flatDev is not None else parts:
+                p.record_stream(stream)             # allocated on another stream, read by this one
+            self._event.record(stream)
+        else:
+            self._event.record()
 
     @property
     def _host(self):
@@ -235,8 +241,14 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
     if ringBuffers:
         second = ctx.__dict__.get('_second_stream')
         if second is None:
-            second = ctx.__dict__['_second_stream'] = torch.cuda.Stream(ctx.torch_device)
+            # high priority: the short stage-B kernels get SM slots as soon as blocks of the long
+            # georeference kernel retire, instead of queueing behind all of its waves
+            second = ctx.__dict__['_second_stream'] = torch.cuda.Stream(ctx.torch_device, priority=-1)
     hSecond = ctypes.c_void_p(second.cuda_stream) if second is not None else None
+    dout = ctx.__dict__.get('_dout_stream')
+    if dout is None:
+        dout = ctx.__dict__['_dout_stream'] = torch.cuda.Stream(ctx.torch_device)
+    hDout = ctypes.c_void_p(dout.cuda_stream)
 
     def ringSet(i, m):
         h, w = m.shape
@@ -318,11 +330,14 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
             grid, info, dImg, dMask, dElev = resampleToDevice(m, pxPerDeg=pxPerDeg, arcsecPerPx=arcsecPerPx)
             f = ResampledFrame(m, grid, info, dImg, dMask, dElev)
             mark('B1', i, second)
-            if toHost:
-                f._startDownload(ctx, pool, depth)
-            mark('D1', i, second)
             done = torch.cuda.Event()
             done.record(second)
+            if toHost:
+                # results leave on their own stream: the copy must not delay the next frame's binning
+                dout.wait_event(done)
+                ctx.use_stream(hDout)
+                f._startDownload(ctx, pool, depth, stream=dout)
+            mark('D1', i, dout if toHost else second)
         ctx.use_stream(hMain)
         slotDone[i % ringLen] = done
         f._done = done
