@@ -36,8 +36,9 @@ ARCSEC_PER_PX = 100
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=None,
+                    help="timed steps (default: 200 for the B200 arm -- a step is ~0.5 ms -- and 2 for --impl reference)")
+    ap.add_argument("--warmup", type=int, default=None, help="untimed steps (default: 10 / 1)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--width", type=int, default=4256)
     ap.add_argument("--height", type=int, default=2832)
@@ -45,7 +46,13 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-scale", type=int, default=1,
                     help="linear down-scale of the frame used for the CPU baseline sample")
-    return ap.parse_args()
+    args = ap.parse_args()
+    ref = args.impl == "reference"
+    if args.steps is None:
+        args.steps = 2 if ref else 200
+    if args.warmup is None:
+        args.warmup = 1 if ref else 10
+    return args
 
 
 def measured_peaks():
@@ -73,7 +80,7 @@ class ClockSampler:
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                 "-lms", "25"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -250,7 +257,8 @@ def run_b200(args, rank, local_rank, world):
                                   ringBuffers=True, transferStats=transfer):
             last = f
         transfer['frames'] = len(hdrs)
-        return last.img, last.elevation, last
+        last._finish()                 # the last frame's results are in its pinned host buffers
+        return None, None, last
 
     def barrier():
         if world > 1:
@@ -359,9 +367,9 @@ def run_b200(args, rank, local_rank, world):
             "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": achieved / peaks["hbm_gbs"], "peak_kind": peak_kind,
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel for this frame size from the
-            # ncu --set full capture in profiles/r01_georef_bin_v3_ncu.txt (writes only; part of the
+            # ncu --set full capture in profiles/r01_kernels_v5_ncu.txt (writes only; part of the
             # last planes is still in L2 when the kernel ends, hence < algorithmic bytes)
-            "traffic": 811.3e6 if (W, H) == (4256, 2832) and not args.fast_center else None,
+            "traffic": 812.0e6 if (W, H) == (4256, 2832) and not args.fast_center else None,
             "kernel_ms": k_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PIXEL_GEOREF * npx,
             # the kernel is FP64-pipe / issue bound, not HBM bound: algorithmic FP64 rate
             # (290 reference-formula ops per pixel) against the DFMA peak measured just now;
@@ -369,8 +377,8 @@ def run_b200(args, rank, local_rank, world):
             "fp64": {"algorithmic_tflops": ALGO_FLOP_PER_PIXEL_GEOREF * npx / (k_ms * 1e-3) / 1e12,
                      "peak_tflops_measured": 2 * fp64_peak / 1e12,
                      "dfma_issue_peak_ginst": fp64_peak / 1e9,
-                     "ncu_pipe_fp64_pct": 63.0, "ncu_issue_active_pct": 75.0,
-                     "ncu_source": "profiles/r01_georef_bin_v3_ncu.txt"},
+                     "ncu_pipe_fp64_pct": 63.7, "ncu_issue_active_pct": 67.5,
+                     "ncu_source": "profiles/r01_kernels_v5_ncu.txt"},
         },
     }
     if not args.no_cpu_baseline and world == 1:
