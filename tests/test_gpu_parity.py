@@ -950,3 +950,30 @@ def test_themis_reproject_and_mapping(env):
         r.checkPlateCarree()
     coll = themis.mappingCollection([m, None], t)
     assert len(coll.mappings) == 1 and coll.identifier == 'THEMIS.2012.02.04.07.56.26'
+
+
+def test_export_handoff_variables(env):
+    """auromat_b200.export.cdfVariables: names, order, shapes and dtypes of the variables the
+    reference's CDF writer stores (export/cdf.py:83-290), for a frame and its resampling."""
+    from auromat_b200 import synthetic
+    from auromat_b200.export import cdfVariables
+    from auromat_b200.mapping.spacecraft import getMapping
+    from auromat_b200.resample import resample
+    W, H = 133, 89
+    m = getMapping(synthetic.issImage(W, H), synthetic.issHeader(W, H), identifier='x')
+    v = cdfVariables(m)
+    assert list(v) == ['Epoch', 'lat', 'lon', 'lat_bounds', 'lon_bounds', 'altitude', 'mlat', 'mlt', 'mlat_bounds',
+                       'mlt_bounds', 'img_red', 'img_green', 'img_blue', 'zenith_angle', 'camera_pos']
+    assert v['lat']['data'].shape == (1, H, W) and v['lat_bounds']['data'].shape == (1, H + 1, W + 1)
+    assert v['altitude']['data'] == 110000 and v['camera_pos']['data'].shape == (1, 3)
+    assert v['img_red']['data'].dtype == np.int16 and v['img_red']['attrs']['FILLVAL'] == -32768
+    masked = ma.getmaskarray(m.latsCenter)
+    assert np.array_equal(v['img_green']['data'][0] == -32768, masked)
+    assert np.array_equal(np.isnan(v['mlt']['data'][0]), masked)
+    assert v['zenith_angle']['data'].dtype == np.float32
+    np.testing.assert_allclose(v['zenith_angle']['data'][0][~masked], 90 - m.elevation.compressed(), atol=1e-4)
+    assert v['mlt']['attrs']['UNITS'] == 'hours' and v['lat']['attrs']['DEPEND_1'] == 'y_pixel'
+    r = resample(m, arcsecPerPx=400)
+    vr = cdfVariables(r, includeBounds=False, includeMagCoords=False)
+    assert list(vr) == ['Epoch', 'lat', 'lon', 'altitude', 'img_red', 'img_green', 'img_blue', 'zenith_angle', 'camera_pos']
+    assert vr['lat']['data'].shape[1:] == r.latsCenter.shape
