@@ -121,9 +121,10 @@ class MosaicAccumulator(object):
         outImg, outMask, outElev = ctx.normalise(g, self.imgDtype, self.channels, self.count, self.sums, self.fsum)
         lat_k, lon_k, lat_c, lon_c = ctx.plate_carree_coords(g.nx, g.ny, info['latMaxInGrid'], info['latMinInGrid'],
                                                              info['lonMinInGrid'], info['lonMaxInGrid'])
-        if info.get('mode', _lib.AMT_PRE_NONE) == _lib.AMT_PRE_WRAP180:
+        mode = info.get('mode', _lib.AMT_PRE_NONE)
+        if mode != _lib.AMT_PRE_NONE:
             from .resample import _preRotation
-            back = _preRotation(_lib.AMT_PRE_WRAP180, template.altitude)
+            back = _preRotation(mode, template.altitude, angle=-90)     # reference resample.py:262-277
             ctx.rotate_coords(lat_k, lon_k, back)
             ctx.rotate_coords(lat_c, lon_c, back)
         img = ctx.to_numpy(outImg)
@@ -148,17 +149,39 @@ def mosaic(mappings, pxPerDeg, group=None):
         pxPerDeg = (pxPerDeg, pxPerDeg)
     boxes = gatherBoundingBoxes([m.boundingBox for m in mappings], group)
     bb = BoundingBox.mergedBoundingBoxes(boxes)
-    if bb.containsPole:
-        raise NotImplementedError('mosaics that enclose a pole need a common pole rotation')
     mode = _lib.AMT_PRE_NONE
-    lonMin, lonMax = bb.lonWest, bb.lonEast
-    if bb.containsDiscontinuity:
+    latMin, latMax, lonMin, lonMax = bb.latSouth, bb.latNorth, bb.lonWest, bb.lonEast
+    if bb.containsPole or any(b.containsPole for b in boxes):
+        # Same trick as resample.py:176-201, applied to every member: all coordinates are rotated
+        # by 90 deg about the x axis, which moves the pole onto the equator of the rotated frame;
+        # the common grid is laid over the min/max of the members' ROTATED outlines (reduced on
+        # the device, exchanged as four floats per mapping), and rotated back in finalise().
+        from .resample import _preRotation
+        mode = _lib.AMT_PRE_POLE
+        local = []
+        for m in mappings:
+            ctx, (h, w) = m.context, m.shape
+            st = ctx.new_stats()
+            ctx.bbox_stats(w, h, m.devicePlanes(), st, pre=_preRotation(mode, mappings[0].altitude))
+            s = ctx.read_stats(st)
+            local.append((s.lat_min, s.lon_min, s.lat_max, s.lon_max))
+        _, world = worldInfo()
+        if world > 1:
+            import torch.distributed as dist
+            gathered = [None] * world
+            dist.all_gather_object(gathered, local, group=group)
+            local = [t for part in gathered for t in part]
+        latMin, lonMin = min(t[0] for t in local), min(t[1] for t in local)
+        latMax, lonMax = max(t[2] for t in local), max(t[3] for t in local)
+        if lonMax - lonMin > 180:
+            raise NotImplementedError('the rotated mosaic still spans more than 180 degrees of longitude')
+    elif bb.containsDiscontinuity:
         # same trick as resample.py:203-218, applied to every member: rotate the longitudes by
         # 180 deg so that the mosaic does not straddle the date line; rotated back in finalise()
         from .mapping.mapping import wrapAt180
         mode = _lib.AMT_PRE_WRAP180
         lonMin, lonMax = wrapAt180(bb.lonWest + 180), wrapAt180(bb.lonEast + 180)
-    grid, info = targetGrid(pxPerDeg, bb.latSouth, bb.latNorth, lonMin, lonMax, mode, mappings[0].altitude)
+    grid, info = targetGrid(pxPerDeg, latMin, latMax, lonMin, lonMax, mode, mappings[0].altitude)
     info['mode'] = mode
     m0 = mappings[0]
     img0 = m0.deviceImage()

@@ -977,3 +977,41 @@ def test_export_handoff_variables(env):
     vr = cdfVariables(r, includeBounds=False, includeMagCoords=False)
     assert list(vr) == ['Epoch', 'lat', 'lon', 'altitude', 'img_red', 'img_green', 'img_blue', 'zenith_angle', 'camera_pos']
     assert vr['lat']['data'].shape[1:] == r.latsCenter.shape
+
+
+def test_mosaic_over_the_pole(env):
+    """A mosaic whose members enclose the pole: common +90 deg pole rotation for all members
+    (resample.py:176-201 applied collection-wide).  One member: identical to resample(); two
+    members: counts and sums are the sums of the members binned alone into the common grid."""
+    import torch
+    from auromat_b200 import parallel, synthetic
+    from auromat_b200.mapping.spacecraft import getMapping
+    from auromat_b200.resample import binMappingInto, resampleToDevice
+    W, H = 300, 200
+    m1 = getMapping(synthetic.issImage(W, H, seed=1), synthetic.issHeaderLookingAt(78.0, 20.0, 89.5, 120.0, W, H),
+                    identifier='polar')
+    m2 = getMapping(synthetic.issImage(W, H, seed=2), synthetic.issHeaderLookingAt(70.0, -60.0, 80.0, -80.0, W, H),
+                    identifier='subpolar')
+    assert m1.containsPole and not m2.containsPole
+    ppd = (4.0, 2.0)
+    mosaic, acc = parallel.mosaic([m1], ppd)
+    grid, info, outImg, outMask, outElev = resampleToDevice(m1, pxPerDeg=ppd)
+    assert (acc.grid.nx, acc.grid.ny) == (grid.nx, grid.ny) and acc.grid.prerotate == 2
+    assert torch.equal(acc.count, info['count'])
+    assert np.array_equal(mosaic.img.filled(0), np.where(outMask.cpu().numpy()[:, :, None] != 0, 0, outImg.cpu().numpy()))
+    # rotated back: the mosaic's corner coordinates surround the pole
+    assert mosaic.lats.max() > 89.0 and mosaic.lons.min() < -170 and mosaic.lons.max() > 170
+    both, acc2 = parallel.mosaic([m1, m2], ppd)
+    cells = acc2.grid.nx * acc2.grid.ny
+    tot_c, tot_s = torch.zeros(cells, dtype=torch.int64, device='cuda'), torch.zeros(3 * cells, dtype=torch.int64, device='cuda')
+    for m in (m1, m2):
+        c = torch.zeros(cells, dtype=torch.int64, device='cuda')
+        s = torch.zeros(3 * cells, dtype=torch.int64, device='cuda')
+        f = torch.zeros(cells, dtype=torch.float64, device='cuda')
+        binMappingInto(m, acc2.grid, c, s, f)
+        # (the outermost half cells of the snapped range are not part of the grid, resample.py:232-237)
+        assert 0.99 * m._deviceStats().n_valid_centers < int(c.sum().item()) <= m._deviceStats().n_valid_centers
+        tot_c += c
+        tot_s += s
+    assert torch.equal(acc2.count, tot_c) and torch.equal(acc2.sums, tot_s)
+    assert (~ma.getmaskarray(both.latsCenter)).sum() > 0
