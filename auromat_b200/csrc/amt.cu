@@ -1343,10 +1343,7 @@ __global__ void __launch_bounds__(256) k_reproject(const double* __restrict__ la
         const double dir[3] = {G[0] - f.cam[0], G[1] - f.cam[1], G[2] - f.cam[2]};
         bool graze;
         if (intersect(f, dir, P, graze)) {
-            double l2, o2;
-            bowring(f.a, f.b_over_a, f.e2a, f.d, P[0], P[1], P[2], l2, o2);
-            ol = l2 * kRad2Deg;
-            oo = o2 * kRad2Deg;
+            bowring(f.a, f.b_over_a, f.e2a, f.d, P[0], P[1], P[2], ol, oo);     // degrees
         }
     }
     lat_out[i] = ol;

@@ -76,19 +76,21 @@ __device__ __forceinline__ double rsqrt_fast(double a) {
     return h + h;
 }
 
-// atan(i/32), i = 0..32
+// atan(i/32) in DEGREES, i = 0..32.  Every consumer of the arctangents wants degrees
+// (lat/lon/MLat, MLT = smlon/15 + 12, elevation), so the conversion factor 180/pi is folded into
+// the table and into the polynomial coefficients instead of costing a multiply per result.
 __constant__ double c_atan_tab[33] = {
-    0, 0.031239833430268277, 0.06241880999595735,
-    0.09347678115858947, 0.12435499454676144, 0.15499674192394097,
-    0.18534794999569476, 0.21535769969773805, 0.24497866312686414,
-    0.27416745111965879, 0.30288486837497142, 0.3310960767041321,
-    0.35877067027057225, 0.38588266939807375, 0.41241044159738732,
-    0.43833655985795783, 0.46364760900080609, 0.48833395105640554,
-    0.51238946031073773, 0.5358112379604637, 0.55859931534356244,
-    0.58075635356767041, 0.60228734613496415, 0.6231993299340659,
-    0.64350110879328437, 0.66320299270609329, 0.68231655487474807,
-    0.70085440788445019, 0.71882999962162453, 0.7362574289814281,
-    0.75315128096219441, 0.7695264804056583, 0.78539816339744828,
+    0.0, 1.7899106082460694, 3.576334374997351,
+    5.35582504285519, 7.125016348901798, 8.880659150520245,
+    10.619655276155134, 12.339087278326195, 14.036243467926479,
+    15.708637829015744, 17.35402463626132, 18.970407808486545,
+    20.556045219583467, 22.109448343751673, 23.629377730656817,
+    25.114834886144564, 26.56505117707799, 27.979474388480146,
+    29.357753542791276, 30.699722550814414, 32.005383208083494,
+    33.274887984834926, 34.5085229876684, 35.706691400602885,
+    36.86989764584402, 37.99873244250467, 39.0938588862295,
+    40.155999624919325, 41.18592516570965, 42.18444331578877,
+    43.15238973400541, 44.09061955080086, 45.0,
 };
 
 // Constants whose low mantissa word is non-zero cannot be instruction immediates; kept in
@@ -96,21 +98,19 @@ __constant__ double c_atan_tab[33] = {
 // UMOV / IMAD.MOV each (the polynomial coefficients alone were 14 of the 54 instructions of the
 // first version of atan2_fast).
 __constant__ double c_fm[8] = {
-    1.0 / 9.0, -1.0 / 7.0, 1.0 / 5.0, -1.0 / 3.0,      // atan Taylor coefficients
-    1.5707963267948966, 3.141592653589793,             // pi/2, pi
-    57.29577951308232, 0.017453292519943295,           // 180/pi, pi/180
+    6.366197723675814, -8.18511135901176, 11.459155902616464, -19.098593171027442, 57.29577951308232,      // (180/pi) * {1/9, -1/7, 1/5, -1/3, 1}: atan Taylor series in degrees
+    0.0, 0.0, 0.0,
 };
-#define AMT_C_HALF_PI c_fm[4]
-#define AMT_C_PI c_fm[5]
 
 __device__ __forceinline__ double fabs_bits(double x) {        // |x| on the integer pipe, not the FP64 pipe
     return __hiloint2double(__double2hiint(x) & 0x7fffffff, __double2loint(x));
 }
 
-// atan(mn/mx) for 0 <= mn <= mx, mx > 0: pick c = i/32 nearest to mn/mx from the MUFU
+// atan(mn/mx) in degrees for 0 <= mn <= mx, mx > 0: pick c = i/32 nearest to mn/mx from the MUFU
 // reciprocal seed, then atan(mn/mx) = atan(c) + atan(t), t = (mn - c*mx)/(mx + c*mn),
-// |t| <= 1/64 + 2^-19, where the degree-9 odd Taylor polynomial is exact to 1e-21.
-__device__ __forceinline__ double atan_ratio(double mn, double mx) {
+// |t| <= 1/64 + 2^-19, where the degree-9 odd Taylor polynomial is exact to 1e-21:
+// result = tab_deg[i] + t * K(1 - s/3 + s^2/5 - s^3/7 + s^4/9), s = t^2  (1 DMUL + 5 DFMA).
+__device__ __forceinline__ double atan_ratio_deg(double mn, double mx) {
     const double q = mn * mufu_rcp(mx);
     // q + 1.5*2^47 has an ulp of exactly 1/32: the sum IS q rounded to a multiple of 1/32,
     // and its low mantissa word is the integer 32*c
@@ -127,43 +127,36 @@ __device__ __forceinline__ double atan_ratio(double mn, double mx) {
     p = fma(p, s, c_fm[1]);
     p = fma(p, s, c_fm[2]);
     p = fma(p, s, c_fm[3]);
-    const double ts = t * s;
-    return c_atan_tab[i] + fma(ts, p, t);
+    p = fma(p, s, c_fm[4]);
+    return fma(t, p, c_atan_tab[i]);
 }
 
-constexpr double kPi = 3.141592653589793;
-constexpr double kHalfPi = 1.5707963267948966;
-
-// atan2(y, x), any quadrant, finite inputs, not both zero.
-__device__ __forceinline__ double atan2_fast(double y, double x) {
+// atan2(y, x) in degrees, any quadrant, finite inputs, not both zero.
+__device__ __forceinline__ double atan2_deg(double y, double x) {
     const double a = fabs_bits(y), b = fabs_bits(x);
     const bool swap = a > b;
-    double r = atan_ratio(swap ? b : a, swap ? a : b);
-    if (swap) r = AMT_C_HALF_PI - r;
-    if (x < 0.0) r = AMT_C_PI - r;
+    double r = atan_ratio_deg(swap ? b : a, swap ? a : b);
+    if (swap) r = 90.0 - r;
+    if (x < 0.0) r = 180.0 - r;
     return copysign(r, y);
 }
 
-// atan2(y, x) for x >= 0 (result in [-pi/2, pi/2]); also serves atan(y/x).
-__device__ __forceinline__ double atan2_posx(double y, double x) {
+// atan2(y, x) in degrees for x >= 0 (result in [-90, 90]); also serves atan(y/x) and asin.
+__device__ __forceinline__ double atan2_posx_deg(double y, double x) {
     const double a = fabs_bits(y);
     const bool swap = a > x;
-    double r = atan_ratio(swap ? x : a, swap ? a : x);
-    if (swap) r = AMT_C_HALF_PI - r;
+    double r = atan_ratio_deg(swap ? x : a, swap ? a : x);
+    if (swap) r = 90.0 - r;
     return copysign(r, y);
 }
 
-// acos(d) for d in [-1, 1] via atan2(sqrt((1-d)(1+d)), d); (1-d) is exact for d >= 0.5.
-__device__ __forceinline__ double acos_fast(double d) {
+// 90 - acos(d) = asin(d) in degrees for d in [-1, 1], via atan2(d, sqrt((1-d)(1+d)));
+// (1-d) is exact for d >= 0.5.
+__device__ __forceinline__ double asin_deg(double d) {
     const double w = (1.0 - d) * (1.0 + d);
     const double s = w > 0.0 ? sqrt_fast(w) : 0.0;
-    const double a = fabs_bits(d);
-    const bool swap = s > a;
-    if (s == 0.0) return d < 0.0 ? kPi : 0.0;
-    double r = atan_ratio(swap ? a : s, swap ? s : a);
-    if (swap) r = AMT_C_HALF_PI - r;
-    if (d < 0.0) r = AMT_C_PI - r;
-    return r;
+    if (s == 0.0) return copysign(90.0, d);
+    return atan2_posx_deg(d, s);
 }
 
 }  // namespace amt

@@ -205,7 +205,7 @@ __device__ __forceinline__ void mat3(const double* __restrict__ M, const double 
 //   p = sqrt(x^2+y^2), r = sqrt(p^2+z^2), tu = b z (1 + d/r)/(a p), cu3 = (1+tu^2)^(-3/2),
 //   lat = atan((z + d cu3 tu^3)/(p - e^2 a cu3)), lon = atan2(y, x)
 // evaluated with one Goldschmidt (sqrt, 1/sqrt) pair per root, no division besides the two
-// inside the arctangents:  tu = (b/a) z (r + d) (1/r)(1/p).  Output in radians.
+// inside the arctangents:  tu = (b/a) z (r + d) (1/r)(1/p).  Output in DEGREES.
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void bowring(double a, double b_over_a, double e2a, double d,
                                         double x, double y, double z, double& lat, double& lon) {
@@ -217,8 +217,8 @@ __device__ __forceinline__ void bowring(double a, double b_over_a, double e2a, d
     const double c = rsqrt_40(fma(tu, tu, 1.0));   // scales the e^2-sized correction terms only
     const double cu3 = (c * c) * c;
     const double su3 = (tu * cu3) * (tu * tu);
-    lat = atan2_posx(fma(d, su3, z), fma(-e2a, cu3, p));
-    lon = atan2_fast(y, x);
+    lat = atan2_posx_deg(fma(d, su3, z), fma(-e2a, cu3, p));
+    lon = atan2_deg(y, x);
     (void)a;
 }
 
@@ -262,8 +262,8 @@ __device__ __forceinline__ void geodetic2ecef(double a, double e2, double lat, d
 // SM Cartesian -> (MLat deg, MLT h): transform.py:104-127 + :419-430 + :373-386.
 __device__ __forceinline__ void sm_to_mlat_mlt(const double S[3], double& mlat, double& mlt) {
     const double s = sqrt_fast(fma(S[0], S[0], S[1] * S[1]));
-    const double smlon = atan2_fast(S[1], S[0]) * kRad2Deg;
-    mlat = atan2_posx(S[2], s) * kRad2Deg;
+    const double smlon = atan2_deg(S[1], S[0]);
+    mlat = atan2_posx_deg(S[2], s);
     mlt = fma(smlon, 24.0 / 360.0, 12.0);
 }
 
@@ -278,17 +278,14 @@ __device__ __forceinline__ double elevation_deg(const double dir[3], const doubl
     double dot = -fma(dir[2], P[2], fma(dir[1], P[1], dir[0] * P[0])) * rsqrt_fast(n2);
     // np.clip(dot, -1, 1)
     dot = fmin(fmax(dot, -1.0), 1.0);
-    return fma(-acos_fast(dot), kRad2Deg, 90.0);
+    return asin_deg(dot);                       // 90 - deg(acos(dot))
 }
 
 // One J2000 intersection point -> lat/lon [deg] (+ MLat/MLT).  transform.py:324-343,403-430.
 __device__ __forceinline__ void point_to_geo(const FrameC& f, const double P[3], double& lat, double& lon) {
     double G[3];
     mat3(f.m_geo, P, G);
-    double la, lo;
-    bowring(f.a, f.b_over_a, f.e2a, f.d, G[0], G[1], G[2], la, lo);
-    lat = la * kRad2Deg;
-    lon = lo * kRad2Deg;
+    bowring(f.a, f.b_over_a, f.e2a, f.d, G[0], G[1], G[2], lat, lon);
 }
 
 __device__ __forceinline__ void point_to_mag(const FrameC& f, const double P[3], double& mlat, double& mlt) {
