@@ -9,19 +9,35 @@
 #include <cstdarg>
 #include <new>
 #include <cuda_runtime.h>
+#include <vector>
 #include "amt_math.cuh"
 
 using namespace amt;
 
 // ============================================================================ context
-struct amt_ctx {
-    int device;
-    int sm_count;
-    unsigned long long launches;
+// Device-side temporaries are owned per (context, stream): calls issued on different streams of
+// one context (the sequence pipeline uses five) never share a scratch arena or a statistics key
+// block.  A context is driven by one host thread at a time.
+struct Workspace {
+    cudaStream_t stream;
     void* scratch;
     size_t scratch_bytes;
     void* stat_keys;          // device StatKeys block, self-cleaning (see k_stats_bits)
 };
+
+struct amt_ctx {
+    int device;
+    int sm_count;
+    unsigned long long launches;
+    std::vector<Workspace> ws;
+};
+
+static Workspace& workspace(amt_ctx* ctx, cudaStream_t st) {
+    for (auto& w : ctx->ws)
+        if (w.stream == st) return w;
+    ctx->ws.push_back(Workspace{st, nullptr, 0, nullptr});
+    return ctx->ws.back();
+}
 
 static thread_local char g_err[512] = "";
 
@@ -55,14 +71,17 @@ static int set_err(int code, const char* fmt, ...) {
                            cudaGetErrorString(_e), __FILE__, __LINE__);                     \
     } while (0)
 
-static int ensure_scratch(amt_ctx* ctx, size_t bytes) {
-    if (ctx->scratch_bytes >= bytes) return AMT_OK;
-    if (ctx->scratch) CUDA_TRY(cudaFree(ctx->scratch));
-    ctx->scratch = nullptr;
-    ctx->scratch_bytes = 0;
-    size_t want = bytes + bytes / 4;
-    CUDA_TRY(cudaMalloc(&ctx->scratch, want));
-    ctx->scratch_bytes = want;
+static int ensure_scratch(amt_ctx* ctx, cudaStream_t st, size_t bytes, void** ptr) {
+    Workspace& w = workspace(ctx, st);
+    if (w.scratch_bytes < bytes) {
+        if (w.scratch) CUDA_TRY(cudaFree(w.scratch));        // synchronises the device: safe, and rare
+        w.scratch = nullptr;
+        w.scratch_bytes = 0;
+        size_t want = bytes + bytes / 4;
+        CUDA_TRY(cudaMalloc(&w.scratch, want));
+        w.scratch_bytes = want;
+    }
+    *ptr = w.scratch;
     return AMT_OK;
 }
 
@@ -87,9 +106,6 @@ extern "C" int amt_ctx_create(int device, amt_ctx** out) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     c->launches = 0;
-    c->scratch = nullptr;
-    c->scratch_bytes = 0;
-    c->stat_keys = nullptr;
     *out = c;
     return AMT_OK;
 }
@@ -97,8 +113,10 @@ extern "C" int amt_ctx_create(int device, amt_ctx** out) {
 extern "C" int amt_ctx_destroy(amt_ctx* ctx) {
     if (!ctx) return AMT_OK;
     cudaSetDevice(ctx->device);
-    if (ctx->scratch) cudaFree(ctx->scratch);
-    if (ctx->stat_keys) cudaFree(ctx->stat_keys);
+    for (auto& w : ctx->ws) {
+        if (w.scratch) cudaFree(w.scratch);
+        if (w.stat_keys) cudaFree(w.stat_keys);
+    }
     delete ctx;
     return AMT_OK;
 }
@@ -183,9 +201,10 @@ extern "C" int amt_measure_fp64_peak(amt_ctx* ctx, double* dfma_per_second) {
     ENTER(ctx);
     CHECK_ARG(dfma_per_second, "amt_measure_fp64_peak: NULL argument");
     const int blocks = ctx->sm_count * 8, iters = 4096;
-    int rc = ensure_scratch(ctx, (size_t)blocks * 256 * sizeof(double));
+    void* scratch = nullptr;
+    int rc = ensure_scratch(ctx, (cudaStream_t)0, (size_t)blocks * 256 * sizeof(double), &scratch);
     if (rc) return rc;
-    double* out = (double*)ctx->scratch;
+    double* out = (double*)scratch;
     cudaEvent_t e0, e1;
     CUDA_TRY(cudaEventCreate(&e0));
     CUDA_TRY(cudaEventCreate(&e1));
@@ -962,10 +981,11 @@ extern "C" int amt_sanitize(amt_ctx* ctx, int32_t W, int32_t H, const amt_georef
     cudaStream_t st = (cudaStream_t)stream;
     const int wk = wpr_of(W + 1), wc = wpr_of(W);
     const size_t nk = (size_t)wk * (H + 1), nc = (size_t)wc * H;
-    int rc = ensure_scratch(ctx, (nk + nc) * 4);
+    void* scratch = nullptr;
+    int rc = ensure_scratch(ctx, st, (nk + nc) * 4, &scratch);
     if (rc) return rc;
     // the kernel reads copies of the input bitmaps and overwrites the originals
-    unsigned* k0 = (unsigned*)ctx->scratch;
+    unsigned* k0 = (unsigned*)scratch;
     unsigned* c0 = k0 + nk;
     if (planes->d_valid_c == planes->d_valid_k + nk) {           // allocated back to back: one copy
         CUDA_TRY(cudaMemcpyAsync(k0, planes->d_valid_k, (nk + nc) * 4, cudaMemcpyDeviceToDevice, st));
@@ -981,12 +1001,13 @@ extern "C" int amt_sanitize(amt_ctx* ctx, int32_t W, int32_t H, const amt_georef
 }
 
 static int get_stat_keys(amt_ctx* ctx, cudaStream_t st, StatKeys** keys) {
-    if (!ctx->stat_keys) {
-        CUDA_TRY(cudaMalloc(&ctx->stat_keys, sizeof(StatKeys)));
-        k_stats_init<<<1, 1, 0, st>>>((StatKeys*)ctx->stat_keys);      // once; afterwards self-cleaning
+    Workspace& w = workspace(ctx, st);
+    if (!w.stat_keys) {
+        CUDA_TRY(cudaMalloc(&w.stat_keys, sizeof(StatKeys)));
+        k_stats_init<<<1, 1, 0, st>>>((StatKeys*)w.stat_keys);         // once per stream; afterwards self-cleaning
         LAUNCH_CHECK(ctx);
     }
-    *keys = (StatKeys*)ctx->stat_keys;
+    *keys = (StatKeys*)w.stat_keys;
     return AMT_OK;
 }
 
@@ -1011,12 +1032,13 @@ extern "C" int amt_bbox_stats_frame(amt_ctx* ctx, const amt_frame* frame, const 
     const int wk = wpr_of(W + 1), wc = wpr_of(W);
     // the frame constants live behind the sanitize scratch bitmap
     const size_t off = ((size_t)wk * (H + 1) * 4 + 255) / 256 * 256;
-    rc = ensure_scratch(ctx, off + sizeof(GeorefParams));
+    void* scratch = nullptr;
+    rc = ensure_scratch(ctx, st, off + sizeof(GeorefParams), &scratch);
     if (rc) return rc;
     StatKeys* keys;
     rc = get_stat_keys(ctx, st, &keys);
     if (rc) return rc;
-    GeorefParams* dp = (GeorefParams*)((unsigned char*)ctx->scratch + off);
+    GeorefParams* dp = (GeorefParams*)((unsigned char*)scratch + off);
     CUDA_TRY(cudaMemcpyAsync(dp, &p, sizeof p, cudaMemcpyHostToDevice, st));
     Bits K{d_valid_k, wk, H + 1}, C{d_valid_c, wc, H};
     const int words = wk * (H + 1);
@@ -1198,9 +1220,10 @@ extern "C" int amt_polygon_center_mask(amt_ctx* ctx, int32_t W, int32_t H, const
     }
     cudaStream_t st = (cudaStream_t)stream;
     const int wk = wpr_of(W + 1);
-    int rc = ensure_scratch(ctx, (size_t)wk * (H + 1) * 4);
+    void* scratch = nullptr;
+    int rc = ensure_scratch(ctx, st, (size_t)wk * (H + 1) * 4, &scratch);
     if (rc) return rc;
-    unsigned* bits = (unsigned*)ctx->scratch;
+    unsigned* bits = (unsigned*)scratch;
     if (d_n_inside) CUDA_TRY(cudaMemsetAsync(d_n_inside, 0, sizeof(uint64_t), st));
     dim3 gk((wk * 32 + 255) / 256, H + 1);
     k_polygon_corner_bits<<<gk, 256, 0, st>>>(W, H, d_lat_k, d_lon_k, d_polygon, n_polygon, g, bits, wk,

@@ -73,6 +73,9 @@ class BaseAstrometryMapping(BaseMapping):
         out = pool.get('_out') if len(fresh) == pool.get('_nplanes', -1) and not self._planes else None
         ctx.georef(self.frameConstants, fresh, stats, out=out)
         self._planes.update(fresh)
+        hook = self.__dict__.pop('_afterGeoref', None)     # the sequence pipeline switches streams here
+        if hook is not None:
+            hook()
         if self._sanitize:
             ctx.sanitize(w, h, self._planes, out=out)
         self.isSanitized = True

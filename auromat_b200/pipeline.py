@@ -245,6 +245,12 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
             # georeference kernel retire, instead of queueing behind all of its waves
             second = ctx.__dict__['_second_stream'] = torch.cuda.Stream(ctx.torch_device, priority=-1)
     hSecond = ctypes.c_void_p(second.cuda_stream) if second is not None else None
+    aux = hAux = None
+    if ringBuffers and coordinates:
+        aux = ctx.__dict__.get('_aux_stream')
+        if aux is None:
+            aux = ctx.__dict__['_aux_stream'] = torch.cuda.Stream(ctx.torch_device, priority=-1)
+        hAux = ctypes.c_void_p(aux.cuda_stream)
     dout = ctx.__dict__.get('_dout_stream')
     if dout is None:
         dout = ctx.__dict__['_dout_stream'] = torch.cuda.Stream(ctx.torch_device)
@@ -292,9 +298,29 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
             m._planeBuffers = ringSet(i, m)
             m._statsDevice = m._planeBuffers['_stats']      # ring-owned statistics block (no per-frame alloc)
         mark('A0', i, main)
-        m.prefetch(magnetic=magnetic)
-        m._startStats()
-        mark('A1', i, main)
+        if aux is None:
+            m.prefetch(magnetic=magnetic)
+            m._startStats()
+            mark('A1', i, main)
+            return m, ev, i
+        # The long georeference kernel stays alone on the caller's stream (back to back from frame
+        # to frame); the short sanitise / statistics launches and the statistics read-back move to
+        # an auxiliary high-priority stream and overlap the next frame's georeferencing.
+        def toAux():
+            evG = torch.cuda.Event()
+            evG.record(main)
+            mark('A1', i, main)
+            aux.wait_event(evG)
+            ctx.use_stream(hAux)
+        m._afterGeoref = toAux
+        with torch.cuda.stream(aux):
+            ctx.use_stream(hMain)              # the georeference launch itself goes to the main stream
+            m.prefetch(magnetic=magnetic)
+            m._startStats()
+            evS = torch.cuda.Event()
+            evS.record(aux)
+        ctx.use_stream(hMain)
+        m._statsReady = evS
         return m, ev, i
 
     def lateUpload(m, i):
@@ -319,8 +345,10 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
             if toHost:
                 f._startDownload(ctx, pool, depth)
             return f
-        evA = torch.cuda.Event()
-        evA.record(main)                        # everything of stage A of this frame
+        evA = m.__dict__.pop('_statsReady', None)
+        if evA is None:
+            evA = torch.cuda.Event()
+            evA.record(main)                    # everything of stage A of this frame
         with torch.cuda.stream(second):
             ctx.use_stream(hSecond)
             second.wait_event(evA)
