@@ -24,16 +24,28 @@ Z = (0.0, 0.0, -1.0)
 def rotation_matrix(angle, direction):
     """3x3 rotation about `direction` by `angle` rad (Rodrigues form; reference
     coordinates/transformations.py:295-336, upper-left block).  Scalar arithmetic in the
-    reference's order: R = diag(cos) + outer(d,d)*(1-cos) + skew(d*sin)."""
+    reference's order: R = diag(cos) + outer(d,d)*(1-cos) + skew(d*sin).  (Filled element by
+    element: building a 3x3 ndarray from nested lists costs more than the arithmetic.)"""
     sina, cosa = math.sin(angle), math.cos(angle)
-    dx, dy, dz = (float(v) for v in direction)
-    n = math.sqrt(dx * dx + dy * dy + dz * dz)
-    dx, dy, dz = dx / n, dy / n, dz / n
+    if direction is X or direction is Y or direction is Z:
+        dx, dy, dz = direction                       # unit axes: the normalisation is the identity
+    else:
+        dx, dy, dz = (float(v) for v in direction)
+        n = math.sqrt(dx * dx + dy * dy + dz * dz)
+        dx, dy, dz = dx / n, dy / n, dz / n
     omc = 1.0 - cosa
     sx, sy, sz = dx * sina, dy * sina, dz * sina
-    return np.array([[cosa + (dx * dx) * omc + 0.0, 0.0 + (dx * dy) * omc + -sz, 0.0 + (dx * dz) * omc + sy],
-                     [0.0 + (dy * dx) * omc + sz, cosa + (dy * dy) * omc + 0.0, 0.0 + (dy * dz) * omc + -sx],
-                     [0.0 + (dz * dx) * omc + -sy, 0.0 + (dz * dy) * omc + sx, cosa + (dz * dz) * omc + 0.0]])
+    m = np.empty((3, 3))
+    m[0, 0] = cosa + (dx * dx) * omc + 0.0
+    m[0, 1] = 0.0 + (dx * dy) * omc + -sz
+    m[0, 2] = 0.0 + (dx * dz) * omc + sy
+    m[1, 0] = 0.0 + (dy * dx) * omc + sz
+    m[1, 1] = cosa + (dy * dy) * omc + 0.0
+    m[1, 2] = 0.0 + (dy * dz) * omc + -sx
+    m[2, 0] = 0.0 + (dz * dx) * omc + -sy
+    m[2, 1] = 0.0 + (dz * dy) * omc + sx
+    m[2, 2] = cosa + (dz * dz) * omc + 0.0
+    return m
 
 
 def euler_matrix_rzxz(ai, aj, ak):
