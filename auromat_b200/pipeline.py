@@ -2,17 +2,19 @@
 
 `getMappingSequence` of the reference (mapping/spacecraft.py:308-332) yields one mapping at a
 time and `ResampleProvider` (resample.py:370-394) maps `resample` over it; every frame is
-independent.  `resampleSequence` is the same composition with the three host-visible phases of
-a frame interleaved across frames so that the GPU never waits for the host:
+independent.  `resampleSequence` is the same composition with the host-visible phases of a
+frame interleaved across frames so that the GPU never waits for the host:
 
-  A(i)   host: per-frame constants; enqueue  H2D image (copy stream) | georeference, sanitise,
-         outline statistics, async read-back of the 88-byte statistics block (compute stream)
-  B(i-1) host: bounding box -> target grid (needs the statistics of frame i-1, long finished);
-         enqueue zero/bin/normalise (+ async D2H of the resampled image and elevation)
-  C(i-2) host: hand the finished frame to the caller
+  A(i)   host: per-frame constants; enqueue the georeference kernel (caller's stream, back to back
+         from frame to frame) and, on an auxiliary high-priority stream, sanitise + outline
+         statistics + the asynchronous read-back of the 104-byte statistics block
+  B(i-d) host: bounding box -> target grid (needs the statistics of frame i-d, long finished);
+         enqueue the upload of the image rows that hold valid pixels (copy stream), zero / bin /
+         normalise (second high-priority stream) and the D2H of the results (their own stream)
+  C      host: hand the finished frame to the caller
 
 The only device->host dependency of the path (grid size depends on the footprint) is thereby
-hidden behind the next frame's georeferencing.  Results are identical to calling
+hidden behind the georeferencing of the next `depth` frames.  Results are identical to calling
 `resample(getMapping(...))` frame by frame.
 """
 from __future__ import annotations
@@ -136,7 +138,7 @@ class ResampledFrame(object):
 
 
 def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, altitude=110,
-                     fastCenterCalculation=False, magnetic=False, metadatas=None, depth=2, toHost=True,
+                     fastCenterCalculation=False, magnetic=False, metadatas=None, depth=3, toHost=True,
                      device=None, ringBuffers=False, coordinates=True, sparseUpload=True, transferStats=None):
     """Generator of `ResampledFrame` for an image sequence (frames in order).
 
@@ -144,7 +146,8 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
                            tensors or image paths
     :param wcsHeaders: iterable of header dicts or `.wcs` paths, same length
     :param magnetic: also produce the MLat/MLT planes of every frame
-    :param depth: frames in flight (>= 1); 1 disables the overlap
+    :param depth: frames whose georeferencing is enqueued ahead of the host-side grid derivation
+        (>= 1; 1 disables the overlap, 3 keeps the GPU fed through host jitter)
     :param toHost: copy the resampled image / mask / elevation to pinned host buffers
     :param coordinates: False = plane-free mode: only the resampling is wanted, the per-pixel
         coordinate planes are never written (hit bitmaps -> outline statistics -> fused
