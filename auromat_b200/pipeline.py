@@ -235,11 +235,12 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
     ring = []
     slotDone = {}            # ring slot -> event recorded after the binning of its last user
     ringLen = depth + 3
-    # With ring buffers the two halves of a frame run on two streams: georeference / sanitise /
-    # statistics of frame i on the caller's stream, zero / bin / normalise / D2H of frame i-1 on a
-    # second one, so that the small kernels and launch gaps of one half hide under the big kernel
-    # of the other.  (Without ring buffers the planes are per-frame allocations of the caller's
-    # stream and everything stays on it.)
+    # With ring buffers the phases of a frame run on separate streams (see the module docstring):
+    # the georeference kernel on the caller's stream, sanitise / statistics on `aux`, zero / bin /
+    # normalise on `second`, uploads on `copy`, result downloads on `dout`, so that the small
+    # kernels and launch gaps hide under the long kernel of the following frames.  (Without ring
+    # buffers the planes are per-frame allocations of the caller's stream and everything stays
+    # on it.)
     second = None
     if ringBuffers:
         second = ctx.__dict__.get('_second_stream')

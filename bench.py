@@ -198,7 +198,7 @@ def workload_config(args, n_gpus):
         "frame": [args.width, args.height], "altitude_km": 110, "arcsec_per_px": ARCSEC_PER_PX,
         "fast_center": bool(args.fast_center), "outputs": "lat/lon/MLat/MLT corners+centres, elevation, resampled RGB+elevation",
         "parallelism": "frames x%d" % n_gpus,
-        "api": "auromat_b200.pipeline.resampleSequence (getMapping + resample per frame, 2 frames in flight)",
+        "api": "auromat_b200.pipeline.resampleSequence (getMapping + resample per frame, pipelined: georeferencing of 3 frames enqueued ahead)",
         "l2": "per-step working set ~0.9 GB (72 B/px planes + image) exceeds the 126 MB L2; no explicit flush",
     }
 
