@@ -1015,3 +1015,41 @@ def test_mosaic_over_the_pole(env):
         tot_s += s
     assert torch.equal(acc2.count, tot_c) and torch.equal(acc2.sums, tot_s)
     assert (~ma.getmaskarray(both.latsCenter)).sum() > 0
+
+
+def test_pipeline_gray_images_plane_free_and_empty_frames(env):
+    """Sequence pipeline corner cases: single-channel (grey-scale) images through the sparse
+    row-range upload, the plane-free mode with host images, a frame that sees no Earth at all
+    (the reference raises on its empty outline; so does the generator, leaving the context usable)."""
+    from auromat_b200 import synthetic
+    from auromat_b200.mapping.spacecraft import getMapping
+    from auromat_b200.pipeline import resampleSequence
+    from auromat_b200.resample import resample
+    W, H, n = 200, 130, 4
+    hdrs = synthetic.sequenceHeaders(n, W, H)
+    rng = np.random.default_rng(3)
+    for shape, dtype in (((H, W, 1), np.uint8), ((H, W, 1), np.uint16)):
+        imgs = [rng.integers(0, 200, shape).astype(dtype) for _ in range(n)]
+        expect = [resample(getMapping(im, h, identifier='x'), arcsecPerPx=400) for im, h in zip(imgs, hdrs)]
+        for ring in (False, True):
+            got = list(resampleSequence(imgs, hdrs, arcsecPerPx=400, ringBuffers=ring))
+            for f, e in zip(got, expect):
+                assert f.img.shape == e.img.shape and f.img.dtype == e.img.dtype
+                assert np.array_equal(ma.getmaskarray(f.img), ma.getmaskarray(e.img))
+                assert np.array_equal(f.img.filled(0), e.img.filled(0))
+    imgs = [synthetic.issImage(W, H, seed=i) for i in range(n)]
+    expect = [resample(getMapping(im, h, identifier='x'), arcsecPerPx=400) for im, h in zip(imgs, hdrs)]
+    tr = {}
+    got = list(resampleSequence(imgs, hdrs, arcsecPerPx=400, coordinates=False, ringBuffers=True, transferStats=tr))
+    assert 0 < tr['h2d_bytes'] < sum(im.nbytes for im in imgs)
+    for f, e in zip(got, expect):
+        assert 'lat_c' not in f.mapping._planes            # really plane-free
+        assert np.array_equal(f.img.filled(0), e.img.filled(0))
+    # a camera that looks away from the Earth: no valid pixel
+    sky = dict(hdrs[0])
+    sky['CRVAL2'] = -hdrs[0]['CRVAL2']
+    sky['CRVAL1'] = (hdrs[0]['CRVAL1'] + 180.0) % 360.0
+    with pytest.raises(ValueError):
+        list(resampleSequence([imgs[0], imgs[1]], [hdrs[0], sky], arcsecPerPx=400, ringBuffers=True))
+    again = list(resampleSequence(imgs[:2], hdrs[:2], arcsecPerPx=400, ringBuffers=True))
+    assert np.array_equal(again[1].img.filled(0), expect[1].img.filled(0))
