@@ -85,6 +85,15 @@ def getPhotoTime(header):
     return _parseDate(dateobs)
 
 
+def getShiftedPhotoTime(header):
+    """DATE-OBS + DATESHIF if a time shift is stored, else DATE-OBS (reference fits.py:381-391)."""
+    date = getPhotoTime(header)
+    shift = header.get('DATESHIF')
+    if date is None or shift is None:
+        return date
+    return date + timedelta(seconds=shift)
+
+
 def getSpacecraftPosition(header):
     """([x,y,z] km in GCRS at DATE-OBS, date) or (None, None)."""
     date = getPhotoTime(header)

@@ -2,22 +2,25 @@
 
 API mirror of `auromat/mapping/spacecraft.py` (getMapping :380-426, _prepareMappingParams
 :428-485, getMappingSequence :308-332, BaseSpacecraftMapping :487-555,
-ArraySpacecraftMapping :583-595).  Camera positions must come from the header
+ArraySpacecraftMapping :583-595, SpacecraftMappingProvider :40-218,
+SpacecraftMappingPathProvider :220-292).  Camera positions must come from the header
 (POSX/Y/Z or POS*SHIF + DATESHIF); the TLE route (pyephem + space-track download,
 :454-483) is outside the hot path.
 """
 from __future__ import annotations
 
 import gc
+import json
 import os
 import warnings
-from datetime import timedelta
+from datetime import datetime, timedelta
 
 import numpy as np
 import numpy.ma as ma
 
 from .. import fits
 from .astrometry import BaseAstrometryMapping
+from .mapping import BaseMappingProvider
 
 
 def _prepareMappingParams(wcsPathOrHeader, timeshift=None, noradId=None, tleFolder=None, spacetrack=None):
@@ -178,3 +181,185 @@ def getMappingSequence(imagePathsOrArrays, wcsPaths, metadatas=None, timeshift=N
         gc.collect()
         return m
     return map(make, zip(imagePathsOrArrays, wcsPaths, metadatas))
+
+
+def _parseDates(dic):
+    """JSON object hook: ISO date strings under 'date' keys become datetimes (reference :599-607)."""
+    for k in ('date', 'date_obs'):
+        v = dic.get(k)
+        if isinstance(v, str):
+            for fmt in ('%Y-%m-%dT%H:%M:%S.%f', '%Y-%m-%dT%H:%M:%S', '%Y-%m-%d %H:%M:%S.%f', '%Y-%m-%d %H:%M:%S'):
+                try:
+                    dic[k] = datetime.strptime(v, fmt)
+                    break
+                except ValueError:
+                    pass
+    return dic
+
+
+def _loadMetadata(path):
+    if path and os.path.exists(path):
+        with open(path, 'r') as fp:
+            return json.load(fp, object_hook=_parseDates)
+    return None
+
+
+def _frameMetadata(metadata, identifier):
+    if not metadata:
+        return None
+    return dict(list(metadata['sequence_metadata'].items()) + list(metadata['image_metadata'][identifier].items()))
+
+
+class SpacecraftMappingProvider(BaseMappingProvider):
+    """Mappings of a folder (or of parallel lists) of images and `.wcs` solutions, ordered by
+    the (shifted) photo time of the headers (reference spacecraft.py:40-218).  `getSequence()`
+    feeds `pipeline.resampleSequence` / `ResampleProvider` directly."""
+
+    def __init__(self, imageSequenceFolder, wcsFolder=None, imageFileExtension=None, timeshift=None,
+                 noradId=None, tleFolder=None, spacetrack=None, altitude=110, maxTimeOffset=3,
+                 sequenceInParallel=False, fastCenterCalculation=False, device=None):
+        BaseMappingProvider.__init__(self, maxTimeOffset=maxTimeOffset)
+        if wcsFolder is None:
+            assert not isinstance(imageSequenceFolder, list), \
+                'The wcsFolder parameter is required if imageSequenceFolder is a list'
+            wcsFolder = imageSequenceFolder
+        self._lists = isinstance(imageSequenceFolder, list)
+        if self._lists != isinstance(wcsFolder, list):
+            raise ValueError('imageSequenceFolder and wcsFolder must be both path lists or folder paths')
+        self._imageFileExtension = imageFileExtension
+        if self._lists:
+            self.imagePaths, self.wcsPaths = list(imageSequenceFolder), list(wcsFolder)
+            self._imageFileExtension = os.path.splitext(self.imagePaths[0])[1][1:]
+            self._index()
+        else:
+            self.imageSequenceFolder, self.wcsFolder = imageSequenceFolder, wcsFolder
+            self.reload()
+        self.timeshift, self.noradId, self.tleFolder, self.spacetrack = timeshift, noradId, tleFolder, spacetrack
+        self.altitude, self.fastCenterCalculation, self.device = altitude, fastCenterCalculation, device
+        self._sequenceInParallel = sequenceInParallel
+        first = self.imagePaths[0] if self.imagePaths else os.path.join(str(imageSequenceFolder), 'x')
+        self.metadata = _loadMetadata(os.path.join(os.path.dirname(first), 'metadata.json'))
+
+    def __len__(self):
+        return len(self.wcsPaths)
+
+    def reload(self):
+        """Refresh to the current disk state (folder mode only)."""
+        self.wcsPaths = sorted(os.path.join(self.wcsFolder, f) for f in os.listdir(self.wcsFolder)
+                               if f.endswith('.wcs'))
+        try:
+            ext = '.' + self.imageFileExtension
+            self.imagePaths = sorted(os.path.join(self.imageSequenceFolder, f)
+                                     for f in os.listdir(self.imageSequenceFolder) if f.endswith(ext))
+        except ValueError:
+            self.imagePaths, self.wcsPaths = [], []
+        self._index()
+
+    def _index(self):
+        """Every solution needs its image; order everything by the header time."""
+        ext = self._imageFileExtension
+        have = {os.path.basename(p) for p in self.imagePaths}
+        ids = [os.path.splitext(os.path.basename(p))[0] for p in self.wcsPaths]
+        missing = [i for i in ids if '%s.%s' % (i, ext) not in have]
+        assert not missing, 'wcs files without image: ' + str(missing)
+        dated = sorted((fits.getShiftedPhotoTime(fits.readHeader(p)), p, i) for p, i in zip(self.wcsPaths, ids))
+        self.dates = [d for d, _, _ in dated]
+        self.wcsPaths = [p for _, p, _ in dated]
+        self.ids = [i for _, _, i in dated]
+        self._imageOf = {os.path.splitext(os.path.basename(p))[0]: p for p in self.imagePaths}
+
+    @property
+    def imageFileExtension(self):
+        """e.g. 'jpg'; derived from the first solved image if not given."""
+        if self._imageFileExtension is None:
+            names = os.listdir(self.imageSequenceFolder)
+            for w in sorted(f for f in os.listdir(self.wcsFolder) if f.endswith('.wcs')):
+                base = os.path.splitext(w)[0]
+                matches = [f for f in names if os.path.splitext(f)[0] == base and not f.endswith('.wcs')]
+                if len(matches) == 1:
+                    self._imageFileExtension = os.path.splitext(matches[0])[1][1:]
+                    break
+                if len(matches) > 1:
+                    raise ValueError('Image file extension not given but multiple candidates exist: ' + str(matches))
+            if self._imageFileExtension is None:
+                raise ValueError('Image file extension could not be determined. Make sure that there exists at '
+                                 'least one .wcs file and a corresponding image with the same filename base.')
+        return self._imageFileExtension
+
+    @property
+    def range(self):
+        return self.dates[0], self.dates[-1]
+
+    @property
+    def unsolvedIds(self):
+        return sorted(i for i in self._imageOf if i not in self.ids)
+
+    def _nearest(self, date):
+        from ..utils import findNearest
+        idx = findNearest(self.dates, date)
+        return idx, abs(self.dates[idx] - date).total_seconds()
+
+    def contains(self, date):
+        return self._nearest(date)[1] <= self.maxTimeOffset
+
+    def _kw(self):
+        return dict(timeshift=self.timeshift, noradId=self.noradId, tleFolder=self.tleFolder,
+                    spacetrack=self.spacetrack, altitude=self.altitude,
+                    fastCenterCalculation=self.fastCenterCalculation, device=self.device)
+
+    def get(self, date):
+        idx, offset = self._nearest(date)
+        if offset > self.maxTimeOffset:
+            raise ValueError('No image found')
+        identifier = self.ids[idx]
+        return getMapping(self._imageOf[identifier], self.wcsPaths[idx],
+                          metadata=_frameMetadata(self.metadata, identifier), **self._kw())
+
+    def getById(self, identifier):
+        matched = [i for i in self.ids if identifier in i]
+        assert len(matched) == 1, 'Ambiguous identifier: ' + str(matched)
+        return self.get(self.dates[self.ids.index(matched[0])])
+
+    def getSequence(self, dateBegin=None, dateEnd=None):
+        assert dateBegin is None and dateEnd is None, 'Date ranges not supported'
+        metadatas = [_frameMetadata(self.metadata, i) for i in self.ids] if self.metadata else None
+        return getMappingSequence([self._imageOf[i] for i in self.ids], self.wcsPaths, metadatas=metadatas,
+                                  parallel=self._sequenceInParallel, **self._kw())
+
+
+class SpacecraftMappingPathProvider(BaseMappingProvider):
+    """Sequence-only provider over explicit image / wcs path lists (reference :220-292)."""
+
+    def __init__(self, imagePaths, wcsPaths, metadataPath=None, timeshift=None, noradId=None, tleFolder=None,
+                 spacetrack=None, altitude=110, maxTimeOffset=3, sequenceInParallel=False,
+                 fastCenterCalculation=False, device=None):
+        BaseMappingProvider.__init__(self, maxTimeOffset=maxTimeOffset)
+        assert len(imagePaths) == len(wcsPaths)
+        pairs = sorted(zip(wcsPaths, imagePaths), key=lambda wp: fits.getPhotoTime(fits.readHeader(wp[0])))
+        self.wcsPaths = [w for w, _ in pairs]
+        self.imagePaths = [i for _, i in pairs]
+        self.timeshift, self.noradId, self.tleFolder, self.spacetrack = timeshift, noradId, tleFolder, spacetrack
+        self.altitude, self.fastCenterCalculation, self.device = altitude, fastCenterCalculation, device
+        self.sequenceInParallel = sequenceInParallel
+        self.metadata = _loadMetadata(metadataPath)
+
+    def __len__(self):
+        return len(self.wcsPaths)
+
+    imageFileExtension = property(lambda self: os.path.splitext(self.imagePaths[0])[1][1:])
+
+    @property
+    def range(self):
+        times = [fits.getShiftedPhotoTime(fits.readHeader(p)) for p in (self.wcsPaths[0], self.wcsPaths[-1])]
+        return times[0], times[1]
+
+    def getSequence(self, dateBegin=None, dateEnd=None):
+        assert dateBegin is None and dateEnd is None, 'Date ranges not supported'
+        metadatas = None
+        if self.metadata:
+            keys = [os.path.splitext(os.path.basename(p))[0] for p in self.imagePaths]
+            metadatas = [_frameMetadata(self.metadata, k) for k in keys]
+        return getMappingSequence(self.imagePaths, self.wcsPaths, metadatas=metadatas, timeshift=self.timeshift,
+                                  noradId=self.noradId, tleFolder=self.tleFolder, spacetrack=self.spacetrack,
+                                  altitude=self.altitude, parallel=self.sequenceInParallel,
+                                  fastCenterCalculation=self.fastCenterCalculation, device=self.device)

@@ -158,3 +158,15 @@ def pointsInsidePolygon(points, polygon):
         inside ^= (f0 != f1) & hit
         x0, y0 = x1, y1
     return inside & ~(np.isnan(tx) | np.isnan(ty))
+
+
+def findNearest(a, x):
+    """Index of the item of the sorted sequence `a` that is closest to `x`; the left one on a tie
+    (reference utils.py:270-285)."""
+    import bisect
+    i = bisect.bisect_left(a, x)
+    if i == len(a):
+        return i - 1
+    if i == 0 or a[i] == x:
+        return i
+    return i - 1 if abs(x - a[i - 1]) <= abs(x - a[i]) else i

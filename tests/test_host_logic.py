@@ -245,3 +245,55 @@ def test_target_grid_round_scale_randomised():
     g, _ = R.targetGrid((10, 10), 10.0, 20.0, 30.0, 50.0)
     ex = np.linspace(g.lo_x, g.hi_x, g.nx + 1)
     assert g.round_x == 10.0 ** (int(-np.log10(np.diff(ex).min())) + 6)
+
+
+def _write_wcs(path, hdr):
+    cards = [_card('SIMPLE', True, 'conforms to FITS standard'), _card('BITPIX', 8), _card('NAXIS', 0)]
+    cards += [_card(k, v, 'x') for k, v in hdr.items()] + ["END".ljust(80)]
+    raw = "".join(cards)
+    path.write_bytes(raw.ljust((len(raw) + 2879) // 2880 * 2880).encode('ascii'))
+
+
+def test_spacecraft_mapping_providers(tmp_path):
+    """SpacecraftMappingProvider / SpacecraftMappingPathProvider (spacecraft.py:40-292): folder
+    scan, solved/unsolved ids, ordering by header time, access by date, metadata merge.  The
+    mappings are lazy -- nothing here touches a GPU."""
+    import json
+    from PIL import Image
+    from auromat_b200.mapping.spacecraft import SpacecraftMappingPathProvider, SpacecraftMappingProvider
+    from auromat_b200.utils import findNearest
+    W, H = 32, 24
+    hdrs = synthetic.sequenceHeaders(3, W, H)
+    names = ['ISS030-E-0003', 'ISS030-E-0001', 'ISS030-E-0002']            # file order != time order
+    for name, hdr in zip(names, hdrs):
+        _write_wcs(tmp_path / (name + '.wcs'), hdr)
+        Image.fromarray(synthetic.issImage(W, H)).save(str(tmp_path / (name + '.png')))
+    Image.fromarray(synthetic.issImage(W, H)).save(str(tmp_path / 'ISS030-E-0009.png'))      # not solved
+    (tmp_path / 'metadata.json').write_text(json.dumps({
+        'sequence_metadata': {'lens': '24mm'},
+        'image_metadata': {n: {'iso': 1000 + i} for i, n in enumerate(names)}}))
+    p = SpacecraftMappingProvider(str(tmp_path), altitude=120, fastCenterCalculation=True)
+    assert len(p) == 3 and p.imageFileExtension == 'png'
+    assert p.ids == names and p.unsolvedIds == ['ISS030-E-0009']         # headers are 1 s apart, in `names` order
+    t0, _ = synthetic.headerTimeAndCamera(hdrs[0])
+    assert p.range == (t0, t0 + datetime.timedelta(seconds=2))
+    assert p.contains(t0 + datetime.timedelta(seconds=1.4)) and not p.contains(t0 + datetime.timedelta(seconds=9))
+    m = p.get(t0 + datetime.timedelta(seconds=1.2))
+    assert m.identifier == names[1] and m.altitude == 120 and m.fastCenterCalculation
+    assert m.photoTime == t0 + datetime.timedelta(seconds=1)
+    assert m.metadata == {'lens': '24mm', 'iso': 1001}
+    assert p.getById('E-0002').identifier == 'ISS030-E-0002'
+    with pytest.raises(ValueError):
+        p.get(t0 + datetime.timedelta(seconds=30))
+    seq = list(p.getSequence())
+    assert [s.identifier for s in seq] == names and seq[2].metadata['iso'] == 1002
+    assert seq[0].img_unmasked.shape == (H, W, 3)
+    q = SpacecraftMappingPathProvider([str(tmp_path / (n + '.png')) for n in reversed(names)],
+                                      [str(tmp_path / (n + '.wcs')) for n in reversed(names)])
+    assert [os.path.basename(w) for w in q.wcsPaths] == [n + '.wcs' for n in names] and q.imageFileExtension == 'png'
+    assert [s.identifier for s in q.getSequence()] == names
+    # lists instead of folders
+    r = SpacecraftMappingProvider([str(tmp_path / (n + '.png')) for n in names], [str(tmp_path / (n + '.wcs')) for n in names])
+    assert r.ids == names
+    assert findNearest([1, 4, 9], 6) == 1 and findNearest([1, 4, 9], 7) == 2 and findNearest([1, 4, 9], 100) == 2
+    assert findNearest([1, 5], 3) == 0 and findNearest([1, 4, 9], -3) == 0
