@@ -1053,3 +1053,62 @@ def test_pipeline_gray_images_plane_free_and_empty_frames(env):
         list(resampleSequence([imgs[0], imgs[1]], [hdrs[0], sky], arcsecPerPx=400, ringBuffers=True))
     again = list(resampleSequence(imgs[:2], hdrs[:2], arcsecPerPx=400, ringBuffers=True))
     assert np.array_equal(again[1].img.filled(0), expect[1].img.filled(0))
+
+
+def test_config3_sip_frame_bands_vs_oracle(env):
+    """BASELINE configs[2] at full size: 6000x4000 frame with SIP order-4 distortion.  Two bands of
+    rows (one through the limb, one near the bottom edge where the distortion is largest) against
+    the oracle, all nine planes, unsanitised so that band edges do not matter; then the fine
+    10 arcsec/px resampling keeps every valid pixel it should (conservation)."""
+    import torch
+    import oracle.auromat_oracle as O
+    from auromat_b200 import synthetic
+    from auromat_b200.mapping.spacecraft import getMapping
+    from auromat_b200.resample import resampleToDevice
+    W, H = 6000, 4000
+    hdr = synthetic.issHeader(W, H, sipOrder=4)
+    t, cam = synthetic.headerTimeAndCamera(hdr)
+    m = getMapping(env.to_device(synthetic.issImage(W, H)), hdr, nosanitize=True, identifier='c3')
+    m.prefetch(magnetic=True)
+    names = dict(lats='lat_k', lons='lon_k', mlat='mlat_k', mlt='mlt_k', latsCenter='lat_c', lonsCenter='lon_c',
+                 mlatCenter='mlat_c', mltCenter='mlt_c', elevation='elev_c')
+    p = m.devicePlanes(magnetic=True)
+    # find the first row with a valid centre: the limb band starts a little above it
+    rows = torch.nonzero(~torch.isnan(p['lat_c'].reshape(H, W)).all(dim=1)).ravel()
+    limb = max(0, int(rows[0].item()) - 8)
+    for y0, nrow in ((limb, 24), (H - 24, 24)):
+        band = dict(hdr)
+        band['IMAGEH'] = nrow
+        band['CRPIX2'] = hdr['CRPIX2'] - y0
+        with quiet():
+            g = O.georeference(band, cam, t, 110)
+        n_graze = 0
+        for oname, pname in names.items():
+            corner = pname.endswith('_k')
+            w1 = W + 1 if corner else W
+            a = env.to_numpy(p[pname].reshape(-1, w1)[y0:y0 + nrow + (1 if corner else 0)])
+            b = g[oname]
+            assert a.shape == b.shape, oname
+            nan_diff = np.isnan(a) != np.isnan(b)
+            n_graze = max(n_graze, int(nan_diff.sum()))
+            both = ~np.isnan(a) & ~np.isnan(b)
+            d = np.abs(a[both] - b[both])
+            if oname.startswith('lon'):
+                d = np.minimum(d, 360 - d)
+            tol = TOL_DEG / 15 if oname.startswith('mlt') else TOL_DEG
+            if oname == 'elevation':
+                s = np.sin(np.deg2rad(np.clip(90 - b[both], 1e-9, None)))
+                tol = TOL_DEG + np.rad2deg(8 * 2.2e-16 / s)
+            assert np.all(d <= tol), (oname, y0, float(d.max()))
+        assert n_graze <= m.illConditionedCount + 2          # hit/miss may differ only for grazing rays
+        if y0 == limb:
+            assert 0 < np.isnan(g['latsCenter']).mean() < 1  # the band really crosses the limb
+    del m
+    ms = getMapping(env.to_device(synthetic.issImage(W, H)), hdr, identifier='c3s')
+    grid, info, outImg, outMask, outElev = resampleToDevice(ms, arcsecPerPx=10)
+    assert grid.nx * grid.ny > 15_000_000                    # ~20 M cells, sparsely filled
+    ps = ms.devicePlanes()
+    ix, iy = env.cell_indices(ps['lat_c'], ps['lon_c'], grid)
+    inside = int(((ix >= 0) & (iy >= 0)).sum().item())
+    assert int(info['count'].sum().item()) == inside
+    assert 0.99 * ms._deviceStats().n_valid_centers < inside <= ms._deviceStats().n_valid_centers
