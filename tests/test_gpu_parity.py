@@ -1112,3 +1112,63 @@ def test_config3_sip_frame_bands_vs_oracle(env):
     inside = int(((ix >= 0) & (iy >= 0)).sum().item())
     assert int(info['count'].sum().item()) == inside
     assert 0.99 * ms._deviceStats().n_valid_centers < inside <= ms._deviceStats().n_valid_centers
+
+
+def test_config4_full_size_sequence_equals_single_frames(env):
+    """BASELINE configs[3] at full size: frames of the synthetic 4256x2832 sequence through the
+    pipelined path (host images, row-range upload, plane rings) are bit-identical to
+    `resample(getMapping(...))` of the same frames."""
+    from auromat_b200 import synthetic
+    from auromat_b200.mapping.spacecraft import getMapping
+    from auromat_b200.pipeline import resampleSequence
+    from auromat_b200.resample import resample
+    n = 5
+    hdrs = synthetic.sequenceHeaders(n)
+    imgs = [synthetic.issImage(seed=1000 + i) for i in range(n)]
+    got = list(resampleSequence(imgs, hdrs, arcsecPerPx=100, magnetic=True, ringBuffers=True))
+    for i in (0, 3, 4):
+        e = resample(getMapping(imgs[i], hdrs[i], identifier='x'), arcsecPerPx=100)
+        f = got[i]
+        assert f.img.shape == e.img.shape
+        assert np.array_equal(ma.getmaskarray(f.img), ma.getmaskarray(e.img))
+        assert np.array_equal(f.img.filled(0), e.img.filled(0))
+        fe, ee = f.elevation.filled(np.nan), e.elevation.filled(np.nan)
+        assert np.array_equal(np.isnan(fe), np.isnan(ee)) and np.nanmax(np.abs(fe - ee)) < 1e-9
+        del e
+
+
+def test_config5_mosaic_of_64_stations_vs_oracle(env):
+    """BASELINE configs[4]: 64 synthetic all-sky stations (256x256, uint16, elevation >= 1 deg) binned
+    into one common 20 px/deg grid: counts and integer sums bit-exact against the serial oracle (sum
+    of per-station histogram2d outputs)."""
+    import datetime
+    import oracle.auromat_oracle as O
+    from auromat_b200 import parallel
+    from auromat_b200.mapping.allsky import getMappingCollection
+    t = datetime.datetime(2012, 3, 4, 17, 19, 0)
+    cals = _stations(64)
+    rng = np.random.default_rng(11)
+    w = 256
+    imgs = [rng.integers(0, 65536, (w, w, 1), dtype=np.uint16) for _ in cals]
+    coll = getMappingCollection(imgs, cals, t, 110, minElevation=1)
+    mosaic, acc = parallel.mosaic(coll.mappings, pxPerDeg=(20, 20))
+    grid = acc.grid
+    bins, rng_ = (grid.nx, grid.ny), [[grid.lo_x, grid.hi_x], [grid.lo_y, grid.hi_y]]
+    tc = np.zeros((grid.ny, grid.nx))
+    ts = np.zeros((grid.ny, grid.nx))
+    for m, im in zip(coll.mappings, imgs):
+        la, lo = m.latsCenter.filled(np.nan).ravel(), m.lonsCenter.filled(np.nan).ravel()
+        if acc.info['mode'] == 1:
+            lo = O.wrap_at_180(lo + 180)
+        ok = ~np.isnan(la)
+        c, s = O.histogram2d_weighted(lo[ok], la[ok], bins, rng_, [None, im.reshape(-1)[ok].astype(float)])
+        tc += c.T[::-1]
+        ts += s.T[::-1]
+    assert np.array_equal(acc.count.cpu().numpy().reshape(grid.ny, grid.nx), tc)
+    assert np.array_equal(acc.sums.cpu().numpy().reshape(grid.ny, grid.nx), ts)
+    assert tc.sum() > 2_000_000 and tc.max() > 4          # overlapping stations really accumulate
+    with np.errstate(invalid='ignore', divide='ignore'):
+        mean = np.round(ts / tc)
+    got = mosaic.img
+    assert np.array_equal(ma.getmaskarray(got)[:, :, 0], tc == 0)
+    assert np.array_equal(got.filled(0)[:, :, 0][tc > 0], mean[tc > 0].astype(np.uint16))
