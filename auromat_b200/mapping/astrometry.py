@@ -93,6 +93,9 @@ class BaseAstrometryMapping(BaseMapping):
                 self._statsDevice = ctx.new_stats()
             ctx.georef(self.frameConstants, bits, None if self._grazingCounted else self._statsDevice)
             self._grazingCounted = True
+            hook = self.__dict__.pop('_afterGeoref', None)     # the sequence pipeline switches streams here
+            if hook is not None:
+                hook()
             if self._sanitize:
                 ctx.sanitize(w, h, bits)
             self._planes.update(bits)

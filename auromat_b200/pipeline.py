@@ -233,6 +233,7 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
     hCopy = ctypes.c_void_p(copy.cuda_stream)
     keepAlive = collections.deque()
     ring = []
+    freeStats = []
     slotDone = {}            # ring slot -> event recorded after the binning of its last user
     ringLen = depth + 3
     # With ring buffers the phases of a frame run on separate streams (see the module docstring):
@@ -250,7 +251,7 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
             second = ctx.__dict__['_second_stream'] = torch.cuda.Stream(ctx.torch_device, priority=-1)
     hSecond = ctypes.c_void_p(second.cuda_stream) if second is not None else None
     aux = hAux = None
-    if ringBuffers and coordinates:
+    if ringBuffers:
         aux = ctx.__dict__.get('_aux_stream')
         if aux is None:
             aux = ctx.__dict__['_aux_stream'] = torch.cuda.Stream(ctx.torch_device, priority=-1)
@@ -291,11 +292,16 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
             m._lateImage = img
         elif sparseUpload and isinstance(img, str):
             m._lateImage = m.img_unmasked        # image file: decoded on the host, uploaded like an array
-        if not coordinates and not magnetic and not fastCenterCalculation:
+        planeFree = not coordinates and not magnetic and not fastCenterCalculation
+        if planeFree:
             m.setPlaneFree(True)
-            m._startStats()
-            return m, ev, i
-        if ringBuffers:
+            if aux is None:
+                m._startStats()
+                return m, ev, i
+            if not freeStats:                   # ring-owned statistics blocks (zeroed once, here)
+                freeStats.extend(ctx.new_stats() for _ in range(ringLen))
+            m._statsDevice = freeStats[i % ringLen]
+        if ringBuffers and not planeFree:
             prev = slotDone.get(i % ringLen)
             if prev is not None:
                 main.wait_event(prev)           # ring slot free: its previous frame has been binned
@@ -319,8 +325,9 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
         m._afterGeoref = toAux
         with torch.cuda.stream(aux):
             ctx.use_stream(hMain)              # the georeference launch itself goes to the main stream
-            m.prefetch(magnetic=magnetic)
-            m._startStats()
+            if not planeFree:
+                m.prefetch(magnetic=magnetic)
+            m._startStats()                    # plane-free: hit-test launch, then sanitise + statistics
             evS = torch.cuda.Event()
             evS.record(aux)
         ctx.use_stream(hMain)
