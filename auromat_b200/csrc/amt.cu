@@ -384,6 +384,47 @@ __global__ void __launch_bounds__(256, AMT_GEOREF_MINBLOCKS) k_georef_points(con
     }
 }
 
+// Validity bitmaps only (plane-free resampling, `intersectsEarth`): both rays of every pixel up
+// to the discriminant -- no square root, no division, no coordinate plane.
+__global__ void __launch_bounds__(256) k_hit_bits(const __grid_constant__ GeorefParams p) {
+    const int W = p.f.W, H = p.f.H;
+    const int y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in_k = x <= W;
+    const bool in_c = x < W && y < H;
+    __shared__ double s_sip[2 * AMT_SIP_MAX_COEF];
+    if (p.f.sip_oa | p.f.sip_ob) {
+        if (threadIdx.x < 2 * AMT_SIP_MAX_COEF)
+            s_sip[threadIdx.x] = threadIdx.x < AMT_SIP_MAX_COEF ? p.sip_a[threadIdx.x]
+                                                                : p.sip_b[threadIdx.x - AMT_SIP_MAX_COEF];
+        __syncthreads();
+    }
+    bool graze_k = false, graze_c = false, hit_k = false, hit_c = false;
+    if (in_k) {
+        double dk[3], dc[3];
+        const double fx = (double)x, fy = (double)y;
+        if (p.f.model == AMT_MODEL_ALLSKY) {
+            pix2dir_allsky(p.f, fx - 0.5, fy - 0.5, dk);
+            pix2dir_allsky(p.f, fx, fy, dc);
+        } else {
+            pix2dir<false>(p.f, s_sip, s_sip + AMT_SIP_MAX_COEF, fx - 0.5, fy - 0.5, dk);
+            pix2dir<false>(p.f, s_sip, s_sip + AMT_SIP_MAX_COEF, fx, fy, dc);
+        }
+        hit_k = intersect_hit(p.f, dk, graze_k);
+        hit_c = intersect_hit(p.f, dc, graze_c) && in_c;
+        graze_c &= in_c;
+    }
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned mk = __ballot_sync(0xffffffffu, hit_k), mc = __ballot_sync(0xffffffffu, hit_c);
+    if (lane == 0) {
+        const int wk = (W + 1 + 31) >> 5, wc = (W + 31) >> 5;
+        const unsigned xw = (unsigned)x >> 5;
+        if (p.o.d_valid_k && xw < (unsigned)wk) p.o.d_valid_k[(unsigned)y * wk + xw] = mk;
+        if (p.o.d_valid_c && y < H && xw < (unsigned)wc) p.o.d_valid_c[(unsigned)y * wc + xw] = mc;
+    }
+    count_grazing(p.ill, graze_k | graze_c, lane);
+}
+
 // fastCenterCalculation == True: a CTA evaluates a (TH+1)x(TW+1) patch of corner rays into
 // shared memory, then derives each centre from the mean of its 4 corner intersection points
 // and (un-normalised) directions: mapping/astrometry.py:154-160 (`_calcCenters`).
@@ -554,6 +595,14 @@ extern "C" int amt_georef(amt_ctx* ctx, const amt_frame* frame, const amt_georef
                             out->d_valid_c;
         if (!want_k && !want_c) return AMT_OK;
         dim3 grid((W + 1 + 255) / 256, want_k ? H + 1 : H);
+        const bool any_plane = out->d_lat_k || out->d_lon_k || out->d_mlat_k || out->d_mlt_k || out->d_lat_c ||
+                               out->d_lon_c || out->d_mlat_c || out->d_mlt_c || out->d_elev_c;
+        if (!any_plane) {                          // validity bitmaps only
+            dim3 gh((W + 1 + 255) / 256, H + 1);
+            k_hit_bits<<<gh, 256, 0, st>>>(p);
+            LAUNCH_CHECK(ctx);
+            return AMT_OK;
+        }
         const bool full = out->d_lat_k && out->d_lon_k && out->d_mlat_k && out->d_mlt_k && out->d_valid_k &&
                           out->d_lat_c && out->d_lon_c && out->d_mlat_c && out->d_mlt_c && out->d_elev_c &&
                           out->d_valid_c;

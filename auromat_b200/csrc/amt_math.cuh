@@ -194,6 +194,24 @@ __device__ __forceinline__ bool intersect(const FrameC& f, const double dir[3], 
     return true;
 }
 
+// Hit test alone (validity bitmaps without any coordinate plane): same discriminant as
+// `intersect`, no square root and no division.  With the origin outside the ellipsoid
+// (oDO > 1) root^2 = dDO^2 - dDD (oDO - 1) < dDO^2, so sign(dDO - root) = sign(dDO); with the
+// origin inside, dDO + root >= 0 always.
+__device__ __forceinline__ bool intersect_hit(const FrameC& f, const double dir[3], bool& graze) {
+    const double D0 = dir[0] * f.rad[0], D1 = dir[1] * f.rad[1], D2 = dir[2] * f.rad[2];
+    const double dDO = fma(D2, f.otr[2], fma(D1, f.otr[1], D0 * f.otr[0]));
+    const double dDD = fma(D2, D2, fma(D1, D1, D0 * D0));
+    const double rt = fma(dDO, dDO, fma(-f.oDO, dDD, dDD));
+    graze = rt >= 0.0 && rt < kGrazeThreshold * dDD;
+    if (!(rt >= 0.0)) return false;
+    if (f.origin_inside) return true;
+    // exactly the t >= 0 test of `intersect` (t = dDO - root), evaluated only in the rare case
+    // where the sign is not obvious
+    if (dDO * dDO > 4.0 * rt) return dDO >= 0.0;
+    return (dDO - (rt > 0.0 ? sqrt_fast(rt) : 0.0)) >= 0.0;
+}
+
 __device__ __forceinline__ void mat3(const double* __restrict__ M, const double v[3], double o[3]) {
     o[0] = fma(M[2], v[2], fma(M[1], v[1], M[0] * v[0]));
     o[1] = fma(M[5], v[2], fma(M[4], v[1], M[3] * v[0]));
