@@ -1172,3 +1172,61 @@ def test_config5_mosaic_of_64_stations_vs_oracle(env):
     got = mosaic.img
     assert np.array_equal(ma.getmaskarray(got)[:, :, 0], tc == 0)
     assert np.array_equal(got.filled(0)[:, :, 0][tc > 0], mean[tc > 0].astype(np.uint16))
+
+
+def test_collections_providers_and_footpoints(env, tmp_path):
+    """The glue around the hot path with real device mappings: `resample(MappingCollection)`,
+    collection members, `cameraFootpoint`, and a folder provider wrapped by
+    MaskByElevationProvider / ResampleProvider (mapping.py:1315-1472, resample.py:143-157,370-394)."""
+    import datetime
+    from PIL import Image
+    import oracle.auromat_oracle as O
+    from auromat_b200 import synthetic
+    from auromat_b200.mapping.allsky import getMappingCollection
+    from auromat_b200.mapping.mapping import BoundingBox, MappingCollection, MaskByElevationProvider
+    from auromat_b200.mapping.spacecraft import SpacecraftMappingProvider, getMapping
+    from auromat_b200.resample import ResampleProvider, resample
+    t = datetime.datetime(2012, 3, 4, 17, 19, 0)
+    cals = _stations(3)
+    w = 96
+    imgs = [np.random.default_rng(i).integers(0, 65536, (w, w, 1), dtype=np.uint16) for i in range(3)]
+    coll = getMappingCollection(imgs, cals, t, 110, minElevation=5)
+    assert isinstance(coll, MappingCollection) and len(coll) == 3 and coll.photoTime == t
+    assert coll.boundingBox == BoundingBox.mergedBoundingBoxes([m.boundingBox for m in coll.mappings])
+    higher = coll.maskedByElevation(30)
+    for a, b in zip(coll.mappings, higher.mappings):
+        assert 0 < (~ma.getmaskarray(b.latsCenter)).sum() < (~ma.getmaskarray(a.latsCenter)).sum()
+        assert b.elevation.min() >= 30
+    rc = resample(coll, pxPerDeg=10)
+    assert isinstance(rc, MappingCollection) and len(rc) == 3 and rc.identifier == coll.identifier
+    for r, m in zip(rc.mappings, coll.mappings):
+        r.checkPlateCarree()
+        r.checkGuarantees()
+        single = resample(m, pxPerDeg=10)
+        assert np.array_equal(r.img.filled(0), single.img.filled(0))
+    # camera footpoint of a spacecraft mapping: Bowring of the GEO camera position
+    W, H = 96, 64
+    hdr = synthetic.issHeader(W, H)
+    tt, cam = synthetic.headerTimeAndCamera(hdr)
+    m = getMapping(synthetic.issImage(W, H), hdr, identifier='fp')
+    g = O.mat_j2000_to_geo(O.date2es(tt)).dot(cam)
+    la, lo = O.ecef2geodetic_scalar(g[0], g[1], g[2])
+    fp = m.cameraFootpoint
+    assert abs(fp.lat - np.rad2deg(la)) < 1e-12 and abs(fp.lon - np.rad2deg(lo)) < 1e-12
+    assert m.rgb.shape == (H, W, 3) and m.rgb_unmasked.dtype == np.uint8
+    # folder provider -> elevation mask -> resampling, all through the wrappers
+    hdrs = synthetic.sequenceHeaders(2, W, H)
+    for i, h in enumerate(hdrs):
+        cards = ["%-8s= %20s" % ('SIMPLE', 'T')] + \
+                ["%-8s= %s" % (k, ("'%s'" % v) if isinstance(v, str) else repr(v)) for k, v in h.items()] + ["END"]
+        raw = "".join(c.ljust(80) for c in cards)
+        (tmp_path / ('f%d.wcs' % i)).write_bytes(raw.ljust((len(raw) + 2879) // 2880 * 2880).encode('ascii'))
+        Image.fromarray(synthetic.issImage(W, H, seed=i)).save(str(tmp_path / ('f%d.png' % i)))
+    prov = ResampleProvider(MaskByElevationProvider(SpacecraftMappingProvider(str(tmp_path)), 20), arcsecPerPx=600)
+    seq = list(prov.getSequence())
+    assert len(seq) == 2
+    direct = resample(getMapping(synthetic.issImage(W, H, seed=1), hdrs[1], identifier='d').maskedByElevation(20),
+                      arcsecPerPx=600)
+    assert np.array_equal(seq[1].img.filled(0), direct.img.filled(0))
+    assert np.array_equal(ma.getmaskarray(seq[1].latsCenter), ma.getmaskarray(direct.latsCenter))
+    assert seq[1].elevation.min() >= 20 - 1e-9
