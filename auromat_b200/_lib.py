@@ -83,6 +83,8 @@ SIGNATURES = {
     "amt_free_pinned": (C.c_int, [C.c_void_p, C.c_void_p]),
     "amt_copy_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "amt_copy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "amt_copy_h2d_2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
+                                  C.c_void_p]),
     "amt_memset_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p]),
     "amt_stream_synchronize": (C.c_int, [C.c_void_p, C.c_void_p]),
     "amt_georef": (C.c_int, [C.c_void_p, C.POINTER(AmtFrame), C.POINTER(AmtGeorefOut), C.c_void_p, C.c_void_p]),

@@ -164,6 +164,15 @@ extern "C" int amt_copy_h2d(amt_ctx* ctx, void* d_dst, const void* h_src, size_t
     CUDA_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
     return AMT_OK;
 }
+extern "C" int amt_copy_h2d_2d(amt_ctx* ctx, void* d_dst, size_t d_pitch, const void* h_src, size_t h_pitch,
+                               size_t width_bytes, size_t rows, void* stream) {
+    ENTER(ctx);
+    CHECK_ARG(width_bytes <= d_pitch && width_bytes <= h_pitch, "amt_copy_h2d_2d: width exceeds a pitch");
+    if (rows == 0 || width_bytes == 0) return AMT_OK;
+    CUDA_TRY(cudaMemcpy2DAsync(d_dst, d_pitch, h_src, h_pitch, width_bytes, rows, cudaMemcpyHostToDevice,
+                               (cudaStream_t)stream));
+    return AMT_OK;
+}
 extern "C" int amt_copy_d2h(amt_ctx* ctx, void* h_dst, const void* d_src, size_t bytes, void* stream) {
     ENTER(ctx);
     CUDA_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));

@@ -186,10 +186,10 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
             ev.record(stream)
             trace.append((tag, i, ev))
 
-    def upload(i, img, rows=None):
-        """Host array -> device on the copy stream; returns (tensor, event).  `rows` = (first,
-        last) restricts the copy to that row range: rows without a single georeferenced pixel
-        are never read by the binning kernel."""
+    def upload(i, img, rows=None, cols=None):
+        """Host array -> device on the copy stream; returns (tensor, event).  `rows` / `cols` =
+        (first, last) restrict the copy to the pixel box that holds georeferenced pixels: the
+        rest of the image is never read by the binning kernel."""
         src = np.ascontiguousarray(img)
         tdtype = {np.dtype(np.uint8): torch.uint8, np.dtype(np.uint16): torch.int16}[src.dtype]
         if ringBuffers:
@@ -213,10 +213,20 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
         mark('H0', i, copy)
         rowBytes = src.strides[0]
         r0, r1 = (0, src.shape[0] - 1) if rows is None else rows
-        nbytes = max(0, r1 - r0 + 1) * rowBytes
-        if nbytes:
-            # plain cudaMemcpyAsync on the copy stream (pinned source => asynchronous)
-            ctx.copy_h2d(d.data_ptr() + r0 * rowBytes, src.ctypes.data + r0 * rowBytes, nbytes, hCopy)
+        nrows = max(0, r1 - r0 + 1)
+        c0, c1 = (0, src.shape[1] - 1) if cols is None else cols
+        pxBytes = src.strides[1]
+        if nrows and c1 >= c0 and (c1 - c0 + 1) * 10 < src.shape[1] * 9:
+            # the valid pixels sit in a narrow column band (limb roughly vertical): copy the box
+            widthBytes = (c1 - c0 + 1) * pxBytes
+            off = r0 * rowBytes + c0 * pxBytes
+            ctx.copy_h2d_2d(d.data_ptr() + off, src.ctypes.data + off, rowBytes, widthBytes, nrows, hCopy)
+            nbytes = widthBytes * nrows
+        else:
+            nbytes = nrows * rowBytes
+            if nbytes:
+                # plain cudaMemcpyAsync on the copy stream (pinned source => asynchronous)
+                ctx.copy_h2d(d.data_ptr() + r0 * rowBytes, src.ctypes.data + r0 * rowBytes, nbytes, hCopy)
         ev = torch.cuda.Event()
         ev.record(copy)
         mark('H1', i, copy)
@@ -341,7 +351,7 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
         if img is None:
             return None
         st = m._deviceStats()
-        dimg, ev = upload(i, img, rows=(st.row_min_c, st.row_max_c))
+        dimg, ev = upload(i, img, rows=(st.row_min_c, st.row_max_c), cols=(st.col_min_c, st.col_max_c))
         m._imgDevice = dimg if dimg.dim() == 3 else dimg[..., None]
         return ev
 

@@ -60,6 +60,10 @@ class Context:
     def copy_h2d(self, d_ptr, h_ptr, nbytes, stream_handle):
         _lib.check(self.lib.amt_copy_h2d(self.handle, C.c_void_p(d_ptr), C.c_void_p(h_ptr), nbytes, stream_handle))
 
+    def copy_h2d_2d(self, d_ptr, h_ptr, pitch, width_bytes, rows, stream_handle):
+        _lib.check(self.lib.amt_copy_h2d_2d(self.handle, C.c_void_p(d_ptr), pitch, C.c_void_p(h_ptr), pitch,
+                                            width_bytes, rows, stream_handle))
+
     def copy_d2h(self, h_ptr, d_ptr, nbytes, stream_handle):
         _lib.check(self.lib.amt_copy_d2h(self.handle, C.c_void_p(h_ptr), C.c_void_p(d_ptr), nbytes, stream_handle))
 

@@ -177,6 +177,11 @@ int amt_free_device(amt_ctx* ctx, void* d_ptr);
 int amt_alloc_pinned(amt_ctx* ctx, size_t bytes, void** h_ptr);
 int amt_free_pinned(amt_ctx* ctx, void* h_ptr);
 int amt_copy_h2d(amt_ctx* ctx, void* d_dst, const void* h_src, size_t bytes, void* stream);
+/* Rectangle of a row-major host image -> the same rectangle of its device copy
+ * (cudaMemcpy2DAsync): the sequence pipeline uploads only the pixel box that holds
+ * georeferenced pixels (amt_stats.row_min_c .. col_max_c).                                 */
+int amt_copy_h2d_2d(amt_ctx* ctx, void* d_dst, size_t d_pitch, const void* h_src, size_t h_pitch,
+                    size_t width_bytes, size_t rows, void* stream);
 int amt_copy_d2h(amt_ctx* ctx, void* h_dst, const void* d_src, size_t bytes, void* stream);
 int amt_memset_device(amt_ctx* ctx, void* d_ptr, int value, size_t bytes, void* stream);
 int amt_stream_synchronize(amt_ctx* ctx, void* stream);

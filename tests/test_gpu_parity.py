@@ -1230,3 +1230,35 @@ def test_collections_providers_and_footpoints(env, tmp_path):
     assert np.array_equal(seq[1].img.filled(0), direct.img.filled(0))
     assert np.array_equal(ma.getmaskarray(seq[1].latsCenter), ma.getmaskarray(direct.latsCenter))
     assert seq[1].elevation.min() >= 20 - 1e-9
+
+
+def test_pipeline_box_upload_for_rolled_cameras(env):
+    """A camera rolled by 90 degrees puts the limb (roughly) vertical: the valid pixels form a
+    column band and the pipeline uploads that pixel box with one 2-D copy.  Results equal the
+    full upload and the frame-by-frame path."""
+    from auromat_b200 import synthetic
+    from auromat_b200.mapping.spacecraft import getMapping
+    from auromat_b200.pipeline import resampleSequence
+    from auromat_b200.resample import resample
+    W, H, n = 320, 200, 3
+    hdrs = []
+    for h in synthetic.sequenceHeaders(n, W, H):
+        h = dict(h)
+        cd = np.array([[h['CD1_1'], h['CD1_2']], [h['CD2_1'], h['CD2_2']]]).dot(np.array([[0.0, -1.0], [1.0, 0.0]]))
+        (h['CD1_1'], h['CD1_2']), (h['CD2_1'], h['CD2_2']) = cd[0], cd[1]
+        hdrs.append(h)
+    imgs = [synthetic.issImage(W, H, seed=70 + i) for i in range(n)]
+    m = getMapping(imgs[0], hdrs[0], identifier='roll')
+    st = m._deviceStats()
+    assert st.n_valid_centers > 0.2 * W * H
+    assert (st.col_max_c - st.col_min_c + 1) < 0.9 * W and (st.row_max_c - st.row_min_c + 1) == H   # a column band
+    expect = [resample(getMapping(im, h, identifier='x'), arcsecPerPx=400) for im, h in zip(imgs, hdrs)]
+    for ring in (False, True):
+        tr = {}
+        got = list(resampleSequence(imgs, hdrs, arcsecPerPx=400, ringBuffers=ring, transferStats=tr))
+        box = sum((f.mapping._deviceStats().col_max_c - f.mapping._deviceStats().col_min_c + 1) *
+                  (f.mapping._deviceStats().row_max_c - f.mapping._deviceStats().row_min_c + 1) * 3 for f in got)
+        assert tr['h2d_bytes'] == box < 0.9 * sum(im.nbytes for im in imgs)
+        for f, e in zip(got, expect):
+            assert np.array_equal(ma.getmaskarray(f.img), ma.getmaskarray(e.img))
+            assert np.array_equal(f.img.filled(0), e.img.filled(0))
