@@ -627,8 +627,8 @@ extern "C" int amt_georef(amt_ctx* ctx, const amt_frame* frame, const amt_georef
 // ============================================== target grid / pre-rotation (shared)
 struct GridC {
     int nx, ny, prerotate;
-    double lo_x, hi_x, step_x, inv_step_x, round_x;
-    double lo_y, hi_y, step_y, inv_step_y, round_y;
+    double lo_x, hi_x, step_x, inv_step_x, round_x, eps_x;
+    double lo_y, hi_y, step_y, inv_step_y, round_y, eps_y;
     double altitude, a, b, e2, e2a, d;
     double rot[9];
 };
@@ -643,6 +643,15 @@ static int fill_grid(const amt_grid* g, GridC& c, bool pre_only = false) {
     c.nx = g->nx; c.ny = g->ny; c.prerotate = g->prerotate;
     c.lo_x = g->lo_x; c.hi_x = g->hi_x; c.step_x = g->step_x; c.inv_step_x = 1.0 / g->step_x; c.round_x = g->round_x;
     c.lo_y = g->lo_y; c.hi_y = g->hi_y; c.step_y = g->step_y; c.inv_step_y = 1.0 / g->step_y; c.round_y = g->round_y;
+    // safety margin (in cells) of the floor shortcut of bin_index: 1e-9 plus 32x the worst-case
+    // rounding of q and of the numpy edges; 1 (= shortcut off) when that is not << 1
+    auto margin = [](double lo, double hi, double inv_step, int n) {
+        const double u = 2.220446049250313e-16;
+        const double e = 1e-9 + 32.0 * u * (fmax(fabs(lo), fabs(hi)) * inv_step + (double)n);
+        return e < 1e-3 ? e : 1.0;
+    };
+    c.eps_x = pre_only ? 1.0 : margin(c.lo_x, c.hi_x, c.inv_step_x, c.nx);
+    c.eps_y = pre_only ? 1.0 : margin(c.lo_y, c.hi_y, c.inv_step_y, c.ny);
     c.altitude = g->altitude; c.a = g->wgs_a; c.b = g->wgs_b;
     volatile double aa = c.a * c.a, bb = c.b * c.b;
     volatile double num = aa - bb;
@@ -1496,8 +1505,8 @@ __device__ __forceinline__ int cell_of(const GridC& g, double la, double lo, int
     if (!(la == la)) return -1;                       // resample.py:316: dropped iff lat is NaN
     prerotate(g, la, lo);
     bool nx_, ny_;
-    ix = bin_index<NEAR>(lo, g.lo_x, g.hi_x, g.step_x, g.inv_step_x, g.nx, g.round_x, nx_);
-    iy = bin_index<NEAR>(la, g.lo_y, g.hi_y, g.step_y, g.inv_step_y, g.ny, g.round_y, ny_);
+    ix = bin_index<NEAR>(lo, g.lo_x, g.hi_x, g.step_x, g.inv_step_x, g.nx, g.round_x, g.eps_x, nx_);
+    iy = bin_index<NEAR>(la, g.lo_y, g.hi_y, g.step_y, g.inv_step_y, g.ny, g.round_y, g.eps_y, ny_);
     near = nx_ || ny_;
     if (ix < 0 || iy < 0) return -1;
     return (g.ny - 1 - iy) * g.nx + ix;               // flipud, resample.py:349

@@ -333,9 +333,22 @@ __device__ __forceinline__ double next_down(double x) { return -next_up(-x); }
 // when lat/lon themselves differ in the last bit).
 template <bool NEAR>
 __device__ __forceinline__ int bin_index(double x, double lo, double hi, double step, double inv_step,
-                                         int n, double round_scale, bool& near) {
+                                         int n, double round_scale, double eps, bool& near) {
     near = false;
     if (x >= lo && x < hi) {
+        if (!NEAR) {
+            // Shortcut: q = (x - lo)/step carries an error of a few ulp of q (<= n * 4e-16), and the
+            // numpy edges fl(fl(k*step) + lo) differ from lo + k*step by <= 2 ulp of max(|lo|,|hi|),
+            // i.e. by far less than `eps` cells (fill_grid sizes eps from exactly these bounds and
+            // sets it to 1 when the grid is too fine for the argument).  A sample whose fractional
+            // position is at least eps away from both ends of its cell is therefore on the same
+            // side of the true edges as of the ideal ones: the floor IS searchsorted(..)-1.
+            const double q = __dmul_rn(__dsub_rn(x, lo), inv_step);
+            const double kf = floor(q);
+            const double fr = q - kf;
+            const int kq = (int)kf;
+            if (fr > eps && fr < 1.0 - eps && kq < n) return kq;
+        }
         // common case, branch-free: floor guess, then one correction step against the true
         // numpy edges e(k) = fl(fl(k*step) + lo), e(n) = hi
         // lo <= x < hi, so the guess is in 0..n (n only through rounding); no clamp of the double
