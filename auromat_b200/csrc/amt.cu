@@ -1524,8 +1524,8 @@ struct Packed {
     static constexpr unsigned long long MASK = (1ULL << BITS) - 1;
 };
 
-template <typename T, int C>
-__device__ __forceinline__ void warp_accumulate(int cell, const unsigned (&val)[C], double side, bool has_side,
+template <typename T, int C, bool SIDE>
+__device__ __forceinline__ void warp_accumulate(int cell, const unsigned (&val)[C], double side,
                                                 unsigned long long* __restrict__ count,
                                                 unsigned long long* __restrict__ sums,
                                                 double* __restrict__ fsum, size_t plane) {
@@ -1545,10 +1545,9 @@ __device__ __forceinline__ void warp_accumulate(int cell, const unsigned (&val)[
     for (int c = 0; c < C; ++c) w[c / P::PER] |= (unsigned long long)val[c] << ((c % P::PER) * P::BITS);
     // a NaN side value (possible only for hand-made mappings) must stay inside its own cell:
     // then the side channel of this warp falls back to one atomic per sample
-    const bool side_direct = has_side && __ballot_sync(0xffffffffu, cell >= 0 && side != side) != 0;
-    if (side_direct) {
+    if (SIDE && __ballot_sync(0xffffffffu, cell >= 0 && side != side) != 0) {
         if (cell >= 0) atomicAdd(&fsum[cell], side);
-        has_side = false;
+        side = 0.0;                                   // the scan below then carries zeros for this warp
     }
     // Segmented inclusive scan (Kogge-Stone on the position inside the run): after the step of
     // distance d a lane holds the sum of the last min(2d, off+1) samples of its run.  Runs are
@@ -1565,7 +1564,7 @@ __device__ __forceinline__ void warp_accumulate(int cell, const unsigned (&val)[
             const unsigned long long t = __shfl_up_sync(0xffffffffu, w[k], d);
             if (off >= (unsigned)d) w[k] += t;
         }
-        if (has_side) {
+        if (SIDE) {
             const double t = __shfl_up_sync(0xffffffffu, s, d);
             if (off >= (unsigned)d) s += t;
         }
@@ -1577,7 +1576,7 @@ __device__ __forceinline__ void warp_accumulate(int cell, const unsigned (&val)[
             const unsigned long long run = (w[c / P::PER] >> ((c % P::PER) * P::BITS)) & P::MASK;
             atomicAdd(&sums[(size_t)c * plane + cell], run);
         }
-        if (has_side) atomicAdd(&fsum[cell], s);
+        if (SIDE) atomicAdd(&fsum[cell], s);
     }
 }
 
@@ -1627,7 +1626,8 @@ __global__ void __launch_bounds__(256) k_bin(const double* __restrict__ lat, con
             for (int c = 0; c < C; ++c) val[k][c] = 0;
             sd[k] = 0.0;
         }
-        warp_accumulate<T, C>(cell, val[k], sd[k], side != nullptr, count, sums, fsum, (size_t)g.nx * g.ny);
+        if (side != nullptr) warp_accumulate<T, C, true>(cell, val[k], sd[k], count, sums, fsum, (size_t)g.nx * g.ny);
+        else warp_accumulate<T, C, false>(cell, val[k], sd[k], count, sums, fsum, (size_t)g.nx * g.ny);
     }
     (void)near_any;
 }
@@ -1792,7 +1792,8 @@ __global__ void __launch_bounds__(256) k_georef_bin_fused(const __grid_constant_
         }
     }
     if (__ballot_sync(0xffffffffu, cell >= 0) == 0) return;
-    warp_accumulate<T, C>(cell, val, side, fsum != nullptr, count, sums, fsum, (size_t)g.nx * g.ny);
+    if (fsum != nullptr) warp_accumulate<T, C, true>(cell, val, side, count, sums, fsum, (size_t)g.nx * g.ny);
+    else warp_accumulate<T, C, false>(cell, val, side, count, sums, fsum, (size_t)g.nx * g.ny);
 }
 
 template <typename T>
