@@ -290,7 +290,8 @@ __device__ __forceinline__ void count_grazing(unsigned long long* counter, bool 
 // cost only the direction + discriminant: a warp whose rays all miss leaves right there.
 // FULL: all nine planes and both bitmaps are requested (the sequence pipeline with MLat/MLT): no
 // null-pointer tests, 32-bit indices.
-template <bool WANT_K, bool WANT_C, bool FULL>
+// PLAIN: pure TAN header and WCS camera model (no SIP polynomial, no fisheye branch in the code).
+template <bool WANT_K, bool WANT_C, bool FULL, bool PLAIN = false>
 #ifndef AMT_GEOREF_MINBLOCKS
 #define AMT_GEOREF_MINBLOCKS 4
 #endif
@@ -301,27 +302,27 @@ __global__ void __launch_bounds__(256, AMT_GEOREF_MINBLOCKS) k_georef_points(con
     const bool in_k = WANT_K && x <= W;
     const bool in_c = WANT_C && x < W && y < H;
     // per-frame SIP coefficients: constant bank -> shared memory once per CTA (uniform branch)
-    __shared__ double s_sip[2 * AMT_SIP_MAX_COEF];
-    if (p.f.sip_oa | p.f.sip_ob) {
+    __shared__ double s_sip[PLAIN ? 1 : 2 * AMT_SIP_MAX_COEF];
+    if (!PLAIN && (p.f.sip_oa | p.f.sip_ob)) {
         if (threadIdx.x < 2 * AMT_SIP_MAX_COEF)
             s_sip[threadIdx.x] = threadIdx.x < AMT_SIP_MAX_COEF ? p.sip_a[threadIdx.x]
                                                                 : p.sip_b[threadIdx.x - AMT_SIP_MAX_COEF];
         __syncthreads();
     }
     const double* sip_a = s_sip;
-    const double* sip_b = s_sip + AMT_SIP_MAX_COEF;
+    const double* sip_b = PLAIN ? s_sip : s_sip + AMT_SIP_MAX_COEF;
     bool graze_k = false, graze_c = false, hit_k = false, hit_c = false;
     double dk[3], Pk[3], dc[3], Pc[3], cam_el = 0.0;
     const double nan = qnan();
     if (in_k | in_c) {
         // wcs.py:41-44: corner grids start at -0.5
         const double fx = (double)x, fy = (double)y;
-        if (p.f.model == AMT_MODEL_ALLSKY) {
+        if (!PLAIN && p.f.model == AMT_MODEL_ALLSKY) {
             if (WANT_K) pix2dir_allsky(p.f, fx - 0.5, fy - 0.5, dk);
             if (WANT_C) cam_el = pix2dir_allsky(p.f, fx, fy, dc);
         } else {
-            if (WANT_K) pix2dir<false>(p.f, sip_a, sip_b, fx - 0.5, fy - 0.5, dk);
-            if (WANT_C) pix2dir<false>(p.f, sip_a, sip_b, fx, fy, dc);
+            if (WANT_K) pix2dir<false, !PLAIN>(p.f, sip_a, sip_b, fx - 0.5, fy - 0.5, dk);
+            if (WANT_C) pix2dir<false, !PLAIN>(p.f, sip_a, sip_b, fx, fy, dc);
         }
         if (WANT_K) hit_k = intersect(p.f, dk, Pk, graze_k) && in_k;
         if (WANT_C) hit_c = intersect(p.f, dc, Pc, graze_c) && in_c;
@@ -388,7 +389,7 @@ __global__ void __launch_bounds__(256, AMT_GEOREF_MINBLOCKS) k_georef_points(con
         }
     }
     if (WANT_C && in_c && (FULL || p.o.d_elev_c)) {
-        double e = p.f.model == AMT_MODEL_ALLSKY ? cam_el : elevation_deg<false>(dc, Pc);
+        double e = (!PLAIN && p.f.model == AMT_MODEL_ALLSKY) ? cam_el : elevation_deg<false>(dc, Pc);
         p.o.d_elev_c[ic] = hit_c ? e : nan;
     }
 }
@@ -615,7 +616,9 @@ extern "C" int amt_georef(amt_ctx* ctx, const amt_frame* frame, const amt_georef
         const bool full = out->d_lat_k && out->d_lon_k && out->d_mlat_k && out->d_mlt_k && out->d_valid_k &&
                           out->d_lat_c && out->d_lon_c && out->d_mlat_c && out->d_mlt_c && out->d_elev_c &&
                           out->d_valid_c;
-        if (full) k_georef_points<true, true, true><<<grid, 256, 0, st>>>(p);
+        const bool plain = frame->model == AMT_MODEL_WCS && frame->sip_order_a == 0 && frame->sip_order_b == 0;
+        if (full && plain) k_georef_points<true, true, true, true><<<grid, 256, 0, st>>>(p);
+        else if (full) k_georef_points<true, true, true><<<grid, 256, 0, st>>>(p);
         else if (want_k && want_c) k_georef_points<true, true, false><<<grid, 256, 0, st>>>(p);
         else if (want_k) k_georef_points<true, false, false><<<grid, 256, 0, st>>>(p);
         else k_georef_points<false, true, false><<<grid, 256, 0, st>>>(p);

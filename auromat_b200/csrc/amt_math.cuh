@@ -91,14 +91,14 @@ __device__ __forceinline__ void sip_distort(const double* __restrict__ ca, int o
     v = v + fv;
 }
 
-template <bool NORMALISE>
+template <bool NORMALISE, bool SIP = true>
 __device__ __forceinline__ void pix2dir(const FrameC& f, const double* __restrict__ sip_a,
                                         const double* __restrict__ sip_b,
                                         double px, double py, double dir[3]) {
     // wcs.py:93-99: (px - CRPIX1) + 1, 0-based pixel coordinates
     double u = (px - f.crpix0) + 1.0;
     double v = (py - f.crpix1) + 1.0;
-    if (f.sip_oa | f.sip_ob) sip_distort(sip_a, f.sip_oa, sip_b, f.sip_ob, u, v);
+    if (SIP && (f.sip_oa | f.sip_ob)) sip_distort(sip_a, f.sip_oa, sip_b, f.sip_ob, u, v);
     // wcs.py:102  xy = CD . pxy
     const double x = fma(f.cd[0], u, f.cd[1] * v);
     const double y = fma(f.cd[2], u, f.cd[3] * v);

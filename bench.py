@@ -339,6 +339,8 @@ def run_b200(args, rank, local_rank, world):
     nk, nc = (W + 1) * (H + 1), npx
     planes = {n: ctx.empty(nk if n.endswith('_k') else nc, torch.float64)
               for n in ('lat_k', 'lon_k', 'mlat_k', 'mlt_k', 'lat_c', 'lon_c', 'mlat_c', 'mlt_c', 'elev_c')}
+    # + the validity bitmaps: exactly the launch the sequence pipeline issues
+    planes['valid_k'], planes['valid_c'] = ctx.new_bitmaps(W, H)
     for _ in range(3):
         ctx.georef(frame, planes)
     torch.cuda.synchronize()
