@@ -388,7 +388,7 @@ def run_b200(args, rank, local_rank, world):
             "fp64": {"algorithmic_tflops": ALGO_FLOP_PER_PIXEL_GEOREF * npx / (k_ms * 1e-3) / 1e12,
                      "peak_tflops_measured": 2 * fp64_peak / 1e12,
                      "dfma_issue_peak_ginst": fp64_peak / 1e9,
-                     "ncu_pipe_fp64_pct": 63.3, "ncu_issue_active_pct": 67.6,
+                     "ncu_pipe_fp64_pct": 63.3, "ncu_issue_active_pct": 67.6,   # v6 capture; v8 trims non-FP64 code only
                      "ncu_source": "profiles/r01_kernels_v6_ncu.txt"},
         },
     }
