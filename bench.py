@@ -378,9 +378,9 @@ def run_b200(args, rank, local_rank, world):
             "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": achieved / peaks["hbm_gbs"], "peak_kind": peak_kind,
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel for this frame size from the
-            # ncu --set full capture in profiles/r01_kernels_v6_ncu.txt (writes only; part of the
+            # ncu --set full capture in profiles/r01_kernels_v8_ncu.txt (writes only; part of the
             # last planes is still in L2 when the kernel ends, hence < algorithmic bytes)
-            "traffic": 813.3e6 if (W, H) == (4256, 2832) and not args.fast_center else None,
+            "traffic": 812.4e6 if (W, H) == (4256, 2832) and not args.fast_center else None,
             "kernel_ms": k_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PIXEL_GEOREF * npx,
             # the kernel is FP64-pipe / issue bound, not HBM bound: algorithmic FP64 rate
             # (290 reference-formula ops per pixel) against the DFMA peak measured just now;
@@ -388,8 +388,8 @@ def run_b200(args, rank, local_rank, world):
             "fp64": {"algorithmic_tflops": ALGO_FLOP_PER_PIXEL_GEOREF * npx / (k_ms * 1e-3) / 1e12,
                      "peak_tflops_measured": 2 * fp64_peak / 1e12,
                      "dfma_issue_peak_ginst": fp64_peak / 1e9,
-                     "ncu_pipe_fp64_pct": 63.3, "ncu_issue_active_pct": 67.6,   # v6 capture; v8 trims non-FP64 code only
-                     "ncu_source": "profiles/r01_kernels_v6_ncu.txt"},
+                     "ncu_pipe_fp64_pct": 64.4, "ncu_issue_active_pct": 65.4,
+                     "ncu_source": "profiles/r01_kernels_v8_ncu.txt"},
         },
     }
     if not args.no_cpu_baseline and world == 1:
