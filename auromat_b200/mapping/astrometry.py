@@ -12,7 +12,7 @@ from __future__ import annotations
 import numpy as np
 
 from ..coordinates.wcs import frameConstants
-from .mapping import BaseMapping, CENTER_PLANES, CORNER_PLANES
+from .mapping import BaseMapping, CORNER_PLANES
 
 
 class BaseAstrometryMapping(BaseMapping):
@@ -124,7 +124,6 @@ class BaseAstrometryMapping(BaseMapping):
         """bit0 / bit1: the geographic north / south pole (at the mapping altitude) is seen by
         a valid pixel.  The pole point is projected through the inverse WCS; replaces the
         azimuth-sum test on a 50-point convex outline (reference mapping.py:705-718)."""
-        from ..coordinates import transform
         from ..coordinates.geodesic import wgs84A, wgs84B
         fr = self.frameConstants
         h, w = self.shape

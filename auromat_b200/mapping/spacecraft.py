@@ -13,7 +13,7 @@ import gc
 import json
 import os
 import warnings
-from datetime import datetime, timedelta
+from datetime import datetime
 
 import numpy as np
 import numpy.ma as ma

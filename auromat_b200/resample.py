@@ -9,7 +9,6 @@ mapping.  Only `method='mean'` is on the B200 path.
 """
 from __future__ import annotations
 
-import copy
 import math
 from functools import partial
 
@@ -20,7 +19,7 @@ from . import _lib
 from .coordinates import geodesic
 from .coordinates.geodesic import Location, wgs84A, wgs84B
 from .coordinates.transform import rotation_matrix
-from .mapping.mapping import BaseMapping, GenericMapping, MappingCollection
+from .mapping.mapping import BaseMapping, MappingCollection
 
 
 def plateCarreeResolution(boundingBox, arcsecPerPx):
