@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libauromat_b200.so")
 
-ABI_VERSION = 2          # AMT_ABI_VERSION of include/auromat_b200.h
+ABI_VERSION = 3          # AMT_ABI_VERSION of include/auromat_b200.h
 AMT_OK, AMT_ERR_INVALID_ARGUMENT, AMT_ERR_UNSUPPORTED, AMT_ERR_CUDA, AMT_ERR_NO_DEVICE = range(5)
 AMT_SIP_MAX_ORDER = 9
 AMT_SIP_MAX_COEF = 55
@@ -65,7 +65,18 @@ class AmtGrid(C.Structure):
         ("round_x", C.c_double), ("round_y", C.c_double),
         ("altitude", C.c_double), ("wgs_a", C.c_double), ("wgs_b", C.c_double),
         ("rot", C.c_double * 9),
+        ("side_scale", C.c_double),
     ]
+
+
+class AmtSeqSlot(C.Structure):
+    _fields_ = [("planes", AmtGeorefOut), ("d_stats", C.c_void_p), ("h_stats", C.c_void_p), ("d_img", C.c_void_p)]
+
+
+class AmtSeqJob(C.Structure):
+    _fields_ = [("grid", C.POINTER(AmtGrid)), ("h_img", C.c_void_p), ("d_img", C.c_void_p),
+                ("row0", C.c_int32), ("row1", C.c_int32), ("col0", C.c_int32), ("col1", C.c_int32),
+                ("d_acc", C.c_void_p), ("d_out", C.c_void_p), ("h_out", C.c_void_p), ("out_bytes", C.c_size_t)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/auromat_b200.h
@@ -117,6 +128,22 @@ SIGNATURES = {
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "amt_bbox_stats_frame": (C.c_int, [C.c_void_p, C.POINTER(AmtFrame), C.c_void_p, C.c_void_p,
                                        C.POINTER(AmtGrid), C.c_void_p, C.c_void_p]),
+    "amt_georef_fused": (C.c_int, [C.c_void_p, C.POINTER(AmtFrame), C.POINTER(AmtGeorefOut), C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_int32, C.c_int32, C.POINTER(AmtGrid), C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]),
+    "amt_sip_distort": (C.c_int, [C.c_void_p, C.POINTER(AmtFrame), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                                  C.c_void_p, C.c_void_p]),
+    "amt_seq_output_layout": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t),
+                                        C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "amt_seq_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "amt_seq_destroy": (C.c_int, [C.c_void_p]),
+    "amt_seq_set_slot": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(AmtSeqSlot)]),
+    "amt_seq_stage_a": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(AmtFrame)]),
+    "amt_seq_wait_stats": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(AmtStats)]),
+    "amt_seq_stage_b": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(AmtSeqJob)]),
+    "amt_seq_wait_result": (C.c_int, [C.c_void_p, C.c_int32]),
+    "amt_seq_h2d_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "amt_georef_bin_fused": (C.c_int, [C.c_void_p, C.POINTER(AmtFrame), C.c_void_p, C.c_void_p, C.c_int32,
                                        C.c_int32, C.POINTER(AmtGrid), C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),

@@ -256,14 +256,18 @@ __device__ __forceinline__ void emit_nan(size_t i, double* __restrict__ a, doubl
 }
 
 // One intersection point -> all requested outputs at flat index i.
-__device__ __forceinline__ void emit_point(const GeorefParams& p, const double P[3], size_t i,
-                                           double* __restrict__ lat_o, double* __restrict__ lon_o,
-                                           double* __restrict__ mlat_o, double* __restrict__ mlt_o) {
+// Returns |P|^2 (needed by the elevation).
+__device__ __forceinline__ double emit_point(const GeorefParams& p, const double P[3], size_t i,
+                                             double* __restrict__ lat_o, double* __restrict__ lon_o,
+                                             double* __restrict__ mlat_o, double* __restrict__ mlt_o) {
+    double r2;
     if (lat_o || lon_o) {
         double lat, lon;
-        point_to_geo(p.f, P, lat, lon);
+        point_to_geo(p.f, P, lat, lon, r2);
         if (lat_o) lat_o[i] = lat;
         if (lon_o) lon_o[i] = lon;
+    } else {
+        r2 = fma(P[2], P[2], fma(P[1], P[1], P[0] * P[0]));
     }
     if (mlat_o || mlt_o) {
         double mlat, mlt;
@@ -271,6 +275,7 @@ __device__ __forceinline__ void emit_point(const GeorefParams& p, const double P
         if (mlat_o) mlat_o[i] = mlat;
         if (mlt_o) mlt_o[i] = mlt;
     }
+    return r2;
 }
 
 __device__ __forceinline__ void count_grazing(unsigned long long* counter, bool graze, unsigned lane) {
@@ -316,13 +321,12 @@ __global__ void __launch_bounds__(256, AMT_GEOREF_MINBLOCKS) k_georef_points(con
     const double nan = qnan();
     if (in_k | in_c) {
         // wcs.py:41-44: corner grids start at -0.5
-        const double fx = (double)x, fy = (double)y;
         if (!PLAIN && p.f.model == AMT_MODEL_ALLSKY) {
+            const double fx = (double)x, fy = (double)y;
             if (WANT_K) pix2dir_allsky(p.f, fx - 0.5, fy - 0.5, dk);
             if (WANT_C) cam_el = pix2dir_allsky(p.f, fx, fy, dc);
         } else {
-            if (WANT_K) pix2dir<false, !PLAIN>(p.f, sip_a, sip_b, fx - 0.5, fy - 0.5, dk);
-            if (WANT_C) pix2dir<false, !PLAIN>(p.f, sip_a, sip_b, fx, fy, dc);
+            dirs_kc<!PLAIN>(p.f, sip_a, sip_b, x, y, dk, dc);
         }
         if (WANT_K) hit_k = intersect(p.f, dk, Pk, graze_k) && in_k;
         if (WANT_C) hit_c = intersect(p.f, dc, Pc, graze_c) && in_c;
@@ -362,10 +366,11 @@ __global__ void __launch_bounds__(256, AMT_GEOREF_MINBLOCKS) k_georef_points(con
     if (!hit_c) Pc[0] = Pc[1] = Pc[2] = nan;
     const bool geo = FULL || p.o.d_lat_k || p.o.d_lon_k || p.o.d_lat_c || p.o.d_lon_c;
     const bool mag = FULL || p.o.d_mlat_k || p.o.d_mlt_k || p.o.d_mlat_c || p.o.d_mlt_c;
+    double r2_c = 0.0;
     if (geo) {
         double la_k, lo_k, la_c, lo_c;
         if (WANT_K) point_to_geo(p.f, Pk, la_k, lo_k);
-        if (WANT_C) point_to_geo(p.f, Pc, la_c, lo_c);
+        if (WANT_C) point_to_geo(p.f, Pc, la_c, lo_c, r2_c);
         if (WANT_K && in_k) {
             if (FULL || p.o.d_lat_k) p.o.d_lat_k[ik] = la_k;
             if (FULL || p.o.d_lon_k) p.o.d_lon_k[ik] = lo_k;
@@ -389,7 +394,8 @@ __global__ void __launch_bounds__(256, AMT_GEOREF_MINBLOCKS) k_georef_points(con
         }
     }
     if (WANT_C && in_c && (FULL || p.o.d_elev_c)) {
-        double e = (!PLAIN && p.f.model == AMT_MODEL_ALLSKY) ? cam_el : elevation_deg<false>(dc, Pc);
+        if (!geo) r2_c = fma(Pc[2], Pc[2], fma(Pc[1], Pc[1], Pc[0] * Pc[0]));
+        double e = (!PLAIN && p.f.model == AMT_MODEL_ALLSKY) ? cam_el : elevation_deg<false>(dc, Pc, r2_c);
         p.o.d_elev_c[ic] = hit_c ? e : nan;
     }
 }
@@ -412,13 +418,12 @@ __global__ void __launch_bounds__(256) k_hit_bits(const __grid_constant__ Georef
     bool graze_k = false, graze_c = false, hit_k = false, hit_c = false;
     if (in_k) {
         double dk[3], dc[3];
-        const double fx = (double)x, fy = (double)y;
         if (p.f.model == AMT_MODEL_ALLSKY) {
+            const double fx = (double)x, fy = (double)y;
             pix2dir_allsky(p.f, fx - 0.5, fy - 0.5, dk);
             pix2dir_allsky(p.f, fx, fy, dc);
         } else {
-            pix2dir<false>(p.f, s_sip, s_sip + AMT_SIP_MAX_COEF, fx - 0.5, fy - 0.5, dk);
-            pix2dir<false>(p.f, s_sip, s_sip + AMT_SIP_MAX_COEF, fx, fy, dc);
+            dirs_kc<true>(p.f, s_sip, s_sip + AMT_SIP_MAX_COEF, x, y, dk, dc);
         }
         hit_k = intersect_hit(p.f, dk, graze_k);
         hit_c = intersect_hit(p.f, dc, graze_c) && in_c;
@@ -433,6 +438,114 @@ __global__ void __launch_bounds__(256) k_hit_bits(const __grid_constant__ Georef
         if (p.o.d_valid_c && y < H && xw < (unsigned)wc) p.o.d_valid_c[(unsigned)y * wc + xw] = mc;
     }
     count_grazing(p.ill, graze_k | graze_c, lane);
+}
+
+// ------------------------------------------------------------------ limb solver
+// Hit bitmaps of a pure-TAN frame in O(H) ray evaluations instead of O(W H).  With the affine ray
+// model the discriminant of the intersection is, along an image row, a QUADRATIC in the pixel
+// index x:  D(x) = D0 + x D1  =>  dDO = d0 + d1 x,  dDD = e0 + e1 x + e2 x^2,
+//     rt(x) = dDO^2 + (1 - oDO) dDD = qa x^2 + qb x + qc.
+// The hit predicate (rt >= 0 and, for a camera outside the ellipsoid, dDO >= 0) can therefore only
+// change at the (at most two) real roots of rt -- dDO changes sign where rt = (1 - oDO) dDD < 0,
+// inside a miss interval.  One warp per row: the roots are located analytically (both branches of
+// an uncertainty band 1e-11 relative on the discriminant of the quadratic, which is 4 orders above
+// the rounding of its coefficients), every 32-pixel bitmap word that lies within 2 pixels of a
+// root interval is evaluated pixel by pixel with the SAME predicate the per-pixel kernels use
+// (dirs_kc + intersect_hit: bit-identical decisions at the limb), every other word is constant
+// and takes the predicate of its first pixel.  Rows whose quadratic degenerates (NaN, no usable
+// pivot) are evaluated completely.  Grazing rays (rt/dDD < 1e-10) sit within 1e-2 pixels of a root,
+// i.e. inside the evaluated words: the n_ill_conditioned count is complete.
+__global__ void __launch_bounds__(128) k_limb_bits(const __grid_constant__ GeorefParams p,
+                                                   uint32_t* __restrict__ valid_k, uint32_t* __restrict__ valid_c) {
+    const int W = p.f.W, H = p.f.H;
+    const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (y > H) return;                                   // warp-uniform
+    const int lane = threadIdx.x & 31;
+    const int wk = (W + 1 + 31) >> 5, wc = (W + 31) >> 5;
+    const FrameC& f = p.f;
+    // root intervals [lo, hi] (pixel index) of the corner row (kind 0) and the centre row (kind 1)
+    double r_lo[2][2], r_hi[2][2];
+    bool full_row = false;
+#pragma unroll
+    for (int kind = 0; kind < 2; ++kind) {
+        double Da[3], Db[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            double a0 = fma((double)y, f.aff_c[k], f.aff_a[k]);
+            if (kind) a0 += f.aff_h[k];
+            Da[k] = a0 * f.rad[k];
+            Db[k] = f.aff_b[k] * f.rad[k];
+        }
+        const double d0 = Da[0] * f.otr[0] + Da[1] * f.otr[1] + Da[2] * f.otr[2];
+        const double d1 = Db[0] * f.otr[0] + Db[1] * f.otr[1] + Db[2] * f.otr[2];
+        const double e0 = Da[0] * Da[0] + Da[1] * Da[1] + Da[2] * Da[2];
+        const double e1 = 2.0 * (Da[0] * Db[0] + Da[1] * Db[1] + Da[2] * Db[2]);
+        const double e2 = Db[0] * Db[0] + Db[1] * Db[1] + Db[2] * Db[2];
+        const double k1 = 1.0 - f.oDO;
+        const double qa = d1 * d1 + k1 * e2, qb = 2.0 * d0 * d1 + k1 * e1, qc = d0 * d0 + k1 * e0;
+        const double disc = qb * qb - 4.0 * qa * qc;
+        const double band = 1e-11 * (qb * qb + fabs(4.0 * qa * qc));
+        const double inf = __longlong_as_double(0x7ff0000000000000LL);
+        r_lo[kind][0] = r_lo[kind][1] = inf;             // empty intervals
+        r_hi[kind][0] = r_hi[kind][1] = -inf;
+        if (!(disc == disc) || !(band == band) || isinf(disc)) {
+            full_row = true;
+        } else if (disc >= -band) {
+            const double sq[2] = {sqrt(fmax(disc - band, 0.0)), sqrt(disc + band)};
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+                // stable quadratic roots: q = -(qb + sign(qb) sq)/2, r1 = q/qa, r2 = qc/q
+                const double q = -0.5 * (qb + copysign(sq[v], qb));
+                const double r1 = q / qa, r2 = qc / q;
+                if (q == 0.0 || !(r2 == r2)) full_row = true;
+                if (r1 == r1) { r_lo[kind][0] = fmin(r_lo[kind][0], r1); r_hi[kind][0] = fmax(r_hi[kind][0], r1); }
+                if (r2 == r2) { r_lo[kind][1] = fmin(r_lo[kind][1], r2); r_hi[kind][1] = fmax(r_hi[kind][1], r2); }
+            }
+        }
+    }
+    unsigned n_graze = 0;
+    for (int base = 0; base < wk; base += 32) {           // warp-uniform
+        const int i = base + lane;
+        // pixels of word i: 32 i .. 32 i + 31; uncertain iff a root interval (+- 2 px) touches them
+        const double x_lo = 32.0 * i - 2.0, x_hi = 32.0 * i + 33.0;
+        bool unc = full_row;
+#pragma unroll
+        for (int kind = 0; kind < 2; ++kind)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) unc |= r_lo[kind][r] <= x_hi && r_hi[kind][r] >= x_lo;
+        unc &= i < wk;
+        unsigned word_k = 0, word_c = 0;
+        if (i < wk && !unc) {                             // constant word: predicate of its first pixel
+            double dk[3], dc[3];
+            bool gz;
+            dirs_kc<false>(f, nullptr, nullptr, 32 * i, y, dk, dc);
+            const int nk = min(32, W + 1 - 32 * i), nc = min(32, W - 32 * i);
+            if (intersect_hit(f, dk, gz)) word_k = nk >= 32 ? 0xffffffffu : ((1u << nk) - 1u);
+            if (nc > 0 && intersect_hit(f, dc, gz)) word_c = nc >= 32 ? 0xffffffffu : ((1u << nc) - 1u);
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, unc);
+        while (todo) {                                    // pixel-by-pixel words, the warp on the 32 pixels
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int x = 32 * (base + src) + lane;
+            bool hk = false, hc = false, gk = false, gc = false;
+            if (x <= W) {
+                double dk[3], dc[3];
+                dirs_kc<false>(f, nullptr, nullptr, x, y, dk, dc);
+                hk = intersect_hit(f, dk, gk);
+                hc = intersect_hit(f, dc, gc) && x < W;
+                gc &= x < W && y < H;
+            }
+            const unsigned bk = __ballot_sync(0xffffffffu, hk), bc = __ballot_sync(0xffffffffu, hc);
+            n_graze += __popc(__ballot_sync(0xffffffffu, gk | gc));
+            if (lane == src) { word_k = bk; word_c = bc; }
+        }
+        if (i < wk) {
+            valid_k[(size_t)y * wk + i] = word_k;
+            if (y < H && i < wc) valid_c[(size_t)y * wc + i] = word_c;
+        }
+    }
+    if (p.ill && n_graze && lane == 0) atomicAdd(p.ill, (unsigned long long)n_graze);
 }
 
 // fastCenterCalculation == True: a CTA evaluates a (TH+1)x(TW+1) patch of corner rays into
@@ -527,8 +640,8 @@ __global__ void __launch_bounds__(TW* TH) k_georef_tiles(const __grid_constant__
         const size_t i = (size_t)y * W + x;
         chit = P[0] == P[0];                        // all four corner rays hit
         if (chit) {
-            emit_point(p, P, i, p.o.d_lat_c, p.o.d_lon_c, p.o.d_mlat_c, p.o.d_mlt_c);
-            if (p.o.d_elev_c) p.o.d_elev_c[i] = elevation_deg<true>(dir, P);
+            const double r2 = emit_point(p, P, i, p.o.d_lat_c, p.o.d_lon_c, p.o.d_mlat_c, p.o.d_mlt_c);
+            if (p.o.d_elev_c) p.o.d_elev_c[i] = elevation_deg<true>(dir, P, r2);
         } else {
             emit_nan(i, p.o.d_lat_c, p.o.d_lon_c, p.o.d_mlat_c, p.o.d_mlt_c);
             if (p.o.d_elev_c) p.o.d_elev_c[i] = qnan();
@@ -580,6 +693,7 @@ static int fill_frame(const amt_frame* fr, GeorefParams& p) {
     f.as_xc = fr->allsky_xc; f.as_yc = fr->allsky_yc; f.as_k = fr->allsky_k; f.as_rot = fr->allsky_rotation;
     memcpy(p.sip_a, fr->sip_a, sizeof p.sip_a);
     memcpy(p.sip_b, fr->sip_b, sizeof p.sip_b);
+    fill_affine(f);
     return AMT_OK;
 }
 
@@ -608,8 +722,13 @@ extern "C" int amt_georef(amt_ctx* ctx, const amt_frame* frame, const amt_georef
         const bool any_plane = out->d_lat_k || out->d_lon_k || out->d_mlat_k || out->d_mlt_k || out->d_lat_c ||
                                out->d_lon_c || out->d_mlat_c || out->d_mlt_c || out->d_elev_c;
         if (!any_plane) {                          // validity bitmaps only
-            dim3 gh((W + 1 + 255) / 256, H + 1);
-            k_hit_bits<<<gh, 256, 0, st>>>(p);
+            const bool affine = frame->model == AMT_MODEL_WCS && frame->sip_order_a == 0 && frame->sip_order_b == 0;
+            if (affine && out->d_valid_k && out->d_valid_c && !getenv("AMT_NO_LIMB_SOLVER")) {
+                k_limb_bits<<<(H + 1 + 3) / 4, 128, 0, st>>>(p, out->d_valid_k, out->d_valid_c);
+            } else {
+                dim3 gh((W + 1 + 255) / 256, H + 1);
+                k_hit_bits<<<gh, 256, 0, st>>>(p);
+            }
             LAUNCH_CHECK(ctx);
             return AMT_OK;
         }
@@ -634,6 +753,7 @@ struct GridC {
     double lo_y, hi_y, step_y, inv_step_y, round_y, eps_y;
     double altitude, a, b, e2, e2a, d;
     double rot[9];
+    double side_scale;        // > 0: the side channel accumulates llrint(value * side_scale) in int64
 };
 
 static int fill_grid(const amt_grid* g, GridC& c, bool pre_only = false) {
@@ -656,6 +776,7 @@ static int fill_grid(const amt_grid* g, GridC& c, bool pre_only = false) {
     c.eps_x = pre_only ? 1.0 : margin(c.lo_x, c.hi_x, c.inv_step_x, c.nx);
     c.eps_y = pre_only ? 1.0 : margin(c.lo_y, c.hi_y, c.inv_step_y, c.ny);
     c.altitude = g->altitude; c.a = g->wgs_a; c.b = g->wgs_b;
+    c.side_scale = g->side_scale > 0 ? g->side_scale : 0.0;
     volatile double aa = c.a * c.a, bb = c.b * c.b;
     volatile double num = aa - bb;
     volatile double e2 = c.a != 0 ? num / aa : 0;
@@ -921,9 +1042,9 @@ __global__ void __launch_bounds__(256) k_stats_bits(int W, int H, Bits K, Bits C
                         la[q] = lat_k[idx];
                         lo[q] = lon_k[idx];
                     } else {
-                        double dir[3], P[3];
+                        double dir[3], dcen[3], P[3];
                         bool gz;
-                        pix2dir<false>(frame->f, frame->sip_a, frame->sip_b, (double)x - 0.5, (double)yy - 0.5, dir);
+                        dirs_kc<true>(frame->f, frame->sip_a, frame->sip_b, x, yy, dir, dcen);
                         intersect(frame->f, dir, P, gz);
                         point_to_geo(frame->f, P, la[q], lo[q]);
                     }
@@ -1436,7 +1557,8 @@ __global__ void __launch_bounds__(256) k_reproject(const double* __restrict__ la
         const double dir[3] = {G[0] - f.cam[0], G[1] - f.cam[1], G[2] - f.cam[2]};
         bool graze;
         if (intersect(f, dir, P, graze)) {
-            bowring(f.a, f.b_over_a, f.e2a, f.d, P[0], P[1], P[2], ol, oo);     // degrees
+            double r2;
+            bowring(f.b_over_a, f.e2a, f.d, P[0], P[1], P[2], ol, oo, r2);     // degrees
         }
     }
     lat_out[i] = ol;
@@ -1527,8 +1649,15 @@ struct Packed {
     static constexpr unsigned long long MASK = (1ULL << BITS) - 1;
 };
 
-template <typename T, int C, bool SIDE>
+// Side channel (elevation) modes: kSideNone; kSideF64 = f64 atomics (any value, NaN included;
+// the sum depends on the order of the atomics in its last bits); kSideFixed = the value is scaled
+// by a power of two chosen by the caller so that the grand total fits 62 bits (amt_grid.side_scale)
+// and accumulated as int64: exact, order independent, run-to-run and rank-to-rank identical.
+enum { kSideNone = 0, kSideF64 = 1, kSideFixed = 2 };
+
+template <typename T, int C, int SIDE>
 __device__ __forceinline__ void warp_accumulate(int cell, const unsigned (&val)[C], double side,
+                                                unsigned long long sfx,
                                                 unsigned long long* __restrict__ count,
                                                 unsigned long long* __restrict__ sums,
                                                 double* __restrict__ fsum, size_t plane) {
@@ -1548,7 +1677,7 @@ __device__ __forceinline__ void warp_accumulate(int cell, const unsigned (&val)[
     for (int c = 0; c < C; ++c) w[c / P::PER] |= (unsigned long long)val[c] << ((c % P::PER) * P::BITS);
     // a NaN side value (possible only for hand-made mappings) must stay inside its own cell:
     // then the side channel of this warp falls back to one atomic per sample
-    if (SIDE && __ballot_sync(0xffffffffu, cell >= 0 && side != side) != 0) {
+    if (SIDE == kSideF64 && __ballot_sync(0xffffffffu, cell >= 0 && side != side) != 0) {
         if (cell >= 0) atomicAdd(&fsum[cell], side);
         side = 0.0;                                   // the scan below then carries zeros for this warp
     }
@@ -1567,9 +1696,13 @@ __device__ __forceinline__ void warp_accumulate(int cell, const unsigned (&val)[
             const unsigned long long t = __shfl_up_sync(0xffffffffu, w[k], d);
             if (off >= (unsigned)d) w[k] += t;
         }
-        if (SIDE) {
+        if (SIDE == kSideF64) {
             const double t = __shfl_up_sync(0xffffffffu, s, d);
             if (off >= (unsigned)d) s += t;
+        }
+        if (SIDE == kSideFixed) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, sfx, d);
+            if (off >= (unsigned)d) sfx += t;
         }
     }
     if (tail && cell >= 0) {
@@ -1579,8 +1712,15 @@ __device__ __forceinline__ void warp_accumulate(int cell, const unsigned (&val)[
             const unsigned long long run = (w[c / P::PER] >> ((c % P::PER) * P::BITS)) & P::MASK;
             atomicAdd(&sums[(size_t)c * plane + cell], run);
         }
-        if (SIDE) atomicAdd(&fsum[cell], s);
+        if (SIDE == kSideF64) atomicAdd(&fsum[cell], s);
+        if (SIDE == kSideFixed) atomicAdd((unsigned long long*)fsum + cell, sfx);
     }
+}
+
+// value -> fixed point; a NaN (hand-made mappings only) cannot be represented and poisons nothing:
+// the caller falls back to kSideF64 for such mappings (amt_grid.side_scale == 0)
+__device__ __forceinline__ unsigned long long to_fixed(double v, double scale) {
+    return (unsigned long long)__double2ll_rn(v * scale);
 }
 
 // Each warp bins kBinSeg consecutive segments of 32 pixels; all global loads of the segments
@@ -1591,7 +1731,7 @@ __device__ __forceinline__ void warp_accumulate(int cell, const unsigned (&val)[
 #endif
 constexpr int kBinSeg = AMT_BIN_SEG;
 
-template <typename T, int C, bool NEAR>
+template <typename T, int C, bool NEAR, int SIDE>
 __global__ void __launch_bounds__(256) k_bin(const double* __restrict__ lat, const double* __restrict__ lon,
                                              const double* __restrict__ side, const T* __restrict__ img, size_t n,
                                              const __grid_constant__ GridC g, unsigned long long* __restrict__ count,
@@ -1608,7 +1748,7 @@ __global__ void __launch_bounds__(256) k_bin(const double* __restrict__ lat, con
         const bool in = i < n;
         la[k] = in ? lat[i] : qnan();
         lo[k] = in ? lon[i] : 0.0;
-        sd[k] = (in && side) ? side[i] : 0.0;
+        sd[k] = (SIDE != kSideNone && in) ? side[i] : 0.0;
 #pragma unroll
         for (int c = 0; c < C; ++c) val[k][c] = in ? (unsigned)img[i * C + c] : 0u;
     }
@@ -1629,23 +1769,32 @@ __global__ void __launch_bounds__(256) k_bin(const double* __restrict__ lat, con
             for (int c = 0; c < C; ++c) val[k][c] = 0;
             sd[k] = 0.0;
         }
-        if (side != nullptr) warp_accumulate<T, C, true>(cell, val[k], sd[k], count, sums, fsum, (size_t)g.nx * g.ny);
-        else warp_accumulate<T, C, false>(cell, val[k], sd[k], count, sums, fsum, (size_t)g.nx * g.ny);
+        warp_accumulate<T, C, SIDE>(cell, val[k], sd[k], SIDE == kSideFixed ? to_fixed(sd[k], g.side_scale) : 0ULL,
+                                    count, sums, fsum, (size_t)g.nx * g.ny);
     }
     (void)near_any;
+}
+
+template <typename T, bool NEAR, int SIDE>
+static void launch_bin_c(int channels, unsigned blocks, cudaStream_t st, const double* lat, const double* lon,
+                         const double* side, const void* img, size_t n, const GridC& g, unsigned long long* count,
+                         unsigned long long* sums, double* fsum, unsigned long long* near) {
+    const T* im = (const T*)img;
+    switch (channels) {
+        case 1: k_bin<T, 1, NEAR, SIDE><<<blocks, 256, 0, st>>>(lat, lon, side, im, n, g, count, sums, fsum, near); break;
+        case 2: k_bin<T, 2, NEAR, SIDE><<<blocks, 256, 0, st>>>(lat, lon, side, im, n, g, count, sums, fsum, near); break;
+        case 3: k_bin<T, 3, NEAR, SIDE><<<blocks, 256, 0, st>>>(lat, lon, side, im, n, g, count, sums, fsum, near); break;
+        case 4: k_bin<T, 4, NEAR, SIDE><<<blocks, 256, 0, st>>>(lat, lon, side, im, n, g, count, sums, fsum, near); break;
+    }
 }
 
 template <typename T, bool NEAR>
 static void launch_bin(int channels, unsigned blocks, cudaStream_t st, const double* lat, const double* lon,
                        const double* side, const void* img, size_t n, const GridC& g, unsigned long long* count,
                        unsigned long long* sums, double* fsum, unsigned long long* near) {
-    const T* im = (const T*)img;
-    switch (channels) {
-        case 1: k_bin<T, 1, NEAR><<<blocks, 256, 0, st>>>(lat, lon, side, im, n, g, count, sums, fsum, near); break;
-        case 2: k_bin<T, 2, NEAR><<<blocks, 256, 0, st>>>(lat, lon, side, im, n, g, count, sums, fsum, near); break;
-        case 3: k_bin<T, 3, NEAR><<<blocks, 256, 0, st>>>(lat, lon, side, im, n, g, count, sums, fsum, near); break;
-        case 4: k_bin<T, 4, NEAR><<<blocks, 256, 0, st>>>(lat, lon, side, im, n, g, count, sums, fsum, near); break;
-    }
+    if (side == nullptr) launch_bin_c<T, NEAR, kSideNone>(channels, blocks, st, lat, lon, side, img, n, g, count, sums, fsum, near);
+    else if (g.side_scale > 0.0) launch_bin_c<T, NEAR, kSideFixed>(channels, blocks, st, lat, lon, side, img, n, g, count, sums, fsum, near);
+    else launch_bin_c<T, NEAR, kSideF64>(channels, blocks, st, lat, lon, side, img, n, g, count, sums, fsum, near);
 }
 
 extern "C" int amt_bin_accumulate(amt_ctx* ctx, const double* d_lat_c, const double* d_lon_c,
@@ -1708,7 +1857,8 @@ extern "C" int amt_cell_indices(amt_ctx* ctx, const double* d_lat_c, const doubl
 template <typename T>
 __global__ void k_normalise(size_t cells, int C, const unsigned long long* __restrict__ count,
                             const unsigned long long* __restrict__ sums, const double* __restrict__ fsum,
-                            T* __restrict__ out_img, unsigned char* __restrict__ out_mask, double* __restrict__ out_side) {
+                            T* __restrict__ out_img, unsigned char* __restrict__ out_mask, double* __restrict__ out_side,
+                            double side_scale) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= cells) return;
     const unsigned long long n = count[i];
@@ -1719,7 +1869,11 @@ __global__ void k_normalise(size_t cells, int C, const unsigned long long* __res
         if (n) v = (T)rint((double)sums[(size_t)c * cells + i] / dn);
         out_img[i * C + c] = v;
     }
-    if (out_side) out_side[i] = n ? fsum[i] / dn : qnan();
+    if (out_side) {
+        double tot = fsum[i];
+        if (side_scale > 0.0) tot = (double)((const long long*)fsum)[i] / side_scale;     // exact: power of two
+        out_side[i] = n ? tot / dn : qnan();
+    }
 }
 
 extern "C" int amt_normalise(amt_ctx* ctx, const amt_grid* grid, int32_t dtype, int32_t channels,
@@ -1736,108 +1890,259 @@ extern "C" int amt_normalise(amt_ctx* ctx, const amt_grid* grid, int32_t dtype, 
     if (dtype == AMT_U8)
         k_normalise<unsigned char><<<blocks, 256, 0, st>>>(cells, channels, (const unsigned long long*)d_count,
                                                           (const unsigned long long*)d_sums, d_fsum,
-                                                          (unsigned char*)d_out_img, d_out_mask, d_out_side);
+                                                          (unsigned char*)d_out_img, d_out_mask, d_out_side,
+                                                          grid->side_scale > 0 ? grid->side_scale : 0.0);
     else if (dtype == AMT_U16)
         k_normalise<unsigned short><<<blocks, 256, 0, st>>>(cells, channels, (const unsigned long long*)d_count,
                                                            (const unsigned long long*)d_sums, d_fsum,
-                                                           (unsigned short*)d_out_img, d_out_mask, d_out_side);
+                                                           (unsigned short*)d_out_img, d_out_mask, d_out_side,
+                                                           grid->side_scale > 0 ? grid->side_scale : 0.0);
     else
         return set_err(AMT_ERR_UNSUPPORTED, "amt_normalise: image dtype must be uint8 or uint16");
     LAUNCH_CHECK(ctx);
     return AMT_OK;
 }
 
-// Fully fused centre chain: pixel -> ray -> intersection -> lat/lon + elevation -> cell ->
-// run-aggregated accumulation, for the centres whose bit is set in the (sanitised) validity
-// bitmap.  No coordinate plane is read or written: 3 B/pixel of image in, the grids out.
-template <typename T, int C>
-__global__ void __launch_bounds__(256) k_georef_bin_fused(const __grid_constant__ GeorefParams p,
-                                                          const uint32_t* __restrict__ valid_c,
-                                                          const T* __restrict__ img, const __grid_constant__ GridC g,
-                                                          unsigned long long* __restrict__ count,
-                                                          unsigned long long* __restrict__ sums,
-                                                          double* __restrict__ fsum) {
-    const int W = p.f.W;
+// ================================================= fused georeference (+ binning) kernel
+// The frame's FINAL validity bitmaps are known before this kernel runs (hit test by the limb
+// solver / k_hit_bits, then the sanitisation stencils on the bitmaps), and with them the outline
+// statistics and therefore the target grid.  One pass then does everything per pixel: corner ray
+// and centre ray -> intersection -> lat/lon, MLat/MLT, elevation -> (PLANES) the nine coordinate
+// planes, NaN where the bitmaps say so -- no later NaN patching -- and (BIN) the cell of the centre
+// on the target grid and the run-aggregated accumulation of its image sample, with the
+// coordinates still in registers: the binning pass never re-reads 27 B/pixel of planes.
+//   PLANES = false, BIN = true is the plane-free resampling (3 B/pixel in, the grids out).
+// A warp whose bitmap words are empty writes its NaNs (PLANES) and leaves.
+template <typename T, int C, bool PLANES, bool MAG, bool BIN, bool SIP>
+__global__ void __launch_bounds__(256, AMT_GEOREF_MINBLOCKS)
+k_georef_fused(const __grid_constant__ GeorefParams p, const uint32_t* __restrict__ valid_k,
+               const uint32_t* __restrict__ valid_c, const T* __restrict__ img, const __grid_constant__ GridC g,
+               unsigned long long* __restrict__ count, unsigned long long* __restrict__ sums,
+               double* __restrict__ fsum) {
+    const int W = p.f.W, H = p.f.H;
     const int y = blockIdx.y;
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    __shared__ double s_sip[2 * AMT_SIP_MAX_COEF];
-    if (p.f.sip_oa | p.f.sip_ob) {
+    __shared__ double s_sip[SIP ? 2 * AMT_SIP_MAX_COEF : 1];
+    if (SIP) {
         if (threadIdx.x < 2 * AMT_SIP_MAX_COEF)
             s_sip[threadIdx.x] = threadIdx.x < AMT_SIP_MAX_COEF ? p.sip_a[threadIdx.x]
                                                                 : p.sip_b[threadIdx.x - AMT_SIP_MAX_COEF];
         __syncthreads();
     }
-    const int wc = (W + 31) >> 5;
-    const unsigned word = (x >> 5) < wc ? valid_c[(size_t)y * wc + (x >> 5)] : 0u;
-    if (word == 0) return;                                 // warp-uniform: nothing valid in this word
-    const bool valid = (word >> (x & 31)) & 1u;
-    int cell = -1;
-    unsigned val[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) val[c] = 0;
-    double side = 0.0;
-    if (valid) {
-        double dir[3], P[3];
-        bool gz;
-        pix2dir<false>(p.f, s_sip, s_sip + AMT_SIP_MAX_COEF, (double)x, (double)y, dir);
-        if (intersect(p.f, dir, P, gz)) {
-            double la, lo;
-            point_to_geo(p.f, P, la, lo);
-            int ix, iy;
-            bool near;
-            cell = cell_of<false>(g, la, lo, ix, iy, near);
-            if (cell >= 0) {
-                const size_t i = (size_t)y * W + x;
-#pragma unroll
-                for (int c = 0; c < C; ++c) val[c] = img[i * C + c];
-                if (fsum) side = elevation_deg<false>(dir, P);
+    const unsigned lane = threadIdx.x & 31, xw = (unsigned)x >> 5;
+    const int wk = (W + 1 + 31) >> 5, wc = (W + 31) >> 5;
+    const unsigned mk = (PLANES && xw < (unsigned)wk) ? valid_k[(unsigned)y * wk + xw] : 0u;
+    const unsigned mc = (y < H && xw < (unsigned)wc) ? valid_c[(unsigned)y * wc + xw] : 0u;
+    const bool in_k = PLANES && x <= W;
+    const bool in_c = x < W && y < H;
+    // fill_frame guarantees (W+1)*(H+1) < 2^31: 32-bit flat indices
+    const unsigned ik = (unsigned)y * (unsigned)(W + 1) + (unsigned)x, ic = (unsigned)y * (unsigned)W + (unsigned)x;
+    const double nan = qnan();
+    if ((mk | mc) == 0) {                    // nothing defined in this warp's 32 pixels
+        if (PLANES) {
+            if (in_k) {
+                p.o.d_lat_k[ik] = nan; p.o.d_lon_k[ik] = nan;
+                if (MAG) { p.o.d_mlat_k[ik] = nan; p.o.d_mlt_k[ik] = nan; }
+            }
+            if (in_c) {
+                p.o.d_lat_c[ic] = nan; p.o.d_lon_c[ic] = nan; p.o.d_elev_c[ic] = nan;
+                if (MAG) { p.o.d_mlat_c[ic] = nan; p.o.d_mlt_c[ic] = nan; }
             }
         }
+        return;
     }
-    if (__ballot_sync(0xffffffffu, cell >= 0) == 0) return;
-    if (fsum != nullptr) warp_accumulate<T, C, true>(cell, val, side, count, sums, fsum, (size_t)g.nx * g.ny);
-    else warp_accumulate<T, C, false>(cell, val, side, count, sums, fsum, (size_t)g.nx * g.ny);
+    const bool vk = (mk >> lane) & 1u, vc = (mc >> lane) & 1u;
+    // the image sample travels with the thread from the start: its latency hides under the FP64 chain
+    unsigned val[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) val[c] = 0u;
+    if (BIN && vc) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) val[c] = (unsigned)img[(size_t)ic * C + c];
+    }
+    double dk[3], dc[3], Pk[3], Pc[3];
+    dirs_kc<SIP>(p.f, s_sip, s_sip + (SIP ? AMT_SIP_MAX_COEF : 0), x, y, dk, dc);
+    bool gz;
+    // valid elements hit by construction (same arithmetic as the hit test); the others carry
+    // whatever comes out -- only the stores are predicated
+    if (PLANES) intersect(p.f, dk, Pk, gz);
+    intersect(p.f, dc, Pc, gz);
+    double la_c, lo_c, r2_c;
+    {
+        double la_k, lo_k;
+        if (PLANES) point_to_geo(p.f, Pk, la_k, lo_k);
+        point_to_geo(p.f, Pc, la_c, lo_c, r2_c);
+        if (PLANES) {
+            if (in_k) { p.o.d_lat_k[ik] = vk ? la_k : nan; p.o.d_lon_k[ik] = vk ? lo_k : nan; }
+            if (in_c) { p.o.d_lat_c[ic] = vc ? la_c : nan; p.o.d_lon_c[ic] = vc ? lo_c : nan; }
+        }
+    }
+    if (PLANES && MAG) {
+        double ml_k, mt_k, ml_c, mt_c;
+        point_to_mag(p.f, Pk, ml_k, mt_k);
+        point_to_mag(p.f, Pc, ml_c, mt_c);
+        if (in_k) { p.o.d_mlat_k[ik] = vk ? ml_k : nan; p.o.d_mlt_k[ik] = vk ? mt_k : nan; }
+        if (in_c) { p.o.d_mlat_c[ic] = vc ? ml_c : nan; p.o.d_mlt_c[ic] = vc ? mt_c : nan; }
+    }
+    double elev = 0.0;
+    if (PLANES || (BIN && fsum != nullptr)) {
+        elev = elevation_deg<false>(dc, Pc, r2_c);
+        if (PLANES && in_c) p.o.d_elev_c[ic] = vc ? elev : nan;
+    }
+    if (BIN) {
+        if (mc == 0) return;                                   // warp-uniform
+        int cell = -1;
+        if (vc) {
+            int ix, iy;
+            bool near;
+            cell = cell_of<false>(g, la_c, lo_c, ix, iy, near);
+        }
+        if (__ballot_sync(0xffffffffu, cell >= 0) == 0) return;
+        if (cell < 0) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) val[c] = 0u;
+        }
+        const size_t plane = (size_t)g.nx * g.ny;
+        if (fsum == nullptr) warp_accumulate<T, C, kSideNone>(cell, val, 0.0, 0ULL, count, sums, fsum, plane);
+        else if (g.side_scale > 0.0)
+            warp_accumulate<T, C, kSideFixed>(cell, val, 0.0, cell >= 0 ? to_fixed(elev, g.side_scale) : 0ULL, count,
+                                              sums, fsum, plane);
+        else warp_accumulate<T, C, kSideF64>(cell, val, cell >= 0 ? elev : 0.0, 0ULL, count, sums, fsum, plane);
+    }
+}
+
+template <typename T, int C, bool PLANES, bool MAG, bool BIN>
+static void launch_fused_sip(bool sip, dim3 grid, cudaStream_t st, const GeorefParams& p, const uint32_t* vk,
+                             const uint32_t* vc, const T* img, const GridC& g, unsigned long long* count,
+                             unsigned long long* sums, double* fsum) {
+    if (sip) k_georef_fused<T, C, PLANES, MAG, BIN, true><<<grid, 256, 0, st>>>(p, vk, vc, img, g, count, sums, fsum);
+    else k_georef_fused<T, C, PLANES, MAG, BIN, false><<<grid, 256, 0, st>>>(p, vk, vc, img, g, count, sums, fsum);
+}
+
+template <typename T, int C>
+static void launch_fused_c(bool planes, bool mag, bool bin, bool sip, dim3 grid, cudaStream_t st,
+                           const GeorefParams& p, const uint32_t* vk, const uint32_t* vc, const void* img,
+                           const GridC& g, unsigned long long* count, unsigned long long* sums, double* fsum) {
+    const T* im = (const T*)img;
+    if (planes && mag && bin) launch_fused_sip<T, C, true, true, true>(sip, grid, st, p, vk, vc, im, g, count, sums, fsum);
+    else if (planes && bin) launch_fused_sip<T, C, true, false, true>(sip, grid, st, p, vk, vc, im, g, count, sums, fsum);
+    else if (bin) launch_fused_sip<T, C, false, false, true>(sip, grid, st, p, vk, vc, im, g, count, sums, fsum);
+    else if (mag) launch_fused_sip<T, 1, true, true, false>(sip, grid, st, p, vk, vc, (const T*)nullptr, g, count, sums, fsum);
+    else launch_fused_sip<T, 1, true, false, false>(sip, grid, st, p, vk, vc, (const T*)nullptr, g, count, sums, fsum);
 }
 
 template <typename T>
-static void launch_fused(int channels, dim3 grid, cudaStream_t st, const GeorefParams& p, const uint32_t* vc,
-                         const void* img, const GridC& g, unsigned long long* count, unsigned long long* sums,
-                         double* fsum) {
-    const T* im = (const T*)img;
+static void launch_fused(int channels, bool planes, bool mag, bool bin, bool sip, dim3 grid, cudaStream_t st,
+                         const GeorefParams& p, const uint32_t* vk, const uint32_t* vc, const void* img,
+                         const GridC& g, unsigned long long* count, unsigned long long* sums, double* fsum) {
+    if (!bin) channels = 1;
     switch (channels) {
-        case 1: k_georef_bin_fused<T, 1><<<grid, 256, 0, st>>>(p, vc, im, g, count, sums, fsum); break;
-        case 2: k_georef_bin_fused<T, 2><<<grid, 256, 0, st>>>(p, vc, im, g, count, sums, fsum); break;
-        case 3: k_georef_bin_fused<T, 3><<<grid, 256, 0, st>>>(p, vc, im, g, count, sums, fsum); break;
-        case 4: k_georef_bin_fused<T, 4><<<grid, 256, 0, st>>>(p, vc, im, g, count, sums, fsum); break;
+        case 1: launch_fused_c<T, 1>(planes, mag, bin, sip, grid, st, p, vk, vc, img, g, count, sums, fsum); break;
+        case 2: launch_fused_c<T, 2>(planes, mag, bin, sip, grid, st, p, vk, vc, img, g, count, sums, fsum); break;
+        case 3: launch_fused_c<T, 3>(planes, mag, bin, sip, grid, st, p, vk, vc, img, g, count, sums, fsum); break;
+        case 4: launch_fused_c<T, 4>(planes, mag, bin, sip, grid, st, p, vk, vc, img, g, count, sums, fsum); break;
     }
+}
+
+// Planes and / or binning of one WCS frame from its final validity bitmaps.
+//   out == NULL        no coordinate plane is written (plane-free resampling);
+//   out != NULL        lat/lon corner + centre planes and the elevation plane are required, the four
+//                      MLat/MLT planes are written iff all four are given; the bitmaps in `out` are ignored;
+//   grid == NULL       no binning (d_img, d_count, d_sums, d_fsum unused).
+static int georef_fused(amt_ctx* ctx, const amt_frame* frame, const amt_georef_out* out, const uint32_t* d_valid_k,
+                        const uint32_t* d_valid_c, const void* d_img, int32_t dtype, int32_t channels,
+                        const amt_grid* grid, uint64_t* d_count, uint64_t* d_sums, double* d_fsum, cudaStream_t st) {
+    CHECK_ARG(frame && d_valid_c, "amt_georef_fused: NULL argument");
+    CHECK_ARG(out || grid, "amt_georef_fused: neither planes nor a grid requested");
+    if (frame->model != AMT_MODEL_WCS || frame->fast_center)
+        return set_err(AMT_ERR_UNSUPPORTED, "amt_georef_fused: WCS frames with fast_center == 0 only "
+                                            "(fast centres need the corner intersection points)");
+    const bool planes = out != nullptr, bin = grid != nullptr;
+    bool mag = false;
+    if (planes) {
+        CHECK_ARG(d_valid_k, "amt_georef_fused: the corner bitmap is required with planes");
+        CHECK_ARG(out->d_lat_k && out->d_lon_k && out->d_lat_c && out->d_lon_c && out->d_elev_c,
+                  "amt_georef_fused: lat/lon corner + centre planes and the elevation plane are required");
+        const int nm = (out->d_mlat_k != nullptr) + (out->d_mlt_k != nullptr) + (out->d_mlat_c != nullptr) +
+                       (out->d_mlt_c != nullptr);
+        CHECK_ARG(nm == 0 || nm == 4, "amt_georef_fused: MLat/MLT planes come as a set of four");
+        mag = nm == 4;
+    }
+    if (bin) {
+        CHECK_ARG(d_img && d_count && d_sums, "amt_georef_fused: image and accumulators are required with a grid");
+        CHECK_ARG(channels >= 1 && channels <= 4, "amt_georef_fused: channels must be 1..4");
+        if (dtype != AMT_U8 && dtype != AMT_U16)
+            return set_err(AMT_ERR_UNSUPPORTED, "amt_georef_fused: image dtype must be uint8 or uint16");
+    }
+    GeorefParams p;
+    memset(&p, 0, sizeof p);
+    int rc = fill_frame(frame, p);
+    if (rc) return rc;
+    if (planes) p.o = *out;
+    GridC g;
+    memset(&g, 0, sizeof g);
+    if (bin) {
+        rc = fill_grid(grid, g);
+        if (rc) return rc;
+    }
+    const bool sip = frame->sip_order_a != 0 || frame->sip_order_b != 0;
+    const int W = frame->width, H = frame->height;
+    dim3 lg(((planes ? W + 1 : W) + 255) / 256, planes ? H + 1 : H);
+    unsigned long long* cnt = (unsigned long long*)d_count;
+    unsigned long long* sm = (unsigned long long*)d_sums;
+    if (bin && dtype == AMT_U16)
+        launch_fused<unsigned short>(channels, planes, mag, bin, sip, lg, st, p, d_valid_k, d_valid_c, d_img, g, cnt, sm, d_fsum);
+    else
+        launch_fused<unsigned char>(channels, planes, mag, bin, sip, lg, st, p, d_valid_k, d_valid_c, d_img, g, cnt, sm, d_fsum);
+    LAUNCH_CHECK(ctx);
+    return AMT_OK;
+}
+
+extern "C" int amt_georef_fused(amt_ctx* ctx, const amt_frame* frame, const amt_georef_out* out,
+                                const uint32_t* d_valid_k, const uint32_t* d_valid_c, const void* d_img,
+                                int32_t dtype, int32_t channels, const amt_grid* grid, uint64_t* d_count,
+                                uint64_t* d_sums, double* d_fsum, void* stream) {
+    ENTER(ctx);
+    return georef_fused(ctx, frame, out, d_valid_k, d_valid_c, d_img, dtype, channels, grid, d_count, d_sums, d_fsum,
+                        (cudaStream_t)stream);
 }
 
 extern "C" int amt_georef_bin_fused(amt_ctx* ctx, const amt_frame* frame, const uint32_t* d_valid_c,
                                     const void* d_img, int32_t dtype, int32_t channels, const amt_grid* grid,
                                     uint64_t* d_count, uint64_t* d_sums, double* d_fsum, void* stream) {
     ENTER(ctx);
-    CHECK_ARG(frame && d_valid_c && d_img && grid && d_count && d_sums, "amt_georef_bin_fused: NULL argument");
-    CHECK_ARG(channels >= 1 && channels <= 4, "amt_georef_bin_fused: channels must be 1..4");
-    if (frame->model != AMT_MODEL_WCS || frame->fast_center)
-        return set_err(AMT_ERR_UNSUPPORTED, "amt_georef_bin_fused: WCS frames with fast_center == 0 only "
-                                            "(fast centres need the corner intersection points)");
-    if (dtype != AMT_U8 && dtype != AMT_U16)
-        return set_err(AMT_ERR_UNSUPPORTED, "amt_georef_bin_fused: image dtype must be uint8 or uint16");
+    CHECK_ARG(grid, "amt_georef_bin_fused: NULL argument");
+    return georef_fused(ctx, frame, nullptr, nullptr, d_valid_c, d_img, dtype, channels, grid, d_count, d_sums, d_fsum,
+                        (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ SIP known-answer access
+// The FITS-SIP forward polynomial of a frame evaluated for n (u, v) pixel offsets:
+// (u', v') = (u + sum A_pq u^p v^q, v + sum B_pq u^p v^q) -- exactly the device function the
+// georeference kernels call, exposed so that tests can pin it against exact rational arithmetic.
+__global__ void k_sip_distort(const __grid_constant__ GeorefParams p, const double* __restrict__ u,
+                              const double* __restrict__ v, size_t n, double* __restrict__ uo, double* __restrict__ vo) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double a = u[i], b = v[i];
+    if (p.f.sip_oa | p.f.sip_ob) sip_distort(p.sip_a, p.f.sip_oa, p.sip_b, p.f.sip_ob, a, b);
+    uo[i] = a;
+    vo[i] = b;
+}
+
+extern "C" int amt_sip_distort(amt_ctx* ctx, const amt_frame* frame, const double* d_u, const double* d_v, size_t n,
+                               double* d_u_out, double* d_v_out, void* stream) {
+    ENTER(ctx);
+    CHECK_ARG(frame && d_u && d_v && d_u_out && d_v_out, "amt_sip_distort: NULL argument");
+    if (n == 0) return AMT_OK;
     GeorefParams p;
     memset(&p, 0, sizeof p);
     int rc = fill_frame(frame, p);
     if (rc) return rc;
-    GridC g;
-    rc = fill_grid(grid, g);
-    if (rc) return rc;
-    dim3 lg((frame->width + 255) / 256, frame->height);
-    cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == AMT_U8)
-        launch_fused<unsigned char>(channels, lg, st, p, d_valid_c, d_img, g, (unsigned long long*)d_count,
-                                    (unsigned long long*)d_sums, d_fsum);
-    else
-        launch_fused<unsigned short>(channels, lg, st, p, d_valid_c, d_img, g, (unsigned long long*)d_count,
-                                     (unsigned long long*)d_sums, d_fsum);
+    k_sip_distort<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, d_u, d_v, n, d_u_out, d_v_out);
     LAUNCH_CHECK(ctx);
     return AMT_OK;
 }
+
+// ================================================================== sequence engine
+#include "amt_seq.cuh"

@@ -16,7 +16,7 @@ namespace amt {
 constexpr double kRad2Deg = 57.29577951308232;   // numpy rad2deg multiplier: 180/pi
 constexpr double kDeg2Rad = 0.017453292519943295; // numpy deg2rad multiplier: pi/180
 
-__device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
+AMT_HD double qnan() { return bits_to_double(0x7ff80000u, 0u); }
 
 // Device copy of the per-frame constants with everything pre-digested for the kernels.
 struct FrameC {
@@ -36,6 +36,12 @@ struct FrameC {
     int sip_oa, sip_ob;
     int model;
     double as_xc, as_yc, as_k, as_rot;   // all-sky fisheye model (mapping/miracle.py:314-347)
+    // Pure TAN headers: wcs.py:93-144 collapses to an AFFINE map from the pixel index to the
+    // (un-normalised) celestial direction, dir = R (-y, x, 180/pi), (x, y) = CD (u, v):
+    //     corner (ix, iy):  dir_k = aff_a + aff_b * ix + aff_c * iy      (pixel (ix - 0.5, iy - 0.5))
+    //     centre (ix, iy):  dir_c = dir_k + aff_h                          (aff_h = (aff_b + aff_c) / 2)
+    // coefficients formed on the host in extended precision (fill_frame).
+    double aff_a[3], aff_b[3], aff_c[3], aff_h[3];
 };
 
 // ---------------------------------------------------------------------------------------
@@ -51,7 +57,7 @@ struct FrameC {
 // round alike).  Coefficients: packed triangular, index(p,q) = p*(order+1) - p*(p-1)/2 + q,
 // staged in shared memory by the kernel (every lane reads the same word: broadcast).
 template <int ORDER>
-__device__ __forceinline__ double sip_poly_fixed(const double* __restrict__ c, double u, double v) {
+AMT_HD double sip_poly_fixed(const double* __restrict__ c, double u, double v) {
     double acc = 0.0;
 #pragma unroll
     for (int p = ORDER; p >= 0; --p) {
@@ -64,7 +70,7 @@ __device__ __forceinline__ double sip_poly_fixed(const double* __restrict__ c, d
     return acc;
 }
 
-__device__ __forceinline__ double sip_poly(const double* __restrict__ c, int order, double u, double v) {
+AMT_HD double sip_poly(const double* __restrict__ c, int order, double u, double v) {
     switch (order) {
         case 2: return sip_poly_fixed<2>(c, u, v);
         case 3: return sip_poly_fixed<3>(c, u, v);
@@ -82,7 +88,7 @@ __device__ __forceinline__ double sip_poly(const double* __restrict__ c, int ord
     return acc;
 }
 
-__device__ __forceinline__ void sip_distort(const double* __restrict__ ca, int oa,
+AMT_HD void sip_distort(const double* __restrict__ ca, int oa,
                                             const double* __restrict__ cb, int ob,
                                             double& u, double& v) {
     const double fu = sip_poly(ca, oa, u, v);
@@ -92,7 +98,7 @@ __device__ __forceinline__ void sip_distort(const double* __restrict__ ca, int o
 }
 
 template <bool NORMALISE, bool SIP = true>
-__device__ __forceinline__ void pix2dir(const FrameC& f, const double* __restrict__ sip_a,
+AMT_HD void pix2dir(const FrameC& f, const double* __restrict__ sip_a,
                                         const double* __restrict__ sip_b,
                                         double px, double py, double dir[3]) {
     // wcs.py:93-99: (px - CRPIX1) + 1, 0-based pixel coordinates
@@ -116,6 +122,44 @@ __device__ __forceinline__ void pix2dir(const FrameC& f, const double* __restric
     dir[0] = fma(f.rot[2], n, fma(f.rot[1], m, f.rot[0] * l));
     dir[1] = fma(f.rot[5], n, fma(f.rot[4], m, f.rot[3] * l));
     dir[2] = fma(f.rot[8], n, fma(f.rot[7], m, f.rot[6] * l));
+}
+
+// Corner and centre direction of pixel index (ix, iy) for the point kernels (directions are not
+// normalised there).  Pure TAN frames use the affine form -- 9 FP64 instructions for both rays
+// instead of 2 x 19 -- everything else the polynomial path.  Every kernel that evaluates a ray of
+// a frame (hit test, limb solver, outline statistics, georeference, fused binning) goes through
+// this one function, so their hit decisions and coordinates agree bit for bit.
+template <bool SIP>
+AMT_HD void dirs_kc(const FrameC& f, const double* __restrict__ sip_a, const double* __restrict__ sip_b,
+                    int ix, int iy, double dk[3], double dc[3]) {
+    const double fx = (double)ix, fy = (double)iy;
+    if (SIP && (f.sip_oa | f.sip_ob)) {
+        pix2dir<false, true>(f, sip_a, sip_b, fx - 0.5, fy - 0.5, dk);
+        pix2dir<false, true>(f, sip_a, sip_b, fx, fy, dc);
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        dk[k] = fma(fx, f.aff_b[k], fma(fy, f.aff_c[k], f.aff_a[k]));
+        dc[k] = dk[k] + f.aff_h[k];
+    }
+}
+
+// Host: coefficients of the affine ray model from (crpix, cd, rot), in extended precision.
+//   u = ix - 0.5 - crpix0 + 1,  v = iy - 0.5 - crpix1 + 1   (corner of pixel index (ix, iy))
+//   dir = rot[:,1] x - rot[:,0] y + rot[:,2] K,  x = cd0 u + cd1 v,  y = cd2 u + cd3 v
+inline void fill_affine(FrameC& f) {
+    const long double K = 180.0L / 3.14159265358979323846264338327950288L;
+    const long double u0 = 0.5L - (long double)f.crpix0, v0 = 0.5L - (long double)f.crpix1;
+    for (int k = 0; k < 3; ++k) {
+        const long double r0 = f.rot[3 * k + 0], r1 = f.rot[3 * k + 1], r2 = f.rot[3 * k + 2];
+        const long double b = r1 * (long double)f.cd[0] - r0 * (long double)f.cd[2];
+        const long double c = r1 * (long double)f.cd[1] - r0 * (long double)f.cd[3];
+        f.aff_b[k] = (double)b;
+        f.aff_c[k] = (double)c;
+        f.aff_a[k] = (double)(r2 * K + b * u0 + c * v0);
+        f.aff_h[k] = (double)((b + c) * 0.5L);
+    }
 }
 
 // numpy floor_divide / remainder for doubles (npy_divmod), used by the astropy-style wrap
@@ -177,7 +221,7 @@ __device__ __forceinline__ double pix2dir_allsky(const FrameC& f, double px, dou
 // ---------------------------------------------------------------------------------------
 constexpr double kGrazeThreshold = 1e-10;
 
-__device__ __forceinline__ bool intersect(const FrameC& f, const double dir[3], double P[3], bool& graze) {
+AMT_HD bool intersect(const FrameC& f, const double dir[3], double P[3], bool& graze) {
     const double D0 = dir[0] * f.rad[0], D1 = dir[1] * f.rad[1], D2 = dir[2] * f.rad[2];
     const double dDO = fma(D2, f.otr[2], fma(D1, f.otr[1], D0 * f.otr[0]));
     const double dDD = fma(D2, D2, fma(D1, D1, D0 * D0));
@@ -198,7 +242,7 @@ __device__ __forceinline__ bool intersect(const FrameC& f, const double dir[3], 
 // `intersect`, no square root and no division.  With the origin outside the ellipsoid
 // (oDO > 1) root^2 = dDO^2 - dDD (oDO - 1) < dDO^2, so sign(dDO - root) = sign(dDO); with the
 // origin inside, dDO + root >= 0 always.
-__device__ __forceinline__ bool intersect_hit(const FrameC& f, const double dir[3], bool& graze) {
+AMT_HD bool intersect_hit(const FrameC& f, const double dir[3], bool& graze) {
     const double D0 = dir[0] * f.rad[0], D1 = dir[1] * f.rad[1], D2 = dir[2] * f.rad[2];
     const double dDO = fma(D2, f.otr[2], fma(D1, f.otr[1], D0 * f.otr[0]));
     const double dDD = fma(D2, D2, fma(D1, D1, D0 * D0));
@@ -212,7 +256,7 @@ __device__ __forceinline__ bool intersect_hit(const FrameC& f, const double dir[
     return (dDO - (rt > 0.0 ? sqrt_fast(rt) : 0.0)) >= 0.0;
 }
 
-__device__ __forceinline__ void mat3(const double* __restrict__ M, const double v[3], double o[3]) {
+AMT_HD void mat3(const double* __restrict__ M, const double v[3], double o[3]) {
     o[0] = fma(M[2], v[2], fma(M[1], v[1], M[0] * v[0]));
     o[1] = fma(M[5], v[2], fma(M[4], v[1], M[3] * v[0]));
     o[2] = fma(M[8], v[2], fma(M[7], v[1], M[6] * v[0]));
@@ -222,22 +266,26 @@ __device__ __forceinline__ void mat3(const double* __restrict__ M, const double 
 // Stage 2b: ECEF -> geodetic, single-iteration Bowring 1985 (coordinates/transform.py:252-297).
 //   p = sqrt(x^2+y^2), r = sqrt(p^2+z^2), tu = b z (1 + d/r)/(a p), cu3 = (1+tu^2)^(-3/2),
 //   lat = atan((z + d cu3 tu^3)/(p - e^2 a cu3)), lon = atan2(y, x)
-// evaluated with one Goldschmidt (sqrt, 1/sqrt) pair per root, no division besides the two
-// inside the arctangents:  tu = (b/a) z (r + d) (1/r)(1/p).  Output in DEGREES.
+// p is a main term of the latitude (<= 1 ulp: Goldschmidt pair with residual step); 1/p, 1/r and
+// cu = (1+tu^2)^(-1/2) only scale the e^2-sized corrections (2^-39 each is 1e-14 rad on the
+// result).  No division besides the two inside the arctangents:
+//   tu = (b/a) (z / p) (1 + d / r),  d su3 = d (tu cu)^3.  Output in DEGREES; r2 = |(x,y,z)|^2
+// is handed back for the elevation (|P|^2 is invariant under the J2000 -> GEO rotation).
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void bowring(double a, double b_over_a, double e2a, double d,
-                                        double x, double y, double z, double& lat, double& lon) {
+AMT_HD void bowring(double b_over_a, double e2a, double d, double x, double y, double z,
+                    double& lat, double& lon, double& r2) {
     const double p2 = fma(x, x, y * y);
-    double p, hp, r, hr;
+    double p, hp;
     sqrt_rsqrt(p2, p, hp);                       // hp = 0.5/p
-    sqrt_rsqrt(fma(z, z, p2), r, hr);            // hr = 0.5/r
-    const double tu = ((b_over_a * z) * (r + d)) * ((hp + hp) * (hr + hr));
-    const double c = rsqrt_40(fma(tu, tu, 1.0));   // scales the e^2-sized correction terms only
-    const double cu3 = (c * c) * c;
-    const double su3 = (tu * cu3) * (tu * tu);
+    r2 = fma(z, z, p2);
+    const double ir = rsqrt_40(r2);
+    const double tu = ((b_over_a * z) * (hp + hp)) * fma(d, ir, 1.0);
+    const double cu = rsqrt_40(fma(tu, tu, 1.0));
+    const double tc = tu * cu;
+    const double cu3 = (cu * cu) * cu;
+    const double su3 = (tc * tc) * tc;
     lat = atan2_posx_deg(fma(d, su3, z), fma(-e2a, cu3, p));
     lon = atan2_deg(y, x);
-    (void)a;
 }
 
 // Reference-order Bowring with libm, used by the (cold) rotatePole path where the result
@@ -278,35 +326,41 @@ __device__ __forceinline__ void geodetic2ecef(double a, double e2, double lat, d
 }
 
 // SM Cartesian -> (MLat deg, MLT h): transform.py:104-127 + :419-430 + :373-386.
-__device__ __forceinline__ void sm_to_mlat_mlt(const double S[3], double& mlat, double& mlt) {
+AMT_HD void sm_to_mlat_mlt(const double S[3], double& mlat, double& mlt) {
     const double s = sqrt_fast(fma(S[0], S[0], S[1] * S[1]));
     const double smlon = atan2_deg(S[1], S[0]);
     mlat = atan2_posx_deg(S[2], s);
     mlt = fma(smlon, 24.0 / 360.0, 12.0);
 }
 
-// elevation, mapping/astrometry.py:200-212 + utils.py:28-46: 90 - acos(clip(-dir . P/|P|)).
-// UNIT_DIR: `dir` is used as is (the reference's own behaviour for fast centres, whose
-// direction is the un-normalised mean of four unit corner directions, astrometry.py:61-62);
-// otherwise `dir` has arbitrary length and is normalised here (one rsqrt for both lengths).
+// elevation, mapping/astrometry.py:200-212 + utils.py:28-46: 90 - acos(clip(-dir . P/|P|)) with
+// `dir` a unit vector, i.e. the angle between -dir and the plane normal to P:
+//     e = atan2(c, sqrt(dd |P|^2 - c^2)),   c = -dir . P,  dd = |dir|^2
+// -- no normalisation, no clip (the root is clamped at 0 instead), and better conditioned near
+// the nadir than acos.  UNIT_DIR: dd := 1, the reference's own behaviour for fast centres, whose
+// direction is the un-normalised mean of four unit corner directions (astrometry.py:61-62).
 template <bool UNIT_DIR>
-__device__ __forceinline__ double elevation_deg(const double dir[3], const double P[3]) {
-    double n2 = fma(P[2], P[2], fma(P[1], P[1], P[0] * P[0]));
-    if (!UNIT_DIR) n2 *= fma(dir[2], dir[2], fma(dir[1], dir[1], dir[0] * dir[0]));
-    double dot = -fma(dir[2], P[2], fma(dir[1], P[1], dir[0] * P[0])) * rsqrt_fast(n2);
-    // np.clip(dot, -1, 1)
-    dot = fmin(fmax(dot, -1.0), 1.0);
-    return asin_deg(dot);                       // 90 - deg(acos(dot))
+AMT_HD double elevation_deg(const double dir[3], const double P[3], double r2) {
+    const double c = -fma(dir[2], P[2], fma(dir[1], P[1], dir[0] * P[0]));
+    double n = r2;
+    if (!UNIT_DIR) n *= fma(dir[2], dir[2], fma(dir[1], dir[1], dir[0] * dir[0]));
+    const double w = fma(-c, c, n);
+    if (!(w > 0.0)) return c == c ? copysign(90.0, c) : c;
+    return atan2_posx_deg(c, sqrt_fast(w));
 }
 
 // One J2000 intersection point -> lat/lon [deg] (+ MLat/MLT).  transform.py:324-343,403-430.
-__device__ __forceinline__ void point_to_geo(const FrameC& f, const double P[3], double& lat, double& lon) {
+AMT_HD void point_to_geo(const FrameC& f, const double P[3], double& lat, double& lon, double& r2) {
     double G[3];
     mat3(f.m_geo, P, G);
-    bowring(f.a, f.b_over_a, f.e2a, f.d, G[0], G[1], G[2], lat, lon);
+    bowring(f.b_over_a, f.e2a, f.d, G[0], G[1], G[2], lat, lon, r2);
+}
+AMT_HD void point_to_geo(const FrameC& f, const double P[3], double& lat, double& lon) {
+    double r2;
+    point_to_geo(f, P, lat, lon, r2);
 }
 
-__device__ __forceinline__ void point_to_mag(const FrameC& f, const double P[3], double& mlat, double& mlt) {
+AMT_HD void point_to_mag(const FrameC& f, const double P[3], double& mlat, double& mlt) {
     double S[3];
     mat3(f.m_sm, P, S);
     sm_to_mlat_mlt(S, mlat, mlt);

@@ -1,0 +1,224 @@
+// Sequence engine: the per-frame launch sequences of the pipelined getMapping + resample path
+// (reference: getMappingSequence, mapping/spacecraft.py:308-332, composed with ResampleProvider,
+// resample.py:370-394) as TWO C calls per frame instead of ~25 Python-level operations.
+//
+//   stage A (frame header only):   hit bitmaps (limb solver for pure TAN frames, per-pixel hit test
+//       otherwise) -> sanitisation stencils on the bitmaps -> outline statistics from the frame
+//       model -> asynchronous copy of the 104-byte statistics block to pinned host memory.
+//       All on the auxiliary high-priority stream: microsecond kernels that overlap the long
+//       kernel of the preceding frames.
+//   host:                          bounding box -> target grid (reference arithmetic, Python).
+//   stage B (grid + image):        upload of the pixel box that holds defined pixels (copy stream)
+//       -> zero the accumulators -> ONE fused kernel: coordinate planes + binning (main stream)
+//       -> normalise -> results to pinned host memory (output stream).
+//
+// The engine owns streams' ORDER (events), never memory: every buffer is provided by the caller
+// (ring slots: planes, bitmaps, statistics block, device image; per frame: accumulators, outputs).
+// One engine per amt_ctx, driven by one host thread.  Included at the end of amt.cu.
+#pragma once
+#include <nvtx3/nvToolsExt.h>
+
+struct SeqSlot {
+    amt_seq_slot buf;
+    bool is_set;
+    amt_frame frame;
+    cudaEvent_t ev_a, ev_up, ev_b, ev_out;
+    bool a_rec, b_rec, out_rec;
+};
+
+struct amt_seq {
+    amt_ctx* ctx;
+    int W, H, C, dtype;
+    cudaStream_t s_main, s_aux, s_copy, s_out;
+    std::vector<SeqSlot> slots;
+    unsigned long long h2d_bytes;
+};
+
+static size_t seq_align64(size_t n) { return (n + 63) / 64 * 64; }
+
+extern "C" int amt_seq_output_layout(int32_t nx, int32_t ny, int32_t channels, int32_t dtype, size_t* off_mask,
+                                     size_t* off_side, size_t* total) {
+    CHECK_ARG(nx > 0 && ny > 0 && channels >= 1 && channels <= 4, "amt_seq_output_layout: bad arguments");
+    CHECK_ARG(dtype == AMT_U8 || dtype == AMT_U16, "amt_seq_output_layout: dtype must be uint8 or uint16");
+    const size_t cells = (size_t)nx * ny, item = dtype == AMT_U8 ? 1 : 2;
+    const size_t om = seq_align64(cells * channels * item), os = seq_align64(om + cells);
+    if (off_mask) *off_mask = om;
+    if (off_side) *off_side = os;
+    if (total) *total = os + cells * 8;
+    return AMT_OK;
+}
+
+extern "C" int amt_seq_create(amt_ctx* ctx, int32_t width, int32_t height, int32_t channels, int32_t dtype,
+                              int32_t n_slots, void* main_stream, void* aux_stream, void* copy_stream,
+                              void* out_stream, amt_seq** out) {
+    ENTER(ctx);
+    CHECK_ARG(out, "amt_seq_create: out is NULL");
+    CHECK_ARG(width > 0 && height > 0 && channels >= 1 && channels <= 4, "amt_seq_create: bad frame shape");
+    CHECK_ARG(dtype == AMT_U8 || dtype == AMT_U16, "amt_seq_create: image dtype must be uint8 or uint16");
+    CHECK_ARG(n_slots >= 1 && n_slots <= 64, "amt_seq_create: 1..64 slots");
+    amt_seq* s = new (std::nothrow) amt_seq();
+    if (!s) return set_err(AMT_ERR_CUDA, "out of host memory");
+    s->ctx = ctx;
+    s->W = width; s->H = height; s->C = channels; s->dtype = dtype;
+    s->s_main = (cudaStream_t)main_stream; s->s_aux = (cudaStream_t)aux_stream;
+    s->s_copy = (cudaStream_t)copy_stream; s->s_out = (cudaStream_t)out_stream;
+    s->h2d_bytes = 0;
+    s->slots.resize(n_slots);
+    for (auto& sl : s->slots) {
+        memset(&sl.buf, 0, sizeof sl.buf);
+        sl.is_set = sl.a_rec = sl.b_rec = sl.out_rec = false;
+        cudaEvent_t* evs[4] = {&sl.ev_a, &sl.ev_up, &sl.ev_b, &sl.ev_out};
+        for (auto e : evs) {
+            cudaError_t err = cudaEventCreateWithFlags(e, cudaEventDisableTiming);
+            if (err != cudaSuccess) {
+                delete s;
+                return set_err(AMT_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(err));
+            }
+        }
+    }
+    *out = s;
+    return AMT_OK;
+}
+
+extern "C" int amt_seq_destroy(amt_seq* seq) {
+    if (!seq) return AMT_OK;
+    cudaSetDevice(seq->ctx->device);
+    for (auto& sl : seq->slots) {
+        cudaEventDestroy(sl.ev_a); cudaEventDestroy(sl.ev_up); cudaEventDestroy(sl.ev_b); cudaEventDestroy(sl.ev_out);
+    }
+    delete seq;
+    return AMT_OK;
+}
+
+#define SEQ_SLOT(seq, slot)                                                                     \
+    CHECK_ARG((seq) != nullptr, "sequence engine is NULL");                                     \
+    CHECK_ARG((slot) >= 0 && (slot) < (int)(seq)->slots.size(), "slot index out of range");     \
+    SeqSlot& sl = (seq)->slots[slot]
+
+extern "C" int amt_seq_set_slot(amt_seq* seq, int32_t slot, const amt_seq_slot* buffers) {
+    SEQ_SLOT(seq, slot);
+    CHECK_ARG(buffers, "amt_seq_set_slot: buffers is NULL");
+    CHECK_ARG(buffers->planes.d_valid_k && buffers->planes.d_valid_c, "amt_seq_set_slot: the validity bitmaps are required");
+    CHECK_ARG(buffers->d_stats && buffers->h_stats, "amt_seq_set_slot: device and pinned statistics blocks are required");
+    sl.buf = *buffers;
+    sl.is_set = true;
+    return AMT_OK;
+}
+
+extern "C" int amt_seq_stage_a(amt_seq* seq, int32_t slot, const amt_frame* frame) {
+    SEQ_SLOT(seq, slot);
+    amt_ctx* ctx = seq->ctx;
+    ENTER(ctx);
+    CHECK_ARG(frame && sl.is_set, "amt_seq_stage_a: frame is NULL or the slot has no buffers");
+    CHECK_ARG(frame->width == seq->W && frame->height == seq->H, "amt_seq_stage_a: frame shape differs from the engine's");
+    if (frame->model != AMT_MODEL_WCS || frame->fast_center)
+        return set_err(AMT_ERR_UNSUPPORTED, "amt_seq_stage_a: WCS frames with fast_center == 0 only");
+    nvtxRangePushA("amt_seq stage A: hit bitmaps, sanitise, outline statistics");
+    sl.frame = *frame;
+    cudaStream_t st = seq->s_aux;
+    // the bitmaps of this slot are read by the fused kernel of the slot's previous frame
+    if (sl.b_rec) CUDA_TRY(cudaStreamWaitEvent(st, sl.ev_b, 0));
+    amt_georef_out bits;
+    memset(&bits, 0, sizeof bits);
+    bits.d_valid_k = sl.buf.planes.d_valid_k;
+    bits.d_valid_c = sl.buf.planes.d_valid_c;
+    int rc = amt_georef(ctx, frame, &bits, sl.buf.d_stats, st);
+    if (!rc) rc = amt_sanitize(ctx, seq->W, seq->H, &bits, st);
+    if (!rc) rc = amt_bbox_stats_frame(ctx, frame, bits.d_valid_k, bits.d_valid_c, nullptr, sl.buf.d_stats, st);
+    if (rc) { nvtxRangePop(); return rc; }
+    CUDA_TRY(cudaMemcpyAsync(sl.buf.h_stats, sl.buf.d_stats, sizeof(amt_stats), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(sl.ev_a, st));
+    sl.a_rec = true;
+    nvtxRangePop();
+    return AMT_OK;
+}
+
+extern "C" int amt_seq_wait_stats(amt_seq* seq, int32_t slot, amt_stats* out) {
+    SEQ_SLOT(seq, slot);
+    CHECK_ARG(sl.a_rec, "amt_seq_wait_stats: stage A has not been submitted for this slot");
+    CUDA_TRY(cudaEventSynchronize(sl.ev_a));
+    if (out) *out = *sl.buf.h_stats;
+    return AMT_OK;
+}
+
+extern "C" int amt_seq_stage_b(amt_seq* seq, int32_t slot, const amt_seq_job* job) {
+    SEQ_SLOT(seq, slot);
+    amt_ctx* ctx = seq->ctx;
+    ENTER(ctx);
+    CHECK_ARG(job && job->grid && job->d_acc && job->d_out, "amt_seq_stage_b: NULL argument");
+    CHECK_ARG(sl.a_rec, "amt_seq_stage_b: stage A has not been submitted for this slot");
+    const amt_grid* g = job->grid;
+    size_t om, os, total;
+    int rc = amt_seq_output_layout(g->nx, g->ny, seq->C, seq->dtype, &om, &os, &total);
+    if (rc) return rc;
+    CHECK_ARG(job->out_bytes >= total, "amt_seq_stage_b: output buffer too small for the grid");
+    nvtxRangePushA("amt_seq stage B: upload, fused georeference + binning, normalise, download");
+    const size_t cells = (size_t)g->nx * g->ny;
+    const size_t item = seq->dtype == AMT_U8 ? 1 : 2, px = item * seq->C, row_bytes = px * seq->W;
+    const void* d_img = job->d_img ? job->d_img : sl.buf.d_img;
+    if (!d_img) { nvtxRangePop(); return set_err(AMT_ERR_INVALID_ARGUMENT, "amt_seq_stage_b: no device image buffer"); }
+    bool uploaded = false;
+    if (job->h_img && !job->d_img) {
+        // the slot's image buffer is read by the fused kernel of the slot's previous frame
+        if (sl.b_rec) CUDA_TRY(cudaStreamWaitEvent(seq->s_copy, sl.ev_b, 0));
+        const int r0 = job->row0 < 0 ? 0 : job->row0, r1 = job->row1 >= seq->H ? seq->H - 1 : job->row1;
+        const int c0 = job->col0 < 0 ? 0 : job->col0, c1 = job->col1 >= seq->W ? seq->W - 1 : job->col1;
+        if (r1 >= r0 && c1 >= c0) {
+            const size_t nrows = (size_t)(r1 - r0 + 1), ncols = (size_t)(c1 - c0 + 1);
+            unsigned char* dst = (unsigned char*)sl.buf.d_img;
+            const unsigned char* src = (const unsigned char*)job->h_img;
+            if (ncols * 10 < (size_t)seq->W * 9) {
+                // the defined pixels sit in a column band (limb roughly vertical): copy the box
+                const size_t off = (size_t)r0 * row_bytes + (size_t)c0 * px;
+                CUDA_TRY(cudaMemcpy2DAsync(dst + off, row_bytes, src + off, row_bytes, ncols * px, nrows,
+                                           cudaMemcpyHostToDevice, seq->s_copy));
+                seq->h2d_bytes += ncols * px * nrows;
+            } else {
+                const size_t off = (size_t)r0 * row_bytes;
+                CUDA_TRY(cudaMemcpyAsync(dst + off, src + off, nrows * row_bytes, cudaMemcpyHostToDevice, seq->s_copy));
+                seq->h2d_bytes += nrows * row_bytes;
+            }
+        }
+        CUDA_TRY(cudaEventRecord(sl.ev_up, seq->s_copy));
+        uploaded = true;
+    }
+    cudaStream_t st = seq->s_main;
+    CUDA_TRY(cudaStreamWaitEvent(st, sl.ev_a, 0));             // final bitmaps of this frame (auxiliary stream)
+    if (uploaded) CUDA_TRY(cudaStreamWaitEvent(st, sl.ev_up, 0));
+    uint64_t* count = job->d_acc;
+    uint64_t* sums = count + cells;
+    double* fsum = (double*)(count + (size_t)(1 + seq->C) * cells);
+    CUDA_TRY(cudaMemsetAsync(job->d_acc, 0, (size_t)(2 + seq->C) * cells * 8, st));
+    const amt_georef_out* planes = sl.buf.planes.d_lat_k ? &sl.buf.planes : nullptr;
+    rc = georef_fused(ctx, &sl.frame, planes, sl.buf.planes.d_valid_k, sl.buf.planes.d_valid_c, d_img, seq->dtype,
+                      seq->C, g, count, sums, fsum, st);
+    unsigned char* o = (unsigned char*)job->d_out;
+    if (!rc) rc = amt_normalise(ctx, g, seq->dtype, seq->C, count, sums, fsum, o, o + om, (double*)(o + os), st);
+    if (rc) { nvtxRangePop(); return rc; }
+    CUDA_TRY(cudaEventRecord(sl.ev_b, st));
+    sl.b_rec = true;
+    if (job->h_out) {
+        // results leave on their own stream: the copy must not delay the next frame's kernel
+        CUDA_TRY(cudaStreamWaitEvent(seq->s_out, sl.ev_b, 0));
+        CUDA_TRY(cudaMemcpyAsync(job->h_out, job->d_out, total, cudaMemcpyDeviceToHost, seq->s_out));
+        CUDA_TRY(cudaEventRecord(sl.ev_out, seq->s_out));
+        sl.out_rec = true;
+    } else {
+        sl.out_rec = false;
+    }
+    nvtxRangePop();
+    return AMT_OK;
+}
+
+extern "C" int amt_seq_wait_result(amt_seq* seq, int32_t slot) {
+    SEQ_SLOT(seq, slot);
+    CHECK_ARG(sl.b_rec, "amt_seq_wait_result: stage B has not been submitted for this slot");
+    CUDA_TRY(cudaEventSynchronize(sl.out_rec ? sl.ev_out : sl.ev_b));
+    return AMT_OK;
+}
+
+extern "C" int amt_seq_h2d_bytes(const amt_seq* seq, uint64_t* bytes) {
+    CHECK_ARG(seq && bytes, "amt_seq_h2d_bytes: NULL argument");
+    *bytes = seq->h2d_bytes;
+    return AMT_OK;
+}

@@ -14,7 +14,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 SOURCES = ["amt.cu"]
-HEADERS = ["amt_math.cuh", os.path.join(ROOT, "include", "auromat_b200.h")]
+# every header next to the sources takes part in the staleness test (a stale .so must never ship)
+HEADERS = sorted(f for f in os.listdir(HERE) if f.endswith((".cuh", ".h"))) + \
+          [os.path.join(ROOT, "include", "auromat_b200.h")]
 LIB = os.path.join(HERE, "libauromat_b200.so")
 
 NVCC_FLAGS = [

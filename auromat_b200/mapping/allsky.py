@@ -60,6 +60,8 @@ class AllSkyMapping(BaseMapping):
     :param img: square (w,w[,n]) uint8/uint16 array or device tensor
     """
 
+    _finiteElevation = True      # the camera elevation angle, finite wherever the centre is defined
+
     def __init__(self, calData, img, photoTime, alti=110, identifier=None, metadata=None, device=None,
                  sanitize=True):
         if identifier is None:

@@ -32,6 +32,7 @@ class BaseAstrometryMapping(BaseMapping):
         self._frame = None
 
     wcsHeader = property(lambda self: self._wcsHeader)
+    _finiteElevation = True      # computed by the georeference kernels: finite wherever the centre is defined
 
     @property
     def shape(self):
@@ -107,6 +108,8 @@ class BaseAstrometryMapping(BaseMapping):
         if self._stats is None and self._statsPending is None:
             ctx = self.context
             vk, vc = self._ensureHitBitmaps()
+            if self._statsDevice is None:
+                self._statsDevice = ctx.new_stats()
             ctx.bbox_stats_frame(self.frameConstants, vk, vc, self._statsDevice)
             self._statsPending = ctx.start_stats_readback(self._statsDevice)
 

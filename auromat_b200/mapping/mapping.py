@@ -518,10 +518,24 @@ class BaseMapping(object):
         m._statsDevice = None
         m._boundingBox = None
         m._outlines = m._centroid = m._pixelScales = None
+        m.__dict__.pop('_ringSlot', None)          # the copy owns its planes
+        m._planeFree = False
         h, w = self.shape
         dmask = deviceMask if deviceMask is not None else (ctx.to_device(mask.ravel()) if mask is not None else None)
         ctx.apply_center_mask(w, h, m._planes, dmask, minElevation)
         return m
+
+    def _detachRing(self):
+        """The sequence pipeline recycles the ring slot whose planes this mapping was showing: drop
+        them (and the ring copy of the image); any later access recomputes into fresh buffers."""
+        if self.__dict__.pop('_ringSlot', None) is None:
+            return
+        ringImg = self._imgDevice is not None and getattr(self, '_imgDevice_in', None) is not self._imgDevice
+        self._planes = {}
+        self.__dict__.pop('_planeBuffers', None)
+        self._planeFree = False
+        if ringImg:
+            self._imgDevice = None
 
     def setDirty(self):
         self._boundingBox = None

@@ -100,11 +100,15 @@ class MosaicAccumulator(object):
         import torch
         self.grid, self.info, self.channels, self.imgDtype, self.ctx = grid, info, channels, imgDtype, context
         self.cells = grid.nx * grid.ny
-        self.acc = context.zeros((1 + channels) * self.cells, torch.int64)
-        self.fsum = context.zeros(self.cells, torch.float64)
+        # one allocation: count | sums[channels] | elevation sums (int64 fixed point when
+        # grid.side_scale > 0, else float64 bits)
+        self.all = context.zeros((2 + channels) * self.cells, torch.int64)
+        self.acc = self.all[:(1 + channels) * self.cells]
+        self.fsum = self.all[(1 + channels) * self.cells:].view(torch.float64)
 
     count = property(lambda self: self.acc[:self.cells])
     sums = property(lambda self: self.acc[self.cells:])
+    exactSide = property(lambda self: self.grid.side_scale > 0)
 
     def add(self, mapping):
         """Bin one mapping into the grids (`amt_bin_accumulate`)."""
@@ -113,7 +117,12 @@ class MosaicAccumulator(object):
         binMappingInto(mapping, self.grid, self.count, self.sums, self.fsum)
 
     def allreduce(self, group=None):
-        allreduceGrids([self.acc, self.fsum], group)
+        """ONE message when the elevation sums are integers too (exact, order independent); else the
+        float plane is reduced on its own."""
+        if self.exactSide:
+            allreduceGrids(self.all, group)
+        else:
+            allreduceGrids([self.acc, self.fsum], group)
 
     def finalise(self, template):
         """Normalise and wrap the mosaic as a GenericMapping (metadata from `template`)."""
@@ -134,12 +143,15 @@ class MosaicAccumulator(object):
                               template.photoTime, 'mosaic', device=ctx.device)
 
 
-def mosaic(mappings, pxPerDeg, group=None):
+def mosaic(mappings, pxPerDeg, group=None, timings=None):
     """Compose the mappings held by ALL ranks (each rank passes its own subset) into one
     mean-binned mosaic on a common grid; every rank returns the full mosaic mapping.
 
     Steps: all-gather the per-mapping bounding boxes -> common `fixedGrid` on every rank ->
-    local binning -> one all-reduce of the sum/count grids -> normalise."""
+    local binning -> one all-reduce of the sum/count grids -> normalise.
+
+    :param timings: optional dict that receives the CUDA-event times of this rank in ms:
+        `bin_ms`, `allreduce_ms`, `normalise_ms` and their sum `total_ms` (synchronises)"""
     from .resample import targetGrid
     mappings = list(mappings)
     assert mappings, 'every rank needs at least one mapping'
@@ -149,6 +161,15 @@ def mosaic(mappings, pxPerDeg, group=None):
         pxPerDeg = (pxPerDeg, pxPerDeg)
     boxes = gatherBoundingBoxes([m.boundingBox for m in mappings], group)
     bb = BoundingBox.mergedBoundingBoxes(boxes)
+    # pixels of ALL members on all ranks (bound of the fixed-point elevation sums) and whether every
+    # member's elevation is device-computed (finite)
+    nSamples = sum(m.shape[0] * m.shape[1] for m in mappings)
+    exact = all(getattr(m, '_finiteElevation', False) for m in mappings)
+    if worldInfo()[1] > 1:
+        import torch.distributed as dist
+        parts = [None] * worldInfo()[1]
+        dist.all_gather_object(parts, (nSamples, exact), group=group)
+        nSamples, exact = sum(p[0] for p in parts), all(p[1] for p in parts)
     mode = _lib.AMT_PRE_NONE
     latMin, latMax, lonMin, lonMax = bb.latSouth, bb.latNorth, bb.lonWest, bb.lonEast
     if bb.containsPole or any(b.containsPole for b in boxes):
@@ -183,10 +204,28 @@ def mosaic(mappings, pxPerDeg, group=None):
         lonMin, lonMax = wrapAt180(bb.lonWest + 180), wrapAt180(bb.lonEast + 180)
     grid, info = targetGrid(pxPerDeg, latMin, latMax, lonMin, lonMax, mode, mappings[0].altitude)
     info['mode'] = mode
+    if exact:
+        from .resample import sideScale
+        grid.side_scale = sideScale(nSamples)
     m0 = mappings[0]
     img0 = m0.deviceImage()
     acc = MosaicAccumulator(grid, info, img0.shape[2], img0.dtype, m0.context)
+    ev = None
+    if timings is not None:
+        import torch
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
     for m in mappings:
         acc.add(m)
+    if ev:
+        ev[1].record()
     acc.allreduce(group)
-    return acc.finalise(m0), acc
+    if ev:
+        ev[2].record()
+    result = acc.finalise(m0)
+    if ev:
+        ev[3].record()
+        ev[3].synchronize()
+        timings.update(bin_ms=ev[0].elapsed_time(ev[1]), allreduce_ms=ev[1].elapsed_time(ev[2]),
+                       normalise_ms=ev[2].elapsed_time(ev[3]), total_ms=ev[0].elapsed_time(ev[3]))
+    return result, acc

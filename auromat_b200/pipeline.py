@@ -1,5 +1,15 @@
 """Software-pipelined getMapping + resample over an image sequence on one GPU.
 
+Two implementations share the public generator `resampleSequence`:
+
+* WCS frames with their own centre rays (the default of `getMapping`) run on the C sequence engine
+  (`amt_seq_*`, csrc/amt_seq.cuh): per frame TWO library calls -- stage A (hit bitmaps by the limb
+  solver, sanitisation and outline statistics on the bitmaps) and, once the 104-byte statistics
+  block is on the host and the grid is derived, stage B (upload of the defined pixel box, ONE fused
+  kernel that writes the coordinate planes and bins the centres, normalise, download).
+* fastCenterCalculation frames keep the Python-orchestrated multi-stream pipeline described below.
+
+
 `getMappingSequence` of the reference (mapping/spacecraft.py:308-332) yields one mapping at a
 time and `ResampleProvider` (resample.py:370-394) maps `resample` over it; every frame is
 independent.  `resampleSequence` is the same composition with the host-visible phases of a
@@ -20,6 +30,8 @@ hidden behind the georeferencing of the next `depth` frames.  Results are identi
 from __future__ import annotations
 
 import collections
+import ctypes
+import os
 import weakref
 
 import numpy as np
@@ -28,6 +40,11 @@ import numpy.ma as ma
 from . import _lib
 from .mapping.spacecraft import getMapping
 from .resample import resampleToDevice
+
+
+class _Waiter(object):
+    def __init__(self, fn):
+        self.synchronize = fn
 
 
 class ResampledFrame(object):
@@ -96,6 +113,14 @@ class ResampledFrame(object):
                                                 for o, n, dt, sh in zip(offs, sizes, dtypes, shapes))
         return self.__dict__['_hostViews']
 
+    def _attachHost(self, flat, offs, sizes, pool_bucket, waiter):
+        """Results arrive in `flat` (pinned) through the sequence engine; `waiter()` blocks until
+        the copy is complete."""
+        parts = (self.deviceImg, self.deviceMask, self.deviceElevation)
+        self._hostFlat = (flat, offs, sizes, [p.dtype for p in parts], [tuple(p.shape) for p in parts])
+        weakref.finalize(self, pool_bucket.append, flat)     # the buffer returns to the pool with the frame
+        self._event = _Waiter(waiter)
+
     def _finish(self):
         if self._event is not None:
             self._event.synchronize()
@@ -158,14 +183,20 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
         frame ~60 % of the image): pixels that see no Earth never influence the result.
         `frame.mapping.img` still is the complete host image.
     :param transferStats: optional dict that receives `h2d_bytes` (image bytes actually copied)
-    :param ringBuffers: keep the coordinate planes of the frames in a fixed ring of depth+3 plane
-        sets (0.9 GB each for a 12-Mpix frame) instead of allocating per frame: constant memory
-        footprint for arbitrarily long sequences, but `frame.mapping`'s planes are only valid
-        until depth+2 further frames have been yielded (the resampled outputs stay valid)
+    :param ringBuffers: keep the coordinate planes of the frames in a fixed ring of
+        depth + AHEAD_B + KEEP_FRAMES + 1 plane sets (0.9 GB each for a 12-Mpix frame) instead of
+        allocating per frame: constant memory footprint for arbitrarily long sequences.  The planes
+        of `frame.mapping` are valid while KEEP_FRAMES + 1 = 3 further frames are taken from the
+        generator; when its ring slot is recycled the mapping is detached from the ring and
+        recomputes its planes on access (the resampled outputs of a frame are never recycled)
     """
     import torch
     from .runtime import get_context
     ctx = get_context(device)
+    if not fastCenterCalculation and os.environ.get('AMT_PIPELINE', 'engine') != 'python':
+        yield from _engineSequence(ctx, imagesOrArrays, wcsHeaders, pxPerDeg, arcsecPerPx, altitude, magnetic,
+                                   metadatas, depth, toHost, ringBuffers, coordinates, sparseUpload, transferStats)
+        return
     main = torch.cuda.current_stream(ctx.torch_device)
     # one copy stream, one image ring and one pinned-buffer pool per context: they survive
     # across sequences (torch caches device blocks per stream)
@@ -245,7 +276,10 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
     ring = []
     freeStats = []
     slotDone = {}            # ring slot -> event recorded after the binning of its last user
-    ringLen = depth + 3
+    slotOwner = {}           # ring slot -> weakref of the mapping that shows its planes
+    # frame i is handed out in iteration i + 2*depth - 1 and its planes stay valid while KEEP_FRAMES + 1
+    # further frames are taken: the slot must not be reused before iteration i + 2*depth + KEEP_FRAMES + 1
+    ringLen = 2 * depth + KEEP_FRAMES + 2
     # With ring buffers the phases of a frame run on separate streams (see the module docstring):
     # the georeference kernel on the caller's stream, sanitise / statistics on `aux`, zero / bin /
     # normalise on `second`, uploads on `copy`, result downloads on `dout`, so that the small
@@ -315,7 +349,13 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
             prev = slotDone.get(i % ringLen)
             if prev is not None:
                 main.wait_event(prev)           # ring slot free: its previous frame has been binned
+            old = slotOwner.get(i % ringLen)
+            old = old() if old is not None else None
+            if old is not None:
+                old._detachRing()                  # it recomputes into fresh buffers if asked again
             m._planeBuffers = ringSet(i, m)
+            m._ringSlot = (None, i % ringLen)
+            slotOwner[i % ringLen] = weakref.ref(m)
             m._statsDevice = m._planeBuffers['_stats']      # ring-owned statistics block (no per-frame alloc)
         mark('A0', i, main)
         if aux is None:
@@ -378,6 +418,11 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
             mark('B0', i, second)
             grid, info, dImg, dMask, dElev = resampleToDevice(m, pxPerDeg=pxPerDeg, arcsecPerPx=arcsecPerPx)
             f = ResampledFrame(m, grid, info, dImg, dMask, dElev)
+            # allocated under `second`, handed to the caller on `main`: the caching allocator must not
+            # recycle these blocks while kernels of the caller's stream still read them
+            for t in (getattr(dImg, '_amt_flat', None), info.get('count')):
+                if t is not None:
+                    t.record_stream(main)
             mark('B1', i, second)
             done = torch.cuda.Event()
             done.record(second)
@@ -416,3 +461,248 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
             yield finish(stageB.popleft())
     finally:
         ctx.use_stream(None)
+
+
+# --------------------------------------------------------------------------- engine path
+KEEP_FRAMES = 2      # ring mode: the planes of a yielded frame stay valid while KEEP_FRAMES + 1 further frames
+                     # are taken from the generator; then the slot is recycled and the mapping detached
+AHEAD_B = 2          # frames whose stage B is enqueued before the oldest one is handed out
+
+
+def _pinnedBuffer(pool, nbytes, hint):
+    """A pinned byte buffer of at least nbytes from the per-context pool (capacity classes: the
+    grid size changes from frame to frame and page-locking is a millisecond-scale call)."""
+    import torch
+    cap = 1 << max(16, (nbytes - 1).bit_length())
+    bucket = pool.setdefault(cap, [])
+    if not bucket and cap not in pool.setdefault('_seen', set()):
+        pool['_seen'].add(cap)
+        bucket.extend(torch.empty(cap, dtype=torch.uint8).pin_memory() for _ in range(hint))
+    if not bucket:
+        pool['grown'] = pool.get('grown', 0) + 1         # page-locking inside a sequence: visible in diagnostics
+    return (bucket.pop() if bucket else torch.empty(cap, dtype=torch.uint8).pin_memory()), bucket
+
+
+class _Engine(object):
+    """One `amt_seq` with its streams and ring buffers; cached per context and configuration (the
+    rings survive across sequences)."""
+
+    def __init__(self, ctx, w, h, channels, npdtype, nslots, magnetic, planes, ring, main):
+        import torch
+        self.ctx, self.w, self.h, self.channels, self.nslots = ctx, w, h, channels, nslots
+        self.magnetic, self.planes, self.ring = magnetic, planes, ring
+        self.tdtype = {np.dtype(np.uint8): torch.uint8, np.dtype(np.uint16): torch.uint16}[np.dtype(npdtype)]
+        self.amtDtype = _lib.AMT_U8 if np.dtype(npdtype) == np.uint8 else _lib.AMT_U16
+        dev = ctx.torch_device
+
+        def stream(name, prio=0):
+            st = ctx.__dict__.get(name)
+            if st is None:
+                st = ctx.__dict__[name] = torch.cuda.Stream(dev, priority=prio)
+            return st
+        self.main = main
+        self.aux, self.copy, self.dout = stream('_aux_stream', -1), stream('_copy_stream'), stream('_dout_stream')
+        self.handle = ctypes.c_void_p()
+        _lib.check(ctx.lib.amt_seq_create(ctx.handle, w, h, channels, self.amtDtype, nslots,
+                                          ctypes.c_void_p(main.cuda_stream), ctypes.c_void_p(self.aux.cuda_stream),
+                                          ctypes.c_void_p(self.copy.cuda_stream),
+                                          ctypes.c_void_p(self.dout.cuda_stream), ctypes.byref(self.handle)))
+        self.slots = [None] * nslots          # per slot: dict of tensors
+        self.owner = [None] * nslots          # weakref to the mapping that currently shows the slot's planes
+        self.hostStats = torch.zeros((nslots, ctypes.sizeof(_lib.AmtStats)), dtype=torch.uint8).pin_memory()
+        self.devStats = torch.zeros((nslots, ctypes.sizeof(_lib.AmtStats)), dtype=torch.uint8, device=dev)
+        self.imgRing = None
+
+    def planeNames(self):
+        if not self.planes:
+            return []
+        return ['lat_k', 'lon_k', 'lat_c', 'lon_c', 'elev_c'] + \
+               (['mlat_k', 'mlt_k', 'mlat_c', 'mlt_c'] if self.magnetic else [])
+
+    def newBuffers(self):
+        import torch
+        ctx, w, h = self.ctx, self.w, self.h
+        b = {n: ctx.empty((h + 1) * (w + 1) if n.endswith('_k') else h * w, torch.float64) for n in self.planeNames()}
+        b['valid_k'], b['valid_c'] = ctx.new_bitmaps(w, h)
+        return b
+
+    def setSlot(self, slot, buffers, needImage):
+        import torch
+        if needImage and self.imgRing is None:
+            with torch.cuda.stream(self.copy):
+                self.imgRing = torch.empty((self.nslots, self.h, self.w, self.channels), dtype=self.tdtype,
+                                           device=self.ctx.torch_device)
+        sl = _lib.AmtSeqSlot()
+        sl.planes = self.ctx.out_struct(buffers)
+        sl.d_stats = self.devStats[slot].data_ptr()
+        sl.h_stats = self.hostStats[slot].data_ptr()
+        sl.d_img = self.imgRing[slot].data_ptr() if self.imgRing is not None else None
+        _lib.check(self.ctx.lib.amt_seq_set_slot(self.handle, slot, ctypes.byref(sl)))
+        self.slots[slot] = buffers
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.ctx.lib.amt_seq_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def _engineSequence(ctx, imagesOrArrays, wcsHeaders, pxPerDeg, arcsecPerPx, altitude, magnetic, metadatas, depth,
+                    toHost, ringBuffers, coordinates, sparseUpload, transferStats):
+    import torch
+    from .resample import deriveGrid
+    lib = ctx.lib
+    main = torch.cuda.current_stream(ctx.torch_device)
+    planes = bool(coordinates or magnetic)
+    depth = max(1, int(depth))
+    nslots = depth + AHEAD_B + KEEP_FRAMES + 1
+    pool = ctx.__dict__.setdefault('_pinned_frames', {})
+    engines = ctx.__dict__.setdefault('_engines', {})
+    metadatas = metadatas if metadatas else None
+    stats = transferStats if transferStats is not None else {}
+    stats.setdefault('h2d_bytes', 0)
+    stageA, stageB = collections.deque(), collections.deque()
+    eng = None
+    h2d0 = ctypes.c_uint64(0)
+
+    def engineFor(w, h, channels, npdtype):
+        key = (w, h, channels, np.dtype(npdtype).str, nslots, bool(magnetic), planes, bool(ringBuffers),
+               main.cuda_stream)
+        e = engines.get(key)
+        if e is None:
+            if len(engines) >= 4:                      # rings are large: keep a handful of configurations
+                engines.pop(next(iter(engines)))
+            e = engines[key] = _Engine(ctx, w, h, channels, npdtype, nslots, magnetic, planes, ringBuffers, main)
+        return e
+
+    def runA(i, img, hdr):
+        nonlocal eng
+        meta = metadatas[i] if metadatas else None
+        m = getMapping(img, hdr, altitude=altitude, metadata=meta,
+                       identifier=None if isinstance(hdr, str) else 'frame%06d' % i, device=ctx.device)
+        hostImg = None
+        if isinstance(img, str):
+            hostImg = m.img_unmasked                    # image file: decoded on the host
+        elif isinstance(img, np.ndarray):
+            hostImg = img
+        if hostImg is not None:
+            hostImg = np.ascontiguousarray(hostImg if hostImg.ndim == 3 else hostImg[..., None])
+            h, w, channels = hostImg.shape
+            npdtype = hostImg.dtype
+        else:
+            dimg = img if img.dim() == 3 else img[..., None]
+            h, w, channels = dimg.shape
+            npdtype = np.uint8 if dimg.dtype == torch.uint8 else np.uint16
+        if eng is None:
+            eng = engineFor(w, h, channels, npdtype)
+            lib.amt_seq_h2d_bytes(eng.handle, ctypes.byref(h2d0))
+        elif (eng.w, eng.h, eng.channels) != (w, h, channels):
+            raise ValueError('all frames of a sequence must have the same shape')
+        slot = i % nslots
+        # the frame that showed this slot's ring planes loses them (it recomputes on access)
+        prev = eng.owner[slot]() if eng.owner[slot] is not None else None
+        if prev is not None:
+            prev._detachRing()
+        if ringBuffers:
+            if eng.slots[slot] is None:
+                eng.setSlot(slot, eng.newBuffers(), hostImg is not None)
+            elif hostImg is not None and eng.imgRing is None:
+                eng.setSlot(slot, eng.slots[slot], True)
+        else:
+            b = eng.newBuffers()                        # per-frame planes: valid as long as the frame lives
+            for t in (b['valid_k'], b['valid_c']):
+                t.record_stream(eng.aux)
+            eng.setSlot(slot, b, hostImg is not None)
+        _lib.check(lib.amt_seq_stage_a(eng.handle, slot, ctypes.byref(m.frameConstants)))
+        return m, slot, hostImg
+
+    def runB(m, slot, hostImg):
+        st = _lib.AmtStats()
+        _lib.check(lib.amt_seq_wait_stats(eng.handle, slot, ctypes.byref(st)))
+        buffers = eng.slots[slot]
+        # the mapping sees its final bitmaps; planes follow once the fused kernel is enqueued
+        m._planes.update(valid_k=buffers['valid_k'], valid_c=buffers['valid_c'])
+        m._grazingCounted = True
+        m.isSanitized = True
+        m._planeFree = True
+        st.pole_flags = m._poleFlags()
+        m._stats = st
+        f = None
+        if st.n_boundary_corners == 0:
+            # nothing of the Earth in this frame: the same error `resample(getMapping(...))` raises
+            m.boundingBox
+        grid, info = deriveGrid(m, pxPerDeg, arcsecPerPx)
+        cells, C = grid.nx * grid.ny, eng.channels
+        offMask, offSide, total = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
+        _lib.check(lib.amt_seq_output_layout(grid.nx, grid.ny, C, eng.amtDtype, ctypes.byref(offMask),
+                                             ctypes.byref(offSide), ctypes.byref(total)))
+        accBytes = (2 + C) * cells * 8
+        # one device allocation per frame: accumulators | image | mask | elevation (caller's stream)
+        flat = torch.empty(accBytes + total.value, dtype=torch.uint8, device=ctx.torch_device)
+        flat.record_stream(eng.dout)
+        out = flat[accBytes:]
+        item = 1 if eng.amtDtype == _lib.AMT_U8 else 2
+        dImg = out[:cells * C * item].view(eng.tdtype).view(grid.ny, grid.nx, C)
+        dMask = out[offMask.value:offMask.value + cells].view(grid.ny, grid.nx)
+        dElev = out[offSide.value:offSide.value + cells * 8].view(torch.float64).view(grid.ny, grid.nx)
+        info['count'] = flat[:cells * 8].view(torch.int64)
+        job = _lib.AmtSeqJob()
+        job.grid = ctypes.pointer(grid)
+        if hostImg is not None:
+            job.h_img = hostImg.ctypes.data
+            if sparseUpload:
+                job.row0, job.row1, job.col0, job.col1 = st.row_min_c, st.row_max_c, st.col_min_c, st.col_max_c
+            else:
+                job.row0, job.row1, job.col0, job.col1 = 0, eng.h - 1, 0, eng.w - 1
+            dimg = eng.imgRing[slot]
+        else:
+            dimg = m._imgDevice if m._imgDevice.dim() == 3 else m._imgDevice[..., None]
+            job.d_img = dimg.data_ptr()
+        job.d_acc = flat.data_ptr()
+        job.d_out = out.data_ptr()
+        job.out_bytes = total.value
+        hostFlat = bucket = None
+        if toHost:
+            hostFlat, bucket = _pinnedBuffer(pool, total.value, 2 * depth + 6)
+            job.h_out = hostFlat.data_ptr()
+        _lib.check(lib.amt_seq_stage_b(eng.handle, slot, ctypes.byref(job)))
+        if planes:
+            m._planes.update({n: buffers[n] for n in eng.planeNames()})
+            m._planeFree = False
+        if hostImg is not None:
+            m._imgDevice = dimg
+        if ringBuffers:
+            m._ringSlot = (eng, slot)
+            eng.owner[slot] = weakref.ref(m)
+        f = ResampledFrame(m, grid, info, dImg, dMask, dElev)
+        f._src = hostImg                                 # the host image must outlive the asynchronous upload
+        if toHost:
+            handle, lib_ = eng.handle, lib
+            f._attachHost(hostFlat, [0, offMask.value, offSide.value],
+                          [cells * C * item, cells, cells * 8], bucket,
+                          lambda: _lib.check(lib_.amt_seq_wait_result(handle, slot)))
+        return f
+
+    try:
+        for i, (img, hdr) in enumerate(zip(imagesOrArrays, wcsHeaders)):
+            stageA.append(runA(i, img, hdr))
+            if len(stageA) >= depth:
+                stageB.append(runB(*stageA.popleft()))
+            while len(stageB) > AHEAD_B:
+                f = stageB.popleft()
+                f._finish()
+                yield f
+        while stageA:
+            stageB.append(runB(*stageA.popleft()))
+        while stageB:
+            f = stageB.popleft()
+            f._finish()
+            yield f
+    finally:
+        if eng is not None:
+            now = ctypes.c_uint64(0)
+            lib.amt_seq_h2d_bytes(eng.handle, ctypes.byref(now))
+            stats['h2d_bytes'] += now.value - h2d0.value
+            stats['pinned_grown'] = pool.get('grown', 0)

@@ -154,6 +154,15 @@ def targetGrid(pxPerDeg, latMin, latMax, lonMin, lonMax, prerotate=_lib.AMT_PRE_
     return g, info
 
 
+def sideScale(nSamples, maxAbs=128.0):
+    """`amt_grid.side_scale` for the fixed-point elevation sums: the largest power of two (<= 2**40)
+    such that nSamples values of magnitude < maxAbs, scaled and rounded, add up below 2**62 -- whatever
+    the distribution of the samples over the cells.  The sums are then exact integers: independent of
+    the order of the atomics, identical from run to run and across ranks."""
+    k = 62 - int(math.ceil(math.log2(maxAbs))) - int(math.ceil(math.log2(max(2, int(nSamples)))))
+    return float(2.0 ** max(1, min(40, k)))
+
+
 def resampleMLatMLT(mapping, **kw):
     """Resample such that MLat/MLT become regular grids (reference resample.py:63-71)."""
     from .mapping.mapping import convertMappingToSM, convertSMMappingToGeo
@@ -178,10 +187,10 @@ def binMappingInto(mapping, grid, count, sums, fsum, nearEdge=None):
                        img[r0:r1 + 1], grid, count, sums, fsum, nearEdge)
 
 
-def resampleToDevice(mapping, pxPerDeg=25, arcsecPerPx=None, containsPole=None):
-    """The device-resident part of `resample`: returns (grid, info, img, mask, elevation)
-    with the outputs still in HBM."""
-    import torch
+def deriveGrid(mapping, pxPerDeg=25, arcsecPerPx=None, containsPole=None):
+    """Target grid of `resample(mapping, ...)`: (amt_grid, info).  Needs the outline statistics of
+    the mapping only (bounding box, pole / date-line flags); with a pre-rotation one more outline
+    reduction in the rotated frame (reference resample.py:95-117,176-227)."""
     ctx = mapping.context
     if containsPole is None:
         containsPole = mapping.containsPole
@@ -217,6 +226,19 @@ def resampleToDevice(mapping, pxPerDeg=25, arcsecPerPx=None, containsPole=None):
     grid, info = targetGrid(pxPerDeg, latMin, latMax, lonMin, lonMax, mode, mapping.altitude)
     info['pxPerDeg'] = pxPerDeg
     info['mode'] = mode
+    if getattr(mapping, '_finiteElevation', False):
+        # elevations computed on the device are finite and in [-90, 90]: exact integer sums
+        grid.side_scale = sideScale(mapping.shape[0] * mapping.shape[1])
+    return grid, info
+
+
+def resampleToDevice(mapping, pxPerDeg=25, arcsecPerPx=None, containsPole=None):
+    """The device-resident part of `resample`: returns (grid, info, img, mask, elevation)
+    with the outputs still in HBM."""
+    import torch
+    ctx = mapping.context
+    grid, info = deriveGrid(mapping, pxPerDeg, arcsecPerPx, containsPole)
+    planeFree = getattr(mapping, '_planeFree', False) and 'lat_c' not in mapping._planes
     img = mapping.deviceImage()
     channels = img.shape[2]
     cells = grid.nx * grid.ny

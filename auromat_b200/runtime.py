@@ -178,6 +178,32 @@ class Context:
                                                  channels, C.byref(grid), self.ptr(count), self.ptr(sums),
                                                  self.ptr(fsum), self.stream()))
 
+    def georef_fused(self, frame: _lib.AmtFrame, valid_k, valid_c, planes=None, out=None, img=None, grid=None,
+                     count=None, sums=None, fsum=None):
+        """`amt_georef_fused`: the coordinate planes (when `planes` / `out` are given) and / or the
+        binning of the centres into `grid` (when given) from the frame's final validity bitmaps."""
+        torch = _torch()
+        if out is None and planes is not None:
+            out = self.out_struct({k: v for k, v in planes.items() if not k.startswith(('valid', '_'))})
+        dtype, channels = _lib.AMT_U8, 1
+        if grid is not None:
+            dtype = {torch.uint8: _lib.AMT_U8, torch.uint16: _lib.AMT_U16}.get(img.dtype)
+            if dtype is None:
+                raise NotImplementedError("image dtype must be uint8 or uint16, got %s" % img.dtype)
+            channels = img.numel() // (frame.width * frame.height)
+        _lib.check(self.lib.amt_georef_fused(self.handle, C.byref(frame), C.byref(out) if out is not None else None,
+                                             self.ptr(valid_k), self.ptr(valid_c), self.ptr(img), dtype, channels,
+                                             C.byref(grid) if grid is not None else None, self.ptr(count),
+                                             self.ptr(sums), self.ptr(fsum), self.stream()))
+
+    def sip_distort(self, frame: _lib.AmtFrame, u, v):
+        """(u', v') of the frame's FITS-SIP forward polynomial for device tensors u, v."""
+        torch = _torch()
+        uo, vo = torch.empty_like(u), torch.empty_like(v)
+        _lib.check(self.lib.amt_sip_distort(self.handle, C.byref(frame), self.ptr(u), self.ptr(v), u.numel(),
+                                            self.ptr(uo), self.ptr(vo), self.stream()))
+        return uo, vo
+
     def apply_center_mask(self, width, height, planes: dict, mask=None, min_elevation=float("nan")):
         out = self.out_struct(planes)
         _lib.check(self.lib.amt_apply_center_mask(self.handle, width, height, self.ptr(mask),
@@ -237,9 +263,14 @@ class Context:
         torch = _torch()
         pool = self.__dict__.setdefault('_pinned_stats', [])
         host = pool.pop() if pool else torch.empty(C.sizeof(_lib.AmtStats), dtype=torch.uint8).pin_memory()
-        host.copy_(stats, non_blocking=True)
+        # copy and event go to the stream the producing kernels were enqueued on (`stream()`: a
+        # pinned pipeline stream or torch's current one), never to whatever stream happens to be
+        # current when a generator is resumed
+        st = self.stream()
+        self.copy_d2h(host.data_ptr(), stats.data_ptr(), C.sizeof(_lib.AmtStats), st)
         ev = torch.cuda.Event()
-        ev.record()
+        ev.record(torch.cuda.ExternalStream(st.value or 0, device=self.torch_device) if st.value else
+                  torch.cuda.default_stream(self.torch_device))
         return host, ev
 
     def finish_stats(self, handle) -> _lib.AmtStats:

@@ -9,7 +9,9 @@ One "step" = one full pass of the hot path over one frame per GPU:
     all pixel corners and centres, mask sanitisation) + resample(arcsecPerPx=100, 'mean').
 N == 1 runs BASELINE.json configs[1] (one synthetic ISS Nikon D3S frame, 4256x2832, FP64, MLat/MLT
 outputs included); N > 1 runs one frame of the configs[3] sequence per rank and step (frame-sharded,
-no data-path collective, weak scaling).  Prints ONE JSON line (rank 0).
+no data-path collective, weak scaling) and, as a variant, the configs[4] mosaic whose sum/count
+grids are all-reduced over NCCL.  The K timed steps are repeated `--repeats` times inside the run
+and the MEDIAN is reported (min / max alongside).  Prints ONE JSON line (rank 0).
 """
 from __future__ import annotations
 
@@ -29,29 +31,33 @@ sys.path.insert(0, ROOT)
 METRIC = "georeferenced+resampled Mpix/s"
 UNIT = "Mpix/s"
 ALGO_BYTES_PER_PIXEL_GEOREF = 72.0      # 4 f64 per corner + 5 f64 per centre written
+ALGO_BYTES_PER_PIXEL_IMAGE = 3.0        # RGB u8 read by the fused binning (SURVEY 8d "fused path")
 ALGO_FLOP_PER_PIXEL_GEOREF = 290.0      # algorithmic FP64 ops per pixel
 ARCSEC_PER_PX = 100
+NCU_JSON = os.path.join(ROOT, "profiles", "r02_ncu_kernels.json")
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None,
-                    help="timed steps (default: 200 for the B200 arm -- a step is ~0.5 ms -- and 2 for --impl reference)")
+                    help="timed steps per repeat (default: 100 for the B200 arm -- a step is ~0.3 ms -- and 2 for "
+                         "--impl reference)")
     ap.add_argument("--warmup", type=int, default=None, help="untimed steps (default: 10 / 1)")
+    ap.add_argument("--repeats", type=int, default=7, help="the K timed steps are repeated this often; median reported")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--width", type=int, default=4256)
     ap.add_argument("--height", type=int, default=2832)
-    ap.add_argument("--fast-center", action="store_true", help="fastCenterCalculation=True variant")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-baseline-scale", type=int, default=1,
-                    help="linear down-scale of the frame used for the CPU baseline sample")
+    ap.add_argument("--fast-center", action="store_true", help="fastCenterCalculation=True variant as the headline")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the oracle leg (and with it the parity gate)")
+    ap.add_argument("--no-variants", action="store_true")
     args = ap.parse_args()
     ref = args.impl == "reference"
     if args.steps is None:
-        args.steps = 2 if ref else 200
+        args.steps = 2 if ref else 100
     if args.warmup is None:
         args.warmup = 1 if ref else 10
+    args.warmup = max(args.warmup, 0 if ref else 3)
     return args
 
 
@@ -61,6 +67,25 @@ def measured_peaks():
         with open(path) as fh:
             return json.load(fh), "measured"
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+def ncu_record(kernel_prefix):
+    """Counters of a kernel from the committed ncu summary (written by scripts/ncu_summary.py json,
+    with the git hash and the command it came from); None when there is no such record."""
+    try:
+        with open(NCU_JSON) as fh:
+            rec = json.load(fh)
+    except Exception:
+        return None
+    for name, k in rec.get("kernels", {}).items():
+        if name.startswith(kernel_prefix):
+            out = dict(k)
+            out["kernel_name"] = name
+            out["ncu_source"] = os.path.relpath(NCU_JSON, ROOT)
+            out["ncu_git"] = rec.get("git")
+            out["ncu_command"] = rec.get("command")
+            return out
+    return None
 
 
 # ------------------------------------------------------------------------------ clocks
@@ -93,7 +118,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             pass
-        sm, smmax, reasons = [], [], set()
+        sm, smmax, power, reasons = [], [], [], set()
         try:
             with open(self.path) as fh:
                 for line in fh:
@@ -103,6 +128,7 @@ class ClockSampler:
                     try:
                         sm.append(float(p[1]))
                         smmax.append(float(p[2]))
+                        power.append(float(p[3]))
                     except ValueError:
                         continue
                     for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
@@ -114,13 +140,13 @@ class ClockSampler:
             pass
         if sm:
             busy = [s for s in sm if s > 0.5 * max(sm)] or sm
-            out = {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(smmax)),
+            out = {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(smmax)), "power_w_max": max(power),
                    "reasons": sorted(reasons), "samples": len(sm)}
         return out
 
 
 # --------------------------------------------------------------------- CPU (oracle) legs
-def _oracle_frame(args):
+def _oracle_frame(args, keep=False):
     """One full pass of the reference algorithm (numpy restatement in oracle/) over a frame."""
     width, height, seed, fast = args
     import io
@@ -139,15 +165,79 @@ def _oracle_frame(args):
                 geo[n][mk] = np.nan
             for n in ('latsCenter', 'lonsCenter', 'mlatCenter', 'mltCenter', 'elevation'):
                 geo[n][mc] = np.nan
-        O.resample_frame(geo, img, 110, arcsec_per_px=ARCSEC_PER_PX)
-    return time.perf_counter() - t0
+        res = O.resample_frame(geo, img, 110, arcsec_per_px=ARCSEC_PER_PX, return_count=True)
+    dt = time.perf_counter() - t0
+    return (dt, geo, res) if keep else dt
 
 
-def cpu_baseline_single(width, height, fast, scale):
-    w, h = width // scale, height // scale
-    dt = _oracle_frame((w, h, 0, fast))
-    return {"value": w * h / dt / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": "1 frame %dx%d, numpy oracle port of the reference path, %.1f s" % (w, h, dt)}
+def cpu_baseline_single(width, height, fast):
+    """The oracle port over ONE complete frame on one core: the reported CPU baseline, and -- its
+    outputs are the reference answer for exactly the frame the GPU arm times -- the parity gate."""
+    dt, geo, res = _oracle_frame((width, height, 0, fast), keep=True)
+    rec = {"value": width * height / dt / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
+           "sample": "1 frame %dx%d, numpy oracle port of the reference path, %.1f s" % (width, height, dt)}
+    return rec, geo, res
+
+
+def parity_gate(ctx, args, geo, res):
+    """Full-frame parity of the measured path (the sequence engine) against the oracle run of the
+    CPU baseline: every plane of the 4256x2832 frame and the resampled grid."""
+    import numpy.ma as ma
+    import torch
+    from auromat_b200 import synthetic
+    from auromat_b200.pipeline import resampleSequence
+    W, H = args.width, args.height
+    hdr = synthetic.issHeader(W, H)
+    img = synthetic.issImage(W, H, 0)
+    f = next(iter(resampleSequence([img], [hdr], arcsecPerPx=ARCSEC_PER_PX, magnetic=True,
+                                   fastCenterCalculation=args.fast_center, toHost=True, ringBuffers=False)))
+    m = f.mapping
+    names = [('lat_k', 'lats', 1.0), ('lon_k', 'lons', 1.0), ('mlat_k', 'mlat', 1.0), ('mlt_k', 'mlt', 15.0),
+             ('lat_c', 'latsCenter', 1.0), ('lon_c', 'lonsCenter', 1.0), ('mlat_c', 'mlatCenter', 1.0),
+             ('mlt_c', 'mltCenter', 15.0), ('elev_c', 'elevation', 1.0)]
+    planes = m.devicePlanes(magnetic=True)
+    out = {"frame": [W, H], "max_abs_deg": {}, "mask_mismatches": 0}
+    for dn, on, scale in names:
+        a = ctx.to_numpy(planes[dn]).reshape(geo[on].shape)
+        na, nb = np.isnan(a), np.isnan(geo[on])
+        out["mask_mismatches"] += int((na != nb).sum())
+        ok = ~(na | nb)
+        d = np.abs(a[ok] - geo[on][ok])
+        if on in ('lons', 'lonsCenter'):
+            d = np.minimum(d, 360.0 - d)
+        if on in ('mlt', 'mltCenter'):
+            d = np.minimum(d, 24.0 - d)
+        out["max_abs_deg"][on] = float(d.max() * scale) if d.size else 0.0
+    st = m._deviceStats()
+    out["n_ill_conditioned"] = int(st.n_ill_conditioned)
+    # resampled grid: counts, rounded means, mask
+    cnt = ctx.to_numpy(f.info['count']).reshape(f.grid.ny, f.grid.nx)
+    same_shape = cnt.shape == res['count'].shape
+    out["grid"] = [int(f.grid.nx), int(f.grid.ny)]
+    out["grid_shape_equal"] = bool(same_shape)
+    if same_shape:
+        out["count_cells_differing"] = int((cnt != res['count']).sum())
+        out["count_total_gpu"], out["count_total_oracle"] = int(cnt.sum()), int(res['count'].sum())
+        gi, oi = f.img, res['img']
+        both = ~(ma.getmaskarray(gi)[:, :, 0] | res['img_mask'][:, :, 0])
+        out["mean_cells_differing"] = int((gi.filled(0)[both] != oi[both]).any(axis=-1).sum())
+        ge, oe = f.elevation.filled(np.nan), res['elevation']
+        ok = ~(np.isnan(ge) | np.isnan(oe)) & (cnt == res['count'])
+        out["elevation_mean_max_rel"] = float(np.max(np.abs(ge[ok] - oe[ok]) / np.abs(oe[ok]))) if ok.any() else 0.0
+    # samples within 1 ulp of a bin edge: the only ones allowed to land in another cell when the
+    # coordinates differ in the last bits
+    near = torch.zeros(1, dtype=torch.int64, device=ctx.torch_device)
+    cells = f.grid.nx * f.grid.ny
+    acc = ctx.zeros(5 * cells, torch.int64)
+    ctx.bin_accumulate(planes['lat_c'], planes['lon_c'], None, m.deviceImage(), f.grid, acc[:cells],
+                       acc[cells:4 * cells], None, near)
+    out["n_near_edge"] = int(near.item())
+    out["counts_equal_to_unfused_binning"] = bool(torch.equal(acc[:cells], f.info['count']))
+    worst = max(v for k, v in out["max_abs_deg"].items() if k != 'elevation')
+    out["tolerance_deg"] = 1e-9
+    out["pass"] = bool(worst <= 1e-9 and out["mask_mismatches"] == 0 and same_shape and
+                       out["counts_equal_to_unfused_binning"])
+    return out
 
 
 def run_reference(args, rank, world):
@@ -198,8 +288,10 @@ def workload_config(args, n_gpus):
         "frame": [args.width, args.height], "altitude_km": 110, "arcsec_per_px": ARCSEC_PER_PX,
         "fast_center": bool(args.fast_center), "outputs": "lat/lon/MLat/MLT corners+centres, elevation, resampled RGB+elevation",
         "parallelism": "frames x%d" % n_gpus,
-        "api": "auromat_b200.pipeline.resampleSequence (getMapping + resample per frame, pipelined: georeferencing of 3 frames enqueued ahead)",
+        "api": "auromat_b200.pipeline.resampleSequence (getMapping + resample per frame on the C sequence engine: "
+               "stage A of 3 frames enqueued ahead, one fused georeference+binning kernel per frame)",
         "l2": "per-step working set ~0.9 GB (72 B/px planes + image) exceeds the 126 MB L2; no explicit flush",
+        "timing": "median of `repeats` passes of `steps` frames each, CUDA events, max over ranks",
     }
 
 
@@ -230,173 +322,372 @@ def run_b200(args, rank, local_rank, world):
         # the per-GPU work (fraction of pixels that see the Earth) the same for every N (weak scaling)
         seq = synthetic.sequenceHeaders(32, W, H)
         headers = [seq[(s * world + rank) % 32] for s in range(total)]
-    img_host = torch.from_numpy(synthetic.issImage(W, H, seed=1000 + rank)).pin_memory()
+    img_np = synthetic.issImage(W, H, seed=1000 + rank)
+    img_host = torch.from_numpy(img_np).pin_memory()
     img_dev = img_host.to(ctx.torch_device)
 
     from auromat_b200.pipeline import resampleSequence
 
     # `value`: inputs resident in HBM -- the public sequence API (getMappingSequence + ResampleProvider
     # of the reference, pipelined) over K frames; every frame runs the full path from scratch.
-    def run_device(hdrs):
+    def run_device(hdrs, **kw):
         last = None
-        for f in resampleSequence([img_dev] * len(hdrs), hdrs, arcsecPerPx=ARCSEC_PER_PX, magnetic=True,
-                                  fastCenterCalculation=args.fast_center, toHost=False, device=local_rank,
-                                  ringBuffers=True):
+        opts = dict(arcsecPerPx=ARCSEC_PER_PX, magnetic=True, fastCenterCalculation=args.fast_center, toHost=False,
+                    device=local_rank, ringBuffers=True)
+        opts.update(kw)
+        for f in resampleSequence([img_dev] * len(hdrs), hdrs, **opts):
             last = f
         return last
 
-    # `e2e`: same call with HOST buffers: pinned image in (H2D every frame), resampled image, mask and
+    # `e2e`: same call with HOST buffers: image in (H2D every frame), resampled image, mask and
     # elevation out (D2H every frame into pinned buffers)
     transfer = {}
 
-    def run_e2e(hdrs, sparse=True):
+    def run_e2e(hdrs, sparse=True, source=None):
         last = None
         transfer.clear()
-        for f in resampleSequence([img_host.numpy()] * len(hdrs), hdrs, arcsecPerPx=ARCSEC_PER_PX, magnetic=True,
+        src = img_host.numpy() if source is None else source
+        for f in resampleSequence([src] * len(hdrs), hdrs, arcsecPerPx=ARCSEC_PER_PX, magnetic=True,
                                   fastCenterCalculation=args.fast_center, toHost=True, device=local_rank,
                                   ringBuffers=True, transferStats=transfer, sparseUpload=sparse):
             last = f
         transfer['frames'] = len(hdrs)
         last._finish()                 # the last frame's results are in its pinned host buffers
-        return None, None, last
-
-    def run_e2e_full_upload(hdrs):
-        return run_e2e(hdrs, sparse=False)
+        return last
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn):
-        fn(headers[:args.warmup])
-        barrier()
-        launches0 = ctx.launch_count
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        t_host = time.perf_counter()
-        out = fn(headers[args.warmup:args.warmup + args.steps])
-        t_host = time.perf_counter() - t_host
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        launches = ctx.launch_count - launches0
-        if os.environ.get("AMT_BENCH_RANKLOG"):
-            # per-rank diagnostics (stderr): device time of this rank and the wall time its host loop needed
-            sys.stderr.write("[rank %d] %s: device %.4f ms/step, host loop %.4f ms/step, cpus %d\n" % (
-                rank, getattr(fn, "__name__", "variant"), ms / args.steps, t_host * 1e3 / args.steps,
-                len(os.sched_getaffinity(0))))
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=ctx.torch_device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, launches, out
+    host_ms = []
 
-    # secondary variants (reported under "variants", not the headline): plane-free resampling
-    # (no coordinate planes, no MLat/MLT) and fastCenterCalculation=True
-    def run_variant(hdrs, **kw):
-        last = None
-        for f in resampleSequence([img_dev] * len(hdrs), hdrs, arcsecPerPx=ARCSEC_PER_PX, toHost=False,
-                                  device=local_rank, ringBuffers=True, **kw):
-            last = f
-        return last
+    def timed(fn, repeats=None, name=None):
+        """warm-up pass, then `repeats` timed passes of args.steps frames; every pass is bracketed by a
+        barrier + synchronize, timed with CUDA events, max over ranks.  Returns (median ms, all ms,
+        launches per pass, last output)."""
+        repeats = repeats or args.repeats
+        fn(headers[:args.warmup])
+        all_ms, launches, out = [], 0, None
+        for r in range(repeats):
+            barrier()
+            launches0 = ctx.launch_count
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            t_host = time.perf_counter()
+            out = fn(headers[args.warmup:args.warmup + args.steps])
+            t_host = time.perf_counter() - t_host
+            e1.record()
+            barrier()
+            ms = e0.elapsed_time(e1)
+            launches = ctx.launch_count - launches0
+            if name:
+                host_ms.append((name, t_host * 1e3 / args.steps, ms / args.steps))
+            if world > 1:
+                t = torch.tensor([ms], dtype=torch.float64, device=ctx.torch_device)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            all_ms.append(ms)
+        return float(np.median(all_ms)), all_ms, launches, out
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_dev, launches, out = timed(run_device)
+    ms_dev, all_dev, launches, out = timed(run_device, name="device")
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e, _, out_e2e = timed(run_e2e)
-    d2h = int(sum(b.numel() * b.element_size() for b in out_e2e[2]._host))
-    # image bytes actually copied per frame: only the row range that holds georeferenced pixels is
+    ms_e2e, all_e2e, _, out_e2e = timed(run_e2e, name="e2e")
+    d2h = int(sum(b.numel() * b.element_size() for b in out_e2e._host))
+    # image bytes actually copied per frame: only the pixel box that holds georeferenced pixels is
     # uploaded (pipeline.resampleSequence(sparseUpload=True)); the complete frame would be h2d_full
     h2d_full = int(img_host.numel() * img_host.element_size())
     h2d = int(transfer['h2d_bytes'] // max(1, transfer['frames']))
+    if os.environ.get("AMT_BENCH_RANKLOG"):
+        for name, h_ms, d_ms in host_ms:
+            sys.stderr.write("[rank %d] %s: device %.4f ms/step, host loop %.4f ms/step, cpus %d\n" % (
+                rank, name, d_ms, h_ms, len(os.sched_getaffinity(0))))
+    host_loop = {n: float(np.median([h for nn, h, _ in host_ms if nn == n])) for n in ("device", "e2e")}
+
+    def per_step(ms):
+        return {"value": args.steps * world * npx / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms / args.steps}
+
     variants = {}
-    if world == 1:
-        # best of 3 timed passes each (secondary numbers; the first pass also warms the allocator for
-        # the variant's own buffer sizes)
-        ms_pf = min(timed(lambda h: run_variant(h, magnetic=False, coordinates=False))[0] for _ in range(3))
-        ms_fc = min(timed(lambda h: run_variant(h, magnetic=True, fastCenterCalculation=True))[0] for _ in range(3))
-        ms_full = min(timed(run_e2e_full_upload)[0] for _ in range(2))
-        variants = {
-            "e2e_full_image_upload": {"value": args.steps * npx / (ms_full * 1e-3) / 1e6, "unit": UNIT,
-                                      "ms_per_step": ms_full / args.steps, "h2d_bytes_per_step": int(
-                                          img_host.numel() * img_host.element_size()),
-                                      "note": "e2e with sparseUpload=False: the complete 36 MB frame is copied every "
-                                              "step although the rows above the limb never influence the result; "
-                                              "PCIe-bound"},
-            "plane_free_resample_only": {"value": args.steps * npx / (ms_pf * 1e-3) / 1e6, "unit": UNIT,
-                                         "ms_per_step": ms_pf / args.steps,
-                                         "note": "resampleSequence(coordinates=False): hit bitmaps + outline stats + "
-                                                 "fused georeference/binning kernel, no planes, no MLat/MLT"},
-            "fast_center": {"value": args.steps * npx / (ms_fc * 1e-3) / 1e6, "unit": UNIT,
-                            "ms_per_step": ms_fc / args.steps, "note": "fastCenterCalculation=True, all 9 planes"},
-        }
-    # dominant kernel alone: the fused georeference kernel (all 9 planes)
-    m = getMapping(img_dev, headers[0], fastCenterCalculation=args.fast_center, identifier="roofline")
-    frame = m.frameConstants
-    nk, nc = (W + 1) * (H + 1), npx
-    planes = {n: ctx.empty(nk if n.endswith('_k') else nc, torch.float64)
-              for n in ('lat_k', 'lon_k', 'mlat_k', 'mlt_k', 'lat_c', 'lon_c', 'mlat_c', 'mlt_c', 'elev_c')}
-    # + the validity bitmaps: exactly the launch the sequence pipeline issues
-    planes['valid_k'], planes['valid_c'] = ctx.new_bitmaps(W, H)
-    for _ in range(3):
-        ctx.georef(frame, planes)
-    torch.cuda.synchronize()
-    reps = 10
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        ctx.georef(frame, planes)
-    e1.record()
-    torch.cuda.synchronize()
-    k_ms = e0.elapsed_time(e1) / reps
-    fp64_peak = ctx.measure_fp64_peak() if rank == 0 else 0.0     # warp-lane DFMA/s (2 FLOP each)
+    if not args.no_variants:
+        variants.update(single_gpu_variants(args, ctx, rank, world, timed, run_device, run_e2e, img_np, per_step)
+                        if world == 1 else {})
+        if world > 1:
+            variants["mosaic"] = mosaic_variant(ctx, rank, local_rank, world)
+
+    # dominant kernel alone: the fused georeference + binning kernel (all 9 planes + the grid), exactly the
+    # launch the sequence engine issues, timed with CUDA events on its launch stream
+    roof = dominant_kernel(args, ctx, img_dev, headers[0], rank)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    peaks, peak_kind = measured_peaks()
     value = args.steps * world * npx / (ms_dev * 1e-3) / 1e6
     e2e_value = args.steps * world * npx / (ms_e2e * 1e-3) / 1e6
-    achieved = ALGO_BYTES_PER_PIXEL_GEOREF * npx / (k_ms * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
         "frames_per_s": args.steps * world / (ms_dev * 1e-3),
+        "repeats": {"n": len(all_dev), "ms_per_step_min": min(all_dev) / args.steps,
+                    "ms_per_step_max": max(all_dev) / args.steps,
+                    "ms_per_step_all": [round(m / args.steps, 5) for m in all_dev],
+                    "e2e_ms_per_step_all": [round(m / args.steps, 5) for m in all_e2e]},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "h2d_bytes_full_frame": h2d_full,
                 "ms_per_step": ms_e2e / args.steps, "frames_per_s": args.steps * world / (ms_e2e * 1e-3)},
+        "host_loop_ms_per_step": host_loop,
         "gpu_launches": int(launches),
         "variants": variants,
         "clocks": clocks,
-        "roofline": {
-            "kernel": "k_georef_tiles" if args.fast_center else "k_georef_points",
-            "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": achieved / peaks["hbm_gbs"], "peak_kind": peak_kind,
-            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel for this frame size from the
-            # ncu --set full capture in profiles/r01_kernels_v8_ncu.txt (writes only; part of the
-            # last planes is still in L2 when the kernel ends, hence < algorithmic bytes)
-            "traffic": 812.4e6 if (W, H) == (4256, 2832) and not args.fast_center else None,
-            "kernel_ms": k_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PIXEL_GEOREF * npx,
-            # the kernel is FP64-pipe / issue bound, not HBM bound: algorithmic FP64 rate
-            # (290 reference-formula ops per pixel) against the DFMA peak measured just now;
-            # executed-instruction pipe utilisation is in profiles/ (ncu sm__pipe_fp64_cycles_active)
-            "fp64": {"algorithmic_tflops": ALGO_FLOP_PER_PIXEL_GEOREF * npx / (k_ms * 1e-3) / 1e12,
-                     "peak_tflops_measured": 2 * fp64_peak / 1e12,
-                     "dfma_issue_peak_ginst": fp64_peak / 1e9,
-                     "ncu_pipe_fp64_pct": 64.4, "ncu_issue_active_pct": 65.4,
-                     "ncu_source": "profiles/r01_kernels_v8_ncu.txt"},
-        },
+        "roofline": roof,
     }
     if not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"] = cpu_baseline_single(W, H, args.fast_center, args.cpu_baseline_scale)
+        base, geo, res = cpu_baseline_single(W, H, args.fast_center)
+        line["cpu_baseline"] = base
+        line["parity"] = parity_gate(ctx, args, geo, res)
+        if not line["parity"]["pass"]:
+            print(json.dumps(line))
+            raise SystemExit("bench.py: full-frame parity against the oracle FAILED: %r" % (line["parity"],))
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def dominant_kernel(args, ctx, img_dev, header, rank):
+    import torch
+    from auromat_b200.mapping.spacecraft import getMapping
+    from auromat_b200.resample import deriveGrid
+    W, H = args.width, args.height
+    npx = W * H
+    m = getMapping(img_dev, header, fastCenterCalculation=args.fast_center, identifier="roofline")
+    frame = m.frameConstants
+    nk, nc = (W + 1) * (H + 1), npx
+    planes = {n: ctx.empty(nk if n.endswith('_k') else nc, torch.float64)
+              for n in ('lat_k', 'lon_k', 'mlat_k', 'mlt_k', 'lat_c', 'lon_c', 'mlat_c', 'mlt_c', 'elev_c')}
+    planes['valid_k'], planes['valid_c'] = ctx.new_bitmaps(W, H)
+    reps = 20
+
+    def timeit(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    if args.fast_center:
+        kernel = "k_georef_tiles"
+        k_ms = timeit(lambda: ctx.georef(frame, planes))
+        algo_bytes = ALGO_BYTES_PER_PIXEL_GEOREF * npx
+        n_valid = None
+    else:
+        kernel = "k_georef_fused"
+        bits = {'valid_k': planes['valid_k'], 'valid_c': planes['valid_c']}
+        ctx.georef(frame, bits)                    # hit bitmaps (limb solver)
+        ctx.sanitize(W, H, bits)
+        m.setPlaneFree(True)
+        m._planes.update(bits)
+        m._grazingCounted = True
+        grid, info = deriveGrid(m, arcsecPerPx=ARCSEC_PER_PX)
+        cells = grid.nx * grid.ny
+        acc = ctx.zeros(5 * cells, torch.int64)
+        img = img_dev
+        k_ms = timeit(lambda: ctx.georef_fused(frame, bits['valid_k'], bits['valid_c'], planes=planes, img=img,
+                                               grid=grid, count=acc[:cells], sums=acc[cells:4 * cells],
+                                               fsum=acc[4 * cells:].view(torch.float64)))
+        n_valid = int(m._deviceStats().n_valid_centers)
+        # planes written for every pixel + the image samples of the defined centres
+        algo_bytes = ALGO_BYTES_PER_PIXEL_GEOREF * npx + ALGO_BYTES_PER_PIXEL_IMAGE * n_valid
+    fp64_peak = ctx.measure_fp64_peak() if rank == 0 else 0.0     # warp-lane DFMA/s (2 FLOP each)
+    peaks, peak_kind = measured_peaks()
+    hbm = algo_bytes / (k_ms * 1e-3) / 1e9
+    tflops = ALGO_FLOP_PER_PIXEL_GEOREF * npx / (k_ms * 1e-3) / 1e12
+    peak_tflops = 2 * fp64_peak / 1e12
+    ncu = ncu_record(kernel)
+    roof = {
+        "kernel": kernel,
+        # the kernel is bound by the FP64 pipe (DESIGN.md 3.1): `achieved` is the ALGORITHMIC FP64 rate --
+        # 290 reference-formula operations per pixel (SURVEY 8d; an arctangent counts as ONE operation,
+        # the kernel spends ~14 FP64 instructions on it) -- against the DFMA peak measured in this run
+        "bound": "fp64", "achieved": tflops, "peak": peak_tflops, "unit": "TFLOP/s",
+        "frac": tflops / peak_tflops if peak_tflops else None,
+        "peak_kind": "measured in this run (amt_measure_fp64_peak: register-resident DFMA stream)",
+        "kernel_ms": k_ms, "algorithmic_flop_per_launch": ALGO_FLOP_PER_PIXEL_GEOREF * npx,
+        "dfma_issue_peak_ginst": fp64_peak / 1e9,
+        # second view: the same launch against the HBM roofline (72 B/px of planes written + 3 B per
+        # defined pixel of image read)
+        "hbm": {"achieved": hbm, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm / peaks["hbm_gbs"],
+                "peak_kind": peak_kind, "algorithmic_bytes_per_launch": algo_bytes},
+        "valid_pixels": n_valid,
+        # executed-instruction view from the committed ncu capture of this kernel (None: no capture yet)
+        "traffic": (ncu or {}).get("dram_bytes"),
+        "ncu": ncu,
+    }
+    return roof
+
+
+def single_gpu_variants(args, ctx, rank, world, timed, run_device, run_e2e, img_np, per_step):
+    """Secondary numbers (N == 1): plane-free resampling, fastCenterCalculation, full-frame and
+    pageable uploads, and BASELINE configs[2] (24 Mpix, SIP order 4, 10 arcsec/px grid)."""
+    import torch
+    from auromat_b200 import synthetic
+    v = {}
+    ms, _, _, _ = timed(lambda h: run_device(h, magnetic=False, coordinates=False), repeats=3)
+    v["plane_free_resample_only"] = dict(per_step(ms), note="resampleSequence(coordinates=False): limb-solver hit "
+                                         "bitmaps + outline statistics + fused kernel without plane stores, no MLat/MLT")
+    ms, _, _, _ = timed(lambda h: run_device(h, fastCenterCalculation=True), repeats=3)
+    v["fast_center"] = dict(per_step(ms), note="fastCenterCalculation=True, all 9 planes (Python-orchestrated pipeline)")
+    ms, _, _, _ = timed(lambda h: run_e2e(h, sparse=False), repeats=3)
+    v["e2e_full_image_upload"] = dict(per_step(ms), h2d_bytes_per_step=int(img_np.nbytes),
+                                      note="e2e with sparseUpload=False: the complete 36 MB frame is copied every step")
+    pageable = np.array(img_np, copy=True)          # ordinary (unpinned) numpy memory, what a reference user passes
+    ms, _, _, _ = timed(lambda h: run_e2e(h, source=pageable), repeats=3)
+    v["e2e_pageable"] = dict(per_step(ms), note="e2e with an unpinned numpy image (cudaMemcpyAsync stages it through "
+                             "the driver's bounce buffer)")
+    try:
+        v["config3_sip_10arcsec"] = config3_variant(ctx)
+    except Exception as e:      # pragma: no cover - reported, never hidden
+        v["config3_sip_10arcsec"] = {"error": repr(e)}
+    return v
+
+
+def config3_variant(ctx):
+    """BASELINE configs[2]: 6000x4000 frame, SIP order 4, resampled to 10 arcsec/px (~20 M cells x 5
+    accumulators: the scatter-contention stress).  Per-kernel CUDA-event times of the path."""
+    import torch
+    from auromat_b200 import synthetic
+    from auromat_b200.mapping.spacecraft import getMapping
+    from auromat_b200.resample import deriveGrid
+    W, H = 6000, 4000
+    hdr = synthetic.issHeader(W, H, sipOrder=4)
+    img = ctx.to_device(synthetic.issImage(W, H, 3))
+    m = getMapping(img, hdr, identifier="config3")
+    frame = m.frameConstants
+    nk, nc = (W + 1) * (H + 1), W * H
+    names = ('lat_k', 'lon_k', 'mlat_k', 'mlt_k', 'lat_c', 'lon_c', 'mlat_c', 'mlt_c', 'elev_c')
+    planes = {n: ctx.empty(nk if n.endswith('_k') else nc, torch.float64) for n in names}
+    bits = {}
+    bits['valid_k'], bits['valid_c'] = ctx.new_bitmaps(W, H)
+    st = ctx.new_stats()
+
+    def timeit(fn, reps=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    raw = {}
+    raw['valid_k'], raw['valid_c'] = ctx.new_bitmaps(W, H)
+    t_hit = timeit(lambda: ctx.georef(frame, raw))
+    t_san = timeit(lambda: ctx.sanitize(W, H, raw))
+    ctx.georef(frame, bits)
+    ctx.sanitize(W, H, bits)
+    t_stats = timeit(lambda: ctx.bbox_stats_frame(frame, bits['valid_k'], bits['valid_c'], st))
+    m.setPlaneFree(True)
+    m._planes.update(bits)
+    m._grazingCounted = True
+    grid, info = deriveGrid(m, arcsecPerPx=10)
+    cells = grid.nx * grid.ny
+    acc = ctx.zeros(5 * cells, torch.int64)
+    parts = (acc[:cells], acc[cells:4 * cells], acc[4 * cells:].view(torch.float64))
+    t_zero = timeit(lambda: acc.zero_())
+    t_fused = timeit(lambda: ctx.georef_fused(frame, bits['valid_k'], bits['valid_c'], planes=planes, img=img, grid=grid,
+                                              count=parts[0], sums=parts[1], fsum=parts[2]))
+    t_planes = timeit(lambda: ctx.georef_fused(frame, bits['valid_k'], bits['valid_c'], planes=planes))
+    t_bin = timeit(lambda: ctx.bin_accumulate(planes['lat_c'], planes['lon_c'], planes['elev_c'], img, grid, *parts))
+    t_norm = timeit(lambda: ctx.normalise(grid, img.dtype, 3, *parts))
+    n_valid = int(m._deviceStats().n_valid_centers)
+    peaks, kind = measured_peaks()
+    # unfused binning kernel (scatter stress): 27 B per pixel read (lat, lon, elevation, RGB) + one
+    # read-modify-write of the 5 accumulator words of every touched cell (<= 1 per defined pixel)
+    bin_bytes = 27.0 * nc + min(n_valid, cells) * 5 * 8 * 2
+    step = t_hit + t_san + t_stats + t_zero + t_fused + t_norm
+    return {
+        "frame": [W, H], "sip_order": 4, "arcsec_per_px": 10, "grid": [int(grid.nx), int(grid.ny)], "cells": int(cells),
+        "valid_pixels": n_valid,
+        "hit_bits_ms": t_hit, "sanitize_ms": t_san, "stats_ms": t_stats, "zero_ms": t_zero,
+        "fused_georef_bin_ms": t_fused, "fused_planes_only_ms": t_planes, "normalise_ms": t_norm,
+        "georef_ms": t_planes, "bin_ms": t_bin,
+        "sum_of_kernels_ms": step, "value": W * H / (step * 1e-3) / 1e6, "unit": UNIT,
+        "roofline_k_bin": {"bound": "hbm", "achieved": bin_bytes / (t_bin * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                           "unit": "GB/s", "frac": bin_bytes / (t_bin * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                           "algorithmic_bytes_per_launch": bin_bytes, "peak_kind": kind,
+                           "ncu": ncu_record("k_bin")},
+        "note": "serial CUDA-event times of each kernel of the path (no overlap); hit test per pixel (SIP frames "
+                "have no limb solver)",
+    }
+
+
+def mosaic_variant(ctx, rank, local_rank, world):
+    """BASELINE configs[4]: 64 synthetic all-sky stations (256x256, uint16, elevation >= 1 deg) sharded
+    i mod N over the ranks, binned into one common 20 px/deg grid; the sum/count grids are all-reduced
+    over NCCL, then normalised.  Timed with CUDA events (max over ranks, median of 10 after 3 warm-up);
+    rank 0 then bins all 64 stations alone and checks the all-reduced grids bit for bit."""
+    import datetime
+    import torch
+    import torch.distributed as dist
+    from auromat_b200 import parallel
+    from auromat_b200.mapping.allsky import AllSkyMapping, CalibrationData
+    n, w = 64, 256
+    rng = np.random.default_rng(2)
+    cals = [CalibrationData('S%02d' % i, 0, 0, float(rng.uniform(55, 70)), float(rng.uniform(-160, -60)),
+                            256.0, 256.0, 155.81, 0.0, None) for i in range(n)]
+    imgs = [np.random.default_rng(50 + i).integers(0, 65536, (w, w, 1), dtype=np.uint16) for i in range(n)]
+    t = datetime.datetime(2012, 3, 4, 17, 19, 0)
+
+    def build(idx):
+        ms = [AllSkyMapping(cals[i], imgs[i], t, 110, device=local_rank).maskedByElevation(1) for i in idx]
+        for m in ms:
+            m.boundingBox                    # georeferencing + statistics done: the timed part is the mosaic
+        return ms
+
+    mine = build(parallel.shardIndices(n))
+    torch.cuda.synchronize()
+    times = []
+    mos = acc = None
+    for r in range(13):
+        tm = {}
+        dist.barrier()
+        torch.cuda.synchronize()
+        mos, acc = parallel.mosaic(mine, pxPerDeg=(20, 20), timings=tm)
+        torch.cuda.synchronize()
+        t_ = torch.tensor([tm['total_ms'], tm['bin_ms'], tm['allreduce_ms'], tm['normalise_ms']], dtype=torch.float64,
+                          device=ctx.torch_device)
+        dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        if r >= 3:
+            times.append(t_.cpu().numpy())
+    med = np.median(np.array(times), axis=0)
+    message = acc.all.numel() * 8
+    ok = True
+    if rank == 0:
+        everything = build(range(n))
+        ref = parallel.MosaicAccumulator(acc.grid, acc.info, 1, torch.uint16, everything[0].context)
+        for m in everything:
+            ref.add(m)
+        ok = bool(torch.equal(ref.all, acc.all)) if acc.exactSide else bool(torch.equal(ref.acc, acc.acc))
+    flag = torch.tensor([1 if ok else 0], device=ctx.torch_device)
+    dist.broadcast(flag, 0)
+    busbw = message * 2 * (world - 1) / world / (med[2] * 1e-3) / 1e9 if med[2] > 0 else None
+    return {"workload": "BASELINE configs[4]: 64 all-sky stations 256x256 uint16, station i -> rank i mod N, common "
+                        "20 px/deg grid, NCCL all-reduce of count | sums | fixed-point elevation sums (one int64 message)",
+            "stations": n, "grid": [int(acc.grid.nx), int(acc.grid.ny)], "samples": int(acc.count.sum().item()),
+            "ms": float(med[0]), "bin_ms": float(med[1]), "allreduce_ms": float(med[2]), "normalise_ms": float(med[3]),
+            "message_MB": message / 1e6, "busbw_GBs": busbw, "exact_elevation_sums": bool(acc.exactSide),
+            "bit_exact": bool(flag.item()), "repeats": len(times)}
 
 
 def main():

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define AMT_ABI_VERSION 2
+#define AMT_ABI_VERSION 3
 
 typedef enum amt_status {
     AMT_OK = 0,
@@ -149,6 +149,13 @@ typedef struct amt_grid {
     double altitude;           /* for AMT_PRE_POLE (transform.py:301-322)                  */
     double wgs_a, wgs_b;
     double rot[9];             /* rotation_matrix(+90deg, X)[:3,:3] for AMT_PRE_POLE       */
+    /* Side channel (elevation sums, the float weight of the histogram2d call at resample.py:119-120,
+     * 337).  0: accumulated with f64 atomics (any value incl. NaN; last bits depend on the order).
+     * > 0 (a power of two): accumulated as int64 of llrint(value * side_scale) -- exact, order
+     * independent, identical from run to run and across ranks; the caller picks the scale so that
+     * |value| * side_scale * (number of samples) < 2^62 and guarantees finite values; `d_fsum`
+     * then holds int64.                                                                          */
+    double side_scale;
 } amt_grid;
 
 typedef enum amt_dtype { AMT_U8 = 0, AMT_U16 = 1 } amt_dtype;
@@ -320,9 +327,90 @@ int amt_normalise(amt_ctx* ctx, const amt_grid* grid, int32_t dtype, int32_t cha
 int amt_bbox_stats_frame(amt_ctx* ctx, const amt_frame* frame, const uint32_t* d_valid_k,
                          const uint32_t* d_valid_c, const amt_grid* pre, amt_stats* d_stats,
                          void* stream);
+/* The fused pass of the sequence pipeline: from the frame's FINAL validity bitmaps (hit test +
+ * amt_sanitize, both on bitmaps; grid derived from amt_bbox_stats_frame) one kernel writes the
+ * coordinate planes -- NaN exactly where the bitmaps say so, nothing is patched afterwards -- and
+ * bins every defined centre into the target grid while its coordinates are still in registers.
+ *   out  != NULL: d_lat_k, d_lon_k, d_lat_c, d_lon_c, d_elev_c are required, the four MLat/MLT
+ *                 planes are written iff all four are given (the bitmap members are ignored);
+ *   out  == NULL: plane-free resampling (== amt_georef_bin_fused);
+ *   grid != NULL: binning into d_count / d_sums / d_fsum as amt_bin_accumulate does (same cells,
+ *                 same sums: the kernel bins the very values it stores);
+ *   grid == NULL: planes only.
+ * Replaces, for WCS frames with fast_center == 0: amt_georef + the plane part of amt_sanitize +
+ * amt_bin_accumulate, i.e. the reference lines cited there.                                     */
+int amt_georef_fused(amt_ctx* ctx, const amt_frame* frame, const amt_georef_out* out,
+                     const uint32_t* d_valid_k, const uint32_t* d_valid_c, const void* d_img,
+                     int32_t dtype, int32_t channels, const amt_grid* grid, uint64_t* d_count,
+                     uint64_t* d_sums, double* d_fsum, void* stream);
 int amt_georef_bin_fused(amt_ctx* ctx, const amt_frame* frame, const uint32_t* d_valid_c,
                          const void* d_img, int32_t dtype, int32_t channels, const amt_grid* grid,
                          uint64_t* d_count, uint64_t* d_sums, double* d_fsum, void* stream);
+
+/* The FITS-SIP forward distortion of `frame` for n pixel offsets (u, v) = (x - CRPIX1, y - CRPIX2)
+ * (1-based x, y):  u' = u + sum_{p+q<=A_ORDER} A_p_q u^p v^q,  v' = v + sum B_p_q u^p v^q  -- the device
+ * function of the georeference kernels, exposed for known-answer tests (the reference reaches SIP only
+ * through astropy.wcs, coordinates/wcs.py:54-56; tests pin this against exact rational arithmetic).  */
+int amt_sip_distort(amt_ctx* ctx, const amt_frame* frame, const double* d_u, const double* d_v, size_t n,
+                    double* d_u_out, double* d_v_out, void* stream);
+
+/* ----------------------------------------------------------------- sequence engine ---- */
+/* The pipelined composition of getMappingSequence (mapping/spacecraft.py:308-332) and
+ * ResampleProvider (resample.py:370-394) for WCS frames with fast_center == 0: two calls per frame.
+ *   amt_seq_stage_a   hit bitmaps (limb solver / per-pixel hit test) -> amt_sanitize on the bitmaps
+ *                     -> amt_bbox_stats_frame -> asynchronous copy of the statistics to pinned memory;
+ *   amt_seq_wait_stats blocks until those statistics are on the host; the caller derives the
+ *                     bounding box and the target grid (reference arithmetic);
+ *   amt_seq_stage_b   upload of the pixel box of the host image that holds defined pixels -> zeroed
+ *                     accumulators -> amt_georef_fused (planes + binning) -> amt_normalise ->
+ *                     asynchronous copy of the results to pinned memory;
+ *   amt_seq_wait_result blocks until the results of the slot are complete.
+ * The engine orders four caller-provided streams with events (long kernels on `main_stream`, the
+ * microsecond kernels of stage A on `aux_stream`, copies on their own streams) and owns NO memory:
+ * ring-slot buffers come through amt_seq_set_slot, per-frame buffers through amt_seq_job.  A slot
+ * may be re-submitted as soon as the caller no longer needs its planes / bitmaps; the engine makes
+ * the new frame's kernels wait for the slot's previous fused kernel.  One host thread per engine;
+ * NVTX ranges mark both stages.                                                                  */
+typedef struct amt_seq amt_seq;
+
+typedef struct amt_seq_slot {
+    amt_georef_out planes;   /* d_valid_k / d_valid_c required; coordinate planes: all of lat/lon corner +
+                                centre + elevation (and optionally the four MLat/MLT planes), or none
+                                (plane-free resampling)                                               */
+    amt_stats* d_stats;      /* device statistics block                                              */
+    amt_stats* h_stats;      /* pinned host copy                                                     */
+    void* d_img;             /* device image buffer height*width*channels (nullable when every job
+                                brings its own d_img)                                                */
+} amt_seq_slot;
+
+typedef struct amt_seq_job {
+    const amt_grid* grid;
+    const void* h_img;       /* host image (pinned for an asynchronous copy), complete frame; NULL: the
+                                image is already on the device                                       */
+    const void* d_img;       /* device image to read instead of the slot's buffer (nullable)        */
+    int32_t row0, row1, col0, col1;  /* pixel box to upload, inclusive (amt_stats.row_min_c ...)     */
+    uint64_t* d_acc;         /* (2 + channels) * nx*ny words: count | sums[channels] | side sums      */
+    void* d_out;             /* image | mask | side, see amt_seq_output_layout                       */
+    void* h_out;             /* pinned host copy of d_out (nullable: results stay on the device)     */
+    size_t out_bytes;        /* capacity of d_out (and h_out)                                        */
+} amt_seq_job;
+
+/* Byte offsets of the mask and of the side (elevation) plane inside the output buffer of a grid,
+ * and its total size: image nx*ny*channels at 0, mask nx*ny bytes and side nx*ny doubles at the
+ * next 64-byte boundaries.  Host only (no CUDA call).                                             */
+int amt_seq_output_layout(int32_t nx, int32_t ny, int32_t channels, int32_t dtype, size_t* off_mask,
+                          size_t* off_side, size_t* total);
+int amt_seq_create(amt_ctx* ctx, int32_t width, int32_t height, int32_t channels, int32_t dtype,
+                   int32_t n_slots, void* main_stream, void* aux_stream, void* copy_stream,
+                   void* out_stream, amt_seq** out);
+int amt_seq_destroy(amt_seq* seq);
+int amt_seq_set_slot(amt_seq* seq, int32_t slot, const amt_seq_slot* buffers);
+int amt_seq_stage_a(amt_seq* seq, int32_t slot, const amt_frame* frame);
+int amt_seq_wait_stats(amt_seq* seq, int32_t slot, amt_stats* out /* nullable */);
+int amt_seq_stage_b(amt_seq* seq, int32_t slot, const amt_seq_job* job);
+int amt_seq_wait_result(amt_seq* seq, int32_t slot);
+/* Image bytes copied host -> device so far (bench.py h2d_bytes_per_step).                         */
+int amt_seq_h2d_bytes(const amt_seq* seq, uint64_t* bytes);
 
 #ifdef __cplusplus
 }

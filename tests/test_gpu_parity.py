@@ -1262,3 +1262,244 @@ def test_pipeline_box_upload_for_rolled_cameras(env):
         for f, e in zip(got, expect):
             assert np.array_equal(ma.getmaskarray(f.img), ma.getmaskarray(e.img))
             assert np.array_equal(f.img.filled(0), e.img.filled(0))
+
+
+# ======================================================================= round 2: fused path
+def _geometries(W, H):
+    """Camera geometries for the limb solver: the ISS frame, random rolls / scales / pointings
+    (limb anywhere, Earth filling the frame, Earth absent), pole and date-line views, nadir."""
+    import math
+    from auromat_b200 import synthetic
+    yield 'iss', synthetic.issHeader(W, H)
+    rng = np.random.default_rng(5)
+    base = synthetic.issHeader(W, H)
+    for i in range(20):
+        h = dict(base)
+        th = rng.uniform(0, 2 * math.pi)
+        s = math.hypot(base['CD1_1'], base['CD1_2']) * rng.uniform(0.5, 2.5)
+        h['CD1_1'], h['CD1_2'] = -s * math.cos(th), -s * math.sin(th)
+        h['CD2_1'], h['CD2_2'] = s * math.sin(th), -s * math.cos(th)
+        h['CRVAL1'] = base['CRVAL1'] + rng.uniform(-40, 40)
+        h['CRVAL2'] = base['CRVAL2'] + rng.uniform(-40, 40)
+        yield 'rand%d' % i, h
+    yield 'pole', synthetic.issHeaderLookingAt(80.0, 10.0, 89.5, 40.0, W, H)
+    yield 'dateline', synthetic.issHeaderLookingAt(50.0, 170.0, 55.0, -178.0, W, H)
+    yield 'nadir', synthetic.issHeaderLookingAt(50.0, 10.0, 50.0, 10.01, W, H)
+
+
+def _hit_bitmaps(ctx, frame, W, H, limb):
+    os.environ.pop('AMT_NO_LIMB_SOLVER', None)
+    if not limb:
+        os.environ['AMT_NO_LIMB_SOLVER'] = '1'
+    try:
+        bits = {}
+        bits['valid_k'], bits['valid_c'] = ctx.new_bitmaps(W, H)
+        st = ctx.new_stats()
+        ctx.georef(frame, bits, st)
+        return bits, int(ctx.read_stats(st).n_ill_conditioned)
+    finally:
+        os.environ.pop('AMT_NO_LIMB_SOLVER', None)
+
+
+@pytest.mark.parametrize("W,H", [(97, 61), (532, 354), (1064, 708)])
+def test_limb_solver_equals_per_pixel_hit_test(env, W, H):
+    """The O(H) limb solver (row-wise roots of the discriminant + exact evaluation near them) gives the
+    same corner and centre hit bitmaps, and the same grazing-ray count, as the per-pixel hit test."""
+    import torch
+    from auromat_b200.mapping.spacecraft import getMapping
+    seen = set()
+    for name, hdr in _geometries(W, H):
+        fr = getMapping(np.zeros((H, W, 1), np.uint8), hdr, identifier=name).frameConstants
+        a, ga = _hit_bitmaps(env, fr, W, H, True)
+        b, gb = _hit_bitmaps(env, fr, W, H, False)
+        assert torch.equal(a['valid_k'], b['valid_k']), name
+        assert torch.equal(a['valid_c'], b['valid_c']), name
+        assert ga == gb, name
+        frac = float((b['valid_c'] != 0).float().mean())
+        seen.add('none' if frac == 0 else 'all' if frac == 1 else 'limb')
+    assert 'limb' in seen
+
+
+@pytest.mark.parametrize("sip", [0, 4])
+@pytest.mark.parametrize("dtype,channels", [(np.uint8, 3), (np.uint16, 1)])
+def test_fused_kernel_equals_unfused_chain(env, sip, dtype, channels):
+    """amt_georef_fused (planes + binning from the final bitmaps) == amt_georef + amt_sanitize +
+    amt_bin_accumulate: all nine planes bit for bit incl. the NaN pattern, counts, integer sums and the
+    fixed-point elevation sums identical; plane-free mode identical too."""
+    import torch
+    from auromat_b200 import synthetic
+    from auromat_b200.mapping.spacecraft import getMapping
+    from auromat_b200.resample import deriveGrid
+    W, H = 532, 354
+    hdr = synthetic.issHeader(W, H, sipOrder=sip)
+    img = np.random.default_rng(1).integers(0, np.iinfo(dtype).max, (H, W, channels)).astype(dtype)
+    m = getMapping(img, hdr, identifier='f')
+    fr = m.frameConstants
+    old = m.devicePlanes(magnetic=True)                    # amt_georef + amt_sanitize
+    bits, _ = _hit_bitmaps(env, fr, W, H, True)
+    env.sanitize(W, H, bits)
+    assert torch.equal(bits['valid_k'], old['valid_k']) and torch.equal(bits['valid_c'], old['valid_c'])
+    names = ('lat_k', 'lon_k', 'mlat_k', 'mlt_k', 'lat_c', 'lon_c', 'mlat_c', 'mlt_c', 'elev_c')
+    dimg = m.deviceImage()
+    for ppd in (None, (360.0, 200.0)):
+        grid, info = deriveGrid(m, pxPerDeg=ppd, arcsecPerPx=None if ppd else 100)
+        assert grid.side_scale > 0
+        cells = grid.nx * grid.ny
+
+        def parts(acc):
+            return acc[:cells], acc[cells:(1 + channels) * cells], acc[(1 + channels) * cells:].view(torch.float64)
+        accA, accB, accC = (env.zeros((2 + channels) * cells, torch.int64) for _ in range(3))
+        env.bin_accumulate(old['lat_c'], old['lon_c'], old['elev_c'], dimg, grid, *parts(accA))
+        new = {n: torch.full_like(old[n], 7.0) for n in names}
+        env.georef_fused(fr, bits['valid_k'], bits['valid_c'], planes=new, img=dimg, grid=grid,
+                         count=parts(accB)[0], sums=parts(accB)[1], fsum=parts(accB)[2])
+        env.georef_fused(fr, None, bits['valid_c'], img=dimg, grid=grid, count=parts(accC)[0],
+                         sums=parts(accC)[1], fsum=parts(accC)[2])
+        for n in names:
+            assert torch.equal(torch.isnan(old[n]), torch.isnan(new[n])), n
+            assert torch.equal(torch.nan_to_num(old[n]), torch.nan_to_num(new[n])), n
+        assert int(accA[:cells].sum()) > 0
+        assert torch.equal(accA, accB) and torch.equal(accA, accC)
+        # the fixed-point elevation mean agrees with the f64-atomic mean far inside the 1e-6 budget
+        scale = grid.side_scale
+        grid.side_scale = 0.0
+        accF = env.zeros((2 + channels) * cells, torch.int64)
+        env.bin_accumulate(old['lat_c'], old['lon_c'], old['elev_c'], dimg, grid, *parts(accF))
+        assert torch.equal(accF[:(1 + channels) * cells], accA[:(1 + channels) * cells])
+        fx = accA[(1 + channels) * cells:].double() / scale
+        ff = parts(accF)[2]
+        hit = accA[:cells] > 0
+        assert float(((fx - ff)[hit].abs() / accA[:cells][hit]).max()) < 1e-9
+
+
+def test_elevation_sums_are_deterministic(env):
+    """Fixed-point side channel: two runs of the same binning give identical bits (the f64-atomic
+    sums of round 1 differed in their last bits from run to run)."""
+    import torch
+    from auromat_b200 import synthetic
+    from auromat_b200.mapping.spacecraft import getMapping
+    from auromat_b200.resample import resampleToDevice
+    hdr = synthetic.issHeader(1064, 708)
+    m = getMapping(synthetic.issImage(1064, 708), hdr, identifier='d')
+    runs = [resampleToDevice(m, pxPerDeg=7)[4].clone() for _ in range(4)]
+    for r in runs[1:]:
+        assert torch.equal(torch.nan_to_num(r), torch.nan_to_num(runs[0]))
+
+
+@pytest.mark.parametrize("depth", [1, 3, 5])
+def test_ring_planes_lifetime(env, depth):
+    """Ring mode: the planes of `frame.mapping` are the frame's own while KEEP_FRAMES + 1 further frames
+    are taken; afterwards the mapping is detached from the ring and recomputes -- it never shows another
+    frame's coordinates."""
+    from auromat_b200 import synthetic
+    from auromat_b200.mapping.spacecraft import getMapping
+    from auromat_b200.pipeline import resampleSequence, KEEP_FRAMES
+    W, H, n = 200, 130, 14
+    hdrs = synthetic.sequenceHeaders(n, W, H)
+    imgs = [synthetic.issImage(W, H, seed=i) for i in range(n)]
+    expect = [getMapping(im, h, identifier='x').latsCenter.filled(np.nan) for im, h in zip(imgs, hdrs)]
+    assert not np.array_equal(expect[0], expect[1], equal_nan=True)
+    held = []
+    for i, f in enumerate(resampleSequence(imgs, hdrs, arcsecPerPx=400, magnetic=True, ringBuffers=True, depth=depth)):
+        held.append(f)
+        # frames taken earlier: still within the promise -> ring planes, later -> detached and recomputed
+        for j in (i, i - KEEP_FRAMES - 1, i - KEEP_FRAMES - 3):
+            if j >= 0:
+                got = held[j].mapping.latsCenter.filled(np.nan)
+                assert np.array_equal(got, expect[j], equal_nan=True), (depth, i, j)
+        if i >= 1:
+            held[i - 1].mapping._host.pop('lat_c', None)      # force the next access to read the device planes again
+    for j, f in enumerate(held):
+        f.mapping._host.pop('lat_c', None)
+        assert np.array_equal(f.mapping.latsCenter.filled(np.nan), expect[j], equal_nan=True), (depth, j)
+        assert np.array_equal(f.mapping.img_unmasked, imgs[j])
+
+
+def test_config4_long_sequence_ring_wraparound(env):
+    """BASELINE configs[3], 64 full-size frames through the ring pipeline: the ring wraps several times,
+    the pinned-buffer pool does not grow after the first frames, and frames from every part of the
+    sequence equal `resample(getMapping(...))`."""
+    from auromat_b200 import synthetic
+    from auromat_b200.mapping.spacecraft import getMapping
+    from auromat_b200.pipeline import resampleSequence
+    from auromat_b200.resample import resample
+    n = 64
+    hdrs = synthetic.sequenceHeaders(n)
+    imgs = [synthetic.issImage(seed=1000 + i) for i in range(3)]
+    check = {0, 9, 31, 62, 63}
+    kept = {}
+    tr = {}
+    # warm the pools with a short sequence, then the long one must not page-lock anything
+    list(resampleSequence([imgs[0]] * 12, hdrs[:12], arcsecPerPx=100, magnetic=True, ringBuffers=True))
+    grown0 = env.__dict__['_pinned_frames'].get('grown', 0)
+    for i, f in enumerate(resampleSequence([imgs[i % 3] for i in range(n)], hdrs, arcsecPerPx=100, magnetic=True,
+                                           ringBuffers=True, transferStats=tr)):
+        if i in check:
+            kept[i] = (f.img, f.elevation.filled(np.nan))
+    assert env.__dict__['_pinned_frames'].get('grown', 0) == grown0
+    for i in sorted(check):
+        e = resample(getMapping(imgs[i % 3], hdrs[i], identifier='x'), arcsecPerPx=100)
+        gi, ge = kept[i]
+        assert np.array_equal(ma.getmaskarray(gi), ma.getmaskarray(e.img)), i
+        assert np.array_equal(gi.filled(0), e.img.filled(0)), i
+        ee = e.elevation.filled(np.nan)
+        assert np.array_equal(np.isnan(ge), np.isnan(ee)) and np.nanmax(np.abs(ge - ee)) < 1e-9, i
+        del e
+
+
+def test_config3_fine_grid_counts_vs_oracle(env):
+    """BASELINE configs[2] numerics on a crop: a 420x300 window of the 6000x4000 SIP order-4 frame
+    resampled at 10 arcsec/px (cells smaller than pixels: one sample per touched cell) -- counts,
+    rounded means and masks against the oracle's histogram of the SAME coordinates, and against the
+    oracle's own chain up to the reported near-edge samples."""
+    import oracle.auromat_oracle as O
+    from auromat_b200 import synthetic
+    from auromat_b200.mapping.spacecraft import getMapping
+    from auromat_b200.resample import resample, resampleToDevice
+    W, H = 6000, 4000
+    full = synthetic.issHeader(W, H, sipOrder=4)
+    x0, y0, w, h = 2900, 2600, 420, 300
+    hdr = dict(full)
+    hdr['IMAGEW'], hdr['IMAGEH'] = w, h
+    hdr['CRPIX1'], hdr['CRPIX2'] = full['CRPIX1'] - x0, full['CRPIX2'] - y0
+    img = synthetic.issImage(w, h, 5)
+    m = getMapping(img, hdr, identifier='crop')
+    geo = {k: v.filled(np.nan) for k, v in gpu_arrays(m).items()}
+    bb = m.boundingBox
+    from auromat_b200.resample import plateCarreeResolution
+    ppd = plateCarreeResolution(bb, 10)
+    r = resample(m, pxPerDeg=ppd)
+    with quiet():
+        o = O.resample_frame(geo, img, 110, px_per_deg=ppd, return_count=True)
+    grid, info, _, _, _ = resampleToDevice(m, pxPerDeg=ppd)
+    cnt = info['count'].cpu().numpy().reshape(grid.ny, grid.nx)
+    assert cnt.shape == o['count'].shape and cnt.size > 20 * w * h        # far more cells than pixels
+    assert np.array_equal(cnt, o['count'])
+    assert cnt.max() <= 2 and int(cnt.sum()) == int((~np.isnan(geo['latsCenter'])).sum())
+    assert np.array_equal(ma.getmaskarray(r.img), o['img_mask'])
+    assert np.array_equal(r.img.filled(0), np.where(o['img_mask'], 0, o['img']))
+    # the sequence engine (fused kernel, SIP variant) gives the same grid
+    from auromat_b200.pipeline import resampleSequence
+    f = next(iter(resampleSequence([img], [hdr], pxPerDeg=ppd)))
+    assert np.array_equal(f.img.filled(0), r.img.filled(0)) and np.array_equal(ma.getmaskarray(f.img), ma.getmaskarray(r.img))
+
+
+def test_sip_device_polynomial_against_exact_rational_arithmetic(env):
+    """The device SIP polynomial (amt_sip_distort: the function the georeference kernels call) against
+    exact rational arithmetic at the same 120 points as the oracle's pin: <= 2 ulp of the distorted
+    coordinate.  Oracle and kernel are thereby pinned independently of each other."""
+    import torch
+    from auromat_b200 import synthetic
+    from auromat_b200.coordinates.wcs import frameConstants
+    from tests.test_oracle_golden import _sip_exact, sip_kat_points
+    hdr = synthetic.issHeader(6000, 4000, sipOrder=4)
+    t, cam = synthetic.headerTimeAndCamera(hdr)
+    fr = frameConstants(hdr, cam, t, 110)
+    u, v = sip_kat_points()
+    uo, vo = env.sip_distort(fr, env.to_device(u), env.to_device(v))
+    uo, vo = uo.cpu().numpy(), vo.cpu().numpy()
+    for i in range(len(u)):
+        eu = float(_sip_exact(hdr, 'A', u[i], v[i]) + __import__('fractions').Fraction(u[i]))
+        ev = float(_sip_exact(hdr, 'B', u[i], v[i]) + __import__('fractions').Fraction(v[i]))
+        assert abs(uo[i] - eu) <= 2 * np.spacing(abs(eu)) + 1e-13, (i, uo[i], eu)
+        assert abs(vo[i] - ev) <= 2 * np.spacing(abs(ev)) + 1e-13, (i, vo[i], ev)

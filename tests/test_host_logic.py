@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(built_lib):
         assert hasattr(lib, name), "missing export: " + name
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     loaded = _lib.load()
-    assert loaded.amt_abi_version() == 2
+    assert loaded.amt_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_struct_layouts_match_header():
@@ -35,7 +35,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.AmtFrame) == 4 * 4 + 8 * (2 + 4 + 9 + 3 + 3 + 9 + 9 + 2) + 2 * 4 + 8 * 2 * 55 + 2 * 4 + 4 * 8
     assert ctypes.sizeof(_lib.AmtGeorefOut) == 11 * 8
     assert ctypes.sizeof(_lib.AmtStats) == 6 * 8 + 5 * 8 + 4 * 4
-    assert ctypes.sizeof(_lib.AmtGrid) == 4 * 4 + 8 * (6 + 2 + 3 + 9)
+    assert ctypes.sizeof(_lib.AmtGrid) == 4 * 4 + 8 * (6 + 2 + 3 + 9 + 1)
 
 
 def test_no_gpu_means_loud_failure():

@@ -172,3 +172,44 @@ def test_themis_reproject_matches_reference_golden():
     # single-iteration Bowring inverse at 110 km height (a few 1e-6 deg, inherent to the reference)
     la, lo = O.themis_reproject(asi, g['lats110'], g['lons110'], 110.0, 110.0)
     assert np.nanmax(np.abs(la - g['lats110'])) < 2e-5 and np.nanmax(np.abs(lo - g['lons110'])) < 2e-5
+
+
+def _sip_exact(header, prefix, u, v):
+    """FITS-SIP forward polynomial sum C_p_q u^p v^q in exact rational arithmetic."""
+    from fractions import Fraction
+    order = int(header[prefix + '_ORDER'])
+    acc = Fraction(0)
+    fu, fv = Fraction(u), Fraction(v)
+    for p in range(order + 1):
+        for q in range(order + 1 - p):
+            c = header.get('%s_%d_%d' % (prefix, p, q))
+            if c is not None:
+                acc += Fraction(float(c)) * fu ** p * fv ** q
+    return acc
+
+
+def sip_kat_points(n=120, seed=9):
+    rng = np.random.default_rng(seed)
+    u = rng.uniform(-3000, 3000, n)
+    v = rng.uniform(-2000, 2000, n)
+    u[:4] = [0.0, 3000.0, -3000.0, 1.0]
+    v[:4] = [0.0, -2000.0, 2000.0, -1.0]
+    return u, v
+
+
+def test_sip_polynomial_against_exact_rational_arithmetic():
+    """Independent pin of the SIP restatement: the FITS-SIP convention u' = u + sum A_p_q u^p v^q evaluated
+    with `fractions.Fraction` (no rounding at all) at 120 points of the configs[2] header; the oracle's
+    fixed-order Horner evaluation must agree to a few ulp of the largest term."""
+    import oracle.auromat_oracle as O
+    from auromat_b200 import synthetic
+    hdr = synthetic.issHeader(6000, 4000, sipOrder=4)
+    oa, A, ob, B = O.sip_coefficients(hdr)
+    u, v = sip_kat_points()
+    fa, fb = O._sip_poly(A, u, v), O._sip_poly(B, u, v)
+    for i in range(len(u)):
+        ea, eb = _sip_exact(hdr, 'A', u[i], v[i]), _sip_exact(hdr, 'B', u[i], v[i])
+        # |distortion| <= ~20 px: 1e-13 px absolute is a handful of ulp of the result
+        assert abs(float(ea) - fa[i]) <= 1e-13 + 4e-16 * abs(float(ea)), (i, float(ea), fa[i])
+        assert abs(float(eb) - fb[i]) <= 1e-13 + 4e-16 * abs(float(eb)), (i, float(eb), fb[i])
+    assert np.abs(fa).max() > 1.0          # the distortion is not trivially small
