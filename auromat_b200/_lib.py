@@ -69,6 +69,17 @@ class AmtGrid(C.Structure):
     ]
 
 
+class AmtGridInfo(C.Structure):
+    _fields_ = [("n_lat", C.c_int32), ("n_lon", C.c_int32),
+                ("lat_min_in_grid", C.c_double), ("lat_max_in_grid", C.c_double),
+                ("lon_min_in_grid", C.c_double), ("lon_max_in_grid", C.c_double),
+                ("lat_step", C.c_double), ("lon_step", C.c_double),
+                ("lat_px_per_deg", C.c_double), ("lon_px_per_deg", C.c_double)]
+
+
+AMT_PLAN_OK, AMT_PLAN_HOST, AMT_PLAN_EMPTY = 0, 1, 2
+
+
 class AmtSeqSlot(C.Structure):
     _fields_ = [("planes", AmtGeorefOut), ("d_stats", C.c_void_p), ("h_stats", C.c_void_p), ("d_img", C.c_void_p)]
 
@@ -133,6 +144,13 @@ SIGNATURES = {
                                    C.c_void_p, C.c_void_p]),
     "amt_sip_distort": (C.c_int, [C.c_void_p, C.POINTER(AmtFrame), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),
+    "amt_plate_carree_resolution": (C.c_int, [C.c_double] * 5 + [c_double_p, c_double_p]),
+    "amt_target_grid": (C.c_int, [C.c_double] * 6 + [C.POINTER(AmtGrid), C.POINTER(AmtGridInfo), C.POINTER(C.c_int32)]),
+    "amt_side_scale": (C.c_double, [C.c_uint64]),
+    "amt_pole_pixels": (C.c_int, [C.POINTER(AmtFrame), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                  C.POINTER(C.c_int32)]),
+    "amt_seq_plan": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_double, C.POINTER(AmtStats),
+                               C.POINTER(AmtGrid), C.POINTER(AmtGridInfo), C.POINTER(C.c_int32)]),
     "amt_seq_output_layout": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t),
                                         C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "amt_seq_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,

@@ -35,7 +35,10 @@ def _inverse(lat1, lon1, lat2, lon2):
     sigma = ss = cs = c2a = c2sm = 0.0
     for _ in range(200):
         sl, cl = math.sin(lam), math.cos(lam)
-        ss = math.hypot(cU2 * sl, cU1 * sU2 - sU1 * cU2 * cl)
+        # plain IEEE operations only (+ - * / sqrt) besides libm's sin/cos/tan/atan/atan2: the C port in
+        # csrc/amt_host.cuh (amt_plate_carree_resolution) reproduces this function bit for bit
+        t1, t2 = cU2 * sl, cU1 * sU2 - sU1 * cU2 * cl
+        ss = math.sqrt(t1 * t1 + t2 * t2)
         if ss == 0:
             return 0.0, 0.0, 0.0
         cs = sU1 * sU2 + cU1 * cU2 * cl
@@ -50,11 +53,11 @@ def _inverse(lat1, lon1, lat2, lon2):
         if done:
             break
     b = WGS84_A_M * (1 - f)
-    u2 = c2a * (WGS84_A_M ** 2 - b ** 2) / b ** 2
+    u2 = c2a * (WGS84_A_M * WGS84_A_M - b * b) / (b * b)
     A = 1 + u2 / 16384 * (4096 + u2 * (-768 + u2 * (320 - 175 * u2)))
     B = u2 / 1024 * (256 + u2 * (-128 + u2 * (74 - 47 * u2)))
-    dsig = B * ss * (c2sm + B / 4 * (cs * (-1 + 2 * c2sm ** 2)
-                                     - B / 6 * c2sm * (-3 + 4 * ss ** 2) * (-3 + 4 * c2sm ** 2)))
+    dsig = B * ss * (c2sm + B / 4 * (cs * (-1 + 2 * c2sm * c2sm)
+                                     - B / 6 * c2sm * (-3 + 4 * ss * ss) * (-3 + 4 * c2sm * c2sm)))
     s12 = b * A * (sigma - dsig)
     azi1 = math.degrees(math.atan2(cU2 * math.sin(lam), cU1 * sU2 - sU1 * cU2 * math.cos(lam)))
     return sigma, s12, azi1

@@ -39,13 +39,19 @@ def _sipPacked(header, prefix):
     return order, packed
 
 
-def frameConstants(header, cameraPosGCRS, photoTime, altitude, fastCenterCalculation=False):
+R_EARTH_SPHERE = 6378.136      # astropy.constants.R_earth [km], the 'sphere' model of mapping.py:1502-1505
+
+
+def frameConstants(header, cameraPosGCRS, photoTime, altitude, fastCenterCalculation=False, earthModel='wgs84'):
     """Build the `amt_frame` for one image.
 
     :param header: dict-like with CTYPE1/2, LATPOLE, LONPOLE, CRVAL1/2, CRPIX1/2, CD*, IMAGEW/H
     :param cameraPosGCRS: (3,) km
     :param datetime photoTime: UTC
     :param altitude: emission altitude in km (inflation of the WGS84 ellipsoid)
+    :param earthModel: 'wgs84' (ellipsoid a, b + altitude) or 'sphere' (radius R_earth + altitude): the two
+        models of the reference's `inflatedEarthIntersection` (mapping/mapping.py:1474-1510); the kernels
+        are generic in the three semi-axes
     """
     if not isTanHeader(header) or header['LATPOLE'] != 0.0:
         # the reference falls back to astropy.wcs for anything else (wcs.py:53-62)
@@ -61,7 +67,12 @@ def frameConstants(header, cameraPosGCRS, photoTime, altitude, fastCenterCalcula
     assert cam.shape == (3,)
     fr.cam[:] = cam.tolist()
     # reference mapping/mapping.py:1497-1500 and intersection.py:66
-    a, b = wgs84A + altitude, wgs84B + altitude
+    if earthModel == 'wgs84':
+        a, b = wgs84A + altitude, wgs84B + altitude
+    elif earthModel == 'sphere':
+        a = b = R_EARTH_SPHERE + altitude
+    else:
+        raise ValueError('unsupported earth model: ' + str(earthModel))
     fr.inv_axes[:] = [1 / a, 1 / a, 1 / b]
     x, y, z = cam
     fr.origin_inside = 1 if (x / a) ** 2 + (y / a) ** 2 + (z / b) ** 2 < 1 else 0   # intersection.py:239-241

@@ -2144,5 +2144,6 @@ extern "C" int amt_sip_distort(amt_ctx* ctx, const amt_frame* frame, const doubl
     return AMT_OK;
 }
 
-// ================================================================== sequence engine
+// ============================================== host arithmetic (grid derivation) + sequence engine
+#include "amt_host.cuh"
 #include "amt_seq.cuh"

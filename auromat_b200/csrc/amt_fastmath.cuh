@@ -78,6 +78,9 @@ AMT_HD double mufu_rsqrt(double a) {
 #endif
 }
 
+// 0.5 * y for a normal, non-tiny y: exponent decrement on the integer pipe instead of a DMUL
+AMT_HD double half_of(double y) { return bits_to_double(hi_word(y) - 0x00100000u, lo_word(y)); }
+
 // 1/a to ~2^-39: ~20-bit seed + one Newton step (2 DFMA).
 AMT_HD double rcp_nr1(double a) {
     const double r = mufu_rcp(a);
@@ -105,7 +108,7 @@ AMT_HD double div_38(double n, double a) {
 AMT_HD void sqrt_rsqrt(double a, double& sq, double& half_rsq) {
     const double y = mufu_rsqrt(a);
     double g = a * y;
-    double h = 0.5 * y;
+    double h = half_of(y);
     const double r = fma(-g, h, 0.5);
     g = fma(g, r, g);
     h = fma(h, r, h);
@@ -116,9 +119,8 @@ AMT_HD void sqrt_rsqrt(double a, double& sq, double& half_rsq) {
 AMT_HD double rsqrt_40(double a) {
     const double y = mufu_rsqrt(a);
     const double g = a * y;
-    double h = 0.5 * y;
-    h = fma(h, fma(-g, h, 0.5), h);
-    return h + h;
+    const double r = fma(-g, half_of(y), 0.5);       // (1 - a y^2) / 2
+    return fma(y, r, y);                             // y (1 + r): 1 DMUL + 2 DFMA
 }
 AMT_HD double sqrt_fast(double a) {
     double s, h;

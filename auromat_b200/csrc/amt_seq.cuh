@@ -141,6 +141,54 @@ extern "C" int amt_seq_wait_stats(amt_seq* seq, int32_t slot, amt_stats* out) {
     return AMT_OK;
 }
 
+// Statistics of the slot's frame -> bounding box -> target grid, entirely in C (amt_host.cuh): what
+// BaseMapping.boundingBox + resample.deriveGrid do in Python.  *outcome: AMT_PLAN_OK (grid, info valid),
+// AMT_PLAN_HOST (the frame encloses a pole or straddles the date line, or the bin-edge bookkeeping needs
+// the materialised edges: the caller derives the grid with the Python path -- rare), AMT_PLAN_EMPTY (no
+// defined corner at all).  `stats_out` always receives the statistics including the pole flags.
+extern "C" int amt_seq_plan(amt_seq* seq, int32_t slot, double arcsec_per_px, double lat_px_per_deg,
+                            double lon_px_per_deg, amt_stats* stats_out, amt_grid* grid, amt_grid_info* info,
+                            int32_t* outcome) {
+    SEQ_SLOT(seq, slot);
+    CHECK_ARG(stats_out && grid && info && outcome, "amt_seq_plan: NULL argument");
+    CHECK_ARG(sl.a_rec, "amt_seq_plan: stage A has not been submitted for this slot");
+    CUDA_TRY(cudaEventSynchronize(sl.ev_a));
+    amt_stats st = *sl.buf.h_stats;
+    // pole containment: is the pixel that shows a pole defined?  (one bitmap word, only when a pole
+    // projects into the pixel array at all)
+    int32_t ix[2], iy[2], in_frame[2];
+    int rc = amt_pole_pixels(&sl.frame, ix, iy, in_frame);
+    if (rc) return rc;
+    st.pole_flags = 0;
+    for (int i = 0; i < 2; ++i) {
+        if (!in_frame[i]) continue;
+        CUDA_TRY(cudaSetDevice(seq->ctx->device));
+        const int wc = (seq->W + 31) / 32;
+        uint32_t word = 0;
+        CUDA_TRY(cudaMemcpyAsync(&word, sl.buf.planes.d_valid_c + (size_t)iy[i] * wc + ix[i] / 32, 4,
+                                 cudaMemcpyDeviceToHost, seq->s_aux));
+        CUDA_TRY(cudaStreamSynchronize(seq->s_aux));
+        if ((word >> (ix[i] % 32)) & 1u) st.pole_flags |= (uint64_t)(1u << i);
+    }
+    *stats_out = st;
+    if (st.n_boundary_corners == 0) { *outcome = AMT_PLAN_EMPTY; return AMT_OK; }
+    // BaseMapping.boundingBox (reference mapping/mapping.py:694-743)
+    double lat_s = st.lat_min, lat_n = st.lat_max, lon_w = st.lon_min, lon_e = st.lon_max;
+    if (st.pole_flags || st.lon_max - st.lon_min > 180) { *outcome = AMT_PLAN_HOST; return AMT_OK; }
+    double px_lat = lat_px_per_deg, px_lon = lon_px_per_deg;
+    if (arcsec_per_px > 0) {
+        rc = amt_plate_carree_resolution(lat_s, lon_w, lat_n, lon_e, arcsec_per_px, &px_lat, &px_lon);
+        if (rc) return rc;
+    }
+    int32_t fb = 0;
+    rc = amt_target_grid(px_lat, px_lon, lat_s, lat_n, lon_w, lon_e, grid, info, &fb);
+    if (rc) return rc;
+    grid->altitude = 0.0;
+    grid->side_scale = amt_side_scale((uint64_t)seq->W * (uint64_t)seq->H);
+    *outcome = fb ? AMT_PLAN_HOST : AMT_PLAN_OK;
+    return AMT_OK;
+}
+
 extern "C" int amt_seq_stage_b(amt_seq* seq, int32_t slot, const amt_seq_job* job) {
     SEQ_SLOT(seq, slot);
     amt_ctx* ctx = seq->ctx;

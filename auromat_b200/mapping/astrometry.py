@@ -22,6 +22,8 @@ class BaseAstrometryMapping(BaseMapping):
         intersection points (reference astrometry.py:24-40,154-160) instead of their own rays.
     """
 
+    earthModel = 'wgs84'         # or 'sphere' (reference mapping/mapping.py:1474-1510); set before first use
+
     def __init__(self, wcsHeader, alti, cameraPosGCRS, photoTime, identifier, metadata=None,
                  fastCenterCalculation=False, device=None, sanitize=True):
         BaseMapping.__init__(self, alti, cameraPosGCRS, photoTime, identifier, metadata, device)
@@ -43,7 +45,7 @@ class BaseAstrometryMapping(BaseMapping):
         """The host-computed `amt_frame` block of this image (built once)."""
         if self._frame is None:
             self._frame = frameConstants(self._wcsHeader, self.cameraPosGCRS, self.photoTime, self.altitude,
-                                         self.fastCenterCalculation)
+                                         self.fastCenterCalculation, self.earthModel)
         return self._frame
 
     def _computePlanes(self, ctx, names):
@@ -125,44 +127,26 @@ class BaseAstrometryMapping(BaseMapping):
 
     def _poleFlags(self):
         """bit0 / bit1: the geographic north / south pole (at the mapping altitude) is seen by
-        a valid pixel.  The pole point is projected through the inverse WCS; replaces the
-        azimuth-sum test on a 50-point convex outline (reference mapping.py:705-718)."""
-        from ..coordinates.geodesic import wgs84A, wgs84B
-        fr = self.frameConstants
+        a valid pixel.  The pole point is projected through the inverse WCS (`amt_pole_pixels`, host
+        arithmetic in C shared with the sequence engine); replaces the azimuth-sum test on a 50-point
+        convex outline (reference mapping.py:705-718)."""
+        import ctypes
+        from .. import _lib
         h, w = self.shape
-        a, b = wgs84A + self.altitude, wgs84B + self.altitude
-        cam = np.asarray(self.cameraPosGCRS, dtype=np.float64)
-        mgeo = np.array(fr.m_geo[:]).reshape(3, 3)
-        rot = np.array(fr.rot[:]).reshape(3, 3)
-        cd = np.array(fr.cd[:]).reshape(2, 2)
-        inside = bool(fr.origin_inside)
+        ix, iy, inFrame = (ctypes.c_int32 * 2)(), (ctypes.c_int32 * 2)(), (ctypes.c_int32 * 2)()
+        _lib.check(_lib.load().amt_pole_pixels(ctypes.byref(self.frameConstants), ix, iy, inFrame))
         flags = 0
-        for bit, sign in ((1, 1.0), (2, -1.0)):
-            P = mgeo.T.dot(np.array([0.0, 0.0, sign * b]))
-            d = P - cam
-            normal = P / np.array([a * a, a * a, b * b])
-            if (np.dot(d, normal) >= 0) != inside:      # far side of the ellipsoid
+        for i, bit in ((0, 1), (1, 2)):
+            if not inFrame[i]:
                 continue
-            lmn = rot.T.dot(d / np.linalg.norm(d))
-            if lmn[2] <= 0:
-                continue
-            K = 180.0 / np.pi
-            xy = np.array([K * lmn[1] / lmn[2], -K * lmn[0] / lmn[2]])
-            uv = np.linalg.solve(cd, xy)
-            if fr.sip_order_a or fr.sip_order_b:
-                uv = self._invertSip(uv)
-            px, py = uv[0] + fr.crpix[0] - 1, uv[1] + fr.crpix[1] - 1
-            if -0.5 <= px <= w - 0.5 and -0.5 <= py <= h - 0.5:
-                ix = min(max(int(np.floor(px + 0.5)), 0), w - 1)
-                iy = min(max(int(np.floor(py + 0.5)), 0), h - 1)
-                if 'lat_c' in self._planes or not getattr(self, '_planeFree', False):
-                    lat = float(self.devicePlanes()['lat_c'][iy * w + ix].item())
-                    valid = lat == lat
-                else:
-                    word = int(self._ensureHitBitmaps()[1][iy * ((w + 31) // 32) + ix // 32].item()) & 0xffffffff
-                    valid = bool((word >> (ix % 32)) & 1)
-                if valid:
-                    flags |= bit
+            if 'lat_c' in self._planes or not getattr(self, '_planeFree', False):
+                lat = float(self.devicePlanes()['lat_c'][iy[i] * w + ix[i]].item())
+                valid = lat == lat
+            else:
+                word = int(self._ensureHitBitmaps()[1][iy[i] * ((w + 31) // 32) + ix[i] // 32].item()) & 0xffffffff
+                valid = bool((word >> (ix[i] % 32)) & 1)
+            if valid:
+                flags |= bit
         return flags
 
     def _invertSip(self, target):

@@ -618,22 +618,35 @@ def _engineSequence(ctx, imagesOrArrays, wcsHeaders, pxPerDeg, arcsecPerPx, alti
         _lib.check(lib.amt_seq_stage_a(eng.handle, slot, ctypes.byref(m.frameConstants)))
         return m, slot, hostImg
 
+    try:
+        pxLat, pxLon = pxPerDeg
+    except TypeError:
+        pxLat = pxLon = pxPerDeg
+    arcsec = float(arcsecPerPx) if arcsecPerPx else 0.0
+
     def runB(m, slot, hostImg):
-        st = _lib.AmtStats()
-        _lib.check(lib.amt_seq_wait_stats(eng.handle, slot, ctypes.byref(st)))
+        # statistics -> pole flags -> bounding box -> target grid in C (amt_seq_plan); frames around a
+        # pole / across the date line take the Python derivation (one more outline reduction)
+        st, grid, ginfo, outcome = _lib.AmtStats(), _lib.AmtGrid(), _lib.AmtGridInfo(), ctypes.c_int32()
+        _lib.check(lib.amt_seq_plan(eng.handle, slot, arcsec, float(pxLat or 0), float(pxLon or 0), ctypes.byref(st),
+                                    ctypes.byref(grid), ctypes.byref(ginfo), ctypes.byref(outcome)))
         buffers = eng.slots[slot]
         # the mapping sees its final bitmaps; planes follow once the fused kernel is enqueued
         m._planes.update(valid_k=buffers['valid_k'], valid_c=buffers['valid_c'])
         m._grazingCounted = True
         m.isSanitized = True
         m._planeFree = True
-        st.pole_flags = m._poleFlags()
         m._stats = st
-        f = None
-        if st.n_boundary_corners == 0:
-            # nothing of the Earth in this frame: the same error `resample(getMapping(...))` raises
-            m.boundingBox
-        grid, info = deriveGrid(m, pxPerDeg, arcsecPerPx)
+        if outcome.value == _lib.AMT_PLAN_EMPTY:
+            m.boundingBox       # nothing of the Earth in this frame: the error `resample(getMapping(...))` raises
+        if outcome.value == _lib.AMT_PLAN_OK:
+            grid.altitude = float(m.altitude)
+            info = dict(nLat=ginfo.n_lat, nLon=ginfo.n_lon, latMinInGrid=ginfo.lat_min_in_grid,
+                        latMaxInGrid=ginfo.lat_max_in_grid, lonMinInGrid=ginfo.lon_min_in_grid,
+                        lonMaxInGrid=ginfo.lon_max_in_grid, latStep=ginfo.lat_step, lonStep=ginfo.lon_step,
+                        pxPerDeg=(ginfo.lat_px_per_deg, ginfo.lon_px_per_deg), mode=_lib.AMT_PRE_NONE)
+        else:
+            grid, info = deriveGrid(m, pxPerDeg, arcsecPerPx)
         cells, C = grid.nx * grid.ny, eng.channels
         offMask, offSide, total = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
         _lib.check(lib.amt_seq_output_layout(grid.nx, grid.ny, C, eng.amtDtype, ctypes.byref(offMask),

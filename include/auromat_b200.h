@@ -354,6 +354,34 @@ int amt_georef_bin_fused(amt_ctx* ctx, const amt_frame* frame, const uint32_t* d
 int amt_sip_distort(amt_ctx* ctx, const amt_frame* frame, const double* d_u, const double* d_v, size_t n,
                     double* d_u_out, double* d_v_out, void* stream);
 
+/* --------------------------------------------------------- host arithmetic of the grid ---- */
+/* Bit-identical C ports of the scalar host code around resample() (no CUDA call; usable without a
+ * GPU): they let the sequence engine derive a frame's target grid without returning to Python.    */
+typedef struct amt_grid_info {
+    int32_t n_lat, n_lon;                        /* nodes of the snapped box (resample.py:297-298)  */
+    double lat_min_in_grid, lat_max_in_grid;     /* fixedGrid, resample.py:293-296                  */
+    double lon_min_in_grid, lon_max_in_grid;
+    double lat_step, lon_step;                   /* np.linspace(..., retstep=True), :222-227        */
+    double lat_px_per_deg, lon_px_per_deg;
+} amt_grid_info;
+
+/* resample.py:36-61 plateCarreeResolution (arc length on the auxiliary sphere by Vincenty's inverse
+ * iteration in place of geographiclib's a12).                                                      */
+int amt_plate_carree_resolution(double lat_south, double lon_west, double lat_north, double lon_east,
+                                double arcsec_per_px, double* lat_px_per_deg, double* lon_px_per_deg);
+/* resample.py:281-299 fixedGrid + :220-241,330-335 and util/histogram.py:185-186,215-219: the
+ * amt_grid of a bounding box without pre-rotation.  *fallback = 1: the decimal of histogram.py:218
+ * needs the materialised bin edges (step within 1e-9 of a power of ten) -- derive it in Python.     */
+int amt_target_grid(double lat_px_per_deg, double lon_px_per_deg, double lat_min, double lat_max,
+                    double lon_min, double lon_max, amt_grid* grid, amt_grid_info* info, int32_t* fallback);
+/* amt_grid.side_scale for n_samples values of magnitude < 128 (elevations).                        */
+double amt_side_scale(uint64_t n_samples);
+/* Pixels of a WCS frame that show the geographic north / south pole at the mapping altitude (inverse
+ * WCS projection of the pole point); in_frame[i] == 0 when pole i is not in the field of view.
+ * Replaces the outline / azimuth-sum test of mapping/mapping.py:705-718, geodesic.py:183-202: the
+ * mapping encloses the pole iff that pixel is defined.                                             */
+int amt_pole_pixels(const amt_frame* frame, int32_t ix[2], int32_t iy[2], int32_t in_frame[2]);
+
 /* ----------------------------------------------------------------- sequence engine ---- */
 /* The pipelined composition of getMappingSequence (mapping/spacecraft.py:308-332) and
  * ResampleProvider (resample.py:370-394) for WCS frames with fast_center == 0: two calls per frame.
@@ -407,6 +435,12 @@ int amt_seq_destroy(amt_seq* seq);
 int amt_seq_set_slot(amt_seq* seq, int32_t slot, const amt_seq_slot* buffers);
 int amt_seq_stage_a(amt_seq* seq, int32_t slot, const amt_frame* frame);
 int amt_seq_wait_stats(amt_seq* seq, int32_t slot, amt_stats* out /* nullable */);
+/* Statistics -> pole flags -> bounding box (mapping/mapping.py:694-743) -> target grid, in C.  One of
+ * arcsec_per_px (> 0) or the pxPerDeg pair selects the resolution (resample.py:95-117).             */
+enum { AMT_PLAN_OK = 0, AMT_PLAN_HOST = 1, AMT_PLAN_EMPTY = 2 };
+int amt_seq_plan(amt_seq* seq, int32_t slot, double arcsec_per_px, double lat_px_per_deg,
+                 double lon_px_per_deg, amt_stats* stats_out, amt_grid* grid, amt_grid_info* info,
+                 int32_t* outcome);
 int amt_seq_stage_b(amt_seq* seq, int32_t slot, const amt_seq_job* job);
 int amt_seq_wait_result(amt_seq* seq, int32_t slot);
 /* Image bytes copied host -> device so far (bench.py h2d_bytes_per_step).                         */

@@ -1503,3 +1503,22 @@ def test_sip_device_polynomial_against_exact_rational_arithmetic(env):
         ev = float(_sip_exact(hdr, 'B', u[i], v[i]) + __import__('fractions').Fraction(v[i]))
         assert abs(uo[i] - eu) <= 2 * np.spacing(abs(eu)) + 1e-13, (i, uo[i], eu)
         assert abs(vo[i] - ev) <= 2 * np.spacing(abs(ev)) + 1e-13, (i, vo[i], ev)
+
+
+def test_sphere_earth_model(env):
+    """`inflatedEarthIntersection(..., earthModel='sphere')` (reference mapping/mapping.py:1502-1505,
+    coordinates/intersection.py:12-56): the kernels are generic in the semi-axes; against the oracle's
+    restatement of sphereLineIntersection."""
+    import oracle.auromat_oracle as O
+    from auromat_b200 import synthetic
+    from auromat_b200.mapping.spacecraft import getMapping
+    W, H = 266, 177
+    hdr = synthetic.issHeader(W, H)
+    t, cam = synthetic.headerTimeAndCamera(hdr)
+    m = getMapping(synthetic.issImage(W, H), hdr, nosanitize=True, identifier='s')
+    m.earthModel = 'sphere'
+    with quiet():
+        g = O.georeference(hdr, cam, t, 110, earth_model='sphere')
+    w = assert_coords_close(gpu_arrays(m), g)
+    e = getMapping(synthetic.issImage(W, H), hdr, nosanitize=True, identifier='e')
+    assert np.nanmax(np.abs(e.latsCenter.filled(np.nan) - m.latsCenter.filled(np.nan))) > 1e-3   # the models differ

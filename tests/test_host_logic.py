@@ -297,3 +297,115 @@ def test_spacecraft_mapping_providers(tmp_path):
     assert r.ids == names
     assert findNearest([1, 4, 9], 6) == 1 and findNearest([1, 4, 9], 7) == 2 and findNearest([1, 4, 9], 100) == 2
     assert findNearest([1, 5], 3) == 0 and findNearest([1, 4, 9], -3) == 0
+
+
+def test_c_grid_derivation_is_bit_identical_to_python():
+    """csrc/amt_host.cuh ports plateCarreeResolution / fixedGrid / targetGrid / sideScale to C for the
+    sequence engine: on thousands of random bounding boxes and resolutions every field equals the
+    Python derivation (which follows the reference's arithmetic) bit for bit."""
+    import ctypes as C
+    from auromat_b200 import resample as R
+    from auromat_b200.mapping.mapping import BoundingBox
+    lib = _lib.load()
+    rng = np.random.default_rng(12)
+    n_ok = 0
+    for i in range(4000):
+        latS = float(rng.uniform(-85, 80))
+        latN = float(min(89.0, latS + rng.uniform(0.3, 30)))
+        lonW = float(rng.uniform(-179, 150))
+        lonE = float(min(179.5, lonW + rng.uniform(0.3, 60)))
+        arcsec = float(rng.choice([10, 25, 100, 400, 977.3, 36.0, 3600.0]))
+        bb = BoundingBox(latS, lonW, latN, lonE)
+        ppd = R.plateCarreeResolution(bb, arcsec)
+        a, b = C.c_double(), C.c_double()
+        assert lib.amt_plate_carree_resolution(latS, lonW, latN, lonE, arcsec, C.byref(a), C.byref(b)) == 0
+        assert (a.value, b.value) == ppd, (i, (a.value, b.value), ppd)
+        if i % 3 == 0:
+            ppd = (float(rng.uniform(1, 50)), float(rng.uniform(1, 50)))
+        try:
+            g, info = R.targetGrid(ppd, latS, latN, lonW, lonE)
+        except ValueError:
+            continue
+        cg, ci, fb = _lib.AmtGrid(), _lib.AmtGridInfo(), C.c_int32()
+        assert lib.amt_target_grid(ppd[0], ppd[1], latS, latN, lonW, lonE, C.byref(cg), C.byref(ci), C.byref(fb)) == 0
+        if fb.value:
+            continue
+        for f in ('nx', 'ny', 'prerotate', 'lo_x', 'hi_x', 'step_x', 'lo_y', 'hi_y', 'step_y', 'round_x', 'round_y',
+                  'wgs_a', 'wgs_b'):
+            assert getattr(cg, f) == getattr(g, f), (i, f, getattr(cg, f), getattr(g, f))
+        assert np.allclose(cg.rot[:], g.rot[:], atol=1e-15)
+        assert (ci.n_lat, ci.n_lon, ci.lat_min_in_grid, ci.lat_max_in_grid, ci.lon_min_in_grid, ci.lon_max_in_grid,
+                ci.lat_step, ci.lon_step) == (info['nLat'], info['nLon'], info['latMinInGrid'], info['latMaxInGrid'],
+                                              info['lonMinInGrid'], info['lonMaxInGrid'], info['latStep'], info['lonStep'])
+        n_ok += 1
+    assert n_ok > 3000
+    lib.amt_side_scale.restype = C.c_double
+    for n in (1, 2, 3, 1000, 65536, 65537, 12052992, 24000000, 2 ** 31, 2 ** 40):
+        assert lib.amt_side_scale(n) == R.sideScale(n), n
+
+
+def test_c_pole_pixels_matches_numpy_projection():
+    """amt_pole_pixels (inverse WCS projection of the pole point, C) against an independent numpy
+    evaluation, for cameras around the pole, elsewhere, and with SIP."""
+    import ctypes as C
+    from auromat_b200 import synthetic
+    from auromat_b200.coordinates.geodesic import wgs84A, wgs84B
+    from auromat_b200.coordinates.wcs import frameConstants
+    lib = _lib.load()
+
+    def numpy_pixels(fr, w, h, altitude):
+        a, b = wgs84A + altitude, wgs84B + altitude
+        cam = np.array(fr.cam[:])
+        mgeo = np.array(fr.m_geo[:]).reshape(3, 3)
+        rot = np.array(fr.rot[:]).reshape(3, 3)
+        cd = np.array(fr.cd[:]).reshape(2, 2)
+        out = []
+        for sign in (1.0, -1.0):
+            P = mgeo.T.dot(np.array([0.0, 0.0, sign * b]))
+            d = P - cam
+            normal = P / np.array([a * a, a * a, b * b])
+            if (np.dot(d, normal) >= 0) != bool(fr.origin_inside):
+                out.append(None)
+                continue
+            lmn = rot.T.dot(d / np.linalg.norm(d))
+            if lmn[2] <= 0:
+                out.append(None)
+                continue
+            K = 180.0 / np.pi
+            uv = np.linalg.solve(cd, np.array([K * lmn[1] / lmn[2], -K * lmn[0] / lmn[2]]))
+            px, py = uv[0] + fr.crpix[0] - 1, uv[1] + fr.crpix[1] - 1
+            if -0.5 <= px <= w - 0.5 and -0.5 <= py <= h - 0.5:
+                out.append((min(max(int(np.floor(px + 0.5)), 0), w - 1), min(max(int(np.floor(py + 0.5)), 0), h - 1)))
+            else:
+                out.append(None)
+        return out
+
+    W, H = 640, 426
+    seen = 0
+    for hdr in [synthetic.issHeader(W, H), synthetic.issHeaderLookingAt(80.0, 10.0, 89.5, 40.0, W, H),
+                synthetic.issHeaderLookingAt(84.0, -120.0, 88.0, 100.0, W, H),
+                synthetic.issHeaderLookingAt(-80.0, 10.0, -89.0, 40.0, W, H),
+                synthetic.issHeaderLookingAt(50.0, 170.0, 55.0, -178.0, W, H)]:
+        t, cam = synthetic.headerTimeAndCamera(hdr)
+        fr = frameConstants(hdr, cam, t, 110)
+        ix, iy, inf = (C.c_int32 * 2)(), (C.c_int32 * 2)(), (C.c_int32 * 2)()
+        assert lib.amt_pole_pixels(C.byref(fr), ix, iy, inf) == 0
+        ref = numpy_pixels(fr, W, H, 110)
+        for i in range(2):
+            if ref[i] is None:
+                assert inf[i] == 0
+            else:
+                assert inf[i] == 1 and (ix[i], iy[i]) == ref[i]
+                seen += 1
+    assert seen >= 3
+
+
+def test_seq_output_layout():
+    import ctypes as C
+    lib = _lib.load()
+    om, os_, tot = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    assert lib.amt_seq_output_layout(484, 412, 3, _lib.AMT_U8, C.byref(om), C.byref(os_), C.byref(tot)) == 0
+    cells = 484 * 412
+    assert om.value == (cells * 3 + 63) // 64 * 64 and os_.value == (om.value + cells + 63) // 64 * 64
+    assert tot.value == os_.value + cells * 8
+    assert lib.amt_seq_output_layout(0, 4, 3, _lib.AMT_U8, None, None, None) == _lib.AMT_ERR_INVALID_ARGUMENT
