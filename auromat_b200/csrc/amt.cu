@@ -1963,31 +1963,34 @@ k_georef_fused(const __grid_constant__ GeorefParams p, const uint32_t* __restric
     double dk[3], dc[3], Pk[3], Pc[3];
     dirs_kc<SIP>(p.f, s_sip, s_sip + (SIP ? AMT_SIP_MAX_COEF : 0), x, y, dk, dc);
     bool gz;
-    // valid elements hit by construction (same arithmetic as the hit test); the others carry
-    // whatever comes out -- only the stores are predicated
+    // valid elements hit by construction (same arithmetic as the hit test).  An undefined element gets
+    // a NaN into the first coordinate of its point: every dot product downstream then is NaN, i.e. all
+    // nine outputs come out NaN without a select per plane (the reference's NaN rows, for free).
     if (PLANES) intersect(p.f, dk, Pk, gz);
     intersect(p.f, dc, Pc, gz);
+    if (PLANES && !vk) Pk[0] = nan;
+    if (!vc) Pc[0] = nan;
     double la_c, lo_c, r2_c;
     {
         double la_k, lo_k;
         if (PLANES) point_to_geo(p.f, Pk, la_k, lo_k);
         point_to_geo(p.f, Pc, la_c, lo_c, r2_c);
         if (PLANES) {
-            if (in_k) { p.o.d_lat_k[ik] = vk ? la_k : nan; p.o.d_lon_k[ik] = vk ? lo_k : nan; }
-            if (in_c) { p.o.d_lat_c[ic] = vc ? la_c : nan; p.o.d_lon_c[ic] = vc ? lo_c : nan; }
+            if (in_k) { p.o.d_lat_k[ik] = la_k; p.o.d_lon_k[ik] = lo_k; }
+            if (in_c) { p.o.d_lat_c[ic] = la_c; p.o.d_lon_c[ic] = lo_c; }
         }
     }
     if (PLANES && MAG) {
         double ml_k, mt_k, ml_c, mt_c;
         point_to_mag(p.f, Pk, ml_k, mt_k);
         point_to_mag(p.f, Pc, ml_c, mt_c);
-        if (in_k) { p.o.d_mlat_k[ik] = vk ? ml_k : nan; p.o.d_mlt_k[ik] = vk ? mt_k : nan; }
-        if (in_c) { p.o.d_mlat_c[ic] = vc ? ml_c : nan; p.o.d_mlt_c[ic] = vc ? mt_c : nan; }
+        if (in_k) { p.o.d_mlat_k[ik] = ml_k; p.o.d_mlt_k[ik] = mt_k; }
+        if (in_c) { p.o.d_mlat_c[ic] = ml_c; p.o.d_mlt_c[ic] = mt_c; }
     }
     double elev = 0.0;
     if (PLANES || (BIN && fsum != nullptr)) {
         elev = elevation_deg<false>(dc, Pc, r2_c);
-        if (PLANES && in_c) p.o.d_elev_c[ic] = vc ? elev : nan;
+        if (PLANES && in_c) p.o.d_elev_c[ic] = elev;
     }
     if (BIN) {
         if (mc == 0) return;                                   // warp-uniform

@@ -245,8 +245,8 @@ AMT_HD double atan_diamond_deg(double a, double b, int k65, unsigned flip) {
     // and its low mantissa word is the integer 64*s
     const double magic = 105553116266496.0;      // 1.5 * 2^46
     const double wi = w + magic;
-    int i = (int)lo_word(wi);
-    i = min(max(i, 0), 64);                      // also keeps NaN inputs inside the table
+    // w is in [0, 1 + 2^-19]; the unsigned clamp also keeps NaN inputs (any bit pattern) inside the table
+    const int i = (int)min(lo_word(wi), 64u);
     const double s = wi - magic;                 // == i/64 exactly (w is in [0, 1])
     const double num = fma(-s, sum, a);
     const double den = fma(s, dif, b);

@@ -8,9 +8,10 @@
 //       All on the auxiliary high-priority stream: microsecond kernels that overlap the long
 //       kernel of the preceding frames.
 //   host:                          bounding box -> target grid (reference arithmetic, Python).
-//   stage B (grid + image):        upload of the pixel box that holds defined pixels (copy stream)
-//       -> zero the accumulators -> ONE fused kernel: coordinate planes + binning (main stream)
-//       -> normalise -> results to pinned host memory (output stream).
+//   stage B (grid + image):        zeroed accumulators + upload of the pixel box that holds defined
+//       pixels (copy stream) -> ONE fused kernel: coordinate planes + binning (main stream, nothing
+//       else ever runs there: the long kernels follow each other back to back) -> normalise ->
+//       results to pinned host memory (output stream).
 //
 // The engine owns streams' ORDER (events), never memory: every buffer is provided by the caller
 // (ring slots: planes, bitmaps, statistics block, device image; per frame: accumulators, outputs).
@@ -205,7 +206,8 @@ extern "C" int amt_seq_stage_b(amt_seq* seq, int32_t slot, const amt_seq_job* jo
     const size_t item = seq->dtype == AMT_U8 ? 1 : 2, px = item * seq->C, row_bytes = px * seq->W;
     const void* d_img = job->d_img ? job->d_img : sl.buf.d_img;
     if (!d_img) { nvtxRangePop(); return set_err(AMT_ERR_INVALID_ARGUMENT, "amt_seq_stage_b: no device image buffer"); }
-    bool uploaded = false;
+    // copy stream: zeroed accumulators of this frame + the pixel box of the host image
+    CUDA_TRY(cudaMemsetAsync(job->d_acc, 0, (size_t)(2 + seq->C) * cells * 8, seq->s_copy));
     if (job->h_img && !job->d_img) {
         // the slot's image buffer is read by the fused kernel of the slot's previous frame
         if (sl.b_rec) CUDA_TRY(cudaStreamWaitEvent(seq->s_copy, sl.ev_b, 0));
@@ -227,33 +229,30 @@ extern "C" int amt_seq_stage_b(amt_seq* seq, int32_t slot, const amt_seq_job* jo
                 seq->h2d_bytes += nrows * row_bytes;
             }
         }
-        CUDA_TRY(cudaEventRecord(sl.ev_up, seq->s_copy));
-        uploaded = true;
     }
+    CUDA_TRY(cudaEventRecord(sl.ev_up, seq->s_copy));
+    // main stream: nothing but the long fused kernels, back to back from frame to frame
     cudaStream_t st = seq->s_main;
     CUDA_TRY(cudaStreamWaitEvent(st, sl.ev_a, 0));             // final bitmaps of this frame (auxiliary stream)
-    if (uploaded) CUDA_TRY(cudaStreamWaitEvent(st, sl.ev_up, 0));
+    CUDA_TRY(cudaStreamWaitEvent(st, sl.ev_up, 0));            // accumulators zeroed, image on the device
     uint64_t* count = job->d_acc;
     uint64_t* sums = count + cells;
     double* fsum = (double*)(count + (size_t)(1 + seq->C) * cells);
-    CUDA_TRY(cudaMemsetAsync(job->d_acc, 0, (size_t)(2 + seq->C) * cells * 8, st));
     const amt_georef_out* planes = sl.buf.planes.d_lat_k ? &sl.buf.planes : nullptr;
     rc = georef_fused(ctx, &sl.frame, planes, sl.buf.planes.d_valid_k, sl.buf.planes.d_valid_c, d_img, seq->dtype,
                       seq->C, g, count, sums, fsum, st);
-    unsigned char* o = (unsigned char*)job->d_out;
-    if (!rc) rc = amt_normalise(ctx, g, seq->dtype, seq->C, count, sums, fsum, o, o + om, (double*)(o + os), st);
     if (rc) { nvtxRangePop(); return rc; }
     CUDA_TRY(cudaEventRecord(sl.ev_b, st));
     sl.b_rec = true;
-    if (job->h_out) {
-        // results leave on their own stream: the copy must not delay the next frame's kernel
-        CUDA_TRY(cudaStreamWaitEvent(seq->s_out, sl.ev_b, 0));
-        CUDA_TRY(cudaMemcpyAsync(job->h_out, job->d_out, total, cudaMemcpyDeviceToHost, seq->s_out));
-        CUDA_TRY(cudaEventRecord(sl.ev_out, seq->s_out));
-        sl.out_rec = true;
-    } else {
-        sl.out_rec = false;
-    }
+    // output stream: normalise, then the results leave for pinned host memory -- neither delays the
+    // next frame's fused kernel
+    CUDA_TRY(cudaStreamWaitEvent(seq->s_out, sl.ev_b, 0));
+    unsigned char* o = (unsigned char*)job->d_out;
+    rc = amt_normalise(ctx, g, seq->dtype, seq->C, count, sums, fsum, o, o + om, (double*)(o + os), seq->s_out);
+    if (rc) { nvtxRangePop(); return rc; }
+    if (job->h_out) CUDA_TRY(cudaMemcpyAsync(job->h_out, job->d_out, total, cudaMemcpyDeviceToHost, seq->s_out));
+    CUDA_TRY(cudaEventRecord(sl.ev_out, seq->s_out));
+    sl.out_rec = true;
     nvtxRangePop();
     return AMT_OK;
 }
@@ -261,6 +260,7 @@ extern "C" int amt_seq_stage_b(amt_seq* seq, int32_t slot, const amt_seq_job* jo
 extern "C" int amt_seq_wait_result(amt_seq* seq, int32_t slot) {
     SEQ_SLOT(seq, slot);
     CHECK_ARG(sl.b_rec, "amt_seq_wait_result: stage B has not been submitted for this slot");
+    // results are produced on the output stream: a host-level wait makes them visible to every stream
     CUDA_TRY(cudaEventSynchronize(sl.out_rec ? sl.ev_out : sl.ev_b));
     return AMT_OK;
 }

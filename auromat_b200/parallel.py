@@ -229,3 +229,70 @@ def mosaic(mappings, pxPerDeg, group=None, timings=None):
         timings.update(bin_ms=ev[0].elapsed_time(ev[1]), allreduce_ms=ev[1].elapsed_time(ev[2]),
                        normalise_ms=ev[2].elapsed_time(ev[3]), total_ms=ev[0].elapsed_time(ev[3]))
     return result, acc
+
+
+def resampleSequenceMultiGPU(imagesOrArrays, wcsHeaders, devices=None, queueDepth=8, **kw):
+    """`pipeline.resampleSequence` over several GPUs of one process, frames handed to ONE consumer in
+    sequence order -- the shape of the reference's `getMappingSequence` (mapping/spacecraft.py:308-332),
+    which yields one mapping after the other to its caller.
+
+    One worker thread per device runs the pipelined sequence of its shard (frame i -> device
+    i mod N; one `amt_ctx` and one sequence engine per device, no state shared between them) and
+    pushes finished frames into a bounded queue; the generator pops the queues round-robin, so the
+    order is that of the input.  The library calls release the GIL; the per-frame Python work
+    (header -> frame constants, result objects) does not, which caps a single process at a few
+    thousand frames per second -- beyond that use one process per GPU (torchrun, `shardSequence`).
+
+    :param devices: CUDA device indices (default: all visible)
+    :param queueDepth: finished frames a worker may hold before it blocks
+    :param kw: as for `pipeline.resampleSequence` (`device` is set per worker)
+    """
+    import queue
+    import threading
+    import torch
+    from .pipeline import resampleSequence
+    images, headers = list(imagesOrArrays), list(wcsHeaders)
+    metadatas = kw.pop('metadatas', None)
+    if devices is None:
+        devices = list(range(torch.cuda.device_count()))
+    n = len(devices)
+    assert n >= 1
+    queues = [queue.Queue(maxsize=queueDepth) for _ in devices]
+    stop = threading.Event()
+    _END = object()
+
+    def worker(k):
+        q = queues[k]
+        try:
+            idx = shardIndices(len(headers), k, n)
+            with torch.cuda.device(devices[k]):
+                opts = dict(kw, device=devices[k])
+                if metadatas:
+                    opts['metadatas'] = [metadatas[i] for i in idx]
+                for f in resampleSequence([images[i] for i in idx], [headers[i] for i in idx], **opts):
+                    while not stop.is_set():
+                        try:
+                            q.put(f, timeout=0.1)
+                            break
+                        except queue.Full:
+                            continue
+                    if stop.is_set():
+                        return
+            q.put(_END)
+        except BaseException as e:        # handed to the consumer, in order
+            q.put(e)
+
+    threads = [threading.Thread(target=worker, args=(k,), daemon=True) for k in range(n)]
+    for t in threads:
+        t.start()
+    try:
+        for i in range(len(headers)):
+            item = queues[i % n].get()
+            if isinstance(item, BaseException):
+                raise item
+            assert item is not _END
+            yield item
+    finally:
+        stop.set()
+        for t in threads:
+            t.join(timeout=5)

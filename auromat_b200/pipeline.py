@@ -654,6 +654,7 @@ def _engineSequence(ctx, imagesOrArrays, wcsHeaders, pxPerDeg, arcsecPerPx, alti
         accBytes = (2 + C) * cells * 8
         # one device allocation per frame: accumulators | image | mask | elevation (caller's stream)
         flat = torch.empty(accBytes + total.value, dtype=torch.uint8, device=ctx.torch_device)
+        flat.record_stream(eng.copy)                     # zeroed there, normalised / downloaded on `dout`
         flat.record_stream(eng.dout)
         out = flat[accBytes:]
         item = 1 if eng.amtDtype == _lib.AMT_U8 else 2
@@ -691,11 +692,13 @@ def _engineSequence(ctx, imagesOrArrays, wcsHeaders, pxPerDeg, arcsecPerPx, alti
             eng.owner[slot] = weakref.ref(m)
         f = ResampledFrame(m, grid, info, dImg, dMask, dElev)
         f._src = hostImg                                 # the host image must outlive the asynchronous upload
+        handle, lib_ = eng.handle, lib
+        waiter = lambda: _lib.check(lib_.amt_seq_wait_result(handle, slot))      # noqa: E731
         if toHost:
-            handle, lib_ = eng.handle, lib
             f._attachHost(hostFlat, [0, offMask.value, offSide.value],
-                          [cells * C * item, cells, cells * 8], bucket,
-                          lambda: _lib.check(lib_.amt_seq_wait_result(handle, slot)))
+                          [cells * C * item, cells, cells * 8], bucket, waiter)
+        else:
+            f._event = _Waiter(waiter)       # normalised on the output stream: complete before the frame is handed out
         return f
 
     try:
@@ -714,6 +717,10 @@ def _engineSequence(ctx, imagesOrArrays, wcsHeaders, pxPerDeg, arcsecPerPx, alti
             f._finish()
             yield f
     finally:
+        if stageA or stageB:
+            # abandoned mid-sequence (error, consumer stopped): frames with work in flight are being
+            # dropped -- their buffers must not return to any allocator before that work is done
+            torch.cuda.synchronize(ctx.torch_device)
         if eng is not None:
             now = ctypes.c_uint64(0)
             lib.amt_seq_h2d_bytes(eng.handle, ctypes.byref(now))

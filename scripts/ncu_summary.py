@@ -2,6 +2,11 @@
 
     python scripts/ncu_summary.py report gpurun_out/prof.ncu-rep  > profiles/rNN_kernel.txt
     python scripts/ncu_summary.py launches gpurun_out/launches.csv > profiles/rNN_launches.txt
+    python scripts/ncu_summary.py json gpurun_out/prof.ncu-rep "<command that was profiled>" > profiles/r02_ncu_kernels.json
+
+The `json` form is what bench.py loads for `roofline.ncu` / `roofline.traffic` (no literals in bench.py):
+per kernel the duration, DRAM bytes, pipe utilisation and executed-instruction counters, stamped with
+the git commit of the tree the summary was made from.
 """
 import collections
 import csv
@@ -85,6 +90,53 @@ def report(path):
             print('  %-10s %14d %5.1f%%' % (k, v, 100.0 * v / max(tot, 1)))
 
 
+def to_json(path, command=''):
+    import json
+    raw = list(csv.reader(io.StringIO(ncu(['-i', path, '--page', 'raw', '--csv']))))
+    hdr = raw[0]
+    kernels = {}
+    short = {
+        'gpu__time_duration.sum': 'duration_ns',
+        'dram__bytes_read.sum': 'dram_bytes_read', 'dram__bytes_write.sum': 'dram_bytes_write',
+        'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active': 'pipe_fp64_pct',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active': 'issue_active_pct',
+        'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active': 'pipe_alu_pct',
+        'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active': 'pipe_fma_pct',
+        'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active': 'pipe_lsu_pct',
+        'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active': 'pipe_xu_pct',
+        'smsp__inst_executed.sum': 'warp_instructions',
+        'smsp__sass_thread_inst_executed_op_dfma_pred_on.sum': 'thread_dfma',
+        'smsp__sass_thread_inst_executed_op_dmul_pred_on.sum': 'thread_dmul',
+        'smsp__sass_thread_inst_executed_op_dadd_pred_on.sum': 'thread_dadd',
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed': 'dram_throughput_pct',
+        'launch__registers_per_thread': 'registers',
+        'sm__warps_active.avg.pct_of_peak_sustained_active': 'warps_active_pct',
+        'lts__t_sectors_op_red.sum': 'l2_red_sectors', 'lts__t_sectors_op_atom.sum': 'l2_atom_sectors',
+    }
+    units = raw[1]
+
+    def scale(v, u):
+        v = float(v.replace(',', ''))
+        return v * {'Mbyte': 1e6, 'Kbyte': 1e3, 'Gbyte': 1e9, 'us': 1e3, 'ms': 1e6, 'msecond': 1e6, 'usecond': 1e3,
+                    'second': 1e9}.get(u, 1.0)
+    for row in raw[2:]:
+        name = row[hdr.index('Kernel Name')].replace('void ', '')
+        if name in kernels:
+            continue
+        k = {}
+        for h, u, v in zip(hdr, units, row):
+            if h in short:
+                try:
+                    k[short[h]] = scale(v, u)
+                except ValueError:
+                    pass
+        if 'dram_bytes_read' in k and 'dram_bytes_write' in k:
+            k['dram_bytes'] = k['dram_bytes_read'] + k['dram_bytes_write']
+        kernels[name] = k
+    git = subprocess.run(['git', 'rev-parse', '--short', 'HEAD'], capture_output=True, text=True).stdout.strip()
+    print(json.dumps({'git': git, 'command': command, 'report': path, 'kernels': kernels}, indent=1))
+
+
 def launches(path):
     rows = [r for r in csv.reader(open(path)) if len(r) > 5]
     hdr = rows[0]
@@ -103,4 +155,4 @@ def launches(path):
 
 
 if __name__ == '__main__':
-    {'report': report, 'launches': launches}[sys.argv[1]](sys.argv[2])
+    {'report': report, 'launches': launches, 'json': to_json}[sys.argv[1]](*sys.argv[2:])

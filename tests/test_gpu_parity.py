@@ -1522,3 +1522,28 @@ def test_sphere_earth_model(env):
     w = assert_coords_close(gpu_arrays(m), g)
     e = getMapping(synthetic.issImage(W, H), hdr, nosanitize=True, identifier='e')
     assert np.nanmax(np.abs(e.latsCenter.filled(np.nan) - m.latsCenter.filled(np.nan))) > 1e-3   # the models differ
+
+
+def test_single_consumer_multi_gpu_sequence(env):
+    """parallel.resampleSequenceMultiGPU hands the frames of all devices to one consumer in sequence
+    order (the shape of getMappingSequence); on every visible device count the results equal the
+    single-device sequence."""
+    import torch
+    from auromat_b200 import synthetic
+    from auromat_b200.parallel import resampleSequenceMultiGPU
+    from auromat_b200.pipeline import resampleSequence
+    W, H, n = 300, 200, 9
+    hdrs = synthetic.sequenceHeaders(n, W, H)
+    imgs = [synthetic.issImage(W, H, seed=70 + i) for i in range(n)]
+    expect = [(f.img, f.mapping.identifier) for f in resampleSequence(imgs, hdrs, arcsecPerPx=400)]
+    for devices in ([0], list(range(torch.cuda.device_count()))):
+        got = list(resampleSequenceMultiGPU(imgs, hdrs, devices=devices, arcsecPerPx=400))
+        assert len(got) == n
+        for f, (e, _) in zip(got, expect):
+            assert np.array_equal(ma.getmaskarray(f.img), ma.getmaskarray(e))
+            assert np.array_equal(f.img.filled(0), e.filled(0))
+    with pytest.raises(ValueError):           # an error in a worker reaches the consumer
+        sky = dict(hdrs[0])
+        sky['CRVAL2'] = -hdrs[0]['CRVAL2']
+        sky['CRVAL1'] = (hdrs[0]['CRVAL1'] + 180.0) % 360.0
+        list(resampleSequenceMultiGPU(imgs[:3], [hdrs[0], sky, hdrs[2]], devices=[0], arcsecPerPx=400))
