@@ -99,6 +99,7 @@ SIGNATURES = {
     "amt_ctx_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "amt_ctx_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "amt_measure_fp64_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    "amt_measure_atomic_peak": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_double)]),
     "amt_alloc_device": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "amt_free_device": (C.c_int, [C.c_void_p, C.c_void_p]),
     "amt_alloc_pinned": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),

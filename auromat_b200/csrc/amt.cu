@@ -235,6 +235,46 @@ extern "C" int amt_measure_fp64_peak(amt_ctx* ctx, double* dfma_per_second) {
     return AMT_OK;
 }
 
+// ------------------------------------------------------------------ L2 atomic peak probe
+// Throughput ceiling of the scatter: u64 atomicAdd (RED) to pseudo-random cells of a grid of `cells`
+// words, 32 distinct addresses per warp instruction -- the pattern of the run tails of the binning.
+__global__ void __launch_bounds__(256) k_atomic_peak(unsigned long long* grid, unsigned int cells, int iters) {
+    unsigned int h = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    for (int i = 0; i < iters; ++i) {
+        h = h * 1664525u + 1013904223u;
+        atomicAdd(&grid[(h >> 4) % cells], 1ULL);
+    }
+}
+
+extern "C" int amt_measure_atomic_peak(amt_ctx* ctx, size_t cells, double* atomics_per_second) {
+    ENTER(ctx);
+    CHECK_ARG(atomics_per_second && cells > 0 && cells < (1ULL << 31), "amt_measure_atomic_peak: bad arguments");
+    void* scratch = nullptr;
+    int rc = ensure_scratch(ctx, (cudaStream_t)0, cells * 8, &scratch);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemset(scratch, 0, cells * 8));
+    const int blocks = ctx->sm_count * 8, iters = 256;
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    k_atomic_peak<<<blocks, 256>>>((unsigned long long*)scratch, (unsigned int)cells, 16);
+    float best = 1e30f;
+    for (int r = 0; r < 5; ++r) {
+        CUDA_TRY(cudaEventRecord(e0));
+        k_atomic_peak<<<blocks, 256>>>((unsigned long long*)scratch, (unsigned int)cells, iters);
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    ctx->launches += 6;
+    *atomics_per_second = (double)blocks * 256 * iters / (best * 1e-3);
+    return AMT_OK;
+}
+
 // ===================================================================== georeference
 struct GeorefParams {
     FrameC f;
@@ -242,8 +282,22 @@ struct GeorefParams {
     double sip_b[AMT_SIP_MAX_COEF];
     amt_georef_out o;
     unsigned long long* ill;     // n_ill_conditioned counter (nullable)
-    unsigned int corner_rows;    // rows of corners handled by blockIdx.y < corner_rows (points kernel)
+    // Row permutation of the point kernels: grid row r works on image row (r * row_stride) % rows,
+    // row_stride coprime to rows and close to rows / golden ratio.  An ISS limb frame is ~40 % sky at
+    // the top: in image order the kernel would first run a store-only phase (NaN rows, HBM bound) and
+    // then an FP64-bound phase; permuted, every window of consecutive CTAs holds the frame's mix of
+    // both, so the NaN stores of some CTAs overlap the arithmetic of their neighbours on the same SM.
+    unsigned int row_stride;
 };
+
+static unsigned int gcd_u(unsigned int a, unsigned int b) { return b ? gcd_u(b, a % b) : a; }
+static unsigned int golden_stride(unsigned int rows) {
+    if (rows < 3 || getenv("AMT_NO_ROW_PERMUTATION")) return 1;
+    unsigned int s = (unsigned int)(rows * 0.6180339887498949);
+    if (s < 1) s = 1;
+    while (gcd_u(s, rows) != 1) ++s;
+    return s % rows ? s % rows : 1;
+}
 
 // Writes NaN to every requested plane of one point (a ray that misses the ellipsoid).
 __device__ __forceinline__ void emit_nan(size_t i, double* __restrict__ a, double* __restrict__ b,
@@ -302,7 +356,7 @@ template <bool WANT_K, bool WANT_C, bool FULL, bool PLAIN = false>
 #endif
 __global__ void __launch_bounds__(256, AMT_GEOREF_MINBLOCKS) k_georef_points(const __grid_constant__ GeorefParams p) {
     const int W = p.f.W, H = p.f.H;
-    const int y = blockIdx.y;
+    const int y = (int)((blockIdx.y * p.row_stride) % gridDim.y);
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in_k = WANT_K && x <= W;
     const bool in_c = WANT_C && x < W && y < H;
@@ -719,6 +773,7 @@ extern "C" int amt_georef(amt_ctx* ctx, const amt_frame* frame, const amt_georef
                             out->d_valid_c;
         if (!want_k && !want_c) return AMT_OK;
         dim3 grid((W + 1 + 255) / 256, want_k ? H + 1 : H);
+        p.row_stride = golden_stride(grid.y);
         const bool any_plane = out->d_lat_k || out->d_lon_k || out->d_mlat_k || out->d_mlt_k || out->d_lat_c ||
                                out->d_lon_c || out->d_mlat_c || out->d_mlt_c || out->d_elev_c;
         if (!any_plane) {                          // validity bitmaps only
@@ -1920,7 +1975,7 @@ k_georef_fused(const __grid_constant__ GeorefParams p, const uint32_t* __restric
                unsigned long long* __restrict__ count, unsigned long long* __restrict__ sums,
                double* __restrict__ fsum) {
     const int W = p.f.W, H = p.f.H;
-    const int y = blockIdx.y;
+    const int y = (int)((blockIdx.y * p.row_stride) % gridDim.y);
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     __shared__ double s_sip[SIP ? 2 * AMT_SIP_MAX_COEF : 1];
     if (SIP) {
@@ -2091,6 +2146,7 @@ static int georef_fused(amt_ctx* ctx, const amt_frame* frame, const amt_georef_o
     const bool sip = frame->sip_order_a != 0 || frame->sip_order_b != 0;
     const int W = frame->width, H = frame->height;
     dim3 lg(((planes ? W + 1 : W) + 255) / 256, planes ? H + 1 : H);
+    p.row_stride = golden_stride(lg.y);
     unsigned long long* cnt = (unsigned long long*)d_count;
     unsigned long long* sm = (unsigned long long*)d_sums;
     if (bin && dtype == AMT_U16)

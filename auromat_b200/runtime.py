@@ -112,6 +112,12 @@ class Context:
         _lib.check(self.lib.amt_measure_fp64_peak(self.handle, C.byref(v)))
         return v.value
 
+    def measure_atomic_peak(self, cells: int) -> float:
+        """u64 atomicAdd per second to pseudo-random words of a `cells`-word grid (L2 scatter ceiling)."""
+        v = C.c_double()
+        _lib.check(self.lib.amt_measure_atomic_peak(self.handle, int(cells), C.byref(v)))
+        return v.value
+
     # ------------------------------------------------------------------ kernels
     @staticmethod
     def out_struct(planes: dict):

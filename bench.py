@@ -507,6 +507,28 @@ def dominant_kernel(args, ctx, img_dev, header, rank):
         # planes written for every pixel + the image samples of the defined centres
         algo_bytes = ALGO_BYTES_PER_PIXEL_GEOREF * npx + ALGO_BYTES_PER_PIXEL_IMAGE * n_valid
     fp64_peak = ctx.measure_fp64_peak() if rank == 0 else 0.0     # warp-lane DFMA/s (2 FLOP each)
+    scatter = None
+    if rank == 0 and not args.fast_center:
+        # the scatter of the fused kernel against the measured L2 atomic ceiling: run tails x (count + channels
+        # + elevation) atomics per launch
+        peak_atomics = ctx.measure_atomic_peak(5 * cells)
+        # exact number of run tails: a run = consecutive lanes of a warp (32 pixels of a row, 32-aligned)
+        # that fall into the same cell
+        ix, iy = ctx.cell_indices(planes['lat_c'], planes['lon_c'], grid)
+        cell = torch.where((ix >= 0) & (iy >= 0), iy.long() * grid.nx + ix.long(), torch.full_like(ix, -1).long())
+        Wp = (W + 31) // 32 * 32
+        padded = torch.full((H, Wp), -1, dtype=torch.long, device=cell.device)
+        padded[:, :W] = cell.view(H, W)
+        lanes = padded.view(H, Wp // 32, 32)
+        head = torch.ones_like(lanes, dtype=torch.bool)
+        head[:, :, 1:] = lanes[:, :, 1:] != lanes[:, :, :-1]
+        runs = int((head & (lanes >= 0)).sum().item())
+        atomics = 5 * runs                   # count + 3 channel sums + elevation per run
+        scatter = {"atomic_peak_per_s": peak_atomics, "cells": int(cells),
+                   "cells_touched": int((acc[:cells] > 0).sum().item()), "runs_per_launch": runs,
+                   "pixels_per_run": n_valid / max(1, runs), "atomics_per_launch": atomics,
+                   "atomic_rate_per_s": atomics / (k_ms * 1e-3),
+                   "frac_of_atomic_peak": atomics / (k_ms * 1e-3) / peak_atomics}
     peaks, peak_kind = measured_peaks()
     hbm = algo_bytes / (k_ms * 1e-3) / 1e9
     tflops = ALGO_FLOP_PER_PIXEL_GEOREF * npx / (k_ms * 1e-3) / 1e12
@@ -527,6 +549,7 @@ def dominant_kernel(args, ctx, img_dev, header, rank):
         "hbm": {"achieved": hbm, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm / peaks["hbm_gbs"],
                 "peak_kind": peak_kind, "algorithmic_bytes_per_launch": algo_bytes},
         "valid_pixels": n_valid,
+        "scatter": scatter,
         # executed-instruction view from the committed ncu capture of this kernel (None: no capture yet)
         "traffic": (ncu or {}).get("dram_bytes"),
         "ncu": ncu,

@@ -178,6 +178,12 @@ int amt_ctx_launch_count(const amt_ctx* ctx, uint64_t* count);
  * roofline denominator of bench.py (FLOP/s = 2 x that).  Synchronises.                      */
 int amt_measure_fp64_peak(amt_ctx* ctx, double* dfma_per_second);
 
+/* Measures the L2 atomic ceiling of the scatter: u64 atomicAdd to pseudo-random words of a grid of
+ * `cells` accumulators (32 distinct addresses per warp instruction, the pattern of the binning's run
+ * tails): *atomics_per_second.  The denominator against which the binning's atomic rate is judged
+ * (why the scatter is not privatised in shared memory).  Synchronises.                 */
+int amt_measure_atomic_peak(amt_ctx* ctx, size_t cells, double* atomics_per_second);
+
 /* Plain memory helpers so that a C caller does not need the CUDA runtime API.            */
 int amt_alloc_device(amt_ctx* ctx, size_t bytes, void** d_ptr);
 int amt_free_device(amt_ctx* ctx, void* d_ptr);

@@ -7,13 +7,12 @@
 import math
 import os
 import sys
-import time
 
 import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from auromat_b200 import synthetic, _lib                                     # noqa: E402
+from auromat_b200 import synthetic                                     # noqa: E402
 from auromat_b200.mapping.spacecraft import getMapping                        # noqa: E402
 from auromat_b200.resample import targetGrid, sideScale, plateCarreeResolution  # noqa: E402
 from auromat_b200.runtime import get_context                                  # noqa: E402
@@ -150,6 +149,10 @@ def main():
         t = {}
         t['georef old (9 planes)'] = timeit(lambda: ctx.georef(fr, old))
         t['fused planes+mag'] = timeit(lambda: ctx.georef_fused(fr, bits['valid_k'], bits['valid_c'], planes=new))
+        os.environ['AMT_NO_ROW_PERMUTATION'] = '1'
+        t['georef old, rows in image order'] = timeit(lambda: ctx.georef(fr, old))
+        t['fused planes+mag, rows in image order'] = timeit(lambda: ctx.georef_fused(fr, bits['valid_k'], bits['valid_c'], planes=new))
+        os.environ.pop('AMT_NO_ROW_PERMUTATION')
         nomag = {k: v for k, v in new.items() if not k.startswith('ml')}
         t['fused planes no mag'] = timeit(lambda: ctx.georef_fused(fr, bits['valid_k'], bits['valid_c'], planes=nomag))
         raw = {}
