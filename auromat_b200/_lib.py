@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libauromat_b200.so")
+# AMT_LIB: development only -- A/B runs of differently compiled builds of the same sources on the GPU box
+LIB_PATH = os.environ.get("AMT_LIB") or os.path.join(_HERE, "csrc", "libauromat_b200.so")
 
 ABI_VERSION = 3          # AMT_ABI_VERSION of include/auromat_b200.h
 AMT_OK, AMT_ERR_INVALID_ARGUMENT, AMT_ERR_UNSUPPORTED, AMT_ERR_CUDA, AMT_ERR_NO_DEVICE = range(5)

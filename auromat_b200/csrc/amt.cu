@@ -1964,35 +1964,142 @@ extern "C" int amt_normalise(amt_ctx* ctx, const amt_grid* grid, int32_t dtype, 
 // statistics and therefore the target grid.  One pass then does everything per pixel: corner ray
 // and centre ray -> intersection -> lat/lon, MLat/MLT, elevation -> (PLANES) the nine coordinate
 // planes, NaN where the bitmaps say so -- no later NaN patching -- and (BIN) the cell of the centre
-// on the target grid and the run-aggregated accumulation of its image sample, with the
-// coordinates still in registers: the binning pass never re-reads 27 B/pixel of planes.
+// on the target grid and the accumulation of its image sample, with the coordinates still in
+// registers: the binning pass never re-reads 27 B/pixel of planes.
 //   PLANES = false, BIN = true is the plane-free resampling (3 B/pixel in, the grids out).
-// A warp whose bitmap words are empty writes its NaNs (PLANES) and leaves.
+//
+// Launch shape: a CTA is a TILE of kFusedCols x kFusedRows pixels (32 x 8: each warp one 32-pixel
+// row segment, i.e. one word of each bitmap and 256-byte coalesced plane stores).  The scatter is
+// PRIVATISED IN SHARED MEMORY per tile (resample.py:330-338 / histogram.py:244-250 `bincount`): the
+// tile's samples land in a small window of the target grid (~12 x 7 cells at 100"/px), whose
+// bounds come from one warp min/max reduction per row segment; samples are added with 32-bit
+// shared-memory atomics (count and u8 channel sums packed two per word, the fixed-point elevation
+// split 24 | 40 bits), and each touched cell of the window is flushed ONCE with global 64-bit
+// reductions.  Per pixel that is 4 ATOMS instead of the ~100-instruction segmented warp scan of
+// warp_accumulate, and ~2x fewer global atomics than the run-aggregated strips.  A tile whose
+// window exceeds the shared-memory capacity (grid much finer than the pixels: every sample its own
+// cell, nothing to privatise) or that needs f64 side sums uses warp_accumulate directly.
+#ifndef AMT_FUSED_ROWS
+#define AMT_FUSED_ROWS 8
+#endif
+constexpr int kFusedRows = AMT_FUSED_ROWS;
+constexpr int kFusedCols = 256 / kFusedRows;
+constexpr int kTileWords = 3072;                 // 12 KB of shared memory per CTA
+static_assert(kFusedCols % 32 == 0 && kFusedCols * kFusedRows == 256, "a warp is one row segment of the tile");
+
+template <typename T, int C>
+struct TileAcc {
+    static constexpr int NF = 1 + C;                       // count + channels
+    static constexpr int PER = sizeof(T) == 1 ? 2 : 1;     // u8: 16-bit fields (256 * 255 < 2^16, count <= 256)
+    static constexpr int SHIFT = 32 / PER;
+    static constexpr int NW = (NF + PER - 1) / PER;
+    static constexpr int WORDS = NW + 2;                   // + fixed-point side channel: low 24 bits | rest
+    static constexpr int CAP = kTileWords / WORDS;         // cells of the window
+    static constexpr unsigned FMASK = PER == 2 ? 0xffffu : 0xffffffffu;
+};
+
+// Tile-privatised accumulation (all 256 threads of the CTA call it; s_acc zeroed, s_win =
+// {INT_MAX, INT_MAX, -1, -1} and a barrier passed since).  (ix, fy) = column and output row of the
+// sample's cell, cell < 0 = no sample.  Returns false if the tile must take the global path.
+template <typename T, int C>
+__device__ __forceinline__ bool tile_accumulate(int cell, int ix, int fy, const unsigned (&val)[C],
+                                                unsigned long long sfx, bool has_side, unsigned* s_acc, int* s_win,
+                                                int nx, size_t plane, unsigned long long* __restrict__ count,
+                                                unsigned long long* __restrict__ sums,
+                                                unsigned long long* __restrict__ fsum) {
+    using A = TileAcc<T, C>;
+    const unsigned lane = threadIdx.x & 31;
+    const bool ok = cell >= 0;
+    const int mnx = __reduce_min_sync(0xffffffffu, ok ? ix : 0x7fffffff);
+    const int mny = __reduce_min_sync(0xffffffffu, ok ? fy : 0x7fffffff);
+    const int mxx = __reduce_max_sync(0xffffffffu, ok ? ix : -1);
+    const int mxy = __reduce_max_sync(0xffffffffu, ok ? fy : -1);
+    if (lane == 0 && mxx >= 0) {
+        atomicMin(&s_win[0], mnx); atomicMin(&s_win[1], mny);
+        atomicMax(&s_win[2], mxx); atomicMax(&s_win[3], mxy);
+    }
+    __syncthreads();
+    const int x0 = s_win[0], y0 = s_win[1], x1 = s_win[2], y1 = s_win[3];
+    if (x1 < 0) return true;                              // no sample of this tile lands in the grid
+    const int wx = x1 - x0 + 1, wy = y1 - y0 + 1;
+    if (wy > A::CAP || wx > A::CAP || wx * wy > A::CAP) return false;      // CTA-uniform
+    if (ok) {
+        const int loc = (fy - y0) * wx + (ix - x0);
+        unsigned w[A::NW];
+#pragma unroll
+        for (int k = 0; k < A::NW; ++k) w[k] = 0u;
+        w[0] = 1u;
+#pragma unroll
+        for (int c = 0; c < C; ++c) w[(c + 1) / A::PER] |= val[c] << (((c + 1) % A::PER) * A::SHIFT);
+#pragma unroll
+        for (int k = 0; k < A::NW; ++k) atomicAdd(&s_acc[k * A::CAP + loc], w[k]);
+        if (has_side) {
+            atomicAdd(&s_acc[A::NW * A::CAP + loc], (unsigned)(sfx & 0xffffffu));
+            atomicAdd(&s_acc[(A::NW + 1) * A::CAP + loc], (unsigned)(int)((long long)sfx >> 24));
+        }
+    }
+    __syncthreads();
+    const int wcells = wx * wy;
+    for (int i = threadIdx.x; i < wcells; i += 256) {
+        unsigned w[A::NW];
+#pragma unroll
+        for (int k = 0; k < A::NW; ++k) w[k] = s_acc[k * A::CAP + i];
+        const unsigned n = w[0] & A::FMASK;
+        if (n == 0) continue;
+        const int ly = i / wx, lx = i - ly * wx;
+        const size_t gc = (size_t)(y0 + ly) * nx + (x0 + lx);
+        atomicAdd(&count[gc], (unsigned long long)n);
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+            atomicAdd(&sums[(size_t)c * plane + gc],
+                      (unsigned long long)((w[(c + 1) / A::PER] >> (((c + 1) % A::PER) * A::SHIFT)) & A::FMASK));
+        if (has_side) {
+            const long long hi = (long long)(int)s_acc[(A::NW + 1) * A::CAP + i];
+            const long long tot = hi * 16777216LL + (long long)s_acc[A::NW * A::CAP + i];
+            atomicAdd(&fsum[gc], (unsigned long long)tot);
+        }
+    }
+    return true;
+}
+
 template <typename T, int C, bool PLANES, bool MAG, bool BIN, bool SIP>
 __global__ void __launch_bounds__(256, AMT_GEOREF_MINBLOCKS)
 k_georef_fused(const __grid_constant__ GeorefParams p, const uint32_t* __restrict__ valid_k,
                const uint32_t* __restrict__ valid_c, const T* __restrict__ img, const __grid_constant__ GridC g,
                unsigned long long* __restrict__ count, unsigned long long* __restrict__ sums,
                double* __restrict__ fsum) {
+    constexpr bool PRIV = BIN && kFusedRows > 1;
     const int W = p.f.W, H = p.f.H;
-    const int y = (int)((blockIdx.y * p.row_stride) % gridDim.y);
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = (int)((blockIdx.y * p.row_stride) % gridDim.y) * kFusedRows + (int)(threadIdx.x / kFusedCols);
+    const int x = blockIdx.x * kFusedCols + (int)(threadIdx.x % kFusedCols);
     __shared__ double s_sip[SIP ? 2 * AMT_SIP_MAX_COEF : 1];
+    __shared__ unsigned s_acc[PRIV ? kTileWords : 1];
+    __shared__ int s_win[4];
     if (SIP) {
         if (threadIdx.x < 2 * AMT_SIP_MAX_COEF)
             s_sip[threadIdx.x] = threadIdx.x < AMT_SIP_MAX_COEF ? p.sip_a[threadIdx.x]
                                                                 : p.sip_b[threadIdx.x - AMT_SIP_MAX_COEF];
-        __syncthreads();
     }
+    if (PRIV) {
+#pragma unroll
+        for (int i = 0; i < kTileWords / 256; ++i) s_acc[i * 256 + threadIdx.x] = 0u;
+        if (threadIdx.x < 4) s_win[threadIdx.x] = threadIdx.x < 2 ? 0x7fffffff : -1;
+    }
+    if (SIP || PRIV) __syncthreads();
     const unsigned lane = threadIdx.x & 31, xw = (unsigned)x >> 5;
     const int wk = (W + 1 + 31) >> 5, wc = (W + 31) >> 5;
-    const unsigned mk = (PLANES && xw < (unsigned)wk) ? valid_k[(unsigned)y * wk + xw] : 0u;
+    const unsigned mk = (PLANES && y <= H && xw < (unsigned)wk) ? valid_k[(unsigned)y * wk + xw] : 0u;
     const unsigned mc = (y < H && xw < (unsigned)wc) ? valid_c[(unsigned)y * wc + xw] : 0u;
-    const bool in_k = PLANES && x <= W;
+    const bool in_k = PLANES && x <= W && y <= H;
     const bool in_c = x < W && y < H;
     // fill_frame guarantees (W+1)*(H+1) < 2^31: 32-bit flat indices
     const unsigned ik = (unsigned)y * (unsigned)(W + 1) + (unsigned)x, ic = (unsigned)y * (unsigned)W + (unsigned)x;
     const double nan = qnan();
+    int cell = -1, cx = -1, cy = -1;
+    unsigned val[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) val[c] = 0u;
+    double elev = 0.0;
     if ((mk | mc) == 0) {                    // nothing defined in this warp's 32 pixels
         if (PLANES) {
             if (in_k) {
@@ -2004,65 +2111,69 @@ k_georef_fused(const __grid_constant__ GeorefParams p, const uint32_t* __restric
                 if (MAG) { p.o.d_mlat_c[ic] = nan; p.o.d_mlt_c[ic] = nan; }
             }
         }
-        return;
-    }
-    const bool vk = (mk >> lane) & 1u, vc = (mc >> lane) & 1u;
-    // the image sample travels with the thread from the start: its latency hides under the FP64 chain
-    unsigned val[C];
+        if (!PRIV) return;
+    } else {
+        const bool vk = (mk >> lane) & 1u, vc = (mc >> lane) & 1u;
+        // the image sample travels with the thread from the start: its latency hides under the FP64 chain
+        if (BIN && vc) {
 #pragma unroll
-    for (int c = 0; c < C; ++c) val[c] = 0u;
-    if (BIN && vc) {
-#pragma unroll
-        for (int c = 0; c < C; ++c) val[c] = (unsigned)img[(size_t)ic * C + c];
-    }
-    double dk[3], dc[3], Pk[3], Pc[3];
-    dirs_kc<SIP>(p.f, s_sip, s_sip + (SIP ? AMT_SIP_MAX_COEF : 0), x, y, dk, dc);
-    bool gz;
-    // valid elements hit by construction (same arithmetic as the hit test).  An undefined element gets
-    // a NaN into the first coordinate of its point: every dot product downstream then is NaN, i.e. all
-    // nine outputs come out NaN without a select per plane (the reference's NaN rows, for free).
-    if (PLANES) intersect(p.f, dk, Pk, gz);
-    intersect(p.f, dc, Pc, gz);
-    if (PLANES && !vk) Pk[0] = nan;
-    if (!vc) Pc[0] = nan;
-    double la_c, lo_c, r2_c;
-    {
-        double la_k, lo_k;
-        if (PLANES) point_to_geo(p.f, Pk, la_k, lo_k);
-        point_to_geo(p.f, Pc, la_c, lo_c, r2_c);
-        if (PLANES) {
-            if (in_k) { p.o.d_lat_k[ik] = la_k; p.o.d_lon_k[ik] = lo_k; }
-            if (in_c) { p.o.d_lat_c[ic] = la_c; p.o.d_lon_c[ic] = lo_c; }
+            for (int c = 0; c < C; ++c) val[c] = (unsigned)img[(size_t)ic * C + c];
         }
-    }
-    if (PLANES && MAG) {
-        double ml_k, mt_k, ml_c, mt_c;
-        point_to_mag(p.f, Pk, ml_k, mt_k);
-        point_to_mag(p.f, Pc, ml_c, mt_c);
-        if (in_k) { p.o.d_mlat_k[ik] = ml_k; p.o.d_mlt_k[ik] = mt_k; }
-        if (in_c) { p.o.d_mlat_c[ic] = ml_c; p.o.d_mlt_c[ic] = mt_c; }
-    }
-    double elev = 0.0;
-    if (PLANES || (BIN && fsum != nullptr)) {
-        elev = elevation_deg<false>(dc, Pc, r2_c);
-        if (PLANES && in_c) p.o.d_elev_c[ic] = elev;
+        double dk[3], dc[3], Pk[3], Pc[3];
+        dirs_kc<SIP>(p.f, s_sip, s_sip + (SIP ? AMT_SIP_MAX_COEF : 0), x, y, dk, dc);
+        bool gz;
+        // valid elements hit by construction (same arithmetic as the hit test).  An undefined element gets
+        // a NaN into the first coordinate of its point: every dot product downstream then is NaN, i.e. all
+        // nine outputs come out NaN without a select per plane (the reference's NaN rows, for free).
+        if (PLANES) intersect(p.f, dk, Pk, gz);
+        intersect(p.f, dc, Pc, gz);
+        if (PLANES && !vk) Pk[0] = nan;
+        if (!vc) Pc[0] = nan;
+        double la_c, lo_c, r2_c;
+        {
+            double la_k, lo_k;
+            if (PLANES) point_to_geo(p.f, Pk, la_k, lo_k);
+            point_to_geo(p.f, Pc, la_c, lo_c, r2_c);
+            if (PLANES) {
+                if (in_k) { p.o.d_lat_k[ik] = la_k; p.o.d_lon_k[ik] = lo_k; }
+                if (in_c) { p.o.d_lat_c[ic] = la_c; p.o.d_lon_c[ic] = lo_c; }
+            }
+        }
+        if (PLANES && MAG) {
+            double ml_k, mt_k, ml_c, mt_c;
+            point_to_mag(p.f, Pk, ml_k, mt_k);
+            point_to_mag(p.f, Pc, ml_c, mt_c);
+            if (in_k) { p.o.d_mlat_k[ik] = ml_k; p.o.d_mlt_k[ik] = mt_k; }
+            if (in_c) { p.o.d_mlat_c[ic] = ml_c; p.o.d_mlt_c[ic] = mt_c; }
+        }
+        if (PLANES || (BIN && fsum != nullptr)) {
+            elev = elevation_deg<false>(dc, Pc, r2_c);
+            if (PLANES && in_c) p.o.d_elev_c[ic] = elev;
+        }
+        if (BIN && vc) {
+            bool near;
+            cell = cell_of<false>(g, la_c, lo_c, cx, cy, near);
+        }
+        if (BIN && !PRIV) {
+            if (__ballot_sync(0xffffffffu, cell >= 0) == 0) return;       // warp-uniform
+        }
     }
     if (BIN) {
-        if (mc == 0) return;                                   // warp-uniform
-        int cell = -1;
-        if (vc) {
-            int ix, iy;
-            bool near;
-            cell = cell_of<false>(g, la_c, lo_c, ix, iy, near);
-        }
-        if (__ballot_sync(0xffffffffu, cell >= 0) == 0) return;
         if (cell < 0) {
 #pragma unroll
             for (int c = 0; c < C; ++c) val[c] = 0u;
         }
         const size_t plane = (size_t)g.nx * g.ny;
+        const bool fixed = g.side_scale > 0.0;
+        if (PRIV && (fsum == nullptr || fixed)) {
+            const unsigned long long sfx = (fsum != nullptr && cell >= 0) ? to_fixed(elev, g.side_scale) : 0ULL;
+            if (tile_accumulate<T, C>(cell, cx, g.ny - 1 - cy, val, sfx, fsum != nullptr, s_acc, s_win, g.nx, plane,
+                                      count, sums, (unsigned long long*)fsum))
+                return;
+        }
+        if (__ballot_sync(0xffffffffu, cell >= 0) == 0) return;
         if (fsum == nullptr) warp_accumulate<T, C, kSideNone>(cell, val, 0.0, 0ULL, count, sums, fsum, plane);
-        else if (g.side_scale > 0.0)
+        else if (fixed)
             warp_accumulate<T, C, kSideFixed>(cell, val, 0.0, cell >= 0 ? to_fixed(elev, g.side_scale) : 0ULL, count,
                                               sums, fsum, plane);
         else warp_accumulate<T, C, kSideF64>(cell, val, cell >= 0 ? elev : 0.0, 0ULL, count, sums, fsum, plane);
@@ -2145,7 +2256,7 @@ static int georef_fused(amt_ctx* ctx, const amt_frame* frame, const amt_georef_o
     }
     const bool sip = frame->sip_order_a != 0 || frame->sip_order_b != 0;
     const int W = frame->width, H = frame->height;
-    dim3 lg(((planes ? W + 1 : W) + 255) / 256, planes ? H + 1 : H);
+    dim3 lg(((planes ? W + 1 : W) + kFusedCols - 1) / kFusedCols, ((planes ? H + 1 : H) + kFusedRows - 1) / kFusedRows);
     p.row_stride = golden_stride(lg.y);
     unsigned long long* cnt = (unsigned long long*)d_count;
     unsigned long long* sm = (unsigned long long*)d_sums;

@@ -508,6 +508,7 @@ class _Engine(object):
                                           ctypes.c_void_p(self.copy.cuda_stream),
                                           ctypes.c_void_p(self.dout.cuda_stream), ctypes.byref(self.handle)))
         self.slots = [None] * nslots          # per slot: dict of tensors
+        self.hasImage = [False] * nslots      # the slot's amt_seq_slot carries its image-ring pointer
         self.owner = [None] * nslots          # weakref to the mapping that currently shows the slot's planes
         self.hostStats = torch.zeros((nslots, ctypes.sizeof(_lib.AmtStats)), dtype=torch.uint8).pin_memory()
         self.devStats = torch.zeros((nslots, ctypes.sizeof(_lib.AmtStats)), dtype=torch.uint8, device=dev)
@@ -539,6 +540,7 @@ class _Engine(object):
         sl.d_img = self.imgRing[slot].data_ptr() if self.imgRing is not None else None
         _lib.check(self.ctx.lib.amt_seq_set_slot(self.handle, slot, ctypes.byref(sl)))
         self.slots[slot] = buffers
+        self.hasImage[slot] = self.imgRing is not None
 
     def __del__(self):
         try:
@@ -608,7 +610,8 @@ def _engineSequence(ctx, imagesOrArrays, wcsHeaders, pxPerDeg, arcsecPerPx, alti
         if ringBuffers:
             if eng.slots[slot] is None:
                 eng.setSlot(slot, eng.newBuffers(), hostImg is not None)
-            elif hostImg is not None and eng.imgRing is None:
+            elif hostImg is not None and not eng.hasImage[slot]:
+                # an engine first used with device images gets its image ring with the first host image
                 eng.setSlot(slot, eng.slots[slot], True)
         else:
             b = eng.newBuffers()                        # per-frame planes: valid as long as the frame lives

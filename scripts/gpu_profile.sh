@@ -1,0 +1,20 @@
+#!/bin/bash
+# ncu evidence of a round (run on the B200 box through gpurun; summaries are made in the build
+# container with scripts/ncu_summary.py and committed under profiles/).
+#   gpurun --timeout 1200 -- 'bash scripts/gpu_profile.sh r02'
+set -u
+tag=${1:-r02}
+out=gpurun_out
+mkdir -p $out
+# 1. every launch of a short bench run with its device time (cold-cache, serialised: compare SHARES)
+ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 400 --csv --log-file $out/launches_$tag.csv \
+    python bench.py --steps 12 --warmup 3 --repeats 1 --no-variants --no-cpu-baseline > $out/bench_under_ncu_$tag.log 2>&1
+# 2. full counter set of one launch of every kernel of the step (after warm-up)
+ncu --set full --clock-control none --import-source on \
+    -k regex:'k_georef_fused|k_limb_bits|k_sanitize_fused|k_stats_bits|k_normalise' -s 40 -c 5 -f -o $out/step_$tag \
+    python bench.py --steps 6 --warmup 3 --repeats 1 --no-variants --no-cpu-baseline > $out/ncu_step_$tag.log 2>&1
+# 3. the scatter in three regimes: atomics / L2 counters of k_bin and k_georef_fused
+ncu --set full --clock-control none -k regex:'k_bin|k_georef_fused' -f -o $out/scatter_$tag \
+    python scripts/bin_scatter.py > $out/ncu_scatter_$tag.log 2>&1
+REPS=10 python scripts/bin_scatter.py > $out/scatter_times_$tag.txt 2>&1
+ls -la $out | tail -12

@@ -32,12 +32,16 @@ def test_reference_arm_json_line():
 
 @pytest.mark.gpu
 def test_b200_arm_json_line():
-    d = _run(["--steps", "4", "--warmup", "3", "--width", "1064", "--height", "708", "--cpu-baseline-scale", "4"])
+    d = _run(["--steps", "4", "--warmup", "3", "--width", "1064", "--height", "708", "--repeats", "2"])
     assert COMMON | {"roofline", "gpu_launches", "clocks", "frames_per_s"} <= set(d)
     assert "impl" not in d and d["n_gpus"] == 1 and d["dtype"] == "f64" and d["data"] == "synthetic"
-    assert d["gpu_launches"] >= 4 * 5
+    assert d["gpu_launches"] >= 4 * 4
     r = d["roofline"]
-    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    # the dominant kernel is bound by the FP64 pipe; the HBM view of the same launch rides along
+    assert r["bound"] == "fp64" and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    h = r["hbm"]
+    assert h["unit"] == "GB/s" and abs(h["frac"] - h["achieved"] / h["peak"]) < 1e-12
+    assert d["parity"]["pass"] is True and d["parity"]["mask_mismatches"] == 0
     # only the image rows that hold georeferenced pixels are uploaded (pipeline sparseUpload)
     full = 1064 * 708 * 3
     assert d["e2e"]["h2d_bytes_full_frame"] == full and 0.4 * full < d["e2e"]["h2d_bytes_per_step"] < 0.8 * full
