@@ -164,6 +164,7 @@ SIGNATURES = {
     "amt_seq_stage_b": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(AmtSeqJob)]),
     "amt_seq_wait_result": (C.c_int, [C.c_void_p, C.c_int32]),
     "amt_seq_h2d_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "amt_seq_trace": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_double)]),
     "amt_georef_bin_fused": (C.c_int, [C.c_void_p, C.POINTER(AmtFrame), C.c_void_p, C.c_void_p, C.c_int32,
                                        C.c_int32, C.POINTER(AmtGrid), C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),

@@ -24,6 +24,7 @@ struct SeqSlot {
     bool is_set;
     amt_frame frame;
     cudaEvent_t ev_a, ev_up, ev_b, ev_out;
+    cudaEvent_t tr_a0, tr_up0, tr_b0;      // trace mode only: starts of stage A, of the upload, of the fused kernel
     bool a_rec, b_rec, out_rec;
 };
 
@@ -33,6 +34,8 @@ struct amt_seq {
     cudaStream_t s_main, s_aux, s_copy, s_out;
     std::vector<SeqSlot> slots;
     unsigned long long h2d_bytes;
+    bool trace;                            // AMT_SEQ_TRACE: timing events, see amt_seq_trace
+    cudaEvent_t ev_base;
 };
 
 static size_t seq_align64(size_t n) { return (n + 63) / 64 * 64; }
@@ -64,13 +67,22 @@ extern "C" int amt_seq_create(amt_ctx* ctx, int32_t width, int32_t height, int32
     s->s_main = (cudaStream_t)main_stream; s->s_aux = (cudaStream_t)aux_stream;
     s->s_copy = (cudaStream_t)copy_stream; s->s_out = (cudaStream_t)out_stream;
     s->h2d_bytes = 0;
+    const char* tr = getenv("AMT_SEQ_TRACE");
+    s->trace = tr && tr[0] && tr[0] != '0';
+    s->ev_base = nullptr;
+    if (s->trace) {
+        CUDA_TRY(cudaEventCreate(&s->ev_base));
+        CUDA_TRY(cudaEventRecord(s->ev_base, s->s_main));
+    }
     s->slots.resize(n_slots);
     for (auto& sl : s->slots) {
         memset(&sl.buf, 0, sizeof sl.buf);
         sl.is_set = sl.a_rec = sl.b_rec = sl.out_rec = false;
-        cudaEvent_t* evs[4] = {&sl.ev_a, &sl.ev_up, &sl.ev_b, &sl.ev_out};
-        for (auto e : evs) {
-            cudaError_t err = cudaEventCreateWithFlags(e, cudaEventDisableTiming);
+        sl.tr_a0 = sl.tr_up0 = sl.tr_b0 = nullptr;
+        cudaEvent_t* evs[7] = {&sl.ev_a, &sl.ev_up, &sl.ev_b, &sl.ev_out, &sl.tr_a0, &sl.tr_up0, &sl.tr_b0};
+        for (int k = 0; k < (s->trace ? 7 : 4); ++k) {
+            cudaEvent_t* e = evs[k];
+            cudaError_t err = cudaEventCreateWithFlags(e, s->trace ? cudaEventDefault : cudaEventDisableTiming);
             if (err != cudaSuccess) {
                 delete s;
                 return set_err(AMT_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(err));
@@ -86,7 +98,9 @@ extern "C" int amt_seq_destroy(amt_seq* seq) {
     cudaSetDevice(seq->ctx->device);
     for (auto& sl : seq->slots) {
         cudaEventDestroy(sl.ev_a); cudaEventDestroy(sl.ev_up); cudaEventDestroy(sl.ev_b); cudaEventDestroy(sl.ev_out);
+        if (seq->trace) { cudaEventDestroy(sl.tr_a0); cudaEventDestroy(sl.tr_up0); cudaEventDestroy(sl.tr_b0); }
     }
+    if (seq->ev_base) cudaEventDestroy(seq->ev_base);
     delete seq;
     return AMT_OK;
 }
@@ -119,6 +133,7 @@ extern "C" int amt_seq_stage_a(amt_seq* seq, int32_t slot, const amt_frame* fram
     cudaStream_t st = seq->s_aux;
     // the bitmaps of this slot are read by the fused kernel of the slot's previous frame
     if (sl.b_rec) CUDA_TRY(cudaStreamWaitEvent(st, sl.ev_b, 0));
+    if (seq->trace) CUDA_TRY(cudaEventRecord(sl.tr_a0, st));
     amt_georef_out bits;
     memset(&bits, 0, sizeof bits);
     bits.d_valid_k = sl.buf.planes.d_valid_k;
@@ -207,6 +222,7 @@ extern "C" int amt_seq_stage_b(amt_seq* seq, int32_t slot, const amt_seq_job* jo
     const void* d_img = job->d_img ? job->d_img : sl.buf.d_img;
     if (!d_img) { nvtxRangePop(); return set_err(AMT_ERR_INVALID_ARGUMENT, "amt_seq_stage_b: no device image buffer"); }
     // copy stream: zeroed accumulators of this frame + the pixel box of the host image
+    if (seq->trace) CUDA_TRY(cudaEventRecord(sl.tr_up0, seq->s_copy));
     CUDA_TRY(cudaMemsetAsync(job->d_acc, 0, (size_t)(2 + seq->C) * cells * 8, seq->s_copy));
     if (job->h_img && !job->d_img) {
         // the slot's image buffer is read by the fused kernel of the slot's previous frame
@@ -239,6 +255,7 @@ extern "C" int amt_seq_stage_b(amt_seq* seq, int32_t slot, const amt_seq_job* jo
     uint64_t* sums = count + cells;
     double* fsum = (double*)(count + (size_t)(1 + seq->C) * cells);
     const amt_georef_out* planes = sl.buf.planes.d_lat_k ? &sl.buf.planes : nullptr;
+    if (seq->trace) CUDA_TRY(cudaEventRecord(sl.tr_b0, st));
     rc = georef_fused(ctx, &sl.frame, planes, sl.buf.planes.d_valid_k, sl.buf.planes.d_valid_c, d_img, seq->dtype,
                       seq->C, g, count, sums, fsum, st);
     if (rc) { nvtxRangePop(); return rc; }
@@ -262,6 +279,25 @@ extern "C" int amt_seq_wait_result(amt_seq* seq, int32_t slot) {
     CHECK_ARG(sl.b_rec, "amt_seq_wait_result: stage B has not been submitted for this slot");
     // results are produced on the output stream: a host-level wait makes them visible to every stream
     CUDA_TRY(cudaEventSynchronize(sl.out_rec ? sl.ev_out : sl.ev_b));
+    return AMT_OK;
+}
+
+// Trace mode (the engine was created with AMT_SEQ_TRACE=1 in the environment): device timeline of the
+// slot's last frame in ms since the engine was created: {stage A start, stage A end (statistics on the
+// host), upload start, upload end, fused kernel start, fused kernel end, results complete}.  Call after
+// amt_seq_wait_result and before the slot is reused.
+extern "C" int amt_seq_trace(amt_seq* seq, int32_t slot, double* out_ms7) {
+    SEQ_SLOT(seq, slot);
+    CHECK_ARG(out_ms7, "amt_seq_trace: NULL argument");
+    if (!seq->trace) return set_err(AMT_ERR_UNSUPPORTED, "amt_seq_trace: engine created without AMT_SEQ_TRACE=1");
+    CHECK_ARG(sl.a_rec && sl.b_rec && sl.out_rec, "amt_seq_trace: the slot has no complete frame");
+    CUDA_TRY(cudaEventSynchronize(sl.ev_out));
+    cudaEvent_t evs[7] = {sl.tr_a0, sl.ev_a, sl.tr_up0, sl.ev_up, sl.tr_b0, sl.ev_b, sl.ev_out};
+    for (int k = 0; k < 7; ++k) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, seq->ev_base, evs[k]));
+        out_ms7[k] = ms;
+    }
     return AMT_OK;
 }
 

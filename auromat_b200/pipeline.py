@@ -445,6 +445,18 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
         return f
 
     ctx.use_stream(hMain)
+    tracing = bool(os.environ.get('AMT_SEQ_TRACE', '').strip('0'))
+
+    def handOut(f):
+        f._finish()
+        if tracing:
+            # device timeline of the frame (amt_seq_trace): ms since the engine was created
+            t = (ctypes.c_double * 7)()
+            _lib.check(lib.amt_seq_trace(eng.handle, f._slot, t))
+            stats.setdefault('trace', []).append(dict(zip(
+                ('a0', 'a1', 'up0', 'up1', 'k0', 'k1', 'out'), [float(v) for v in t])))
+        return f
+
     try:
         for i, (img, hdr) in enumerate(zip(imagesOrArrays, wcsHeaders)):
             stageA.append(runA(i, img, hdr))
@@ -695,6 +707,7 @@ def _engineSequence(ctx, imagesOrArrays, wcsHeaders, pxPerDeg, arcsecPerPx, alti
             eng.owner[slot] = weakref.ref(m)
         f = ResampledFrame(m, grid, info, dImg, dMask, dElev)
         f._src = hostImg                                 # the host image must outlive the asynchronous upload
+        f._slot = slot
         handle, lib_ = eng.handle, lib
         waiter = lambda: _lib.check(lib_.amt_seq_wait_result(handle, slot))      # noqa: E731
         if toHost:
@@ -704,21 +717,29 @@ def _engineSequence(ctx, imagesOrArrays, wcsHeaders, pxPerDeg, arcsecPerPx, alti
             f._event = _Waiter(waiter)       # normalised on the output stream: complete before the frame is handed out
         return f
 
+    tracing = bool(os.environ.get('AMT_SEQ_TRACE', '').strip('0'))
+
+    def handOut(f):
+        f._finish()
+        if tracing:
+            # device timeline of the frame (amt_seq_trace): ms since the engine was created
+            t = (ctypes.c_double * 7)()
+            _lib.check(lib.amt_seq_trace(eng.handle, f._slot, t))
+            stats.setdefault('trace', []).append(dict(zip(
+                ('a0', 'a1', 'up0', 'up1', 'k0', 'k1', 'out'), [float(v) for v in t])))
+        return f
+
     try:
         for i, (img, hdr) in enumerate(zip(imagesOrArrays, wcsHeaders)):
             stageA.append(runA(i, img, hdr))
             if len(stageA) >= depth:
                 stageB.append(runB(*stageA.popleft()))
             while len(stageB) > AHEAD_B:
-                f = stageB.popleft()
-                f._finish()
-                yield f
+                yield handOut(stageB.popleft())
         while stageA:
             stageB.append(runB(*stageA.popleft()))
         while stageB:
-            f = stageB.popleft()
-            f._finish()
-            yield f
+            yield handOut(stageB.popleft())
     finally:
         if stageA or stageB:
             # abandoned mid-sequence (error, consumer stopped): frames with work in flight are being

@@ -451,6 +451,12 @@ int amt_seq_stage_b(amt_seq* seq, int32_t slot, const amt_seq_job* job);
 int amt_seq_wait_result(amt_seq* seq, int32_t slot);
 /* Image bytes copied host -> device so far (bench.py h2d_bytes_per_step).                         */
 int amt_seq_h2d_bytes(const amt_seq* seq, uint64_t* bytes);
+/* Tracing (the reference logs wall-clock durations per stage, e.g. resample.py:139-141):
+ * with AMT_SEQ_TRACE=1 in the environment when the engine is created, every stream event of the engine
+ * carries a time stamp; out_ms7 = device times in ms since engine creation of {stage A start, stage A
+ * end, upload start, upload end, fused kernel start, fused kernel end, results complete} of the slot's
+ * last frame.  Call after amt_seq_wait_result, before the slot is reused. */
+int amt_seq_trace(amt_seq* seq, int32_t slot, double* out_ms7);
 
 #ifdef __cplusplus
 }
