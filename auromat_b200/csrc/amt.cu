@@ -1982,6 +1982,9 @@ extern "C" int amt_normalise(amt_ctx* ctx, const amt_grid* grid, int32_t dtype, 
 #ifndef AMT_FUSED_ROWS
 #define AMT_FUSED_ROWS 8
 #endif
+#ifndef AMT_FUSED_PRIV
+#define AMT_FUSED_PRIV 0
+#endif
 constexpr int kFusedRows = AMT_FUSED_ROWS;
 constexpr int kFusedCols = 256 / kFusedRows;
 constexpr int kTileWords = 3072;                 // 12 KB of shared memory per CTA
@@ -2068,7 +2071,7 @@ k_georef_fused(const __grid_constant__ GeorefParams p, const uint32_t* __restric
                const uint32_t* __restrict__ valid_c, const T* __restrict__ img, const __grid_constant__ GridC g,
                unsigned long long* __restrict__ count, unsigned long long* __restrict__ sums,
                double* __restrict__ fsum) {
-    constexpr bool PRIV = BIN && kFusedRows > 1;
+    constexpr bool PRIV = BIN && kFusedRows > 1 && AMT_FUSED_PRIV != 0;
     const int W = p.f.W, H = p.f.H;
     const int y = (int)((blockIdx.y * p.row_stride) % gridDim.y) * kFusedRows + (int)(threadIdx.x / kFusedCols);
     const int x = blockIdx.x * kFusedCols + (int)(threadIdx.x % kFusedCols);

@@ -8,8 +8,8 @@
 //       All on the auxiliary high-priority stream: microsecond kernels that overlap the long
 //       kernel of the preceding frames.
 //   host:                          bounding box -> target grid (reference arithmetic, Python).
-//   stage B (grid + image):        zeroed accumulators + upload of the pixel box that holds defined
-//       pixels (copy stream) -> ONE fused kernel: coordinate planes + binning (main stream, nothing
+//   stage B (grid + image):        zeroed accumulators (auxiliary stream) + upload of the pixel box that holds defined
+//       pixels (copy stream: DMA only) -> ONE fused kernel: coordinate planes + binning (main stream, nothing
 //       else ever runs there: the long kernels follow each other back to back) -> normalise ->
 //       results to pinned host memory (output stream).
 //
@@ -23,7 +23,7 @@ struct SeqSlot {
     amt_seq_slot buf;
     bool is_set;
     amt_frame frame;
-    cudaEvent_t ev_a, ev_up, ev_b, ev_out;
+    cudaEvent_t ev_a, ev_up, ev_b, ev_out, ev_zero;
     cudaEvent_t tr_a0, tr_up0, tr_b0;      // trace mode only: starts of stage A, of the upload, of the fused kernel
     bool a_rec, b_rec, out_rec;
 };
@@ -79,8 +79,8 @@ extern "C" int amt_seq_create(amt_ctx* ctx, int32_t width, int32_t height, int32
         memset(&sl.buf, 0, sizeof sl.buf);
         sl.is_set = sl.a_rec = sl.b_rec = sl.out_rec = false;
         sl.tr_a0 = sl.tr_up0 = sl.tr_b0 = nullptr;
-        cudaEvent_t* evs[7] = {&sl.ev_a, &sl.ev_up, &sl.ev_b, &sl.ev_out, &sl.tr_a0, &sl.tr_up0, &sl.tr_b0};
-        for (int k = 0; k < (s->trace ? 7 : 4); ++k) {
+        cudaEvent_t* evs[8] = {&sl.ev_a, &sl.ev_up, &sl.ev_b, &sl.ev_out, &sl.ev_zero, &sl.tr_a0, &sl.tr_up0, &sl.tr_b0};
+        for (int k = 0; k < (s->trace ? 8 : 5); ++k) {
             cudaEvent_t* e = evs[k];
             cudaError_t err = cudaEventCreateWithFlags(e, s->trace ? cudaEventDefault : cudaEventDisableTiming);
             if (err != cudaSuccess) {
@@ -98,6 +98,7 @@ extern "C" int amt_seq_destroy(amt_seq* seq) {
     cudaSetDevice(seq->ctx->device);
     for (auto& sl : seq->slots) {
         cudaEventDestroy(sl.ev_a); cudaEventDestroy(sl.ev_up); cudaEventDestroy(sl.ev_b); cudaEventDestroy(sl.ev_out);
+        cudaEventDestroy(sl.ev_zero);
         if (seq->trace) { cudaEventDestroy(sl.tr_a0); cudaEventDestroy(sl.tr_up0); cudaEventDestroy(sl.tr_b0); }
     }
     if (seq->ev_base) cudaEventDestroy(seq->ev_base);
@@ -221,9 +222,15 @@ extern "C" int amt_seq_stage_b(amt_seq* seq, int32_t slot, const amt_seq_job* jo
     const size_t item = seq->dtype == AMT_U8 ? 1 : 2, px = item * seq->C, row_bytes = px * seq->W;
     const void* d_img = job->d_img ? job->d_img : sl.buf.d_img;
     if (!d_img) { nvtxRangePop(); return set_err(AMT_ERR_INVALID_ARGUMENT, "amt_seq_stage_b: no device image buffer"); }
-    // copy stream: zeroed accumulators of this frame + the pixel box of the host image
+    // zeroed accumulators of this frame: a memset is a KERNEL, and a kernel of an ordinary-priority stream
+    // gets its first CTA only when the fused kernel of the preceding frame has dispatched all of its own
+    // (47 k CTAs): on the copy stream it held back the upload behind it until that kernel's tail, i.e.
+    // upload and kernel ran one after the other (0.72 ms/frame instead of max(0.41, 0.31); AMT_SEQ_TRACE
+    // timeline, profiles/r02_seq_trace.txt).  The auxiliary stream has high priority: its CTAs go first.
+    CUDA_TRY(cudaMemsetAsync(job->d_acc, 0, (size_t)(2 + seq->C) * cells * 8, seq->s_aux));
+    CUDA_TRY(cudaEventRecord(sl.ev_zero, seq->s_aux));
+    // copy stream: nothing but DMA -- the pixel box of the host image
     if (seq->trace) CUDA_TRY(cudaEventRecord(sl.tr_up0, seq->s_copy));
-    CUDA_TRY(cudaMemsetAsync(job->d_acc, 0, (size_t)(2 + seq->C) * cells * 8, seq->s_copy));
     if (job->h_img && !job->d_img) {
         // the slot's image buffer is read by the fused kernel of the slot's previous frame
         if (sl.b_rec) CUDA_TRY(cudaStreamWaitEvent(seq->s_copy, sl.ev_b, 0));
@@ -250,7 +257,8 @@ extern "C" int amt_seq_stage_b(amt_seq* seq, int32_t slot, const amt_seq_job* jo
     // main stream: nothing but the long fused kernels, back to back from frame to frame
     cudaStream_t st = seq->s_main;
     CUDA_TRY(cudaStreamWaitEvent(st, sl.ev_a, 0));             // final bitmaps of this frame (auxiliary stream)
-    CUDA_TRY(cudaStreamWaitEvent(st, sl.ev_up, 0));            // accumulators zeroed, image on the device
+    CUDA_TRY(cudaStreamWaitEvent(st, sl.ev_up, 0));            // image on the device
+    CUDA_TRY(cudaStreamWaitEvent(st, sl.ev_zero, 0));          // accumulators zeroed
     uint64_t* count = job->d_acc;
     uint64_t* sums = count + cells;
     double* fsum = (double*)(count + (size_t)(1 + seq->C) * cells);

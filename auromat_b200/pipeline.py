@@ -669,7 +669,7 @@ def _engineSequence(ctx, imagesOrArrays, wcsHeaders, pxPerDeg, arcsecPerPx, alti
         accBytes = (2 + C) * cells * 8
         # one device allocation per frame: accumulators | image | mask | elevation (caller's stream)
         flat = torch.empty(accBytes + total.value, dtype=torch.uint8, device=ctx.torch_device)
-        flat.record_stream(eng.copy)                     # zeroed there, normalised / downloaded on `dout`
+        flat.record_stream(eng.aux)                      # zeroed there, normalised / downloaded on `dout`
         flat.record_stream(eng.dout)
         out = flat[accBytes:]
         item = 1 if eng.amtDtype == _lib.AMT_U8 else 2

@@ -1492,7 +1492,12 @@ def test_sip_device_polynomial_against_exact_rational_arithmetic(env):
     import torch
     from auromat_b200 import synthetic
     from auromat_b200.coordinates.wcs import frameConstants
-    from tests.test_oracle_golden import _sip_exact, sip_kat_points
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        'amt_test_oracle_golden', os.path.join(os.path.dirname(os.path.abspath(__file__)), 'test_oracle_golden.py'))
+    kat = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(kat)
+    _sip_exact, sip_kat_points = kat._sip_exact, kat.sip_kat_points
     hdr = synthetic.issHeader(6000, 4000, sipOrder=4)
     t, cam = synthetic.headerTimeAndCamera(hdr)
     fr = frameConstants(hdr, cam, t, 110)
