@@ -2124,12 +2124,11 @@ k_georef_fused(const __grid_constant__ GeorefParams p, const uint32_t* __restric
         }
         double dk[3], dc[3], Pk[3], Pc[3];
         dirs_kc<SIP>(p.f, s_sip, s_sip + (SIP ? AMT_SIP_MAX_COEF : 0), x, y, dk, dc);
-        bool gz;
         // valid elements hit by construction (same arithmetic as the hit test).  An undefined element gets
         // a NaN into the first coordinate of its point: every dot product downstream then is NaN, i.e. all
         // nine outputs come out NaN without a select per plane (the reference's NaN rows, for free).
-        if (PLANES) intersect(p.f, dk, Pk, gz);
-        intersect(p.f, dc, Pc, gz);
+        if (PLANES) intersect_valid(p.f, dk, Pk);
+        intersect_valid(p.f, dc, Pc);
         if (PLANES && !vk) Pk[0] = nan;
         if (!vc) Pc[0] = nan;
         double la_c, lo_c, r2_c;

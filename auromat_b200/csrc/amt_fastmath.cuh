@@ -154,7 +154,7 @@ AMT_HD double rsqrt_fast(double a) {
 // lat/lon/MLat, MLT = smlon/15 + 12, elevation).
 // FP64 instructions: 14 (+2 MUFU); the version with octant selects had 19 + 6 FSEL + 2 ISETP.
 // ---------------------------------------------------------------------------------------
-#define AMT_ATAN_TABLE                                                                       \
+#define AMT_ATAN_TABLE \
     0.0, 0.9093804491991414, 1.8476102659945957, \
     2.815556684211228, 3.8140748342903543, 4.844000375080679, \
     5.9061411137704996, 7.001267557495338, 8.130102354155978, \
@@ -176,51 +176,76 @@ AMT_HD double rsqrt_fast(double a) {
     79.5085229876684, 80.70669140060288, 81.86989764584402, \
     82.99873244250466, 84.0938588862295, 85.15599962491932, \
     86.18592516570965, 87.18444331578877, 88.15238973400541, \
-    89.09061955080085, 90.0, 180.0, \
-    179.09061955080085, 178.1523897340054, 177.18444331578877, \
-    176.18592516570965, 175.15599962491933, 174.0938588862295, \
-    172.99873244250466, 171.86989764584402, 170.7066914006029, \
-    169.5085229876684, 168.27488798483492, 167.0053832080835, \
-    165.6997225508144, 164.35775354279127, 162.97947438848016, \
-    161.56505117707798, 160.11483488614456, 158.6293777306568, \
-    157.10944834375167, 155.55604521958347, 153.97040780848656, \
-    152.35402463626133, 150.70863782901574, 149.03624346792648, \
-    147.3390872783262, 145.61965527615513, 143.88065915052024, \
-    142.1250163489018, 140.3558250428552, 138.57633437499734, \
-    136.78991060824606, 135.0, 133.21008939175394, \
-    131.42366562500266, 129.6441749571448, 127.8749836510982, \
-    126.11934084947976, 124.38034472384487, 122.66091272167381, \
-    120.96375653207352, 119.29136217098426, 117.64597536373867, \
-    116.02959219151346, 114.44395478041653, 112.89055165624832, \
-    111.37062226934319, 109.88516511385544, 108.43494882292201, \
-    107.02052561151986, 105.64224645720873, 104.30027744918559, \
-    102.9946167919165, 101.72511201516508, 100.4914770123316, \
-    99.29330859939712, 98.13010235415598, 97.00126755749534, \
-    95.9061411137705, 94.84400037508068, 93.81407483429035, \
-    92.81555668421123, 91.84761026599459, 90.90938044919915, \
-    90.0, \
+    89.09061955080085, 90.0, \
+    /* 65..127: padding, the x < 0 half starts at index 128 (one shift of the sign bit) */ \
+    0.0, 0.0, 0.0, \
+    0.0, 0.0, 0.0, \
+    0.0, 0.0, 0.0, \
+    0.0, 0.0, 0.0, \
+    0.0, 0.0, 0.0, \
+    0.0, 0.0, 0.0, \
+    0.0, 0.0, 0.0, \
+    0.0, 0.0, 0.0, \
+    0.0, 0.0, 0.0, \
+    0.0, 0.0, 0.0, \
+    0.0, 0.0, 0.0, \
+    0.0, 0.0, 0.0, \
+    0.0, 0.0, 0.0, \
+    0.0, 0.0, 0.0, \
+    0.0, 0.0, 0.0, \
+    0.0, 0.0, 0.0, \
+    0.0, 0.0, 0.0, \
+    0.0, 0.0, 0.0, \
+    0.0, 0.0, 0.0, \
+    0.0, 0.0, 0.0, \
+    0.0, 0.0, 0.0, \
+    180.0, 179.09061955080085, 178.1523897340054, \
+    177.18444331578877, 176.18592516570965, 175.15599962491933, \
+    174.0938588862295, 172.99873244250466, 171.86989764584402, \
+    170.7066914006029, 169.5085229876684, 168.27488798483492, \
+    167.0053832080835, 165.6997225508144, 164.35775354279127, \
+    162.97947438848016, 161.56505117707798, 160.11483488614456, \
+    158.6293777306568, 157.10944834375167, 155.55604521958347, \
+    153.97040780848656, 152.35402463626133, 150.70863782901574, \
+    149.03624346792648, 147.3390872783262, 145.61965527615513, \
+    143.88065915052024, 142.1250163489018, 140.3558250428552, \
+    138.57633437499734, 136.78991060824606, 135.0, \
+    133.21008939175394, 131.42366562500266, 129.6441749571448, \
+    127.8749836510982, 126.11934084947976, 124.38034472384487, \
+    122.66091272167381, 120.96375653207352, 119.29136217098426, \
+    117.64597536373867, 116.02959219151346, 114.44395478041653, \
+    112.89055165624832, 111.37062226934319, 109.88516511385544, \
+    108.43494882292201, 107.02052561151986, 105.64224645720873, \
+    104.30027744918559, 102.9946167919165, 101.72511201516508, \
+    100.4914770123316, 99.29330859939712, 98.13010235415598, \
+    97.00126755749534, 95.9061411137705, 94.84400037508068, \
+    93.81407483429035, 92.81555668421123, 91.84761026599459, \
+    90.90938044919915, 90.0, \
 
 #ifdef __CUDACC__
-__constant__ double c_atan_tab[130] = {
+__constant__ double c_atan_tab[193] = {
 AMT_ATAN_TABLE
 };
 // Constants whose low mantissa word is non-zero cannot be instruction immediates; kept in
 // constant memory they become direct c[bank][offset] operands of DFMA/DADD/DMUL instead of two
 // UMOV / IMAD.MOV each.
 __constant__ double c_fm[4] = {
-    11.459155902616464, -19.098593171027442, 57.29577951308232, 0.0,      // (180/pi) * {1/5, -1/3, 1}
+    11.459155902616464, -19.098593171027442, 57.29577951308232,           // (180/pi) * {1/5, -1/3, 1}
+    24.0 / 360.0,                                                         // hours per degree (smLonToMLT)
 };
 #endif
-static const double h_atan_tab[130] = {
+static const double h_atan_tab[193] = {
 AMT_ATAN_TABLE
 };
-static const double h_fm[4] = {11.459155902616464, -19.098593171027442, 57.29577951308232, 0.0};
+static const double h_fm[4] = {11.459155902616464, -19.098593171027442, 57.29577951308232, 24.0 / 360.0};
 
-AMT_HD double atan_tab(int i) {
+// entry at BYTE offset `off` (index * 8 + 1024 for the x < 0 half): the callers form the offset with one
+// multiply-add from the table index and the shifted sign bit
+AMT_HD double atan_tab_at(unsigned off) {
 #ifdef __CUDA_ARCH__
-    return c_atan_tab[i];
+    return *(const double*)((const char*)c_atan_tab + off);
 #else
-    return h_atan_tab[i];
+    return h_atan_tab[off >> 3];
 #endif
 }
 AMT_HD double fm_const(int i) {
@@ -235,9 +260,10 @@ AMT_HD double fabs_bits(double x) {        // |x| on the integer pipe, not the F
     return bits_to_double(hi_word(x) & 0x7fffffffu, lo_word(x));
 }
 
-// Angle of (b, a), a >= 0, b >= 0 (not both zero), plus table offset `k65` (0 or 65) and the
-// sign mask `flip` (0 or 0x80000000) applied to the remainder: the caller's quadrant logic.
-AMT_HD double atan_diamond_deg(double a, double b, int k65, unsigned flip) {
+// Angle of (b, a), a >= 0, b >= 0 (not both zero).  `xs` = sign bit of the caller's x (0 or
+// 0x80000000): it selects the table half (theta or 180 - theta, 1024 bytes further) and flips the
+// sign of the remainder -- the caller's quadrant logic in two integer instructions.
+AMT_HD double atan_diamond_deg(double a, double b, unsigned xs) {
     const double sum = a + b;
     const double dif = a - b;
     const double w = a * mufu_rcp(sum);
@@ -246,30 +272,36 @@ AMT_HD double atan_diamond_deg(double a, double b, int k65, unsigned flip) {
     const double magic = 105553116266496.0;      // 1.5 * 2^46
     const double wi = w + magic;
     // w is in [0, 1 + 2^-19]; the unsigned clamp also keeps NaN inputs (any bit pattern) inside the table
-    const int i = (int)min(lo_word(wi), 64u);
+    const unsigned off = min(lo_word(wi), 64u) * 8u + (xs >> 21);
     const double s = wi - magic;                 // == i/64 exactly (w is in [0, 1])
     const double num = fma(-s, sum, a);
     const double den = fma(s, dif, b);
     double t = div_38(num, den);
-    t = bits_to_double(hi_word(t) ^ flip, lo_word(t));
+    t = bits_to_double(hi_word(t) ^ xs, lo_word(t));
     const double z = t * t;
     double p = fm_const(0);
     p = fma(p, z, fm_const(1));
     p = fma(p, z, fm_const(2));
-    return fma(t, p, atan_tab(i + k65));
+    return fma(t, p, atan_tab_at(off));
 }
+
+// The diamond angle is >= 0 (theta >= 0 and the remainder cannot take it below: s = 0 means t >= 0, and
+// the x < 0 half starts at 180 - ...), so the sign of y is ORed in: one LOP3, no mask of the old sign.
+AMT_HD double with_sign_of(double r, unsigned ysign) { return bits_to_double(hi_word(r) | ysign, lo_word(r)); }
 
 // atan2(y, x) in degrees, any quadrant, finite inputs, not both zero.
 AMT_HD double atan2_deg(double y, double x) {
-    const unsigned xs = hi_word(x) & 0x80000000u;
-    const double r = atan_diamond_deg(fabs_bits(y), fabs_bits(x), xs ? 65 : 0, xs);
-    return bits_to_double((hi_word(r) & 0x7fffffffu) | (hi_word(y) & 0x80000000u), lo_word(r));
+    const unsigned ys = hi_word(y) & 0x80000000u, xs = hi_word(x) & 0x80000000u;
+    const double r = atan_diamond_deg(bits_to_double(hi_word(y) ^ ys, lo_word(y)),
+                                      bits_to_double(hi_word(x) ^ xs, lo_word(x)), xs);
+    return with_sign_of(r, ys);
 }
 
 // atan2(y, x) in degrees for x >= 0 (result in [-90, 90]); also serves atan(y/x) and asin.
 AMT_HD double atan2_posx_deg(double y, double x) {
-    const double r = atan_diamond_deg(fabs_bits(y), x, 0, 0u);
-    return bits_to_double((hi_word(r) & 0x7fffffffu) | (hi_word(y) & 0x80000000u), lo_word(r));
+    const unsigned ys = hi_word(y) & 0x80000000u;
+    const double r = atan_diamond_deg(bits_to_double(hi_word(y) ^ ys, lo_word(y)), x, 0u);
+    return with_sign_of(r, ys);
 }
 
 }  // namespace amt

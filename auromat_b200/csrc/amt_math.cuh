@@ -238,6 +238,24 @@ AMT_HD bool intersect(const FrameC& f, const double dir[3], double P[3], bool& g
     return true;
 }
 
+// The same point for a ray that is KNOWN to hit (the fused kernel reads the frame's final validity
+// bitmaps, which were produced with this very discriminant): no miss / behind-the-camera tests, no
+// grazing-ray bookkeeping, no branch -- the arithmetic of `intersect`, instruction for instruction, so
+// the coordinates are bit-identical.  For a ray that does not hit, the result is garbage or NaN; the
+// caller overwrites it.  `sgn` = +1 if the origin is inside the ellipsoid, else -1 (t = dDO + sgn root).
+AMT_HD void intersect_valid(const FrameC& f, const double dir[3], double P[3]) {
+    const double D0 = dir[0] * f.rad[0], D1 = dir[1] * f.rad[1], D2 = dir[2] * f.rad[2];
+    const double dDO = fma(D2, f.otr[2], fma(D1, f.otr[1], D0 * f.otr[0]));
+    const double dDD = fma(D2, D2, fma(D1, D1, D0 * D0));
+    const double rt = fma(dDO, dDO, fma(-f.oDO, dDD, dDD));
+    const double root = rt > 0.0 ? sqrt_fast(rt) : 0.0;
+    const double sgn = f.origin_inside ? 1.0 : -1.0;            // uniform
+    const double t = div_fast(fma(sgn, root, dDO), dDD);        // dDO +- root, exactly
+    P[0] = fma(dir[0], t, f.cam[0]);
+    P[1] = fma(dir[1], t, f.cam[1]);
+    P[2] = fma(dir[2], t, f.cam[2]);
+}
+
 // Hit test alone (validity bitmaps without any coordinate plane): same discriminant as
 // `intersect`, no square root and no division.  With the origin outside the ellipsoid
 // (oDO > 1) root^2 = dDO^2 - dDD (oDO - 1) < dDO^2, so sign(dDO - root) = sign(dDO); with the
@@ -330,7 +348,7 @@ AMT_HD void sm_to_mlat_mlt(const double S[3], double& mlat, double& mlt) {
     const double s = sqrt_fast(fma(S[0], S[0], S[1] * S[1]));
     const double smlon = atan2_deg(S[1], S[0]);
     mlat = atan2_posx_deg(S[2], s);
-    mlt = fma(smlon, 24.0 / 360.0, 12.0);
+    mlt = fma(smlon, fm_const(3), 12.0);
 }
 
 // elevation, mapping/astrometry.py:200-212 + utils.py:28-46: 90 - acos(clip(-dir . P/|P|)) with
@@ -389,20 +407,26 @@ template <bool NEAR>
 __device__ __forceinline__ int bin_index(double x, double lo, double hi, double step, double inv_step,
                                          int n, double round_scale, double eps, bool& near) {
     near = false;
+    if (!NEAR) {
+        // Shortcut: q = (x - lo)/step carries an error of a few ulp of q (<= n * 4e-16), and the
+        // numpy edges fl(fl(k*step) + lo) differ from lo + k*step by <= 2 ulp of max(|lo|,|hi|),
+        // i.e. by far less than `eps` cells (fill_grid sizes eps from exactly these bounds and
+        // sets it to 1 when the grid is too fine for the argument).  A sample whose fractional
+        // position is at least eps away from both ends of its cell is therefore on the same
+        // side of the true edges as of the ideal ones: the floor IS searchsorted(..)-1.
+        // Evaluated without floor / convert / range compares: qh = q - 1/2 rounded to the nearest
+        // integer by adding 1.5 * 2^52 is floor(q) (ties only for fr = 0, rejected below); the integer
+        // sits in the low mantissa word, and the high word equals that of the magic constant exactly
+        // when 0 <= floor(q) < 2^32 -- so two integer compares replace x >= lo, x < hi and k < n, and a
+        // NaN or an out-of-range sample falls through to the exact path.
+        const double magic = 6755399441055744.0;         // 1.5 * 2^52
+        const double qh = fma(__dsub_rn(x, lo), inv_step, -0.5);
+        const double tq = __dadd_rn(qh, magic);
+        const double d = __dsub_rn(qh, __dsub_rn(tq, magic));      // q - (floor(q) + 1/2)
+        const unsigned kq = lo_word(tq);
+        if (fabs(d) < 0.5 - eps && hi_word(tq) == 0x43380000u && kq < (unsigned)n) return (int)kq;
+    }
     if (x >= lo && x < hi) {
-        if (!NEAR) {
-            // Shortcut: q = (x - lo)/step carries an error of a few ulp of q (<= n * 4e-16), and the
-            // numpy edges fl(fl(k*step) + lo) differ from lo + k*step by <= 2 ulp of max(|lo|,|hi|),
-            // i.e. by far less than `eps` cells (fill_grid sizes eps from exactly these bounds and
-            // sets it to 1 when the grid is too fine for the argument).  A sample whose fractional
-            // position is at least eps away from both ends of its cell is therefore on the same
-            // side of the true edges as of the ideal ones: the floor IS searchsorted(..)-1.
-            const double q = __dmul_rn(__dsub_rn(x, lo), inv_step);
-            const double kf = floor(q);
-            const double fr = q - kf;
-            const int kq = (int)kf;
-            if (fr > eps && fr < 1.0 - eps && kq < n) return kq;
-        }
         // common case, branch-free: floor guess, then one correction step against the true
         // numpy edges e(k) = fl(fl(k*step) + lo), e(n) = hi
         // lo <= x < hi, so the guess is in 0..n (n only through rounding); no clamp of the double
