@@ -1985,8 +1985,13 @@ extern "C" int amt_normalise(amt_ctx* ctx, const amt_grid* grid, int32_t dtype, 
 #ifndef AMT_FUSED_PRIV
 #define AMT_FUSED_PRIV 0
 #endif
+#ifndef AMT_FUSED_ITER
+#define AMT_FUSED_ITER 4
+#endif
 constexpr int kFusedRows = AMT_FUSED_ROWS;
 constexpr int kFusedCols = 256 / kFusedRows;
+constexpr int kFusedIter = AMT_FUSED_ITER;       // 32 x 8 tiles per CTA (<= 32: one lane per iteration holds its bitmap words)
+static_assert(kFusedIter >= 1 && kFusedIter <= 32, "one lane per iteration");
 constexpr int kTileWords = 3072;                 // 12 KB of shared memory per CTA
 static_assert(kFusedCols % 32 == 0 && kFusedCols * kFusedRows == 256, "a warp is one row segment of the tile");
 
@@ -2065,34 +2070,16 @@ __device__ __forceinline__ bool tile_accumulate(int cell, int ix, int fy, const 
     return true;
 }
 
-template <typename T, int C, bool PLANES, bool MAG, bool BIN, bool SIP>
-__global__ void __launch_bounds__(256, AMT_GEOREF_MINBLOCKS)
-k_georef_fused(const __grid_constant__ GeorefParams p, const uint32_t* __restrict__ valid_k,
-               const uint32_t* __restrict__ valid_c, const T* __restrict__ img, const __grid_constant__ GridC g,
-               unsigned long long* __restrict__ count, unsigned long long* __restrict__ sums,
-               double* __restrict__ fsum) {
-    constexpr bool PRIV = BIN && kFusedRows > 1 && AMT_FUSED_PRIV != 0;
+// One 32-pixel row segment of the tile: everything the fused kernel does for pixel (x, y), given the
+// words mk / mc of the frame's final bitmaps that cover the warp's 32 corners / centres.
+template <typename T, int C, bool PLANES, bool MAG, bool BIN, bool SIP, bool PRIV>
+__device__ __forceinline__ void fused_row(const GeorefParams& p, const double* s_sip, unsigned* s_acc, int* s_win,
+                                          const int x, const int y, const unsigned mk, const unsigned mc,
+                                          const T* __restrict__ img, const GridC& g,
+                                          unsigned long long* __restrict__ count,
+                                          unsigned long long* __restrict__ sums, double* __restrict__ fsum) {
     const int W = p.f.W, H = p.f.H;
-    const int y = (int)((blockIdx.y * p.row_stride) % gridDim.y) * kFusedRows + (int)(threadIdx.x / kFusedCols);
-    const int x = blockIdx.x * kFusedCols + (int)(threadIdx.x % kFusedCols);
-    __shared__ double s_sip[SIP ? 2 * AMT_SIP_MAX_COEF : 1];
-    __shared__ unsigned s_acc[PRIV ? kTileWords : 1];
-    __shared__ int s_win[4];
-    if (SIP) {
-        if (threadIdx.x < 2 * AMT_SIP_MAX_COEF)
-            s_sip[threadIdx.x] = threadIdx.x < AMT_SIP_MAX_COEF ? p.sip_a[threadIdx.x]
-                                                                : p.sip_b[threadIdx.x - AMT_SIP_MAX_COEF];
-    }
-    if (PRIV) {
-#pragma unroll
-        for (int i = 0; i < kTileWords / 256; ++i) s_acc[i * 256 + threadIdx.x] = 0u;
-        if (threadIdx.x < 4) s_win[threadIdx.x] = threadIdx.x < 2 ? 0x7fffffff : -1;
-    }
-    if (SIP || PRIV) __syncthreads();
-    const unsigned lane = threadIdx.x & 31, xw = (unsigned)x >> 5;
-    const int wk = (W + 1 + 31) >> 5, wc = (W + 31) >> 5;
-    const unsigned mk = (PLANES && y <= H && xw < (unsigned)wk) ? valid_k[(unsigned)y * wk + xw] : 0u;
-    const unsigned mc = (y < H && xw < (unsigned)wc) ? valid_c[(unsigned)y * wc + xw] : 0u;
+    const unsigned lane = threadIdx.x & 31;
     const bool in_k = PLANES && x <= W && y <= H;
     const bool in_c = x < W && y < H;
     // fill_frame guarantees (W+1)*(H+1) < 2^31: 32-bit flat indices
@@ -2182,6 +2169,53 @@ k_georef_fused(const __grid_constant__ GeorefParams p, const uint32_t* __restric
     }
 }
 
+// A CTA works on kFusedIter vertically adjacent 32 x 8 tiles, one after the other (warp w: row w of each).
+// The bitmap words of ALL its row segments are fetched by one load per bitmap at the start (lane r holds the
+// words of iteration r): the ~1 us of launch + L2 latency that precedes the first FP64 instruction of a warp
+// -- 16 % of all warp residency in the one-row-per-warp version (profiles/r02_fused_stalls.txt) -- is paid
+// once per kFusedIter rows.
+template <typename T, int C, bool PLANES, bool MAG, bool BIN, bool SIP>
+__global__ void __launch_bounds__(256, AMT_GEOREF_MINBLOCKS)
+k_georef_fused(const __grid_constant__ GeorefParams p, const uint32_t* __restrict__ valid_k,
+               const uint32_t* __restrict__ valid_c, const T* __restrict__ img, const __grid_constant__ GridC g,
+               unsigned long long* __restrict__ count, unsigned long long* __restrict__ sums,
+               double* __restrict__ fsum) {
+    constexpr bool PRIV = BIN && kFusedRows > 1 && AMT_FUSED_PRIV != 0;
+    const int W = p.f.W, H = p.f.H;
+    const int ty = (int)((blockIdx.y * p.row_stride) % gridDim.y);
+    const int y0 = ty * (kFusedRows * kFusedIter) + (int)(threadIdx.x / kFusedCols);
+    const int x = blockIdx.x * kFusedCols + (int)(threadIdx.x % kFusedCols);
+    __shared__ double s_sip[SIP ? 2 * AMT_SIP_MAX_COEF : 1];
+    __shared__ unsigned s_acc[PRIV ? kTileWords : 1];
+    __shared__ int s_win[4];
+    if (SIP) {
+        if (threadIdx.x < 2 * AMT_SIP_MAX_COEF)
+            s_sip[threadIdx.x] = threadIdx.x < AMT_SIP_MAX_COEF ? p.sip_a[threadIdx.x]
+                                                                : p.sip_b[threadIdx.x - AMT_SIP_MAX_COEF];
+        __syncthreads();
+    }
+    const unsigned lane = threadIdx.x & 31, xw = (unsigned)x >> 5;
+    const int wk = (W + 1 + 31) >> 5, wc = (W + 31) >> 5;
+    const int yl = y0 + (int)lane * kFusedRows;               // lane r < kFusedIter: the row of iteration r
+    const bool mine = lane < (unsigned)kFusedIter;
+    const unsigned mkv = (PLANES && mine && yl <= H && xw < (unsigned)wk) ? valid_k[(unsigned)yl * wk + xw] : 0u;
+    const unsigned mcv = (mine && yl < H && xw < (unsigned)wc) ? valid_c[(unsigned)yl * wc + xw] : 0u;
+#pragma unroll 1
+    for (int r = 0; r < kFusedIter; ++r) {
+        const int y = y0 + r * kFusedRows;
+        if (!PRIV && y > H) break;                            // warp-uniform
+        const unsigned mk = __shfl_sync(0xffffffffu, mkv, r), mc = __shfl_sync(0xffffffffu, mcv, r);
+        if (PRIV) {
+            if (r) __syncthreads();
+#pragma unroll
+            for (int i = 0; i < kTileWords / 256; ++i) s_acc[i * 256 + threadIdx.x] = 0u;
+            if (threadIdx.x < 4) s_win[threadIdx.x] = threadIdx.x < 2 ? 0x7fffffff : -1;
+            __syncthreads();
+        }
+        fused_row<T, C, PLANES, MAG, BIN, SIP, PRIV>(p, s_sip, s_acc, s_win, x, y, mk, mc, img, g, count, sums, fsum);
+    }
+}
+
 template <typename T, int C, bool PLANES, bool MAG, bool BIN>
 static void launch_fused_sip(bool sip, dim3 grid, cudaStream_t st, const GeorefParams& p, const uint32_t* vk,
                              const uint32_t* vc, const T* img, const GridC& g, unsigned long long* count,
@@ -2258,7 +2292,8 @@ static int georef_fused(amt_ctx* ctx, const amt_frame* frame, const amt_georef_o
     }
     const bool sip = frame->sip_order_a != 0 || frame->sip_order_b != 0;
     const int W = frame->width, H = frame->height;
-    dim3 lg(((planes ? W + 1 : W) + kFusedCols - 1) / kFusedCols, ((planes ? H + 1 : H) + kFusedRows - 1) / kFusedRows);
+    const int tile_rows = kFusedRows * kFusedIter;
+    dim3 lg(((planes ? W + 1 : W) + kFusedCols - 1) / kFusedCols, ((planes ? H + 1 : H) + tile_rows - 1) / tile_rows);
     p.row_stride = golden_stride(lg.y);
     unsigned long long* cnt = (unsigned long long*)d_count;
     unsigned long long* sm = (unsigned long long*)d_sums;

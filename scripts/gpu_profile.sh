@@ -7,7 +7,7 @@ tag=${1:-r02}
 out=gpurun_out
 mkdir -p $out
 # 1. every launch of a short bench run with its device time (cold-cache, serialised: compare SHARES)
-ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 400 --csv --log-file $out/launches_$tag.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 300 --csv --log-file $out/launches_$tag.csv \
     python bench.py --steps 12 --warmup 3 --repeats 1 --no-variants --no-cpu-baseline > $out/bench_under_ncu_$tag.log 2>&1
 # 2. full counter set of one launch of every kernel of the step (after warm-up)
 ncu --set full --clock-control none --import-source on \
