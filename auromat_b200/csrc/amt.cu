@@ -736,7 +736,7 @@ static int fill_frame(const amt_frame* fr, GeorefParams& p) {
     volatile double num = aa - bb;
     volatile double e2 = num / aa;
     f.a = a; f.b = b;
-    f.b_over_a = b / a;
+    f.b_over_a = 2.0 * (b / a);       // 2 b/a: the kernels hold 0.5/p (an exact doubling folded into the constant)
     f.e2a = e2 * a;
     f.d = num / b;
     f.sip_oa = fr->sip_order_a; f.sip_ob = fr->sip_order_b;
@@ -1288,7 +1288,8 @@ extern "C" int amt_bbox_stats_frame(amt_ctx* ctx, const amt_frame* frame, const 
     CUDA_TRY(cudaMemcpyAsync(dp, &p, sizeof p, cudaMemcpyHostToDevice, st));
     Bits K{d_valid_k, wk, H + 1}, C{d_valid_c, wc, H};
     const int words = wk * (H + 1);
-    const int blocks = max(1, min(ctx->sm_count * 4, (words + 255) / 256));
+    static const int per_sm = getenv("AMT_STATS_BLOCKS_PER_SM") ? atoi(getenv("AMT_STATS_BLOCKS_PER_SM")) : 4;
+    const int blocks = max(1, min(ctx->sm_count * per_sm, (words + 255) / 256));
     k_stats_bits<<<blocks, 256, 0, st>>>(W, H, K, C, nullptr, nullptr, g, keys, dp, d_stats);
     LAUNCH_CHECK(ctx);
     return AMT_OK;
@@ -1988,12 +1989,16 @@ extern "C" int amt_normalise(amt_ctx* ctx, const amt_grid* grid, int32_t dtype, 
 #ifndef AMT_FUSED_ITER
 #define AMT_FUSED_ITER 4
 #endif
-constexpr int kFusedRows = AMT_FUSED_ROWS;
-constexpr int kFusedCols = 256 / kFusedRows;
+constexpr int kFusedRows = AMT_FUSED_ROWS;       // rows of a tile = warps of the CTA
+constexpr int kFusedCols = 32;
+constexpr int kFusedThreads = kFusedCols * kFusedRows;
+#ifndef AMT_FUSED_MINBLOCKS
+#define AMT_FUSED_MINBLOCKS (AMT_GEOREF_MINBLOCKS * 256 / (32 * AMT_FUSED_ROWS))
+#endif
 constexpr int kFusedIter = AMT_FUSED_ITER;       // 32 x 8 tiles per CTA (<= 32: one lane per iteration holds its bitmap words)
 static_assert(kFusedIter >= 1 && kFusedIter <= 32, "one lane per iteration");
 constexpr int kTileWords = 3072;                 // 12 KB of shared memory per CTA
-static_assert(kFusedCols % 32 == 0 && kFusedCols * kFusedRows == 256, "a warp is one row segment of the tile");
+static_assert(AMT_FUSED_PRIV == 0 || kFusedThreads == 256, "the privatised scatter is written for 256-thread tiles");
 
 template <typename T, int C>
 struct TileAcc {
@@ -2175,7 +2180,12 @@ __device__ __forceinline__ void fused_row(const GeorefParams& p, const double* s
 // -- 16 % of all warp residency in the one-row-per-warp version (profiles/r02_fused_stalls.txt) -- is paid
 // once per kFusedIter rows.
 template <typename T, int C, bool PLANES, bool MAG, bool BIN, bool SIP>
-__global__ void __launch_bounds__(256, AMT_GEOREF_MINBLOCKS)
+__global__ void
+#ifdef AMT_FUSED_MAXNREG
+__maxnreg__(AMT_FUSED_MAXNREG)
+#else
+__launch_bounds__(kFusedThreads, AMT_FUSED_MINBLOCKS)
+#endif
 k_georef_fused(const __grid_constant__ GeorefParams p, const uint32_t* __restrict__ valid_k,
                const uint32_t* __restrict__ valid_c, const T* __restrict__ img, const __grid_constant__ GridC g,
                unsigned long long* __restrict__ count, unsigned long long* __restrict__ sums,
@@ -2189,9 +2199,8 @@ k_georef_fused(const __grid_constant__ GeorefParams p, const uint32_t* __restric
     __shared__ unsigned s_acc[PRIV ? kTileWords : 1];
     __shared__ int s_win[4];
     if (SIP) {
-        if (threadIdx.x < 2 * AMT_SIP_MAX_COEF)
-            s_sip[threadIdx.x] = threadIdx.x < AMT_SIP_MAX_COEF ? p.sip_a[threadIdx.x]
-                                                                : p.sip_b[threadIdx.x - AMT_SIP_MAX_COEF];
+        for (int i = threadIdx.x; i < 2 * AMT_SIP_MAX_COEF; i += kFusedThreads)
+            s_sip[i] = i < AMT_SIP_MAX_COEF ? p.sip_a[i] : p.sip_b[i - AMT_SIP_MAX_COEF];
         __syncthreads();
     }
     const unsigned lane = threadIdx.x & 31, xw = (unsigned)x >> 5;
@@ -2220,8 +2229,8 @@ template <typename T, int C, bool PLANES, bool MAG, bool BIN>
 static void launch_fused_sip(bool sip, dim3 grid, cudaStream_t st, const GeorefParams& p, const uint32_t* vk,
                              const uint32_t* vc, const T* img, const GridC& g, unsigned long long* count,
                              unsigned long long* sums, double* fsum) {
-    if (sip) k_georef_fused<T, C, PLANES, MAG, BIN, true><<<grid, 256, 0, st>>>(p, vk, vc, img, g, count, sums, fsum);
-    else k_georef_fused<T, C, PLANES, MAG, BIN, false><<<grid, 256, 0, st>>>(p, vk, vc, img, g, count, sums, fsum);
+    if (sip) k_georef_fused<T, C, PLANES, MAG, BIN, true><<<grid, kFusedThreads, 0, st>>>(p, vk, vc, img, g, count, sums, fsum);
+    else k_georef_fused<T, C, PLANES, MAG, BIN, false><<<grid, kFusedThreads, 0, st>>>(p, vk, vc, img, g, count, sums, fsum);
 }
 
 template <typename T, int C>

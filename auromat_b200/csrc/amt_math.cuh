@@ -32,7 +32,7 @@ struct FrameC {
     double m_geo[9];
     double m_sm[9];
     double a, b, e2a, d;    // Bowring constants        transform.py:254-255,290
-    double b_over_a;
+    double b_over_a;        // 2 b/a (see bowring)
     int sip_oa, sip_ob;
     int model;
     double as_xc, as_yc, as_k, as_rot;   // all-sky fisheye model (mapping/miracle.py:314-347)
@@ -297,7 +297,7 @@ AMT_HD void bowring(double b_over_a, double e2a, double d, double x, double y, d
     sqrt_rsqrt(p2, p, hp);                       // hp = 0.5/p
     r2 = fma(z, z, p2);
     const double ir = rsqrt_40(r2);
-    const double tu = ((b_over_a * z) * (hp + hp)) * fma(d, ir, 1.0);
+    const double tu = ((b_over_a * z) * hp) * fma(d, ir, 1.0);        // b_over_a = 2 b/a, hp = 0.5/p: bit-identical to (b/a z)(2 hp)
     const double cu = rsqrt_40(fma(tu, tu, 1.0));
     const double tc = tu * cu;
     const double cu3 = (cu * cu) * cu;

@@ -28,8 +28,20 @@ struct SeqSlot {
     bool a_rec, b_rec, out_rec;
 };
 
+// Development builds only (-DAMT_DEV_SKIP): AMT_SEQ_SKIP is a bit mask of launches the engine leaves out once every
+// slot has seen a frame (1 statistics, 2 sanitise, 4 hit bitmaps, 8 memset, 16 normalise, 32 download).  With a
+// sequence of IDENTICAL frames the stale buffers hold the right values, so the timeline shows what each launch
+// costs the fused kernel it overlaps (scripts/seq_trace.py).  Not compiled into the product library.
+#ifdef AMT_DEV_SKIP
+static int seq_skip_mask() { static int m = getenv("AMT_SEQ_SKIP") ? atoi(getenv("AMT_SEQ_SKIP")) : 0; return m; }
+#define SEQ_SKIP(seq, bit) ((seq_skip_mask() & (bit)) && (seq)->frames_a > 2 * (seq)->slots.size())
+#else
+#define SEQ_SKIP(seq, bit) false
+#endif
+
 struct amt_seq {
     amt_ctx* ctx;
+    size_t frames_a = 0;
     int W, H, C, dtype;
     cudaStream_t s_main, s_aux, s_copy, s_out;
     std::vector<SeqSlot> slots;
@@ -139,9 +151,11 @@ extern "C" int amt_seq_stage_a(amt_seq* seq, int32_t slot, const amt_frame* fram
     memset(&bits, 0, sizeof bits);
     bits.d_valid_k = sl.buf.planes.d_valid_k;
     bits.d_valid_c = sl.buf.planes.d_valid_c;
-    int rc = amt_georef(ctx, frame, &bits, sl.buf.d_stats, st);
-    if (!rc) rc = amt_sanitize(ctx, seq->W, seq->H, &bits, st);
-    if (!rc) rc = amt_bbox_stats_frame(ctx, frame, bits.d_valid_k, bits.d_valid_c, nullptr, sl.buf.d_stats, st);
+    ++seq->frames_a;
+    int rc = SEQ_SKIP(seq, 4) ? 0 : amt_georef(ctx, frame, &bits, sl.buf.d_stats, st);
+    if (!rc && !SEQ_SKIP(seq, 2)) rc = amt_sanitize(ctx, seq->W, seq->H, &bits, st);
+    if (!rc && !SEQ_SKIP(seq, 1))
+        rc = amt_bbox_stats_frame(ctx, frame, bits.d_valid_k, bits.d_valid_c, nullptr, sl.buf.d_stats, st);
     if (rc) { nvtxRangePop(); return rc; }
     CUDA_TRY(cudaMemcpyAsync(sl.buf.h_stats, sl.buf.d_stats, sizeof(amt_stats), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaEventRecord(sl.ev_a, st));
@@ -227,7 +241,7 @@ extern "C" int amt_seq_stage_b(amt_seq* seq, int32_t slot, const amt_seq_job* jo
     // (47 k CTAs): on the copy stream it held back the upload behind it until that kernel's tail, i.e.
     // upload and kernel ran one after the other (0.72 ms/frame instead of max(0.41, 0.31); AMT_SEQ_TRACE
     // timeline, profiles/r02_seq_trace.txt).  The auxiliary stream has high priority: its CTAs go first.
-    CUDA_TRY(cudaMemsetAsync(job->d_acc, 0, (size_t)(2 + seq->C) * cells * 8, seq->s_aux));
+    if (!SEQ_SKIP(seq, 8)) CUDA_TRY(cudaMemsetAsync(job->d_acc, 0, (size_t)(2 + seq->C) * cells * 8, seq->s_aux));
     CUDA_TRY(cudaEventRecord(sl.ev_zero, seq->s_aux));
     // copy stream: nothing but DMA -- the pixel box of the host image
     if (seq->trace) CUDA_TRY(cudaEventRecord(sl.tr_up0, seq->s_copy));
@@ -273,9 +287,10 @@ extern "C" int amt_seq_stage_b(amt_seq* seq, int32_t slot, const amt_seq_job* jo
     // next frame's fused kernel
     CUDA_TRY(cudaStreamWaitEvent(seq->s_out, sl.ev_b, 0));
     unsigned char* o = (unsigned char*)job->d_out;
-    rc = amt_normalise(ctx, g, seq->dtype, seq->C, count, sums, fsum, o, o + om, (double*)(o + os), seq->s_out);
+    if (!SEQ_SKIP(seq, 16))
+        rc = amt_normalise(ctx, g, seq->dtype, seq->C, count, sums, fsum, o, o + om, (double*)(o + os), seq->s_out);
     if (rc) { nvtxRangePop(); return rc; }
-    if (job->h_out) CUDA_TRY(cudaMemcpyAsync(job->h_out, job->d_out, total, cudaMemcpyDeviceToHost, seq->s_out));
+    if (job->h_out && !SEQ_SKIP(seq, 32)) CUDA_TRY(cudaMemcpyAsync(job->h_out, job->d_out, total, cudaMemcpyDeviceToHost, seq->s_out));
     CUDA_TRY(cudaEventRecord(sl.ev_out, seq->s_out));
     sl.out_rec = true;
     nvtxRangePop();

@@ -124,8 +124,10 @@ class MosaicAccumulator(object):
         else:
             allreduceGrids([self.acc, self.fsum], group)
 
-    def finalise(self, template):
-        """Normalise and wrap the mosaic as a GenericMapping (metadata from `template`)."""
+    def finalise(self, template, deviceDone=None):
+        """Normalise and wrap the mosaic as a GenericMapping (metadata from `template`).
+        `deviceDone`: optional CUDA event recorded once the device part (normalise, grid coordinates,
+        back-rotation) is enqueued; what follows is the host-side wrapping (download + masked array)."""
         ctx, g, info = self.ctx, self.grid, self.info
         outImg, outMask, outElev = ctx.normalise(g, self.imgDtype, self.channels, self.count, self.sums, self.fsum)
         lat_k, lon_k, lat_c, lon_c = ctx.plate_carree_coords(g.nx, g.ny, info['latMaxInGrid'], info['latMinInGrid'],
@@ -136,6 +138,8 @@ class MosaicAccumulator(object):
             back = _preRotation(mode, template.altitude, angle=-90)     # reference resample.py:262-277
             ctx.rotate_coords(lat_k, lon_k, back)
             ctx.rotate_coords(lat_c, lon_c, back)
+        if deviceDone is not None:
+            deviceDone.record()
         img = ctx.to_numpy(outImg)
         mask = ctx.to_numpy(outMask).astype(bool)
         img = ma.masked_array(img, mask=np.repeat(mask[:, :, None], img.shape[2], 2))
@@ -151,7 +155,9 @@ def mosaic(mappings, pxPerDeg, group=None, timings=None):
     local binning -> one all-reduce of the sum/count grids -> normalise.
 
     :param timings: optional dict that receives the CUDA-event times of this rank in ms:
-        `bin_ms`, `allreduce_ms`, `normalise_ms` and their sum `total_ms` (synchronises)"""
+        `bin_ms`, `allreduce_ms`, `normalise_ms` (normalise + target-grid coordinates on the device),
+        `wrap_ms` (download of image and mask, numpy masked array, GenericMapping) and their sum
+        `total_ms` (synchronises)"""
     from .resample import targetGrid
     mappings = list(mappings)
     assert mappings, 'every rank needs at least one mapping'
@@ -213,7 +219,7 @@ def mosaic(mappings, pxPerDeg, group=None, timings=None):
     ev = None
     if timings is not None:
         import torch
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         ev[0].record()
     for m in mappings:
         acc.add(m)
@@ -222,12 +228,13 @@ def mosaic(mappings, pxPerDeg, group=None, timings=None):
     acc.allreduce(group)
     if ev:
         ev[2].record()
-    result = acc.finalise(m0)
+    result = acc.finalise(m0, ev[3] if ev else None)
     if ev:
-        ev[3].record()
-        ev[3].synchronize()
+        ev[4].record()
+        ev[4].synchronize()
         timings.update(bin_ms=ev[0].elapsed_time(ev[1]), allreduce_ms=ev[1].elapsed_time(ev[2]),
-                       normalise_ms=ev[2].elapsed_time(ev[3]), total_ms=ev[0].elapsed_time(ev[3]))
+                       normalise_ms=ev[2].elapsed_time(ev[3]), wrap_ms=ev[3].elapsed_time(ev[4]),
+                       total_ms=ev[0].elapsed_time(ev[4]))
     return result, acc
 
 

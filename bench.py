@@ -688,7 +688,7 @@ def mosaic_variant(ctx, rank, local_rank, world):
         torch.cuda.synchronize()
         mos, acc = parallel.mosaic(mine, pxPerDeg=(20, 20), timings=tm)
         torch.cuda.synchronize()
-        t_ = torch.tensor([tm['total_ms'], tm['bin_ms'], tm['allreduce_ms'], tm['normalise_ms']], dtype=torch.float64,
+        t_ = torch.tensor([tm['total_ms'], tm['bin_ms'], tm['allreduce_ms'], tm['normalise_ms'], tm['wrap_ms']], dtype=torch.float64,
                           device=ctx.torch_device)
         dist.all_reduce(t_, op=dist.ReduceOp.MAX)
         if r >= 3:
@@ -709,6 +709,7 @@ def mosaic_variant(ctx, rank, local_rank, world):
                         "20 px/deg grid, NCCL all-reduce of count | sums | fixed-point elevation sums (one int64 message)",
             "stations": n, "grid": [int(acc.grid.nx), int(acc.grid.ny)], "samples": int(acc.count.sum().item()),
             "ms": float(med[0]), "bin_ms": float(med[1]), "allreduce_ms": float(med[2]), "normalise_ms": float(med[3]),
+            "wrap_ms": float(med[4]), "device_ms": float(med[1] + med[2] + med[3]),
             "message_MB": message / 1e6, "busbw_GBs": busbw, "exact_elevation_sums": bool(acc.exactSide),
             "bit_exact": bool(flag.item()), "repeats": len(times)}
 

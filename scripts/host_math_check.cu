@@ -55,7 +55,7 @@ int main() {
         rotz(2 * PI * U(rng), A); rotx(0.3 * U(rng), B); mm(A, B, C);
         for (int k = 0; k < 9; ++k) f.m_sm[k] = (double)C[k];
         const double wa = 6378.137, wb = 6378.137 * (1 - 1 / 298.257223563);
-        f.a = wa; f.b = wb; f.b_over_a = wb / wa;
+        f.a = wa; f.b = wb; f.b_over_a = 2.0 * (wb / wa);
         f.e2a = (wa * wa - wb * wb) / (wa * wa) * wa; f.d = (wa * wa - wb * wb) / wb;
         fill_affine(f);
         for (int s = 0; s < 4000; ++s) {

@@ -148,6 +148,55 @@ def test_vincenty_a12_sanity():
     assert 10.8 < a < 10.95       # 19 deg of longitude at 55N ~ 10.87 deg of arc
 
 
+def test_karney_restatement_against_published_geodesics():
+    """oracle/karney_geodesic.py (Karney 2013 restated from the paper; geographiclib itself is absent)
+    against the two worked examples of the GeographicLib documentation: JFK -> LHR of the GeodSolve
+    manual (s12 = 5551759.400 m) and Wellington -> Salamanca of the Python package's introduction
+    (a12, s12 and both azimuths as printed there)."""
+    from oracle import karney_geodesic as K
+    r = K.inverse(40.6, -73.8, 51.6, -0.5)
+    assert abs(r['s12'] - 5551759.400) < 1e-3
+    r = K.inverse(-41.32, 174.81, 40.96, -5.50)
+    assert abs(r['a12'] - 179.6197069334283) < 1e-12
+    assert abs(r['s12'] - 19959679.26735382) < 1e-7
+    assert abs(r['azi1'] - 161.06766998615873) < 1e-9
+    assert abs(r['azi2'] - 18.825195123248484) < 1e-9
+    # closed forms: meridian arc pole to pole = 2 quarter meridians; equator
+    assert abs(K.inverse(-90, 0, 90, 0)['a12'] - 180) < 1e-12
+    assert abs(K.inverse(-90, 0, 90, 0)['s12'] - 2 * 10001965.729) < 2e-3
+    assert abs(K.inverse(0, 0, 0, 90)['s12'] - 6378137.0 * np.pi / 2) < 1e-8
+    assert K.inverse(10, 20, 10, 20)['a12'] == 0
+
+
+def test_angular_distance_vincenty_against_karney():
+    """The product's `angularDistance` (Vincenty's iteration, coordinates/geodesic.py) and the oracle's own
+    Vincenty restatement against the independent Karney restatement: the auxiliary-sphere arc `a12` that
+    reference geodesic.py:35-44 takes from geographiclib.  Random pairs over the globe (nearly antipodal pairs,
+    where Vincenty's iteration does not converge and which no bounding box of this path produces, excluded)
+    and bounding-box-sized pairs as plateCarreeResolution forms them (resample.py:281-299)."""
+    from oracle import karney_geodesic as K
+    from auromat_b200.coordinates import geodesic as G
+    rng = np.random.default_rng(11)
+    worst = 0.0
+    for _ in range(3000):
+        la1, la2 = rng.uniform(-89, 89, 2)
+        lo1, lo2 = rng.uniform(-180, 180, 2)
+        k = K.angularDistance(la1, lo1, la2, lo2)
+        if k > 175:
+            continue
+        worst = max(worst, abs(G.angularDistance(G.Location(la1, lo1), G.Location(la2, lo2)) - k),
+                    abs(O.vincenty_a12(la1, lo1, la2, lo2) - k))
+    assert worst < 2e-9, worst
+    worst = 0.0
+    for _ in range(3000):
+        la1, lo1 = rng.uniform(-85, 85), rng.uniform(-180, 180)
+        la2, lo2 = float(np.clip(la1 + rng.uniform(-20, 20), -89, 89)), lo1 + rng.uniform(-40, 40)
+        k = K.angularDistance(la1, lo1, la2, lo2)
+        v = G.angularDistance(G.Location(la1, lo1), G.Location(la2, lo2))
+        worst = max(worst, abs(v - k) / max(k, 1e-9))
+    assert worst < 1e-10, worst
+
+
 def test_allsky_matches_reference_golden():
     """mapping/miracle.py model (reference outputs with the documented np.indices patch)."""
     g = np.load(os.path.join(GOLDEN, "allsky_SOD_96.npz"))
