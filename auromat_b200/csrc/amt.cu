@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <new>
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <vector>
 #include "amt_math.cuh"
 
@@ -22,7 +23,8 @@ struct Workspace {
     cudaStream_t stream;
     void* scratch;
     size_t scratch_bytes;
-    void* stat_keys;          // device StatKeys block, self-cleaning (see k_stats_bits)
+    void* stat_keys;          // device StatKeys block, self-cleaning (see k_outline_eval)
+    void* stat_queue;         // outline node queue (kStatQueue flat corner indices)
 };
 
 struct amt_ctx {
@@ -35,7 +37,7 @@ struct amt_ctx {
 static Workspace& workspace(amt_ctx* ctx, cudaStream_t st) {
     for (auto& w : ctx->ws)
         if (w.stream == st) return w;
-    ctx->ws.push_back(Workspace{st, nullptr, 0, nullptr});
+    ctx->ws.push_back(Workspace{st, nullptr, 0, nullptr, nullptr});
     return ctx->ws.back();
 }
 
@@ -116,6 +118,7 @@ extern "C" int amt_ctx_destroy(amt_ctx* ctx) {
     for (auto& w : ctx->ws) {
         if (w.scratch) cudaFree(w.scratch);
         if (w.stat_keys) cudaFree(w.stat_keys);
+        if (w.stat_queue) cudaFree(w.stat_queue);
     }
     delete ctx;
     return AMT_OK;
@@ -878,6 +881,7 @@ struct StatKeys {
     unsigned int pole_flags;
     unsigned int blocks_done;
     unsigned int row_min, row_max, col_min, col_max;    // pixel box of the valid centres
+    unsigned int queue_n;                               // outline nodes in the stream's node queue
 };
 
 __device__ __forceinline__ void stats_reset(StatKeys* s) {
@@ -886,6 +890,7 @@ __device__ __forceinline__ void stats_reset(StatKeys* s) {
     s->n_valid_k = s->n_boundary = s->n_valid_c = 0ULL;
     s->pole_flags = 0u;
     s->blocks_done = 0u;
+    s->queue_n = 0u;
     s->row_min = s->col_min = 0xffffffffu;
     s->row_max = s->col_max = 0u;
 }
@@ -1003,162 +1008,217 @@ struct SanitizeWords {
     }
 };
 
-__global__ void __launch_bounds__(128) k_sanitize_fused(int W, int H, Bits K0, Bits C0, unsigned* __restrict__ kout,
+// Launch shape: grid-stride over the (row, word) positions with a few hundred CTAs.  The work is a few
+// hundred bit operations per word on an L2-resident working set, i.e. the kernel is latency bound, and in
+// the sequence engine it runs BESIDE the long fused kernel of other frames: what it costs there is the
+// residency of its CTAs (each one displaces a CTA of the fused kernel for its lifetime), so it uses few
+// CTAs that each do several positions -- 5666 CTAs of 128 threads cost the fused kernel 8 us per frame
+// (AMT_SEQ_SKIP timeline, profiles/r02_stage_a_interference.txt).
+// WRITE_ALL: every word of the result is stored (kout / cout are different buffers than K0 / C0: no copy
+// of the input needed); otherwise only the words that change (in place on a copy of the input).
+template <bool WRITE_ALL>
+__global__ void __launch_bounds__(256) k_sanitize_fused(int W, int H, Bits K0, Bits C0, unsigned* __restrict__ kout,
                                                         unsigned* __restrict__ cout, amt_georef_out o) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (i >= K0.wpr || y > H) return;
     const SanitizeWords sw{K0, C0};
-    // k1 on rows y-1 .. y+1, words i-1 .. i+1
-    unsigned k1[3][3];
+    const int total = K0.wpr * (H + 1);
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int y = t / K0.wpr, i = t - y * K0.wpr;
+        // k1 on rows y-1 .. y+1, words i-1 .. i+1
+        unsigned k1[3][3];
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
+        for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) k1[r][c] = sw.k1(y - 1 + r, i - 1 + c);
-    // step 2: c1 on rows y-1 .. y, words i-1 .. i  (all four corners valid in k1)
-    unsigned c1[2][2];
+            for (int c = 0; c < 3; ++c) k1[r][c] = sw.k1(y - 1 + r, i - 1 + c);
+        // step 2: c1 on rows y-1 .. y, words i-1 .. i  (all four corners valid in k1)
+        unsigned c1[2][2];
 #pragma unroll
-    for (int r = 0; r < 2; ++r)
+        for (int r = 0; r < 2; ++r)
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            const unsigned a = k1[r][c], a_r = (a >> 1) | (k1[r][c + 1] << 31);
-            const unsigned b = k1[r + 1][c], b_r = (b >> 1) | (k1[r + 1][c + 1] << 31);
-            c1[r][c] = C0.at(y - 1 + r, i - 1 + c) & a & a_r & b & b_r;
+            for (int c = 0; c < 2; ++c) {
+                const unsigned a = k1[r][c], a_r = (a >> 1) | (k1[r][c + 1] << 31);
+                const unsigned b = k1[r + 1][c], b_r = (b >> 1) | (k1[r + 1][c + 1] << 31);
+                c1[r][c] = C0.at(y - 1 + r, i - 1 + c) & a & a_r & b & b_r;
+            }
+        // step 3: corners once more against the updated centres
+        const unsigned up_l = (c1[0][1] << 1) | (c1[0][0] >> 31), dn_l = (c1[1][1] << 1) | (c1[1][0] >> 31);
+        const unsigned k2 = k1[1][1] & (up_l | c1[0][1] | dn_l | c1[1][1]);
+        const unsigned k_old = K0.at(y, i);
+        if (WRITE_ALL || k2 != k_old) {
+            kout[(size_t)y * K0.wpr + i] = k2;
+            if (k2 != k_old) nan_corners(o, (size_t)y * (W + 1) + 32 * i, k_old & ~k2);
         }
-    // step 3: corners once more against the updated centres
-    const unsigned up_l = (c1[0][1] << 1) | (c1[0][0] >> 31), dn_l = (c1[1][1] << 1) | (c1[1][0] >> 31);
-    const unsigned k2 = k1[1][1] & (up_l | c1[0][1] | dn_l | c1[1][1]);
-    const unsigned k_old = K0.at(y, i);
-    if (k2 != k_old) {
-        kout[(size_t)y * K0.wpr + i] = k2;
-        nan_corners(o, (size_t)y * (W + 1) + 32 * i, k_old & ~k2);
-    }
-    if (y < H && i < C0.wpr) {
-        const unsigned c_old = C0.at(y, i), c_new = c1[1][1];
-        if (c_new != c_old) {
-            cout[(size_t)y * C0.wpr + i] = c_new;
-            nan_centers(o, (size_t)y * W + 32 * i, c_old & ~c_new);
+        if (y < H && i < C0.wpr) {
+            const unsigned c_old = C0.at(y, i), c_new = c1[1][1];
+            if (WRITE_ALL || c_new != c_old) {
+                cout[(size_t)y * C0.wpr + i] = c_new;
+                if (c_new != c_old) nan_centers(o, (size_t)y * W + 32 * i, c_old & ~c_new);
+            }
         }
     }
+}
+
+static inline int sanitize_blocks(const amt_ctx* ctx, size_t words) {
+    static const int per_sm = getenv("AMT_SANITIZE_BLOCKS_PER_SM") ? atoi(getenv("AMT_SANITIZE_BLOCKS_PER_SM")) : 2;
+    return (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->sm_count * per_sm, (words + 255) / 256));
 }
 
 __device__ __forceinline__ unsigned long long umin64(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
 __device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
 
 // Bounding box over the outline (valid corners with an invalid / out-of-array 4-neighbour,
-// mapping.py:672-703,729-737) + valid counts, from the bitmaps.  Grid-stride over words,
-// block-level reduction, one set of atomics per block.
-// outline coordinates either from the planes or (lat_k == NULL) recomputed from the frame model
-// for the few outline nodes -- the plane-free (fused) resampling path
-__global__ void __launch_bounds__(256) k_stats_bits(int W, int H, Bits K, Bits C, const double* __restrict__ lat_k,
-                                                    const double* __restrict__ lon_k,
-                                                    const __grid_constant__ GridC g, StatKeys* s,
-                                                    const GeorefParams* __restrict__ frame, amt_stats* out) {
+// mapping.py:672-703,729-737) + valid counts, from the bitmaps.
+// Outline coordinates either from the planes (lat_k != NULL) or recomputed from the frame model for the few
+// outline nodes -- the plane-free (fused) resampling path and the sequence engine, where this kernel runs
+// BEFORE the planes exist.
+//
+// Two launches.  k_outline_collect (<= 1 CTA per SM; four independent bitmap words per thread and step,
+// 20 loads in flight) classifies the words, counts, and COMPACTS the outline nodes into a queue in global
+// memory (one atomic per warp that found any).  k_outline_eval evaluates the queue densely, one node per
+// thread, and the last of its CTAs converts the keys.  An ISS frame has ~14 k outline nodes, 10 k of them
+// one per bitmap word (left / right frame edge) and 4 k in one row (bottom edge): evaluated word by word
+// (32 lanes on the 32 bits of a word: the first version) that was ~6000 warp-level passes of the
+// ~400-instruction FP64 chain, most with one active lane, in 592 long-lived CTAs, which cost the fused
+// kernel they ran beside 10 us per frame (AMT_SEQ_SKIP timeline, profiles/r02_stage_a_interference.txt);
+// compacted per CTA it is unbalanced (the bottom row lands in one CTA); from the global queue it is ~55
+// CTAs with one node per thread.
+constexpr unsigned kStatQueue = 1u << 20;        // nodes (4 MB per stream); the excess is evaluated in place
+
+struct OutlineAcc {
     unsigned long long mn_la = ~0ULL, mx_la = 0ULL, mn_lo = ~0ULL, mx_lo = 0ULL, mn_pos = ~0ULL, mx_neg = 0ULL;
+    __device__ __forceinline__ void add(const GridC& g, double a_, double o_) {
+        if (g.prerotate != AMT_PRE_NONE) prerotate(g, a_, o_);
+        const unsigned long long kla = dkey(a_), klo = dkey(o_);
+        mn_la = umin64(mn_la, kla); mx_la = umax64(mx_la, kla);
+        mn_lo = umin64(mn_lo, klo); mx_lo = umax64(mx_lo, klo);
+        if (o_ > 0.0) mn_pos = umin64(mn_pos, klo); else mx_neg = umax64(mx_neg, klo);
+    }
+    __device__ __forceinline__ void flush(StatKeys* s) const {
+        if (mn_la == ~0ULL) return;
+        atomicMin(&s->lat_min, mn_la); atomicMax(&s->lat_max, mx_la);
+        atomicMin(&s->lon_min, mn_lo); atomicMax(&s->lon_max, mx_lo);
+        if (mn_pos != ~0ULL) atomicMin(&s->lon_min_pos, mn_pos);
+        if (mx_neg != 0ULL) atomicMax(&s->lon_max_neg, mx_neg);
+    }
+};
+
+// coordinates of corner node `idx` (flat index into the (H+1) x (W+1) corner array)
+template <bool FRAME>
+__device__ __noinline__ void outline_coord(const GeorefParams& frame, const double* __restrict__ lat_k,
+                                           const double* __restrict__ lon_k, int W, unsigned idx, double& la,
+                                           double& lo) {
+    if (FRAME) {
+        const int y = (int)(idx / (unsigned)(W + 1)), x = (int)(idx - (unsigned)y * (unsigned)(W + 1));
+        double dir[3], dcen[3], P[3];
+        bool gz;
+        dirs_kc<true>(frame.f, frame.sip_a, frame.sip_b, x, y, dir, dcen);
+        intersect(frame.f, dir, P, gz);
+        point_to_geo(frame.f, P, la, lo);
+    } else {
+        la = lat_k[idx];
+        lo = lon_k[idx];
+    }
+}
+
+template <bool FRAME>
+__global__ void __launch_bounds__(256, 4) k_outline_collect(int W, int H, Bits K, Bits C,
+                                                            const double* __restrict__ lat_k,
+                                                            const double* __restrict__ lon_k,
+                                                            const __grid_constant__ GridC g, StatKeys* s,
+                                                            const __grid_constant__ GeorefParams frame,
+                                                            unsigned* __restrict__ queue) {
+    OutlineAcc acc;                                      // nodes beyond the queue capacity only
     unsigned nvk = 0, nb = 0, nvc = 0;
-    // Each lane classifies one bitmap word (coalesced); the outline nodes of the warp's words are
-    // then handled cooperatively: one word per step with the 32 lanes on its 32 bits (coalesced
-    // coordinate loads), four words in flight per step so that the limb rows -- 32 full outline
-    // words per warp -- cost 8 dependent memory round trips instead of 32.
-    const int lane_ = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
+    constexpr int U = 4;
     const int nwk = K.wpr * (H + 1);
-    const int t_first = blockIdx.x * blockDim.x + threadIdx.x - lane_;
-    for (int t0 = t_first; t0 < nwk; t0 += gridDim.x * blockDim.x) {        // warp-uniform
-        const int t = t0 + lane_;
-        unsigned b = 0;
-        int y = 0, i = 0;
-        if (t < nwk) {
-            y = t / K.wpr;
-            i = t - y * K.wpr;
-            const unsigned v = K.w[t];
-            if (v) {
-                nvk += __popc(v);
-                const unsigned interior = v & K.from_left(y, i) & K.from_right(y, i) & K.at(y - 1, i) & K.at(y + 1, i);
-                b = v & ~interior;
+    for (int base = blockIdx.x * (256 * U); base < nwk; base += gridDim.x * (256 * U)) {
+        unsigned v[U], lf[U], rt[U], up[U], dn[U];
+        int yy[U], ii[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {                    // all loads of the step first
+            const int t = base + u * 256 + threadIdx.x;
+            const bool in = t < nwk;
+            const int y = in ? t / K.wpr : 0, i = in ? t - y * K.wpr : 0;
+            yy[u] = y; ii[u] = i;
+            v[u] = in ? K.w[t] : 0u;
+            lf[u] = in ? K.at(y, i - 1) : 0u;
+            rt[u] = in ? K.at(y, i + 1) : 0u;
+            up[u] = in ? K.at(y - 1, i) : 0u;
+            dn[u] = in ? K.at(y + 1, i) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            unsigned b = 0;
+            if (v[u]) {
+                nvk += __popc(v[u]);
+                const unsigned interior = v[u] & ((v[u] << 1) | (lf[u] >> 31)) & ((v[u] >> 1) | (rt[u] << 31)) & up[u] & dn[u];
+                b = v[u] & ~interior;
                 nb += __popc(b);
             }
-        }
-        unsigned act = __ballot_sync(0xffffffffu, b != 0);
-        while (act) {
-            constexpr int Q = 4;
-            bool on[Q];
-            double la[Q], lo[Q];
+            if (__ballot_sync(0xffffffffu, b != 0) == 0) continue;           // warp-uniform
+            // warp-aggregated append: one atomic per warp
+            const unsigned n = __popc(b);
+            unsigned incl = n;
 #pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                const int src = act ? __ffs(act) - 1 : 0;
-                const unsigned bb = act ? __shfl_sync(0xffffffffu, b, src) : 0u;
-                const int yy = __shfl_sync(0xffffffffu, y, src), ii = __shfl_sync(0xffffffffu, i, src);
-                act &= act - 1;                                  // 0 stays 0
-                on[q] = (bb >> lane_) & 1u;
-                la[q] = lo[q] = 0.0;
-                if (on[q]) {
-                    const int x = 32 * ii + lane_;
-                    if (lat_k) {
-                        const size_t idx = (size_t)yy * (W + 1) + x;
-                        la[q] = lat_k[idx];
-                        lo[q] = lon_k[idx];
-                    } else {
-                        double dir[3], dcen[3], P[3];
-                        bool gz;
-                        dirs_kc<true>(frame->f, frame->sip_a, frame->sip_b, x, yy, dir, dcen);
-                        intersect(frame->f, dir, P, gz);
-                        point_to_geo(frame->f, P, la[q], lo[q]);
-                    }
-                }
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned t_ = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t_;
             }
-#pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                if (!on[q]) continue;
-                double a_ = la[q], o_ = lo[q];
-                if (g.prerotate != AMT_PRE_NONE) prerotate(g, a_, o_);
-                const unsigned long long kla = dkey(a_), klo = dkey(o_);
-                mn_la = umin64(mn_la, kla); mx_la = umax64(mx_la, kla);
-                mn_lo = umin64(mn_lo, klo); mx_lo = umax64(mx_lo, klo);
-                if (o_ > 0.0) mn_pos = umin64(mn_pos, klo); else mx_neg = umax64(mx_neg, klo);
+            unsigned wbase = 0;
+            if (lane == 31) wbase = atomicAdd(&s->queue_n, incl);
+            wbase = __shfl_sync(0xffffffffu, wbase, 31);
+            unsigned off = wbase + incl - n;
+            const unsigned first = (unsigned)yy[u] * (unsigned)(W + 1) + 32u * (unsigned)ii[u];
+            while (b) {
+                const unsigned idx = first + (unsigned)(__ffs(b) - 1);
+                b &= b - 1;
+                if (off < kStatQueue) {
+                    queue[off] = idx;
+                } else {                                 // queue full (pathological masks): evaluate in place
+                    double la, lo;
+                    outline_coord<FRAME>(frame, lat_k, lon_k, W, idx, la, lo);
+                    acc.add(g, la, lo);
+                }
+                ++off;
             }
         }
     }
+    acc.flush(s);
     const int nwc = C.wpr * H;
     unsigned r_lo = 0xffffffffu, r_hi = 0u, c_lo = 0xffffffffu, c_hi = 0u;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nwc; t += gridDim.x * blockDim.x) {
-        const unsigned v = C.w[t];
-        if (!v) continue;
-        nvc += __popc(v);
-        const unsigned y = t / C.wpr, i = t - y * C.wpr;
-        r_lo = min(r_lo, y); r_hi = max(r_hi, y);
-        c_lo = min(c_lo, 32u * i + (unsigned)(__ffs(v) - 1));
-        c_hi = max(c_hi, 32u * i + (unsigned)(31 - __clz(v)));
+    for (int base = blockIdx.x * (256 * U); base < nwc; base += gridDim.x * (256 * U)) {
+        unsigned v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int t = base + u * 256 + threadIdx.x;
+            v[u] = t < nwc ? C.w[t] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!v[u]) continue;
+            const int t = base + u * 256 + threadIdx.x;
+            nvc += __popc(v[u]);
+            const unsigned y = t / C.wpr, i = t - y * C.wpr;
+            r_lo = min(r_lo, y); r_hi = max(r_hi, y);
+            c_lo = min(c_lo, 32u * i + (unsigned)(__ffs(v[u]) - 1));
+            c_hi = max(c_hi, 32u * i + (unsigned)(31 - __clz(v[u])));
+        }
     }
     r_lo = __reduce_min_sync(0xffffffffu, r_lo); r_hi = __reduce_max_sync(0xffffffffu, r_hi);
     c_lo = __reduce_min_sync(0xffffffffu, c_lo); c_hi = __reduce_max_sync(0xffffffffu, c_hi);
-
-    __shared__ unsigned long long sh[6][8];
+    nvk = __reduce_add_sync(0xffffffffu, nvk);
+    nb = __reduce_add_sync(0xffffffffu, nb);
+    nvc = __reduce_add_sync(0xffffffffu, nvc);
     __shared__ unsigned shc[3][8];
     __shared__ unsigned shr[4][8];
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        mn_la = umin64(mn_la, __shfl_xor_sync(0xffffffffu, mn_la, o));
-        mx_la = umax64(mx_la, __shfl_xor_sync(0xffffffffu, mx_la, o));
-        mn_lo = umin64(mn_lo, __shfl_xor_sync(0xffffffffu, mn_lo, o));
-        mx_lo = umax64(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, o));
-        mn_pos = umin64(mn_pos, __shfl_xor_sync(0xffffffffu, mn_pos, o));
-        mx_neg = umax64(mx_neg, __shfl_xor_sync(0xffffffffu, mx_neg, o));
-        nvk += __shfl_xor_sync(0xffffffffu, nvk, o);
-        nb += __shfl_xor_sync(0xffffffffu, nb, o);
-        nvc += __shfl_xor_sync(0xffffffffu, nvc, o);
-    }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
     if (lane == 0) {
-        sh[0][warp] = mn_la; sh[1][warp] = mx_la; sh[2][warp] = mn_lo; sh[3][warp] = mx_lo;
-        sh[4][warp] = mn_pos; sh[5][warp] = mx_neg;
         shc[0][warp] = nvk; shc[1][warp] = nb; shc[2][warp] = nvc;
         shr[0][warp] = r_lo; shr[1][warp] = r_hi; shr[2][warp] = c_lo; shr[3][warp] = c_hi;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < 8; ++w) {
-            sh[0][0] = umin64(sh[0][0], sh[0][w]); sh[1][0] = umax64(sh[1][0], sh[1][w]);
-            sh[2][0] = umin64(sh[2][0], sh[2][w]); sh[3][0] = umax64(sh[3][0], sh[3][w]);
-            sh[4][0] = umin64(sh[4][0], sh[4][w]); sh[5][0] = umax64(sh[5][0], sh[5][w]);
             shc[0][0] += shc[0][w]; shc[1][0] += shc[1][w]; shc[2][0] += shc[2][w];
             shr[0][0] = min(shr[0][0], shr[0][w]); shr[1][0] = max(shr[1][0], shr[1][w]);
             shr[2][0] = min(shr[2][0], shr[2][w]); shr[3][0] = max(shr[3][0], shr[3][w]);
@@ -1169,14 +1229,51 @@ __global__ void __launch_bounds__(256) k_stats_bits(int W, int H, Bits K, Bits C
         }
         if (shc[0][0]) atomicAdd(&s->n_valid_k, (unsigned long long)shc[0][0]);
         if (shc[2][0]) atomicAdd(&s->n_valid_c, (unsigned long long)shc[2][0]);
-        if (shc[1][0]) {
-            atomicAdd(&s->n_boundary, (unsigned long long)shc[1][0]);
-            atomicMin(&s->lat_min, sh[0][0]); atomicMax(&s->lat_max, sh[1][0]);
-            atomicMin(&s->lon_min, sh[2][0]); atomicMax(&s->lon_max, sh[3][0]);
-            if (sh[4][0] != ~0ULL) atomicMin(&s->lon_min_pos, sh[4][0]);
-            if (sh[5][0] != 0ULL) atomicMax(&s->lon_max_neg, sh[5][0]);
+        if (shc[1][0]) atomicAdd(&s->n_boundary, (unsigned long long)shc[1][0]);
+    }
+}
+
+// One queued outline node per thread; CTAs beyond the queue's length leave at once.  The last CTA to
+// arrive converts the keys and leaves the key block (and the queue counter) clean for the next call.
+template <bool FRAME>
+__global__ void __launch_bounds__(256, 4) k_outline_eval(int W, const double* __restrict__ lat_k,
+                                                         const double* __restrict__ lon_k,
+                                                         const __grid_constant__ GridC g, StatKeys* s,
+                                                         const __grid_constant__ GeorefParams frame,
+                                                         const unsigned* __restrict__ queue, amt_stats* out) {
+    const unsigned n = min(*(volatile unsigned*)&s->queue_n, kStatQueue);
+    OutlineAcc acc;
+    for (unsigned j = blockIdx.x * 256 + threadIdx.x; j < n; j += gridDim.x * 256) {
+        double la, lo;
+        outline_coord<FRAME>(frame, lat_k, lon_k, W, queue[j], la, lo);
+        acc.add(g, la, lo);
+    }
+    unsigned long long mn_la = acc.mn_la, mx_la = acc.mx_la, mn_lo = acc.mn_lo, mx_lo = acc.mx_lo, mn_pos = acc.mn_pos,
+                       mx_neg = acc.mx_neg;
+    __shared__ unsigned long long sh[6][8];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        mn_la = umin64(mn_la, __shfl_xor_sync(0xffffffffu, mn_la, o));
+        mx_la = umax64(mx_la, __shfl_xor_sync(0xffffffffu, mx_la, o));
+        mn_lo = umin64(mn_lo, __shfl_xor_sync(0xffffffffu, mn_lo, o));
+        mx_lo = umax64(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, o));
+        mn_pos = umin64(mn_pos, __shfl_xor_sync(0xffffffffu, mn_pos, o));
+        mx_neg = umax64(mx_neg, __shfl_xor_sync(0xffffffffu, mx_neg, o));
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        sh[0][warp] = mn_la; sh[1][warp] = mx_la; sh[2][warp] = mn_lo; sh[3][warp] = mx_lo;
+        sh[4][warp] = mn_pos; sh[5][warp] = mx_neg;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        OutlineAcc t;
+        for (int w = 0; w < 8; ++w) {
+            t.mn_la = umin64(t.mn_la, sh[0][w]); t.mx_la = umax64(t.mx_la, sh[1][w]);
+            t.mn_lo = umin64(t.mn_lo, sh[2][w]); t.mx_lo = umax64(t.mx_lo, sh[3][w]);
+            t.mn_pos = umin64(t.mn_pos, sh[4][w]); t.mx_neg = umax64(t.mx_neg, sh[5][w]);
         }
-        // the last block to arrive converts the keys and leaves the block clean for the next call
+        t.flush(s);
         __threadfence();
         if (atomicAdd(&s->blocks_done, 1u) == gridDim.x - 1) {
             __threadfence();
@@ -1184,6 +1281,12 @@ __global__ void __launch_bounds__(256) k_stats_bits(int W, int H, Bits K, Bits C
         }
     }
 }
+
+static inline int stats_blocks(const amt_ctx* ctx, int words) {
+    static const int per_sm = getenv("AMT_STATS_BLOCKS_PER_SM") ? atoi(getenv("AMT_STATS_BLOCKS_PER_SM")) : 1;
+    return std::max(1, std::min(ctx->sm_count * per_sm, (words + 1023) / 1024));
+}
+constexpr int kOutlineEvalBlocks = 64;           // 16 k nodes with one node per thread; longer queues loop
 
 // Pole test for mappings without a camera model (GenericMapping): the longitudes of the 4
 // corners of a valid pixel wind once around (+-360 deg) iff the quad encloses a pole.
@@ -1240,8 +1343,33 @@ extern "C" int amt_sanitize(amt_ctx* ctx, int32_t W, int32_t H, const amt_georef
         CUDA_TRY(cudaMemcpyAsync(c0, planes->d_valid_c, nc * 4, cudaMemcpyDeviceToDevice, st));
     }
     Bits K0{k0, wk, H + 1}, C0{c0, wc, H};
-    dim3 gk((wk + 127) / 128, H + 1);
-    k_sanitize_fused<<<gk, 128, 0, st>>>(W, H, K0, C0, planes->d_valid_k, planes->d_valid_c, *planes);
+    k_sanitize_fused<false><<<sanitize_blocks(ctx, nk), 256, 0, st>>>(W, H, K0, C0, planes->d_valid_k,
+                                                                       planes->d_valid_c, *planes);
+    LAUNCH_CHECK(ctx);
+    return AMT_OK;
+}
+
+// Final validity bitmaps of a WCS frame straight from its header (stage A of the sequence engine): the raw
+// hit bitmaps go to the stream's scratch buffer, the sanitisation stencils read them there and write
+// every word of the final bitmaps -- no copy of the input, two launches.
+static int hit_bits_sanitized(amt_ctx* ctx, const amt_frame* frame, uint32_t* d_valid_k, uint32_t* d_valid_c,
+                              amt_stats* d_stats, cudaStream_t st) {
+    const int W = frame->width, H = frame->height;
+    const int wk = wpr_of(W + 1), wc = wpr_of(W);
+    const size_t nk = (size_t)wk * (H + 1), nc = (size_t)wc * H;
+    void* scratch = nullptr;
+    int rc = ensure_scratch(ctx, st, (nk + nc) * 4, &scratch);
+    if (rc) return rc;
+    amt_georef_out raw;
+    memset(&raw, 0, sizeof raw);
+    raw.d_valid_k = (uint32_t*)scratch;
+    raw.d_valid_c = raw.d_valid_k + nk;
+    rc = amt_georef(ctx, frame, &raw, d_stats, st);
+    if (rc) return rc;
+    Bits K0{raw.d_valid_k, wk, H + 1}, C0{raw.d_valid_c, wc, H};
+    amt_georef_out none;
+    memset(&none, 0, sizeof none);
+    k_sanitize_fused<true><<<sanitize_blocks(ctx, nk), 256, 0, st>>>(W, H, K0, C0, d_valid_k, d_valid_c, none);
     LAUNCH_CHECK(ctx);
     return AMT_OK;
 }
@@ -1249,6 +1377,7 @@ extern "C" int amt_sanitize(amt_ctx* ctx, int32_t W, int32_t H, const amt_georef
 static int get_stat_keys(amt_ctx* ctx, cudaStream_t st, StatKeys** keys) {
     Workspace& w = workspace(ctx, st);
     if (!w.stat_keys) {
+        CUDA_TRY(cudaMalloc(&w.stat_queue, (size_t)kStatQueue * sizeof(unsigned)));
         CUDA_TRY(cudaMalloc(&w.stat_keys, sizeof(StatKeys)));
         k_stats_init<<<1, 1, 0, st>>>((StatKeys*)w.stat_keys);         // once per stream; afterwards self-cleaning
         LAUNCH_CHECK(ctx);
@@ -1276,21 +1405,16 @@ extern "C" int amt_bbox_stats_frame(amt_ctx* ctx, const amt_frame* frame, const 
     }
     const int W = frame->width, H = frame->height;
     const int wk = wpr_of(W + 1), wc = wpr_of(W);
-    // the frame constants live behind the sanitize scratch bitmap
-    const size_t off = ((size_t)wk * (H + 1) * 4 + 255) / 256 * 256;
-    void* scratch = nullptr;
-    rc = ensure_scratch(ctx, st, off + sizeof(GeorefParams), &scratch);
-    if (rc) return rc;
     StatKeys* keys;
     rc = get_stat_keys(ctx, st, &keys);
     if (rc) return rc;
-    GeorefParams* dp = (GeorefParams*)((unsigned char*)scratch + off);
-    CUDA_TRY(cudaMemcpyAsync(dp, &p, sizeof p, cudaMemcpyHostToDevice, st));
     Bits K{d_valid_k, wk, H + 1}, C{d_valid_c, wc, H};
     const int words = wk * (H + 1);
-    static const int per_sm = getenv("AMT_STATS_BLOCKS_PER_SM") ? atoi(getenv("AMT_STATS_BLOCKS_PER_SM")) : 4;
-    const int blocks = max(1, min(ctx->sm_count * per_sm, (words + 255) / 256));
-    k_stats_bits<<<blocks, 256, 0, st>>>(W, H, K, C, nullptr, nullptr, g, keys, dp, d_stats);
+    // the frame constants travel as a kernel parameter (constant bank), like in the georeference kernels
+    unsigned* queue = (unsigned*)workspace(ctx, st).stat_queue;
+    k_outline_collect<true><<<stats_blocks(ctx, words), 256, 0, st>>>(W, H, K, C, nullptr, nullptr, g, keys, p, queue);
+    LAUNCH_CHECK(ctx);
+    k_outline_eval<true><<<kOutlineEvalBlocks, 256, 0, st>>>(W, nullptr, nullptr, g, keys, p, queue, d_stats);
     LAUNCH_CHECK(ctx);
     return AMT_OK;
 }
@@ -1312,14 +1436,17 @@ extern "C" int amt_bbox_stats(amt_ctx* ctx, int32_t W, int32_t H, const double* 
     int rc = get_stat_keys(ctx, st, &keys);
     if (rc) return rc;
     Bits K{d_valid_k, wk, H + 1}, C{d_valid_c, wc, H};
-    if (pole_test) {                     // ORs into the key block; converted and reset by k_stats_bits
+    if (pole_test) {                     // ORs into the key block; converted and reset by k_outline_eval
         dim3 grid((W + 255) / 256, H);
         k_pole_test<<<grid, 256, 0, st>>>(W, H, C, d_lat_k, d_lon_k, keys);
         LAUNCH_CHECK(ctx);
     }
     const int words = wk * (H + 1);
-    const int blocks = max(1, min(ctx->sm_count * 4, (words + 255) / 256));
-    k_stats_bits<<<blocks, 256, 0, st>>>(W, H, K, C, d_lat_k, d_lon_k, g, keys, nullptr, d_stats);
+    static const GeorefParams no_frame = {};
+    unsigned* queue = (unsigned*)workspace(ctx, st).stat_queue;
+    k_outline_collect<false><<<stats_blocks(ctx, words), 256, 0, st>>>(W, H, K, C, d_lat_k, d_lon_k, g, keys, no_frame, queue);
+    LAUNCH_CHECK(ctx);
+    k_outline_eval<false><<<kOutlineEvalBlocks, 256, 0, st>>>(W, d_lat_k, d_lon_k, g, keys, no_frame, queue, d_stats);
     LAUNCH_CHECK(ctx);
     return AMT_OK;
 }

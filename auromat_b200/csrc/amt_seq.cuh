@@ -29,7 +29,7 @@ struct SeqSlot {
 };
 
 // Development builds only (-DAMT_DEV_SKIP): AMT_SEQ_SKIP is a bit mask of launches the engine leaves out once every
-// slot has seen a frame (1 statistics, 2 sanitise, 4 hit bitmaps, 8 memset, 16 normalise, 32 download).  With a
+// slot has seen a frame (1 statistics, 4 hit bitmaps + sanitise, 8 memset, 16 normalise, 32 download).  With a
 // sequence of IDENTICAL frames the stale buffers hold the right values, so the timeline shows what each launch
 // costs the fused kernel it overlaps (scripts/seq_trace.py).  Not compiled into the product library.
 #ifdef AMT_DEV_SKIP
@@ -152,8 +152,7 @@ extern "C" int amt_seq_stage_a(amt_seq* seq, int32_t slot, const amt_frame* fram
     bits.d_valid_k = sl.buf.planes.d_valid_k;
     bits.d_valid_c = sl.buf.planes.d_valid_c;
     ++seq->frames_a;
-    int rc = SEQ_SKIP(seq, 4) ? 0 : amt_georef(ctx, frame, &bits, sl.buf.d_stats, st);
-    if (!rc && !SEQ_SKIP(seq, 2)) rc = amt_sanitize(ctx, seq->W, seq->H, &bits, st);
+    int rc = SEQ_SKIP(seq, 4) ? 0 : hit_bits_sanitized(ctx, frame, bits.d_valid_k, bits.d_valid_c, sl.buf.d_stats, st);
     if (!rc && !SEQ_SKIP(seq, 1))
         rc = amt_bbox_stats_frame(ctx, frame, bits.d_valid_k, bits.d_valid_c, nullptr, sl.buf.d_stats, st);
     if (rc) { nvtxRangePop(); return rc; }
