@@ -2096,7 +2096,7 @@ extern "C" int amt_normalise(amt_ctx* ctx, const amt_grid* grid, int32_t dtype, 
 // registers: the binning pass never re-reads 27 B/pixel of planes.
 //   PLANES = false, BIN = true is the plane-free resampling (3 B/pixel in, the grids out).
 //
-// Launch shape: a CTA is a TILE of kFusedCols x kFusedRows pixels (32 x 8: each warp one 32-pixel
+// Launch shape: a CTA is a TILE of kFusedCols x kFusedRows pixels (32 x 4: each warp one 32-pixel
 // row segment, i.e. one word of each bitmap and 256-byte coalesced plane stores).  The scatter is
 // PRIVATISED IN SHARED MEMORY per tile (resample.py:330-338 / histogram.py:244-250 `bincount`): the
 // tile's samples land in a small window of the target grid (~12 x 7 cells at 100"/px), whose
@@ -2108,7 +2108,7 @@ extern "C" int amt_normalise(amt_ctx* ctx, const amt_grid* grid, int32_t dtype, 
 // window exceeds the shared-memory capacity (grid much finer than the pixels: every sample its own
 // cell, nothing to privatise) or that needs f64 side sums uses warp_accumulate directly.
 #ifndef AMT_FUSED_ROWS
-#define AMT_FUSED_ROWS 8
+#define AMT_FUSED_ROWS 4
 #endif
 #ifndef AMT_FUSED_PRIV
 #define AMT_FUSED_PRIV 0
@@ -2119,8 +2119,13 @@ extern "C" int amt_normalise(amt_ctx* ctx, const amt_grid* grid, int32_t dtype, 
 constexpr int kFusedRows = AMT_FUSED_ROWS;       // rows of a tile = warps of the CTA
 constexpr int kFusedCols = 32;
 constexpr int kFusedThreads = kFusedCols * kFusedRows;
+// Resident CTAs per SM the kernel is compiled for.  128-thread CTAs at 8 per SM are the 64-register budget of
+// the point kernels; the pure TAN instantiation fits 56 registers without spilling (9 CTAs' worth of
+// registers), which leaves room for the CTAs of the small stage-A kernels of other frames to run BESIDE
+// the fused kernel's instead of displacing them (in the engine: 0.276 -> 0.262 ms per frame together with
+// the smaller CTAs; the SIP instantiation needs its 64 registers).
 #ifndef AMT_FUSED_MINBLOCKS
-#define AMT_FUSED_MINBLOCKS (AMT_GEOREF_MINBLOCKS * 256 / (32 * AMT_FUSED_ROWS))
+#define AMT_FUSED_MINBLOCKS(SIP) ((AMT_GEOREF_MINBLOCKS * 256 / (32 * AMT_FUSED_ROWS)) + ((SIP) ? 0 : 1))
 #endif
 constexpr int kFusedIter = AMT_FUSED_ITER;       // 32 x 8 tiles per CTA (<= 32: one lane per iteration holds its bitmap words)
 static_assert(kFusedIter >= 1 && kFusedIter <= 32, "one lane per iteration");
@@ -2307,12 +2312,7 @@ __device__ __forceinline__ void fused_row(const GeorefParams& p, const double* s
 // -- 16 % of all warp residency in the one-row-per-warp version (profiles/r02_fused_stalls.txt) -- is paid
 // once per kFusedIter rows.
 template <typename T, int C, bool PLANES, bool MAG, bool BIN, bool SIP>
-__global__ void
-#ifdef AMT_FUSED_MAXNREG
-__maxnreg__(AMT_FUSED_MAXNREG)
-#else
-__launch_bounds__(kFusedThreads, AMT_FUSED_MINBLOCKS)
-#endif
+__global__ void __launch_bounds__(kFusedThreads, AMT_FUSED_MINBLOCKS(SIP))
 k_georef_fused(const __grid_constant__ GeorefParams p, const uint32_t* __restrict__ valid_k,
                const uint32_t* __restrict__ valid_c, const T* __restrict__ img, const __grid_constant__ GridC g,
                unsigned long long* __restrict__ count, unsigned long long* __restrict__ sums,
