@@ -9,10 +9,14 @@ mkdir -p $out
 # 1. every launch of a short bench run with its device time (cold-cache, serialised: compare SHARES)
 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 300 --csv --log-file $out/launches_$tag.csv \
     python bench.py --steps 12 --warmup 3 --repeats 1 --no-variants --no-cpu-baseline > $out/bench_under_ncu_$tag.log 2>&1
-# 2. full counter set of one launch of every kernel of the step (after warm-up)
+# 2. full counter set of one launch of every kernel of the step (after warm-up): the long kernel and the
+#    normalisation, then the stage-A kernels (they run three frames ahead of their fused kernel)
 ncu --set full --clock-control none --import-source on \
-    -k regex:'k_georef_fused|k_limb_bits|k_sanitize_fused|k_outline_collect|k_outline_eval|k_normalise' -s 40 -c 10 -f -o $out/step_$tag \
+    -k regex:'k_georef_fused|k_normalise' -s 40 -c 4 -f -o $out/step_$tag \
     python bench.py --steps 6 --warmup 3 --repeats 1 --no-variants --no-cpu-baseline > $out/ncu_step_$tag.log 2>&1
+ncu --set full --clock-control none --import-source on \
+    -k regex:'k_limb_bits|k_sanitize_fused|k_outline_collect|k_outline_eval' -s 24 -c 8 -f -o $out/stagea_$tag \
+    python bench.py --steps 6 --warmup 3 --repeats 1 --no-variants --no-cpu-baseline > $out/ncu_stagea_$tag.log 2>&1
 # 3. the scatter in three regimes: atomics / L2 counters of k_bin and k_georef_fused
 ncu --set full --clock-control none -k regex:'k_bin|k_georef_fused' -f -o $out/scatter_$tag \
     python scripts/bin_scatter.py > $out/ncu_scatter_$tag.log 2>&1

@@ -90,11 +90,19 @@ def report(path):
             print('  %-10s %14d %5.1f%%' % (k, v, 100.0 * v / max(tot, 1)))
 
 
-def to_json(path, command=''):
+def to_json(paths, command=''):
+    """`paths`: one report or several separated by commas (the first occurrence of a kernel wins)."""
     import json
+    kernels = {}
+    for path in paths.split(','):
+        _json_kernels(path, kernels)
+    git = subprocess.run(['git', 'rev-parse', '--short', 'HEAD'], capture_output=True, text=True).stdout.strip()
+    print(json.dumps({'git': git, 'command': command, 'report': paths, 'kernels': kernels}, indent=1))
+
+
+def _json_kernels(path, kernels):
     raw = list(csv.reader(io.StringIO(ncu(['-i', path, '--page', 'raw', '--csv']))))
     hdr = raw[0]
-    kernels = {}
     short = {
         'gpu__time_duration.sum': 'duration_ns',
         'dram__bytes_read.sum': 'dram_bytes_read', 'dram__bytes_write.sum': 'dram_bytes_write',
@@ -133,8 +141,6 @@ def to_json(path, command=''):
         if 'dram_bytes_read' in k and 'dram_bytes_write' in k:
             k['dram_bytes'] = k['dram_bytes_read'] + k['dram_bytes_write']
         kernels[name] = k
-    git = subprocess.run(['git', 'rev-parse', '--short', 'HEAD'], capture_output=True, text=True).stdout.strip()
-    print(json.dumps({'git': git, 'command': command, 'report': path, 'kernels': kernels}, indent=1))
 
 
 def launches(path):
