@@ -21,4 +21,14 @@ ncu --set full --clock-control none --import-source on \
 ncu --set full --clock-control none -k regex:'k_bin|k_georef_fused' -f -o $out/scatter_$tag \
     python scripts/bin_scatter.py > $out/ncu_scatter_$tag.log 2>&1
 REPS=10 python scripts/bin_scatter.py > $out/scatter_times_$tag.txt 2>&1
-ls -la $out | tail -12
+# 4. summaries are made HERE (gpurun brings back at most 64 MiB and a report with imported source is ~30 MB):
+#    text + JSON of every report, then only the step report itself travels
+python scripts/ncu_summary.py launches $out/launches_$tag.csv > $out/${tag}_launches.txt
+python scripts/ncu_summary.py report $out/step_$tag.ncu-rep > $out/${tag}_step_ncu.txt
+python scripts/ncu_summary.py report $out/stagea_$tag.ncu-rep > $out/${tag}_stagea_ncu.txt
+python scripts/ncu_summary.py report $out/scatter_$tag.ncu-rep > $out/${tag}_scatter_ncu.txt
+python scripts/ncu_summary.py json $out/step_$tag.ncu-rep,$out/stagea_$tag.ncu-rep,$out/scatter_$tag.ncu-rep \
+    "bash scripts/gpu_profile.sh $tag" > $out/${tag}_ncu_kernels.json
+ncu -i $out/step_$tag.ncu-rep --page source --csv --kernel-name regex:k_georef_fused --launch-count 1 > $out/${tag}_fused_source.csv 2>/dev/null
+rm -f $out/stagea_$tag.ncu-rep $out/scatter_$tag.ncu-rep
+ls -la $out | tail -16

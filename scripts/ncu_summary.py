@@ -96,7 +96,9 @@ def to_json(paths, command=''):
     kernels = {}
     for path in paths.split(','):
         _json_kernels(path, kernels)
-    git = subprocess.run(['git', 'rev-parse', '--short', 'HEAD'], capture_output=True, text=True).stdout.strip()
+    import os
+    git = os.environ.get('AMT_GIT') or subprocess.run(['git', 'rev-parse', '--short', 'HEAD'], capture_output=True,
+                                                      text=True).stdout.strip()
     print(json.dumps({'git': git, 'command': command, 'report': paths, 'kernels': kernels}, indent=1))
 
 
