@@ -1057,9 +1057,80 @@ __global__ void __launch_bounds__(256) k_sanitize_fused(int W, int H, Bits K0, B
     }
 }
 
+// The same three steps with the intermediate words kept in shared memory: a CTA owns kSanRows full rows, forms
+// k1 for its rows + 1 halo row either side, c1 for its rows + 1 above, then the results -- each intermediate
+// word is computed ~1.1 times instead of 9 (k1) / 4 (c1) times as in the register-only version above:
+// 6.5 M -> <1 M warp instructions per 12-Mpix frame (profiles/r02_kernels_ncu.txt), which is what the kernel
+// takes away from the fused kernel it runs beside in the sequence engine.  Dynamic shared memory:
+// (2 kSanRows + 3) (wpr + 2) words; frames too wide for 48 KB use the register-only kernel.
+constexpr int kSanRows = 14;
+template <bool WRITE_ALL>
+__global__ void __launch_bounds__(256) k_sanitize_tile(int W, int H, Bits K0, Bits C0, unsigned* __restrict__ kout,
+                                                       unsigned* __restrict__ cout, amt_georef_out o) {
+    extern __shared__ unsigned s_san[];
+    const SanitizeWords sw{K0, C0};
+    const int wk = K0.wpr, pitch = wk + 2;
+    unsigned* s_k1 = s_san;                               // rows y0-1 .. y0+kSanRows, words -1 .. wk
+    unsigned* s_c1 = s_san + (kSanRows + 2) * pitch;      // rows y0-1 .. y0+kSanRows-1, words -1 .. wk
+    const int y0 = blockIdx.x * kSanRows;
+    for (int idx = threadIdx.x; idx < (kSanRows + 2) * pitch; idx += 256) {
+        const int r = idx / pitch, c = idx - r * pitch;
+        s_k1[idx] = sw.k1(y0 - 1 + r, c - 1);
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < (kSanRows + 1) * pitch; idx += 256) {
+        const int r = idx / pitch, c = idx - r * pitch;
+        unsigned v = 0u;
+        if (c + 1 < pitch) {                              // word wk has no right neighbour in the tile and is never used
+            const unsigned a = s_k1[r * pitch + c], a_r = (a >> 1) | (s_k1[r * pitch + c + 1] << 31);
+            const unsigned b = s_k1[(r + 1) * pitch + c], b_r = (b >> 1) | (s_k1[(r + 1) * pitch + c + 1] << 31);
+            v = C0.at(y0 - 1 + r, c - 1) & a & a_r & b & b_r;
+        }
+        s_c1[idx] = v;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < kSanRows * wk; idx += 256) {
+        const int r = idx / wk, i = idx - r * wk, y = y0 + r;
+        if (y > H) break;
+        // c1 rows: r -> y-1, r+1 -> y; columns: i -> word i-1, i+1 -> word i
+        const unsigned c_up = s_c1[r * pitch + i + 1], c_up_l = s_c1[r * pitch + i];
+        const unsigned c_dn = s_c1[(r + 1) * pitch + i + 1], c_dn_l = s_c1[(r + 1) * pitch + i];
+        const unsigned up_l = (c_up << 1) | (c_up_l >> 31), dn_l = (c_dn << 1) | (c_dn_l >> 31);
+        const unsigned k2 = s_k1[(r + 1) * pitch + i + 1] & (up_l | c_up | dn_l | c_dn);
+        const unsigned k_old = K0.at(y, i);
+        if (WRITE_ALL || k2 != k_old) {
+            kout[(size_t)y * wk + i] = k2;
+            if (k2 != k_old) nan_corners(o, (size_t)y * (W + 1) + 32 * i, k_old & ~k2);
+        }
+        if (y < H && i < C0.wpr) {
+            const unsigned c_old = C0.at(y, i);
+            if (WRITE_ALL || c_dn != c_old) {
+                cout[(size_t)y * C0.wpr + i] = c_dn;
+                if (c_dn != c_old) nan_centers(o, (size_t)y * W + 32 * i, c_old & ~c_dn);
+            }
+        }
+    }
+}
+
+template <bool WRITE_ALL>
+static void launch_sanitize(const amt_ctx* ctx, cudaStream_t st, int W, int H, const Bits& K0, const Bits& C0,
+                            unsigned* kout, unsigned* cout, const amt_georef_out& o);
+
 static inline int sanitize_blocks(const amt_ctx* ctx, size_t words) {
     static const int per_sm = getenv("AMT_SANITIZE_BLOCKS_PER_SM") ? atoi(getenv("AMT_SANITIZE_BLOCKS_PER_SM")) : 2;
     return (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->sm_count * per_sm, (words + 255) / 256));
+}
+
+template <bool WRITE_ALL>
+static void launch_sanitize(const amt_ctx* ctx, cudaStream_t st, int W, int H, const Bits& K0, const Bits& C0,
+                            unsigned* kout, unsigned* cout, const amt_georef_out& o) {
+    const size_t smem = (size_t)(2 * kSanRows + 3) * (K0.wpr + 2) * sizeof(unsigned);
+    if (smem <= 48 * 1024 && !getenv("AMT_SANITIZE_REGISTERS")) {
+        k_sanitize_tile<WRITE_ALL><<<(H + 1 + kSanRows - 1) / kSanRows, 256, smem, st>>>(W, H, K0, C0, kout, cout, o);
+    } else {
+        const size_t nk = (size_t)K0.wpr * (H + 1);
+        k_sanitize_fused<WRITE_ALL><<<sanitize_blocks(ctx, nk), 256, 0, st>>>(W, H, K0, C0, kout, cout, o);
+    }
 }
 
 __device__ __forceinline__ unsigned long long umin64(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
@@ -1343,8 +1414,7 @@ extern "C" int amt_sanitize(amt_ctx* ctx, int32_t W, int32_t H, const amt_georef
         CUDA_TRY(cudaMemcpyAsync(c0, planes->d_valid_c, nc * 4, cudaMemcpyDeviceToDevice, st));
     }
     Bits K0{k0, wk, H + 1}, C0{c0, wc, H};
-    k_sanitize_fused<false><<<sanitize_blocks(ctx, nk), 256, 0, st>>>(W, H, K0, C0, planes->d_valid_k,
-                                                                       planes->d_valid_c, *planes);
+    launch_sanitize<false>(ctx, st, W, H, K0, C0, planes->d_valid_k, planes->d_valid_c, *planes);
     LAUNCH_CHECK(ctx);
     return AMT_OK;
 }
@@ -1369,7 +1439,7 @@ static int hit_bits_sanitized(amt_ctx* ctx, const amt_frame* frame, uint32_t* d_
     Bits K0{raw.d_valid_k, wk, H + 1}, C0{raw.d_valid_c, wc, H};
     amt_georef_out none;
     memset(&none, 0, sizeof none);
-    k_sanitize_fused<true><<<sanitize_blocks(ctx, nk), 256, 0, st>>>(W, H, K0, C0, d_valid_k, d_valid_c, none);
+    launch_sanitize<true>(ctx, st, W, H, K0, C0, d_valid_k, d_valid_c, none);
     LAUNCH_CHECK(ctx);
     return AMT_OK;
 }

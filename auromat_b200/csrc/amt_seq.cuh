@@ -23,7 +23,7 @@ struct SeqSlot {
     amt_seq_slot buf;
     bool is_set;
     amt_frame frame;
-    cudaEvent_t ev_a, ev_up, ev_b, ev_out, ev_zero;
+    cudaEvent_t ev_a, ev_up, ev_b, ev_out, ev_zero, ev_fork;
     cudaEvent_t tr_a0, tr_up0, tr_b0;      // trace mode only: starts of stage A, of the upload, of the fused kernel
     bool a_rec, b_rec, out_rec;
 };
@@ -44,6 +44,12 @@ struct amt_seq {
     size_t frames_a = 0;
     int W, H, C, dtype;
     cudaStream_t s_main, s_aux, s_copy, s_out;
+    // Second stream for the long kernels (same priority as s_main), used by every other frame: the fused
+    // kernels of consecutive frames are independent (own ring slot, own accumulators), and on two streams the
+    // next one starts dispatching as soon as the current one has dispatched its last CTA -- the head of frame
+    // i+1 fills the SMs that the tail of frame i leaves idle.  On one stream it waited for the last CTA to finish.
+    cudaStream_t s_main2;
+    size_t frames_b = 0;
     std::vector<SeqSlot> slots;
     unsigned long long h2d_bytes;
     bool trace;                            // AMT_SEQ_TRACE: timing events, see amt_seq_trace
@@ -79,6 +85,12 @@ extern "C" int amt_seq_create(amt_ctx* ctx, int32_t width, int32_t height, int32
     s->s_main = (cudaStream_t)main_stream; s->s_aux = (cudaStream_t)aux_stream;
     s->s_copy = (cudaStream_t)copy_stream; s->s_out = (cudaStream_t)out_stream;
     s->h2d_bytes = 0;
+    s->s_main2 = nullptr;
+    if (!getenv("AMT_SEQ_ONE_MAIN_STREAM")) {
+        int lo = 0, hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&s->s_main2, cudaStreamNonBlocking, lo));
+    }
     const char* tr = getenv("AMT_SEQ_TRACE");
     s->trace = tr && tr[0] && tr[0] != '0';
     s->ev_base = nullptr;
@@ -91,8 +103,9 @@ extern "C" int amt_seq_create(amt_ctx* ctx, int32_t width, int32_t height, int32
         memset(&sl.buf, 0, sizeof sl.buf);
         sl.is_set = sl.a_rec = sl.b_rec = sl.out_rec = false;
         sl.tr_a0 = sl.tr_up0 = sl.tr_b0 = nullptr;
-        cudaEvent_t* evs[8] = {&sl.ev_a, &sl.ev_up, &sl.ev_b, &sl.ev_out, &sl.ev_zero, &sl.tr_a0, &sl.tr_up0, &sl.tr_b0};
-        for (int k = 0; k < (s->trace ? 8 : 5); ++k) {
+        cudaEvent_t* evs[9] = {&sl.ev_a, &sl.ev_up, &sl.ev_b, &sl.ev_out, &sl.ev_zero, &sl.ev_fork, &sl.tr_a0, &sl.tr_up0,
+                               &sl.tr_b0};
+        for (int k = 0; k < (s->trace ? 9 : 6); ++k) {
             cudaEvent_t* e = evs[k];
             cudaError_t err = cudaEventCreateWithFlags(e, s->trace ? cudaEventDefault : cudaEventDisableTiming);
             if (err != cudaSuccess) {
@@ -111,9 +124,11 @@ extern "C" int amt_seq_destroy(amt_seq* seq) {
     for (auto& sl : seq->slots) {
         cudaEventDestroy(sl.ev_a); cudaEventDestroy(sl.ev_up); cudaEventDestroy(sl.ev_b); cudaEventDestroy(sl.ev_out);
         cudaEventDestroy(sl.ev_zero);
+        cudaEventDestroy(sl.ev_fork);
         if (seq->trace) { cudaEventDestroy(sl.tr_a0); cudaEventDestroy(sl.tr_up0); cudaEventDestroy(sl.tr_b0); }
     }
     if (seq->ev_base) cudaEventDestroy(seq->ev_base);
+    if (seq->s_main2) cudaStreamDestroy(seq->s_main2);
     delete seq;
     return AMT_OK;
 }
@@ -268,7 +283,12 @@ extern "C" int amt_seq_stage_b(amt_seq* seq, int32_t slot, const amt_seq_job* jo
     }
     CUDA_TRY(cudaEventRecord(sl.ev_up, seq->s_copy));
     // main stream: nothing but the long fused kernels, back to back from frame to frame
-    cudaStream_t st = seq->s_main;
+    cudaStream_t st = (seq->s_main2 && (seq->frames_b++ & 1)) ? seq->s_main2 : seq->s_main;
+    if (st != seq->s_main) {
+        // whatever the caller has enqueued on its stream so far (e.g. the kernel that produced a device image)
+        CUDA_TRY(cudaEventRecord(sl.ev_fork, seq->s_main));
+        CUDA_TRY(cudaStreamWaitEvent(st, sl.ev_fork, 0));
+    }
     CUDA_TRY(cudaStreamWaitEvent(st, sl.ev_a, 0));             // final bitmaps of this frame (auxiliary stream)
     CUDA_TRY(cudaStreamWaitEvent(st, sl.ev_up, 0));            // image on the device
     CUDA_TRY(cudaStreamWaitEvent(st, sl.ev_zero, 0));          // accumulators zeroed

@@ -513,7 +513,7 @@ class _Engine(object):
                 st = ctx.__dict__[name] = torch.cuda.Stream(dev, priority=prio)
             return st
         self.main = main
-        self.aux, self.copy, self.dout = stream('_aux_stream', -1), stream('_copy_stream'), stream('_dout_stream')
+        self.aux, self.copy, self.dout = stream('_aux_stream', int(os.environ.get('AMT_SEQ_AUX_PRIORITY', '-1'))), stream('_copy_stream'), stream('_dout_stream')
         self.handle = ctypes.c_void_p()
         _lib.check(ctx.lib.amt_seq_create(ctx.handle, w, h, channels, self.amtDtype, nslots,
                                           ctypes.c_void_p(main.cuda_stream), ctypes.c_void_p(self.aux.cuda_stream),
