@@ -15,7 +15,7 @@ ncu --set full --clock-control none --import-source on \
     -k regex:'k_georef_fused|k_normalise' -s 40 -c 4 -f -o $out/step_$tag \
     python bench.py --steps 6 --warmup 3 --repeats 1 --no-variants --no-cpu-baseline > $out/ncu_step_$tag.log 2>&1
 ncu --set full --clock-control none --import-source on \
-    -k regex:'k_limb_bits|k_sanitize_fused|k_outline_collect|k_outline_eval' -s 24 -c 8 -f -o $out/stagea_$tag \
+    -k regex:'k_limb_bits|k_sanitize|k_outline_collect|k_outline_eval' -s 24 -c 8 -f -o $out/stagea_$tag \
     python bench.py --steps 6 --warmup 3 --repeats 1 --no-variants --no-cpu-baseline > $out/ncu_stagea_$tag.log 2>&1
 # 3. the scatter in three regimes: atomics / L2 counters of k_bin and k_georef_fused
 ncu --set full --clock-control none -k regex:'k_bin|k_georef_fused' -f -o $out/scatter_$tag \
