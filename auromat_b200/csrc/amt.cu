@@ -605,6 +605,98 @@ __global__ void __launch_bounds__(128) k_limb_bits(const __grid_constant__ Geore
     if (p.ill && n_graze && lane == 0) atomicAdd(p.ill, (unsigned long long)n_graze);
 }
 
+// The same for TAN-SIP frames.  Pixel (x, y) looks where the pure TAN model looks at (x + fx, y + fy) with
+// |fx| <= sip_dx, |fy| <= sip_dy (rigorous bounds of the polynomial over the frame, fill_sip_bounds), and the
+// discriminant of the pure TAN model is a quadratic FORM Q(x', y') of the (real-valued) pixel position.  For a
+// bitmap word (32 pixels of a row, corner and centre rays) all positions lie in the box
+//     [32 i - 1 - sip_dx, 32 i + 32 + sip_dx] x [y - 1 - sip_dy, y + 1 + sip_dy];
+// Q at the box centre, its exact gradient and Hessian bound the variation over the box:
+//     |Q(c + d) - Q(c)| <= |Qx| hx + |Qy| hy + (|Qxx| hx^2 + 2 |Qxy| hx hy + |Qyy| hy^2) / 2.
+// If |Q(c)| exceeds the bound (with a 1e-6 relative reserve for the rounding of either evaluation), every
+// ray of the word is on the same side of the limb: the word is constant and takes the EXACT predicate
+// (SIP polynomial, dirs_kc + intersect_hit) of its first pixel -- where Q > 0 throughout, dDO cannot change
+// sign either (it vanishes only where rt < 0).  Every other word is evaluated pixel by pixel with that
+// predicate.  Same bitmaps as k_hit_bits, bit for bit (tests), at ~1/20 of its ray evaluations.
+__global__ void __launch_bounds__(128) k_limb_bits_sip(const __grid_constant__ GeorefParams p,
+                                                       uint32_t* __restrict__ valid_k,
+                                                       uint32_t* __restrict__ valid_c) {
+    const int W = p.f.W, H = p.f.H;
+    __shared__ double s_sip[2 * AMT_SIP_MAX_COEF];
+    for (int i = threadIdx.x; i < 2 * AMT_SIP_MAX_COEF; i += blockDim.x)
+        s_sip[i] = i < AMT_SIP_MAX_COEF ? p.sip_a[i] : p.sip_b[i - AMT_SIP_MAX_COEF];
+    __syncthreads();
+    const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (y > H) return;                                   // warp-uniform
+    const int lane = threadIdx.x & 31;
+    const int wk = (W + 1 + 31) >> 5, wc = (W + 31) >> 5;
+    const FrameC& f = p.f;
+    const double* sa = s_sip;
+    const double* sb = s_sip + AMT_SIP_MAX_COEF;
+    double Dx[3], Dy[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { Dx[k] = f.aff_b[k] * f.rad[k]; Dy[k] = f.aff_c[k] * f.rad[k]; }
+    const double k1 = 1.0 - f.oDO;
+    const double ox = Dx[0] * f.otr[0] + Dx[1] * f.otr[1] + Dx[2] * f.otr[2];
+    const double oy = Dy[0] * f.otr[0] + Dy[1] * f.otr[1] + Dy[2] * f.otr[2];
+    const double q_xx = 2.0 * ox * ox + k1 * 2.0 * (Dx[0] * Dx[0] + Dx[1] * Dx[1] + Dx[2] * Dx[2]);
+    const double q_xy = 2.0 * ox * oy + k1 * 2.0 * (Dx[0] * Dy[0] + Dx[1] * Dy[1] + Dx[2] * Dy[2]);
+    const double q_yy = 2.0 * oy * oy + k1 * 2.0 * (Dy[0] * Dy[0] + Dy[1] * Dy[1] + Dy[2] * Dy[2]);
+    const double hx = 16.5 + f.sip_dx, hy = 1.0 + f.sip_dy;
+    const double curv = 0.5 * (fabs(q_xx) * hx * hx + 2.0 * fabs(q_xy) * hx * hy + fabs(q_yy) * hy * hy);
+    unsigned n_graze = 0;
+    for (int base = 0; base < wk; base += 32) {           // warp-uniform
+        const int i = base + lane;
+        bool unc = true;
+        if (i < wk) {
+            const double cx = 32.0 * i + 15.5, cy = (double)y;          // corner-model coordinates of the box centre
+            double Dc[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) Dc[k] = (f.aff_a[k] + f.aff_b[k] * cx + f.aff_c[k] * cy) * f.rad[k];
+            const double dDO = Dc[0] * f.otr[0] + Dc[1] * f.otr[1] + Dc[2] * f.otr[2];
+            const double dDD = Dc[0] * Dc[0] + Dc[1] * Dc[1] + Dc[2] * Dc[2];
+            const double Q = dDO * dDO + k1 * dDD;
+            const double q_x = 2.0 * dDO * ox + k1 * 2.0 * (Dc[0] * Dx[0] + Dc[1] * Dx[1] + Dc[2] * Dx[2]);
+            const double q_y = 2.0 * dDO * oy + k1 * 2.0 * (Dc[0] * Dy[0] + Dc[1] * Dy[1] + Dc[2] * Dy[2]);
+            const double bound = fabs(q_x) * hx + fabs(q_y) * hy + curv;
+            // reserve: 1e-6 of the bound and of the cancelling terms of Q itself
+            const double reserve = 1e-6 * (bound + dDO * dDO + fabs(k1 * dDD));
+            unc = !(fabs(Q) > bound + reserve);              // NaN -> uncertain
+        }
+        unc &= i < wk;
+        unsigned word_k = 0, word_c = 0;
+        if (i < wk && !unc) {                             // constant word: exact predicate of its first pixel
+            double dk[3], dc[3];
+            bool gz;
+            dirs_kc<true>(f, sa, sb, 32 * i, y, dk, dc);
+            const int nk = min(32, W + 1 - 32 * i), nc = min(32, W - 32 * i);
+            if (intersect_hit(f, dk, gz)) word_k = nk >= 32 ? 0xffffffffu : ((1u << nk) - 1u);
+            if (nc > 0 && intersect_hit(f, dc, gz)) word_c = nc >= 32 ? 0xffffffffu : ((1u << nc) - 1u);
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, unc);
+        while (todo) {                                    // pixel-by-pixel words, the warp on the 32 pixels
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int x = 32 * (base + src) + lane;
+            bool hk = false, hc = false, gk = false, gc = false;
+            if (x <= W) {
+                double dk[3], dc[3];
+                dirs_kc<true>(f, sa, sb, x, y, dk, dc);
+                hk = intersect_hit(f, dk, gk);
+                hc = intersect_hit(f, dc, gc) && x < W;
+                gc &= x < W && y < H;
+            }
+            const unsigned bk = __ballot_sync(0xffffffffu, hk), bc = __ballot_sync(0xffffffffu, hc);
+            n_graze += __popc(__ballot_sync(0xffffffffu, gk | gc));
+            if (lane == src) { word_k = bk; word_c = bc; }
+        }
+        if (i < wk) {
+            valid_k[(size_t)y * wk + i] = word_k;
+            if (y < H && i < wc) valid_c[(size_t)y * wc + i] = word_c;
+        }
+    }
+    if (p.ill && n_graze && lane == 0) atomicAdd(p.ill, (unsigned long long)n_graze);
+}
+
 // fastCenterCalculation == True: a CTA evaluates a (TH+1)x(TW+1) patch of corner rays into
 // shared memory, then derives each centre from the mean of its 4 corner intersection points
 // and (un-normalised) directions: mapping/astrometry.py:154-160 (`_calcCenters`).
@@ -751,6 +843,8 @@ static int fill_frame(const amt_frame* fr, GeorefParams& p) {
     memcpy(p.sip_a, fr->sip_a, sizeof p.sip_a);
     memcpy(p.sip_b, fr->sip_b, sizeof p.sip_b);
     fill_affine(f);
+    f.sip_dx = f.sip_dy = 0.0;
+    if (f.sip_oa | f.sip_ob) fill_sip_bounds(f, p.sip_a, p.sip_b);
     return AMT_OK;
 }
 
@@ -781,8 +875,12 @@ extern "C" int amt_georef(amt_ctx* ctx, const amt_frame* frame, const amt_georef
                                out->d_lon_c || out->d_mlat_c || out->d_mlt_c || out->d_elev_c;
         if (!any_plane) {                          // validity bitmaps only
             const bool affine = frame->model == AMT_MODEL_WCS && frame->sip_order_a == 0 && frame->sip_order_b == 0;
-            if (affine && out->d_valid_k && out->d_valid_c && !getenv("AMT_NO_LIMB_SOLVER")) {
+            const bool solver = frame->model == AMT_MODEL_WCS && out->d_valid_k && out->d_valid_c &&
+                                !getenv("AMT_NO_LIMB_SOLVER");
+            if (solver && affine) {
                 k_limb_bits<<<(H + 1 + 3) / 4, 128, 0, st>>>(p, out->d_valid_k, out->d_valid_c);
+            } else if (solver) {
+                k_limb_bits_sip<<<(H + 1 + 3) / 4, 128, 0, st>>>(p, out->d_valid_k, out->d_valid_c);
             } else {
                 dim3 gh((W + 1 + 255) / 256, H + 1);
                 k_hit_bits<<<gh, 256, 0, st>>>(p);
@@ -2176,26 +2274,42 @@ extern "C" int amt_cell_indices(amt_ctx* ctx, const double* d_lat_c, const doubl
 
 // resample.py:339-351 + :128-136: mean = sum/count in float64, NaN where count == 0,
 // np.round (half-even) + cast for integer images.
+// rint(sum / n) of the reference (float64 division, round half to even) for integer sums: when sum and n fit
+// 32 bits the quotient is formed in integers -- exact, and equal to the float64 result (sum/n = q + r/n with
+// |r/n - 1/2| >= 1/(2n) >= 2^-33, far more than an ulp of a quotient < 2^32, so the rounded division cannot
+// create or remove a tie); an IEEE double division costs ~40 instructions, and at 10"/px a frame has 20 M cells.
+__device__ __forceinline__ unsigned long long mean_rint(unsigned long long sum, unsigned long long n) {
+    if ((sum | n) >> 32) return (unsigned long long)rint((double)sum / (double)n);
+    const unsigned s32 = (unsigned)sum, n32 = (unsigned)n;
+    const unsigned q = s32 / n32, r = s32 - q * n32;
+    const unsigned twice = 2u * r;                      // r < n < 2^32: the carry is the comparison
+    const bool above = twice < r || twice > n32;        // 2r > n
+    return q + ((above || (twice == n32 && (q & 1u))) ? 1u : 0u);
+}
+
 template <typename T>
-__global__ void k_normalise(size_t cells, int C, const unsigned long long* __restrict__ count,
+__global__ void __launch_bounds__(256) k_normalise(size_t cells, int C, const unsigned long long* __restrict__ count,
                             const unsigned long long* __restrict__ sums, const double* __restrict__ fsum,
                             T* __restrict__ out_img, unsigned char* __restrict__ out_mask, double* __restrict__ out_side,
-                            double side_scale) {
+                            double side_scale, double inv_scale) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= cells) return;
     const unsigned long long n = count[i];
-    if (out_mask) out_mask[i] = n == 0;
-    const double dn = (double)n;
-    for (int c = 0; c < C; ++c) {
-        T v = 0;
-        if (n) v = (T)rint((double)sums[(size_t)c * cells + i] / dn);
-        out_img[i * C + c] = v;
-    }
+    // every load of the cell is issued before the first use (the sums used to wait for the count)
+    unsigned long long sm[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        if (c < C) sm[c] = sums[(size_t)c * cells + i];
+    double tot = 0.0;
     if (out_side) {
-        double tot = fsum[i];
-        if (side_scale > 0.0) tot = (double)((const long long*)fsum)[i] / side_scale;     // exact: power of two
-        out_side[i] = n ? tot / dn : qnan();
+        tot = fsum[i];
+        if (side_scale > 0.0) tot = (double)((const long long*)fsum)[i] * inv_scale;      // exact: power of two
     }
+    if (out_mask) out_mask[i] = n == 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        if (c < C) out_img[i * C + c] = n ? (T)mean_rint(sm[c], n) : (T)0;
+    if (out_side) out_side[i] = n ? div_fast(tot, (double)n) : qnan();       // <= 1 ulp (amt_fastmath.cuh)
 }
 
 extern "C" int amt_normalise(amt_ctx* ctx, const amt_grid* grid, int32_t dtype, int32_t channels,
@@ -2213,12 +2327,14 @@ extern "C" int amt_normalise(amt_ctx* ctx, const amt_grid* grid, int32_t dtype, 
         k_normalise<unsigned char><<<blocks, 256, 0, st>>>(cells, channels, (const unsigned long long*)d_count,
                                                           (const unsigned long long*)d_sums, d_fsum,
                                                           (unsigned char*)d_out_img, d_out_mask, d_out_side,
-                                                          grid->side_scale > 0 ? grid->side_scale : 0.0);
+                                                          grid->side_scale > 0 ? grid->side_scale : 0.0,
+                                                          grid->side_scale > 0 ? 1.0 / grid->side_scale : 0.0);
     else if (dtype == AMT_U16)
         k_normalise<unsigned short><<<blocks, 256, 0, st>>>(cells, channels, (const unsigned long long*)d_count,
                                                            (const unsigned long long*)d_sums, d_fsum,
                                                            (unsigned short*)d_out_img, d_out_mask, d_out_side,
-                                                           grid->side_scale > 0 ? grid->side_scale : 0.0);
+                                                           grid->side_scale > 0 ? grid->side_scale : 0.0,
+                                                           grid->side_scale > 0 ? 1.0 / grid->side_scale : 0.0);
     else
         return set_err(AMT_ERR_UNSUPPORTED, "amt_normalise: image dtype must be uint8 or uint16");
     LAUNCH_CHECK(ctx);

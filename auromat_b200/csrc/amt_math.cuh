@@ -42,6 +42,10 @@ struct FrameC {
     //     centre (ix, iy):  dir_c = dir_k + aff_h                          (aff_h = (aff_b + aff_c) / 2)
     // coefficients formed on the host in extended precision (fill_frame).
     double aff_a[3], aff_b[3], aff_c[3], aff_h[3];
+    // SIP frames: rigorous bounds of the polynomial displacement over the pixel array, in pixels
+    // (sum |A_pq| U^p V^q with U, V the largest |u|, |v| of the frame): pixel (x, y) looks where the pure TAN
+    // model looks at (x + fx, y + fy), |fx| <= sip_dx, |fy| <= sip_dy (k_limb_bits_sip)
+    double sip_dx, sip_dy;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -148,6 +152,22 @@ AMT_HD void dirs_kc(const FrameC& f, const double* __restrict__ sip_a, const dou
 // Host: coefficients of the affine ray model from (crpix, cd, rot), in extended precision.
 //   u = ix - 0.5 - crpix0 + 1,  v = iy - 0.5 - crpix1 + 1   (corner of pixel index (ix, iy))
 //   dir = rot[:,1] x - rot[:,0] y + rot[:,2] K,  x = cd0 u + cd1 v,  y = cd2 u + cd3 v
+inline void fill_sip_bounds(FrameC& f, const double* sip_a, const double* sip_b) {
+    const double U = fmax(fabs(0.5 - f.crpix0), fabs((double)f.W + 1.0 - f.crpix0)) + 1.0;
+    const double V = fmax(fabs(0.5 - f.crpix1), fabs((double)f.H + 1.0 - f.crpix1)) + 1.0;
+    const double* coef[2] = {sip_a, sip_b};
+    const int order[2] = {f.sip_oa, f.sip_ob};
+    double bound[2] = {0.0, 0.0};
+    for (int w = 0; w < 2; ++w) {
+        // packed triangular coefficients of sip_poly: index(p, q) = p (order + 1) - p (p - 1) / 2 + q
+        for (int pp = 0; pp <= order[w]; ++pp)
+            for (int q = 0; pp + q <= order[w]; ++q)
+                bound[w] += fabs(coef[w][pp * (order[w] + 1) - (pp * (pp - 1)) / 2 + q]) * pow(U, pp) * pow(V, q);
+    }
+    f.sip_dx = bound[0];
+    f.sip_dy = bound[1];
+}
+
 inline void fill_affine(FrameC& f) {
     const long double K = 180.0L / 3.14159265358979323846264338327950288L;
     const long double u0 = 0.5L - (long double)f.crpix0, v0 = 0.5L - (long double)f.crpix1;

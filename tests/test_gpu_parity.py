@@ -1320,6 +1320,33 @@ def test_limb_solver_equals_per_pixel_hit_test(env, W, H):
     assert 'limb' in seen
 
 
+@pytest.mark.parametrize("W,H,order", [(97, 61, 2), (532, 354, 4), (1064, 708, 3), (700, 500, 5)])
+def test_sip_limb_solver_equals_per_pixel_hit_test(env, W, H, order):
+    """TAN-SIP frames: words whose displacement-inflated box is provably on one side of the limb (quadratic-form
+    bound, k_limb_bits_sip) take the exact predicate of their first pixel, all others are evaluated per pixel
+    -- same bitmaps and the same grazing-ray count as the per-pixel hit test, over random camera geometries
+    and random SIP polynomials (displacements of a few to tens of pixels)."""
+    import torch
+    from auromat_b200 import synthetic
+    from auromat_b200.mapping.spacecraft import getMapping
+    seen, evaluated = set(), []
+    for k, (name, hdr) in enumerate(_geometries(W, H)):
+        sip = synthetic.issHeader(W, H, sipOrder=order, seed=10 + k)
+        h = dict(hdr)
+        for key, v in sip.items():
+            if key.startswith(('A_', 'B_', 'CTYPE')):
+                h[key] = v
+        fr = getMapping(np.zeros((H, W, 1), np.uint8), h, identifier=name).frameConstants
+        a, ga = _hit_bitmaps(env, fr, W, H, True)
+        b, gb = _hit_bitmaps(env, fr, W, H, False)
+        assert torch.equal(a['valid_k'], b['valid_k']), name
+        assert torch.equal(a['valid_c'], b['valid_c']), name
+        assert ga == gb, name
+        frac = float((b['valid_c'] != 0).float().mean())
+        seen.add('none' if frac == 0 else 'all' if frac == 1 else 'limb')
+    assert 'limb' in seen
+
+
 @pytest.mark.parametrize("sip", [0, 4])
 @pytest.mark.parametrize("dtype,channels", [(np.uint8, 3), (np.uint16, 1)])
 def test_fused_kernel_equals_unfused_chain(env, sip, dtype, channels):
