@@ -1158,7 +1158,7 @@ __global__ void __launch_bounds__(256) k_sanitize_fused(int W, int H, Bits K0, B
 // The same three steps with the intermediate words kept in shared memory: a CTA owns kSanRows full rows, forms
 // k1 for its rows + 1 halo row either side, c1 for its rows + 1 above, then the results -- each intermediate
 // word is computed ~1.1 times instead of 9 (k1) / 4 (c1) times as in the register-only version above:
-// 6.5 M -> <1 M warp instructions per 12-Mpix frame (profiles/r02_kernels_ncu.txt), which is what the kernel
+// 6.5 M -> 3.7 M warp instructions per 12-Mpix frame (profiles/r02_stagea_ncu.txt), which is what the kernel
 // takes away from the fused kernel it runs beside in the sequence engine.  Dynamic shared memory:
 // (2 kSanRows + 3) (wpr + 2) words; frames too wide for 48 KB use the register-only kernel.
 constexpr int kSanRows = 14;
