@@ -57,8 +57,9 @@ struct FrameC {
 // call, <= 2 ulp from the reference's value.
 // ---------------------------------------------------------------------------------------
 // f(u,v) = sum_{p+q<=order} C_pq u^p v^q, Horner in v inside Horner in u, highest power first
-// (the fixed evaluation order of oracle/_sip_poly; plain multiply + add so that both sides
-// round alike).  Coefficients: packed triangular, index(p,q) = p*(order+1) - p*(p-1)/2 + q,
+// (the evaluation order of oracle/_sip_poly; each Horner step is ONE fused multiply-add here -- half the FP64
+// instructions of multiply + add and one rounding instead of two: both sides are held to <= 2 ulp of the
+// exact rational value of the polynomial, tests/test_gpu_parity.py::test_sip_device_polynomial_...).  Coefficients: packed triangular, index(p,q) = p*(order+1) - p*(p-1)/2 + q,
 // staged in shared memory by the kernel (every lane reads the same word: broadcast).
 template <int ORDER>
 AMT_HD double sip_poly_fixed(const double* __restrict__ c, double u, double v) {
@@ -68,8 +69,8 @@ AMT_HD double sip_poly_fixed(const double* __restrict__ c, double u, double v) {
         const int base = p * (ORDER + 1) - (p * (p - 1)) / 2;
         double inner = 0.0;
 #pragma unroll
-        for (int q = ORDER - p; q >= 0; --q) inner = inner * v + c[base + q];
-        acc = acc * u + inner;
+        for (int q = ORDER - p; q >= 0; --q) inner = fma(inner, v, c[base + q]);
+        acc = fma(acc, u, inner);
     }
     return acc;
 }
@@ -86,8 +87,8 @@ AMT_HD double sip_poly(const double* __restrict__ c, int order, double u, double
     for (int p = order; p >= 0; --p) {
         const int base = p * (order + 1) - (p * (p - 1)) / 2;
         double inner = 0.0;
-        for (int q = order - p; q >= 0; --q) inner = inner * v + c[base + q];
-        acc = acc * u + inner;
+        for (int q = order - p; q >= 0; --q) inner = fma(inner, v, c[base + q]);
+        acc = fma(acc, u, inner);
     }
     return acc;
 }
