@@ -575,6 +575,23 @@ def single_gpu_variants(args, ctx, rank, world, timed, run_device, run_e2e, img_
     ms, _, _, _ = timed(lambda h: run_e2e(h, source=pageable), repeats=3)
     v["e2e_pageable"] = dict(per_step(ms), note="e2e with an unpinned numpy image (cudaMemcpyAsync stages it through "
                              "the driver's bounce buffer)")
+    # the plain two-call API of the reference, one frame at a time, nothing pipelined: what a drop-in user of
+    # `resample(getMapping(img, header), arcsecPerPx=100)` waits for (host image in, masked numpy arrays out)
+    from auromat_b200.mapping.spacecraft import getMapping
+    from auromat_b200.resample import resample
+    hdr = synthetic.issHeader(args.width, args.height)
+    lat = []
+    for r in range(8):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = resample(getMapping(pageable, hdr, identifier="single%d" % r), arcsecPerPx=ARCSEC_PER_PX)
+        _ = res.img.shape, res.elevation.shape
+        torch.cuda.synchronize()
+        lat.append((time.perf_counter() - t0) * 1e3)
+    v["single_call_latency"] = {"ms": float(np.median(lat[2:])), "ms_all": [round(x, 3) for x in lat],
+                                "value": args.width * args.height / (float(np.median(lat[2:])) * 1e-3) / 1e6, "unit": UNIT,
+                                "note": "resample(getMapping(numpy image, header), arcsecPerPx=100): unpinned host image "
+                                        "in, masked numpy image + elevation out, wall clock of one unpipelined call"}
     try:
         v["config3_sip_10arcsec"] = config3_variant(ctx)
     except Exception as e:      # pragma: no cover - reported, never hidden
