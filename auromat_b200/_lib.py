@@ -149,6 +149,7 @@ SIGNATURES = {
     "amt_plate_carree_resolution": (C.c_int, [C.c_double] * 5 + [c_double_p, c_double_p]),
     "amt_target_grid": (C.c_int, [C.c_double] * 6 + [C.POINTER(AmtGrid), C.POINTER(AmtGridInfo), C.POINTER(C.c_int32)]),
     "amt_side_scale": (C.c_double, [C.c_uint64]),
+    "amt_sip_displacement_bound": (C.c_int, [C.POINTER(AmtFrame), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "amt_pole_pixels": (C.c_int, [C.POINTER(AmtFrame), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                   C.POINTER(C.c_int32)]),
     "amt_seq_plan": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_double, C.POINTER(AmtStats),

@@ -165,6 +165,17 @@ extern "C" double amt_side_scale(uint64_t n_samples) {
     return ldexp(1.0, k);
 }
 
+extern "C" int amt_sip_displacement_bound(const amt_frame* fr, double* dx, double* dy) {
+    CHECK_ARG(fr && dx && dy, "amt_sip_displacement_bound: NULL argument");
+    GeorefParams p;
+    memset(&p, 0, sizeof p);
+    int rc = fill_frame(fr, p);
+    if (rc) return rc;
+    *dx = p.f.sip_dx;
+    *dy = p.f.sip_dy;
+    return AMT_OK;
+}
+
 // Where the geographic poles (on the inflated ellipsoid) appear in a WCS frame: the pole point is
 // projected through the inverse WCS (TAN, SIP undone by fixed-point iteration).  in_frame[i] != 0 when
 // pole i (0: north, 1: south) faces the camera, lies in front of the tangent plane and projects into

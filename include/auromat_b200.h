@@ -387,6 +387,12 @@ double amt_side_scale(uint64_t n_samples);
  * Replaces the outline / azimuth-sum test of mapping/mapping.py:705-718, geodesic.py:183-202: the
  * mapping encloses the pole iff that pixel is defined.                                             */
 int amt_pole_pixels(const amt_frame* frame, int32_t ix[2], int32_t iy[2], int32_t in_frame[2]);
+/* Rigorous bounds, in pixels, of the FITS-SIP displacement (u, v) -> (u + f(u,v), v + g(u,v)) over the pixel
+ * array of a frame (coordinates/wcs.py:54-56: the reference hands -SIP headers to astropy/wcslib):
+ * sum |A_pq| U^p V^q with U, V the largest |u|, |v| of the frame.  Host arithmetic, no device needed; 0, 0 for
+ * a header without SIP.  The hit-bitmap solver of TAN-SIP frames (amt_georef with only the bitmaps requested)
+ * inflates the box of every bitmap word by these bounds.                                                 */
+int amt_sip_displacement_bound(const amt_frame* frame, double* dx, double* dy);
 
 /* ----------------------------------------------------------------- sequence engine ---- */
 /* The pipelined composition of getMappingSequence (mapping/spacecraft.py:308-332) and

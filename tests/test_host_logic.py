@@ -344,6 +344,40 @@ def test_c_grid_derivation_is_bit_identical_to_python():
         assert lib.amt_side_scale(n) == R.sideScale(n), n
 
 
+def test_c_sip_displacement_bound_encloses_the_polynomial():
+    """amt_sip_displacement_bound (the box inflation of the TAN-SIP hit-bitmap solver): never below the
+    largest displacement the oracle's SIP polynomial produces anywhere on the corner / centre lattice of the
+    frame (a bound that is too small would let the solver fill a word it should have evaluated), and not
+    absurdly above it; zero for a pure TAN header."""
+    import ctypes as C
+    from auromat_b200.coordinates.wcs import frameConstants
+    lib = _lib.load()
+    for W, H, order, seed in [(97, 61, 2, 3), (532, 354, 4, 4), (1064, 708, 3, 5), (700, 500, 5, 6), (6000, 4000, 4, 7)]:
+        hdr = synthetic.issHeader(W, H, sipOrder=order, seed=seed)
+        t, cam = synthetic.headerTimeAndCamera(hdr)
+        fr = frameConstants(hdr, cam, t, 110)
+        dx, dy = C.c_double(), C.c_double()
+        assert lib.amt_sip_displacement_bound(C.byref(fr), C.byref(dx), C.byref(dy)) == 0
+        oa, A, ob, B = O.sip_coefficients(hdr)
+        # every ray the kernels evaluate: corners at x - 0.5 and centres at x, x = 0 .. W (wcs.py:93-99: + 1 - CRPIX)
+        step = max(1, W // 400)
+        xs = np.unique(np.concatenate([np.arange(0, W + 1, step), [W]])).astype(float)
+        ys = np.unique(np.concatenate([np.arange(0, H + 1, step), [H]])).astype(float)
+        worst = [0.0, 0.0]
+        for off in (-0.5, 0.0):
+            u, v = np.meshgrid(xs + off - hdr['CRPIX1'] + 1, ys + off - hdr['CRPIX2'] + 1)
+            worst[0] = max(worst[0], float(np.abs(O._sip_poly(A, u, v)).max()))
+            worst[1] = max(worst[1], float(np.abs(O._sip_poly(B, u, v)).max()))
+        assert worst[0] <= dx.value <= 12 * worst[0] + 1e-9, (W, H, order, worst, dx.value)
+        assert worst[1] <= dy.value <= 12 * worst[1] + 1e-9, (W, H, order, worst, dy.value)
+    hdr = synthetic.issHeader(640, 426)
+    t, cam = synthetic.headerTimeAndCamera(hdr)
+    fr = frameConstants(hdr, cam, t, 110)
+    dx, dy = C.c_double(1.0), C.c_double(1.0)
+    assert lib.amt_sip_displacement_bound(C.byref(fr), C.byref(dx), C.byref(dy)) == 0
+    assert dx.value == 0.0 and dy.value == 0.0
+
+
 def test_c_pole_pixels_matches_numpy_projection():
     """amt_pole_pixels (inverse WCS projection of the pole point, C) against an independent numpy
     evaluation, for cameras around the pole, elsewhere, and with SIP."""
