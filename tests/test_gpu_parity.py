@@ -1264,6 +1264,43 @@ def test_pipeline_box_upload_for_rolled_cameras(env):
             assert np.array_equal(f.img.filled(0), e.img.filled(0))
 
 
+def test_outline_queue_overflow_noise_mask(env):
+    """A hand-made mapping whose validity is salt-and-pepper noise: more outline corners (1.4 M) than the node
+    queue of k_outline_collect holds (2^20), so the excess is evaluated in place by the collecting kernel --
+    bounding box, pixel box and counts must still equal numpy's over the sanitised masks."""
+    import datetime
+    import torch
+    from auromat_b200.mapping.mapping import GenericMapping
+    h, w = 1900, 2000
+    rng = np.random.default_rng(12)
+    lats = np.linspace(60, 40, h + 1)[:, None] + rng.uniform(-1e-3, 1e-3, (h + 1, w + 1))
+    lons = np.linspace(-20, 25, w + 1)[None, :] + rng.uniform(-1e-3, 1e-3, (h + 1, w + 1))
+    latsC = 0.25 * (lats[:-1, :-1] + lats[1:, :-1] + lats[:-1, 1:] + lats[1:, 1:])
+    lonsC = 0.25 * (lons[:-1, :-1] + lons[1:, :-1] + lons[:-1, 1:] + lons[1:, 1:])
+    # 2 x 2 blocks of pixels survive with probability 1/2: after sanitisation the valid region is a foam
+    # in which nearly every valid corner touches an invalid neighbour
+    keep = np.kron(rng.random((h // 2, w // 2)) < 0.5, np.ones((2, 2), bool))
+    latsC = np.where(keep, latsC, np.nan)
+    lonsC = np.where(keep, lonsC, np.nan)
+    img = rng.integers(0, 255, (h, w, 1), dtype=np.uint8)
+    m = GenericMapping(lats, lons, latsC, lonsC, np.full((h, w), 30.0), 110, img, np.zeros(3),
+                       datetime.datetime(2012, 1, 1), 'noise')
+    st = m._deviceStats()
+    p = m.devicePlanes()
+    vk = ~torch.isnan(p['lat_k']).reshape(h + 1, w + 1).cpu().numpy()
+    vc = ~torch.isnan(p['lat_c']).reshape(h, w).cpu().numpy()
+    pad = np.pad(vk, 1)
+    interior = pad[1:-1, 1:-1] & pad[:-2, 1:-1] & pad[2:, 1:-1] & pad[1:-1, :-2] & pad[1:-1, 2:]
+    outline = vk & ~interior
+    assert outline.sum() > 2 ** 20                      # the queue does overflow
+    assert st.n_boundary_corners == outline.sum() and st.n_valid_corners == vk.sum() and st.n_valid_centers == vc.sum()
+    la, lo = p['lat_k'].reshape(h + 1, w + 1).cpu().numpy(), p['lon_k'].reshape(h + 1, w + 1).cpu().numpy()
+    assert (st.lat_min, st.lat_max, st.lon_min, st.lon_max) == (la[outline].min(), la[outline].max(),
+                                                                lo[outline].min(), lo[outline].max())
+    rows, cols = np.nonzero(vc)
+    assert (st.row_min_c, st.row_max_c, st.col_min_c, st.col_max_c) == (rows.min(), rows.max(), cols.min(), cols.max())
+
+
 # ======================================================================= round 2: fused path
 def _geometries(W, H):
     """Camera geometries for the limb solver: the ISS frame, random rolls / scales / pointings
