@@ -313,12 +313,19 @@ def test_generic_mapping_resample_branches(env, mode):
         assert d.max() <= tol
 
 
-def test_sanitize_matches_oracle(env):
+@pytest.mark.parametrize("kernel,h,w", [("tile", 130, 170), ("registers", 130, 170), ("tile", 61, 1500), ("tile", 3, 5)])
+def test_sanitize_matches_oracle(env, kernel, h, w, monkeypatch):
+    """_doSanitize on the bitmaps against the oracle (itself bit-equal to the reference): the shared-memory
+    tile kernel (several row tiles, partial last tile, a frame narrower than a word) and the register-only
+    kernel that very wide frames fall back to."""
     import torch
     import oracle.auromat_oracle as O
     ctx = env
+    if kernel == "registers":
+        monkeypatch.setenv("AMT_SANITIZE_REGISTERS", "1")
+    else:
+        monkeypatch.delenv("AMT_SANITIZE_REGISTERS", raising=False)
     rng = np.random.default_rng(5)
-    h, w = 130, 170
     lat_k = rng.uniform(0, 1, (h + 1, w + 1))
     lat_k[rng.uniform(size=lat_k.shape) < 0.2] = np.nan
     lat_c = rng.uniform(0, 1, (h, w))
