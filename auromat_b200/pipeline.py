@@ -513,7 +513,11 @@ class _Engine(object):
                 st = ctx.__dict__[name] = torch.cuda.Stream(dev, priority=prio)
             return st
         self.main = main
-        self.aux, self.copy, self.dout = stream('_aux_stream', int(os.environ.get('AMT_SEQ_AUX_PRIORITY', '-1'))), stream('_copy_stream'), stream('_dout_stream')
+        # stage A and the accumulator memset run at HIGH priority: at ordinary priority they would wait until the
+        # long kernel has dispatched its last CTA (0.328 instead of 0.262 ms per frame,
+        # profiles/r02_stage_a_interference.txt; AMT_SEQ_AUX_PRIORITY=0 reproduces that measurement)
+        auxPriority = int(os.environ.get('AMT_SEQ_AUX_PRIORITY', '-1'))
+        self.aux, self.copy, self.dout = stream('_aux_stream', auxPriority), stream('_copy_stream'), stream('_dout_stream')
         self.handle = ctypes.c_void_p()
         _lib.check(ctx.lib.amt_seq_create(ctx.handle, w, h, channels, self.amtDtype, nslots,
                                           ctypes.c_void_p(main.cuda_stream), ctypes.c_void_p(self.aux.cuda_stream),
