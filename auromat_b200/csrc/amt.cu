@@ -2465,6 +2465,18 @@ __device__ __forceinline__ bool tile_accumulate(int cell, int ix, int fy, const 
 // One 32-pixel row segment of the tile: everything the fused kernel does for pixel (x, y), given the
 // words mk / mc of the frame's final bitmaps that cover the warp's 32 corners / centres.
 template <typename T, int C, bool PLANES, bool MAG, bool BIN, bool SIP, bool PRIV>
+// The 817 MB of coordinate planes a frame writes are never read again by this kernel: streaming stores
+// (st.global.cs, evict-first in L2) keep them from displacing the L2-resident working set of everything that
+// runs beside the kernel -- the grid accumulators of its own atomics (8 MB), the bitmaps and node queue of the
+// stage-A kernels of other frames.  Kernel alone 237.5 -> 236.1 us, frame period in the engine 0.261 -> 0.257 ms.
+#ifndef AMT_PLANE_STCS
+#define AMT_PLANE_STCS 1
+#endif
+#if AMT_PLANE_STCS
+#define PLANE_ST(ptr, v) __stcs((ptr), (v))
+#else
+#define PLANE_ST(ptr, v) (*(ptr) = (v))
+#endif
 __device__ __forceinline__ void fused_row(const GeorefParams& p, const double* s_sip, unsigned* s_acc, int* s_win,
                                           const int x, const int y, const unsigned mk, const unsigned mc,
                                           const T* __restrict__ img, const GridC& g,
@@ -2485,12 +2497,12 @@ __device__ __forceinline__ void fused_row(const GeorefParams& p, const double* s
     if ((mk | mc) == 0) {                    // nothing defined in this warp's 32 pixels
         if (PLANES) {
             if (in_k) {
-                p.o.d_lat_k[ik] = nan; p.o.d_lon_k[ik] = nan;
-                if (MAG) { p.o.d_mlat_k[ik] = nan; p.o.d_mlt_k[ik] = nan; }
+                PLANE_ST(&p.o.d_lat_k[ik], nan); PLANE_ST(&p.o.d_lon_k[ik], nan);
+                if (MAG) { PLANE_ST(&p.o.d_mlat_k[ik], nan); PLANE_ST(&p.o.d_mlt_k[ik], nan); }
             }
             if (in_c) {
-                p.o.d_lat_c[ic] = nan; p.o.d_lon_c[ic] = nan; p.o.d_elev_c[ic] = nan;
-                if (MAG) { p.o.d_mlat_c[ic] = nan; p.o.d_mlt_c[ic] = nan; }
+                PLANE_ST(&p.o.d_lat_c[ic], nan); PLANE_ST(&p.o.d_lon_c[ic], nan); PLANE_ST(&p.o.d_elev_c[ic], nan);
+                if (MAG) { PLANE_ST(&p.o.d_mlat_c[ic], nan); PLANE_ST(&p.o.d_mlt_c[ic], nan); }
             }
         }
         if (!PRIV) return;
@@ -2516,20 +2528,20 @@ __device__ __forceinline__ void fused_row(const GeorefParams& p, const double* s
             if (PLANES) point_to_geo(p.f, Pk, la_k, lo_k);
             point_to_geo(p.f, Pc, la_c, lo_c, r2_c);
             if (PLANES) {
-                if (in_k) { p.o.d_lat_k[ik] = la_k; p.o.d_lon_k[ik] = lo_k; }
-                if (in_c) { p.o.d_lat_c[ic] = la_c; p.o.d_lon_c[ic] = lo_c; }
+                if (in_k) { PLANE_ST(&p.o.d_lat_k[ik], la_k); PLANE_ST(&p.o.d_lon_k[ik], lo_k); }
+                if (in_c) { PLANE_ST(&p.o.d_lat_c[ic], la_c); PLANE_ST(&p.o.d_lon_c[ic], lo_c); }
             }
         }
         if (PLANES && MAG) {
             double ml_k, mt_k, ml_c, mt_c;
             point_to_mag(p.f, Pk, ml_k, mt_k);
             point_to_mag(p.f, Pc, ml_c, mt_c);
-            if (in_k) { p.o.d_mlat_k[ik] = ml_k; p.o.d_mlt_k[ik] = mt_k; }
-            if (in_c) { p.o.d_mlat_c[ic] = ml_c; p.o.d_mlt_c[ic] = mt_c; }
+            if (in_k) { PLANE_ST(&p.o.d_mlat_k[ik], ml_k); PLANE_ST(&p.o.d_mlt_k[ik], mt_k); }
+            if (in_c) { PLANE_ST(&p.o.d_mlat_c[ic], ml_c); PLANE_ST(&p.o.d_mlt_c[ic], mt_c); }
         }
         if (PLANES || (BIN && fsum != nullptr)) {
             elev = elevation_deg<false>(dc, Pc, r2_c);
-            if (PLANES && in_c) p.o.d_elev_c[ic] = elev;
+            if (PLANES && in_c) PLANE_ST(&p.o.d_elev_c[ic], elev);
         }
         if (BIN && vc) {
             bool near;
