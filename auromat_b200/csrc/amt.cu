@@ -2161,11 +2161,12 @@ __global__ void __launch_bounds__(256) k_bin(const double* __restrict__ lat, con
     for (int k = 0; k < kBinSeg; ++k) {
         const size_t i = base + 32 * k;
         const bool in = i < n;
-        la[k] = in ? lat[i] : qnan();
-        lo[k] = in ? lon[i] : 0.0;
-        sd[k] = (SIDE != kSideNone && in) ? side[i] : 0.0;
+        // read once: streaming loads (evict-first) leave the L2 to the grid accumulators
+        la[k] = in ? __ldcs(&lat[i]) : qnan();
+        lo[k] = in ? __ldcs(&lon[i]) : 0.0;
+        sd[k] = (SIDE != kSideNone && in) ? __ldcs(&side[i]) : 0.0;
 #pragma unroll
-        for (int c = 0; c < C; ++c) val[k][c] = in ? (unsigned)img[i * C + c] : 0u;
+        for (int c = 0; c < C; ++c) val[k][c] = in ? (unsigned)__ldcs(&img[i * C + c]) : 0u;
     }
     bool near_any = false;
 #pragma unroll
