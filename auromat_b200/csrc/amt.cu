@@ -302,14 +302,28 @@ static unsigned int golden_stride(unsigned int rows) {
     return s % rows ? s % rows : 1;
 }
 
+// The 817 MB of coordinate planes a frame writes are never read again by the kernel that writes them (the passes that follow read
+// them from DRAM anyway: 868 MB against 126 MB of L2): streaming stores
+// (st.global.cs, evict-first in L2) keep them from displacing the L2-resident working set of everything that
+// runs beside the kernel -- the grid accumulators of its own atomics (8 MB), the bitmaps and node queue of the
+// stage-A kernels of other frames.  Kernel alone 237.5 -> 236.1 us, frame period in the engine 0.261 -> 0.257 ms.
+#ifndef AMT_PLANE_STCS
+#define AMT_PLANE_STCS 1
+#endif
+#if AMT_PLANE_STCS
+#define PLANE_ST(ptr, v) __stcs((ptr), (v))
+#else
+#define PLANE_ST(ptr, v) (*(ptr) = (v))
+#endif
+
 // Writes NaN to every requested plane of one point (a ray that misses the ellipsoid).
 __device__ __forceinline__ void emit_nan(size_t i, double* __restrict__ a, double* __restrict__ b,
                                          double* __restrict__ c, double* __restrict__ d) {
     const double nan = qnan();
-    if (a) a[i] = nan;
-    if (b) b[i] = nan;
-    if (c) c[i] = nan;
-    if (d) d[i] = nan;
+    if (a) PLANE_ST(&a[i], nan);
+    if (b) PLANE_ST(&b[i], nan);
+    if (c) PLANE_ST(&c[i], nan);
+    if (d) PLANE_ST(&d[i], nan);
 }
 
 // One intersection point -> all requested outputs at flat index i.
@@ -321,16 +335,16 @@ __device__ __forceinline__ double emit_point(const GeorefParams& p, const double
     if (lat_o || lon_o) {
         double lat, lon;
         point_to_geo(p.f, P, lat, lon, r2);
-        if (lat_o) lat_o[i] = lat;
-        if (lon_o) lon_o[i] = lon;
+        if (lat_o) PLANE_ST(&lat_o[i], lat);
+        if (lon_o) PLANE_ST(&lon_o[i], lon);
     } else {
         r2 = fma(P[2], P[2], fma(P[1], P[1], P[0] * P[0]));
     }
     if (mlat_o || mlt_o) {
         double mlat, mlt;
         point_to_mag(p.f, P, mlat, mlt);
-        if (mlat_o) mlat_o[i] = mlat;
-        if (mlt_o) mlt_o[i] = mlt;
+        if (mlat_o) PLANE_ST(&mlat_o[i], mlat);
+        if (mlt_o) PLANE_ST(&mlt_o[i], mlt);
     }
     return r2;
 }
@@ -403,17 +417,17 @@ __global__ void __launch_bounds__(256, AMT_GEOREF_MINBLOCKS) k_georef_points(con
     const unsigned ik = (unsigned)y * (unsigned)(W + 1) + (unsigned)x, ic = (unsigned)y * (unsigned)W + (unsigned)x;
     if ((mk | mc) == 0) {                    // the whole warp looks at space
         if (FULL) {
-            if (in_k) { p.o.d_lat_k[ik] = nan; p.o.d_lon_k[ik] = nan; p.o.d_mlat_k[ik] = nan; p.o.d_mlt_k[ik] = nan; }
+            if (in_k) { PLANE_ST(&p.o.d_lat_k[ik], nan); PLANE_ST(&p.o.d_lon_k[ik], nan); PLANE_ST(&p.o.d_mlat_k[ik], nan); PLANE_ST(&p.o.d_mlt_k[ik], nan); }
             if (in_c) {
-                p.o.d_lat_c[ic] = nan; p.o.d_lon_c[ic] = nan; p.o.d_mlat_c[ic] = nan; p.o.d_mlt_c[ic] = nan;
-                p.o.d_elev_c[ic] = nan;
+                PLANE_ST(&p.o.d_lat_c[ic], nan); PLANE_ST(&p.o.d_lon_c[ic], nan); PLANE_ST(&p.o.d_mlat_c[ic], nan); PLANE_ST(&p.o.d_mlt_c[ic], nan);
+                PLANE_ST(&p.o.d_elev_c[ic], nan);
             }
             return;
         }
         if (in_k) emit_nan(ik, p.o.d_lat_k, p.o.d_lon_k, p.o.d_mlat_k, p.o.d_mlt_k);
         if (in_c) {
             emit_nan(ic, p.o.d_lat_c, p.o.d_lon_c, p.o.d_mlat_c, p.o.d_mlt_c);
-            if (p.o.d_elev_c) p.o.d_elev_c[ic] = nan;
+            if (p.o.d_elev_c) PLANE_ST(&p.o.d_elev_c[ic], nan);
         }
         return;
     }
@@ -429,12 +443,12 @@ __global__ void __launch_bounds__(256, AMT_GEOREF_MINBLOCKS) k_georef_points(con
         if (WANT_K) point_to_geo(p.f, Pk, la_k, lo_k);
         if (WANT_C) point_to_geo(p.f, Pc, la_c, lo_c, r2_c);
         if (WANT_K && in_k) {
-            if (FULL || p.o.d_lat_k) p.o.d_lat_k[ik] = la_k;
-            if (FULL || p.o.d_lon_k) p.o.d_lon_k[ik] = lo_k;
+            if (FULL || p.o.d_lat_k) PLANE_ST(&p.o.d_lat_k[ik], la_k);
+            if (FULL || p.o.d_lon_k) PLANE_ST(&p.o.d_lon_k[ik], lo_k);
         }
         if (WANT_C && in_c) {
-            if (FULL || p.o.d_lat_c) p.o.d_lat_c[ic] = la_c;
-            if (FULL || p.o.d_lon_c) p.o.d_lon_c[ic] = lo_c;
+            if (FULL || p.o.d_lat_c) PLANE_ST(&p.o.d_lat_c[ic], la_c);
+            if (FULL || p.o.d_lon_c) PLANE_ST(&p.o.d_lon_c[ic], lo_c);
         }
     }
     if (mag) {
@@ -442,18 +456,18 @@ __global__ void __launch_bounds__(256, AMT_GEOREF_MINBLOCKS) k_georef_points(con
         if (WANT_K) point_to_mag(p.f, Pk, ml_k, mt_k);
         if (WANT_C) point_to_mag(p.f, Pc, ml_c, mt_c);
         if (WANT_K && in_k) {
-            if (FULL || p.o.d_mlat_k) p.o.d_mlat_k[ik] = ml_k;
-            if (FULL || p.o.d_mlt_k) p.o.d_mlt_k[ik] = mt_k;
+            if (FULL || p.o.d_mlat_k) PLANE_ST(&p.o.d_mlat_k[ik], ml_k);
+            if (FULL || p.o.d_mlt_k) PLANE_ST(&p.o.d_mlt_k[ik], mt_k);
         }
         if (WANT_C && in_c) {
-            if (FULL || p.o.d_mlat_c) p.o.d_mlat_c[ic] = ml_c;
-            if (FULL || p.o.d_mlt_c) p.o.d_mlt_c[ic] = mt_c;
+            if (FULL || p.o.d_mlat_c) PLANE_ST(&p.o.d_mlat_c[ic], ml_c);
+            if (FULL || p.o.d_mlt_c) PLANE_ST(&p.o.d_mlt_c[ic], mt_c);
         }
     }
     if (WANT_C && in_c && (FULL || p.o.d_elev_c)) {
         if (!geo) r2_c = fma(Pc[2], Pc[2], fma(Pc[1], Pc[1], Pc[0] * Pc[0]));
         double e = (!PLAIN && p.f.model == AMT_MODEL_ALLSKY) ? cam_el : elevation_deg<false>(dc, Pc, r2_c);
-        p.o.d_elev_c[ic] = hit_c ? e : nan;
+        PLANE_ST(&p.o.d_elev_c[ic], hit_c ? e : nan);
     }
 }
 
@@ -790,10 +804,10 @@ __global__ void __launch_bounds__(TW* TH) k_georef_tiles(const __grid_constant__
         chit = P[0] == P[0];                        // all four corner rays hit
         if (chit) {
             const double r2 = emit_point(p, P, i, p.o.d_lat_c, p.o.d_lon_c, p.o.d_mlat_c, p.o.d_mlt_c);
-            if (p.o.d_elev_c) p.o.d_elev_c[i] = elevation_deg<true>(dir, P, r2);
+            if (p.o.d_elev_c) PLANE_ST(&p.o.d_elev_c[i], elevation_deg<true>(dir, P, r2));
         } else {
             emit_nan(i, p.o.d_lat_c, p.o.d_lon_c, p.o.d_mlat_c, p.o.d_mlt_c);
-            if (p.o.d_elev_c) p.o.d_elev_c[i] = qnan();
+            if (p.o.d_elev_c) PLANE_ST(&p.o.d_elev_c[i], qnan());
         }
     }
     __syncwarp();
@@ -2466,18 +2480,6 @@ __device__ __forceinline__ bool tile_accumulate(int cell, int ix, int fy, const 
 // One 32-pixel row segment of the tile: everything the fused kernel does for pixel (x, y), given the
 // words mk / mc of the frame's final bitmaps that cover the warp's 32 corners / centres.
 template <typename T, int C, bool PLANES, bool MAG, bool BIN, bool SIP, bool PRIV>
-// The 817 MB of coordinate planes a frame writes are never read again by this kernel: streaming stores
-// (st.global.cs, evict-first in L2) keep them from displacing the L2-resident working set of everything that
-// runs beside the kernel -- the grid accumulators of its own atomics (8 MB), the bitmaps and node queue of the
-// stage-A kernels of other frames.  Kernel alone 237.5 -> 236.1 us, frame period in the engine 0.261 -> 0.257 ms.
-#ifndef AMT_PLANE_STCS
-#define AMT_PLANE_STCS 1
-#endif
-#if AMT_PLANE_STCS
-#define PLANE_ST(ptr, v) __stcs((ptr), (v))
-#else
-#define PLANE_ST(ptr, v) (*(ptr) = (v))
-#endif
 __device__ __forceinline__ void fused_row(const GeorefParams& p, const double* s_sip, unsigned* s_acc, int* s_win,
                                           const int x, const int y, const unsigned mk, const unsigned mc,
                                           const T* __restrict__ img, const GridC& g,
