@@ -625,7 +625,11 @@ def _engineSequence(ctx, imagesOrArrays, wcsHeaders, pxPerDeg, arcsecPerPx, alti
             prev._detachRing()
         if ringBuffers:
             if eng.slots[slot] is None:
-                eng.setSlot(slot, eng.newBuffers(), hostImg is not None)
+                # the whole ring at once (8 plane sets, 7 GB for a 12-Mpix frame): a sequence reaches its steady
+                # state with its first frame instead of paying a device allocation per slot over its first frames
+                for s_ in range(nslots):
+                    if eng.slots[s_] is None:
+                        eng.setSlot(s_, eng.newBuffers(), hostImg is not None)
             elif hostImg is not None and not eng.hasImage[slot]:
                 # an engine first used with device images gets its image ring with the first host image
                 eng.setSlot(slot, eng.slots[slot], True)

@@ -44,7 +44,7 @@ def parse_args():
                     help="timed steps per repeat (default: 100 for the B200 arm -- a step is ~0.3 ms -- and 2 for "
                          "--impl reference)")
     ap.add_argument("--warmup", type=int, default=None, help="untimed steps (default: 10 / 1)")
-    ap.add_argument("--repeats", type=int, default=7, help="the K timed steps are repeated this often; median reported")
+    ap.add_argument("--repeats", type=int, default=9, help="the K timed steps are repeated this often; median reported")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--width", type=int, default=4256)
     ap.add_argument("--height", type=int, default=2832)
