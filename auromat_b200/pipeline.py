@@ -458,10 +458,14 @@ def resampleSequence(imagesOrArrays, wcsHeaders, pxPerDeg=25, arcsecPerPx=None, 
         return f
 
     try:
+        launched = 0
         for i, (img, hdr) in enumerate(zip(imagesOrArrays, wcsHeaders)):
             stageA.append(runA(i, img, hdr))
-            if len(stageA) >= depth:
+            # the look-ahead builds up from one frame to `depth`: the first frame's upload and long kernel are
+            # enqueued right after its own stage A instead of after `depth` host iterations (0.1 ms each)
+            if len(stageA) >= min(depth, launched + 1):
                 stageB.append(runB(*stageA.popleft()))
+                launched += 1
             while len(stageB) > depth:
                 ctx.use_stream(None)
                 yield finish(stageB.popleft())
@@ -738,10 +742,14 @@ def _engineSequence(ctx, imagesOrArrays, wcsHeaders, pxPerDeg, arcsecPerPx, alti
         return f
 
     try:
+        launched = 0
         for i, (img, hdr) in enumerate(zip(imagesOrArrays, wcsHeaders)):
             stageA.append(runA(i, img, hdr))
-            if len(stageA) >= depth:
+            # the look-ahead builds up from one frame to `depth`: the first frame's upload and long kernel are
+            # enqueued right after its own stage A instead of after `depth` host iterations (0.1 ms each)
+            if len(stageA) >= min(depth, launched + 1):
                 stageB.append(runB(*stageA.popleft()))
+                launched += 1
             while len(stageB) > AHEAD_B:
                 yield handOut(stageB.popleft())
         while stageA:
